@@ -1,0 +1,322 @@
+"""Scenario model shared by the parity tests.
+
+A Scenario describes a bank of voices (unit chains), the control writes each
+voice's A2S program would perform and when, and the render settings.  It can be
+turned into
+
+  * an .a2s script for the reference (`to_a2s`),  run through oracle/_ref/a2render
+  * an event list for the C port              (`run_oracle`)
+  * calls into the CUDA engine's C ABI         (`run_cuda`, tests/ only on GPU)
+
+so the three can be compared bit for bit on identical inputs.  All values are
+16:16 fixed point integers, exactly what the VM registers would hold; script
+literals are printed so that the compiler's floor(v * 65536 + .5)
+(compiler.c:494-503) reproduces them.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GENERATORS = {"wtosc", "fm1", "fm2", "fm3", "fm4", "fm3p", "fm4p", "fm2r", "fm4r"}
+FM_OPS = {"fm1": 1, "fm2": 2, "fm3": 3, "fm4": 4, "fm3p": 3, "fm4p": 4,
+          "fm2r": 2, "fm4r": 4}
+# (mininputs, maxinputs, minoutputs, maxoutputs, matchio)
+UNIT_IO = {"panmix": (1, 2, 1, 2, False), "filter12": (1, 2, 1, 2, True),
+           "waveshaper": (1, 2, 1, 2, True)}
+for _g in GENERATORS:
+    UNIT_IO[_g] = (0, 0, 1, 1, False)
+
+REGS = {
+    "wtosc": ["w", "p", "a", "phase"],
+    "panmix": ["vol", "pan"],
+    "filter12": ["cutoff", "q", "lp", "bp", "hp"],
+    "waveshaper": ["amount"],
+}
+for _k, _n in FM_OPS.items():
+    r = ["phase", "p", "a", "fb"]
+    for _o in range(1, _n):
+        r += ["p%d" % _o, "a%d" % _o, "fb%d" % _o]
+    REGS[_k] = r
+
+KIND_CODE = {"wtosc": 1, "panmix": 2, "filter12": 3, "waveshaper": 4,
+             "fm1": 16, "fm2": 17, "fm3": 18, "fm4": 19, "fm3p": 20,
+             "fm4p": 21, "fm2r": 22, "fm4r": 23}
+
+
+ROOT_WAKE_PERIOD = 1000000     # core.c:1195
+
+
+def fx(x):
+    """float -> 16:16 like a2c_Num2VM (compiler.c:494-503)."""
+    return int(np.floor(x * 65536.0 + 0.5))
+
+
+def lit(v):
+    """16:16 int -> script literal that compiles back to exactly v."""
+    s = "%.9f" % (v / 65536.0)   # a2_GetNum overflows at 10 decimals (compiler.c:876,889)
+    s = s.rstrip("0").rstrip(".")
+    return s if s not in ("", "-0") else "0"
+
+
+def autowire(kinds, voice_channels=2):
+    """Default-I/O autowiring of a struct: compiler.c:3036-3138 followed by the
+    instantiation rules of core.c:163-243. Returns a list of
+    (kind, ninputs, noutputs, add, wireout)."""
+    out = []
+    chain = 0
+    n = len(kinds)
+    for i, k in enumerate(kinds):
+        mini, maxi, mino, maxo, matchio = UNIT_IO[k]
+        add = 0
+        if maxi == 0:
+            nin = 0
+            if chain:
+                add = 1
+        else:
+            nin = mini
+            if not chain:
+                raise ValueError("A2_NOINPUT: %s has inputs but no chain" % k)
+            if nin != chain:
+                # default mininputs == 1; a 2-channel chain needs explicit I/O
+                nin = chain
+        dsi = any(UNIT_IO[kk][1] > 0 for kk in kinds[i + 1:])
+        if i == n - 1 or not dsi:
+            wireout = 1
+            add = 1
+            lo, hi = (nin, nin) if matchio else (mino, maxo)
+            nout = min(max(voice_channels, lo), hi)
+            chain = 0
+        else:
+            wireout = 0
+            nout = chain if chain else mino
+            if matchio:
+                nout = nin
+            if chain and not nin:
+                add = 1
+            chain = nout
+        out.append((KIND_CODE[k], nin, nout, add, wireout))
+    return out
+
+
+class Voice:
+    """One leaf voice: a struct (list of unit kinds) and a program: a list of
+    steps. Steps:
+        ("set", unit, reg, value)         '@reg value'  (immediate, dur 0)
+        ("ramp", unit, reg, value)        'reg value'   (applied at next delay)
+        ("d", ms_16_16)                   'd ms'
+    The program ends with an endless sleep."""
+
+    def __init__(self, kinds, steps, group=-1, transpose=0):
+        self.kinds = list(kinds)
+        self.steps = list(steps)
+        self.group = group
+        self.transpose = transpose
+
+
+class Scenario:
+    def __init__(self, samplerate=48000, channels=2, buffer=64, frames=4800,
+                 noiseseed=None):
+        self.samplerate = samplerate
+        self.channels = channels
+        self.buffer = buffer
+        self.frames = frames
+        self.noiseseed = noiseseed
+        self.transpose = 0        # Song-level 'tr', inherited by every voice
+        self.voices = []
+        self.ngroups = 0
+        self.group_steps = {}     # group -> steps on its panmix (unit 0)
+        self.waves = []           # names of builtin waves, index = wave id
+
+    def wave(self, name):
+        if name not in self.waves:
+            self.waves.append(name)
+        return self.waves.index(name)
+
+    def add_group(self, steps=()):
+        self.group_steps[self.ngroups] = list(steps)
+        self.ngroups += 1
+        return self.ngroups - 1
+
+    def add_voice(self, kinds, steps, group=-1):
+        self.voices.append(Voice(kinds, steps, group, self.transpose))
+        return len(self.voices) - 1
+
+    # ------------------------------------------------------------------
+    def msdur(self):
+        return int(np.float32(self.samplerate) * np.float32(65.536) + np.float32(.5))
+
+    def ms2t(self, d):
+        """core.c:1127-1130"""
+        return ((d * self.msdur() + 0x7fffff) >> 24) & 0xffffffff
+
+    def _unit_names(self, kinds):
+        names, seen = [], {}
+        for k in kinds:
+            c = seen.get(k, 0)
+            seen[k] = c + 1
+            names.append(None if c == 0 else "u%d" % (len(names) + 1))
+        return names
+
+    def _regname(self, kinds, names, unit, reg):
+        r = REGS[kinds[unit]][reg]
+        return r if names[unit] is None else "%s.%s" % (names[unit], r)
+
+    def _steps_to_events(self, steps, target, kind_write, kinds):
+        """Mirror of the VM: returns event tuples
+        (time, kind, target, unit, reg, value, dur)."""
+        ev = []
+        t = 0
+        pending = []
+        for st in steps:
+            if st[0] == "set":
+                _, u, r, v = st
+                pending = [p for p in pending if (p[0], p[1]) != (u, r)]
+                ev.append((t, kind_write, target, u, r, v, 0))
+            elif st[0] == "ramp":
+                _, u, r, v = st
+                for p in pending:
+                    if (p[0], p[1]) == (u, r):
+                        p[2] = v
+                        break
+                else:
+                    pending.append([u, r, v])
+            elif st[0] == "d":
+                dt = self.ms2t(st[1])
+                for u, r, v in pending:
+                    ev.append((t, kind_write, target, u, r, v, dt))
+                pending = []
+                t += dt
+                ev.append((t, 1, target, 0, 0, 0, 0))   # wake-up
+        return ev
+
+    def events(self):
+        from oracle import a2oracle as ao
+        ev = []
+        for vi, v in enumerate(self.voices):
+            ev += self._steps_to_events(v.steps, vi, ao.EV_WRITE, v.kinds)
+        for g, steps in self.group_steps.items():
+            e = self._steps_to_events(steps, g, ao.EV_GROUPWRITE, ["panmix"])
+            # the group's own wake-ups: GROUPWRITE with reg -1 (split only);
+            # its children are split implicitly by the inline recursion
+            # (core.c:1769-1776)
+            for x in e:
+                if x[1] == ao.EV_WAKE:
+                    ev.append((x[0], ao.EV_GROUPWRITE, g, 0, -1, 0, 0))
+                else:
+                    ev.append(x)
+        # The root voice runs a2_rootdriver, whose program falls into OP_END
+        # while attached: it re-arms its wake-up every 1000000 (24:8) time
+        # units (core.c:1191-1216), splitting every voice's segments there.
+        t = ROOT_WAKE_PERIOD
+        while t < (self.frames << 8):
+            ev.append((t, ao.EV_ROOTWRITE, 0, 0, -1, 0, 0))
+            t += ROOT_WAKE_PERIOD
+        order = sorted(range(len(ev)), key=lambda i: ev[i][0])
+        arr = np.zeros(len(ev), dtype=ao.EVENT_DTYPE)
+        for j, i in enumerate(order):
+            arr[j] = ev[i]
+        return arr
+
+    # ------------------------------------------------------------------
+    def to_a2s(self):
+        """Script whose Song() spawns every group and voice at time 0."""
+        L = ['def title "generated"', 'def a2sversion "1.9"', ""]
+
+        def body(kinds, steps, names):
+            out = []
+            for st in steps:
+                if st[0] == "set":
+                    rn = self._regname(kinds, names, st[1], st[2])
+                    val = self.waves[st[3] >> 16] if st[2] == 0 and \
+                        kinds[st[1]] == "wtosc" else lit(st[3])
+                    out.append("\t@%s %s" % (rn, val))
+                elif st[0] == "ramp":
+                    rn = self._regname(kinds, names, st[1], st[2])
+                    val = self.waves[st[3] >> 16] if st[2] == 0 and \
+                        kinds[st[1]] == "wtosc" else lit(st[3])
+                    out.append("\t%s %s" % (rn, val))
+                elif st[0] == "d":
+                    out.append("\td %s" % lit(st[1]))
+            out.append("\tfor { d 30000 }")
+            return out
+
+        for vi, v in enumerate(self.voices):
+            names = self._unit_names(v.kinds)
+            units = "; ".join(k if nm is None else "%s %s" % (k, nm)
+                              for k, nm in zip(v.kinds, names))
+            L.append("V%d()" % vi)
+            L.append("{")
+            L.append("\tstruct { %s }" % units)
+            L += body(v.kinds, v.steps, names)
+            L.append("}")
+            L.append("")
+        # Groups: { inline 0 *; panmix * > } == a2_groupdriver numerically
+        for g in range(self.ngroups):
+            members = [vi for vi, v in enumerate(self.voices) if v.group == g]
+            L.append("G%d()" % g)
+            L.append("{")
+            L.append("\tstruct { inline 0 *; panmix * > }")
+            for vi in members:
+                L.append("\tV%d" % vi)
+            L += body(["panmix"], self.group_steps[g], [None])
+            L.append("}")
+            L.append("")
+        # Spawn order: my engines process newest-first at every level, like
+        # a2_VoiceNew's head insertion; creation order here = index order.
+        L.append("export Song()")
+        L.append("{")
+        if self.transpose:
+            L.append("\ttr %s" % lit(self.transpose))
+        # root children in creation order: groups are created before the
+        # voices that reference them, voices with group -1 in index order
+        items = []
+        for g in range(self.ngroups):
+            items.append(("g", g))
+        for vi, v in enumerate(self.voices):
+            if v.group < 0:
+                items.append(("v", vi))
+        for kind, idx in items:
+            L.append("\t%s%d" % ("G" if kind == "g" else "V", idx))
+        L.append("\tfor { d 30000 }")
+        L.append("}")
+        return "\n".join(L) + "\n"
+
+
+def run_ref(scn, path):
+    from oracle import a2oracle as ao
+    with open(path, "w") as f:
+        f.write(scn.to_a2s())
+    out, info = ao.ref_render(path, "Song", samplerate=scn.samplerate,
+                              channels=scn.channels, buffer=scn.buffer,
+                              frames=scn.frames, noiseseed=scn.noiseseed)
+    if info["rt_error"]:
+        raise RuntimeError("reference reported RT error %d" % info["rt_error"])
+    return out
+
+
+def build_engine(scn, eng, kindmod):
+    """Create waves, groups and voices of `scn` in `eng` (oracle or cuda
+    wrapper: both expose builtin_wave/new_group/new_voice)."""
+    for w in scn.waves:
+        eng.builtin_wave(w)
+    for _ in range(scn.ngroups):
+        eng.new_group()
+    for v in scn.voices:
+        eng.new_voice(autowire(v.kinds), transpose=v.transpose, substart=0,
+                      group=v.group)
+
+
+def run_oracle(scn):
+    from oracle import a2oracle as ao
+    o = ao.Oracle(scn.samplerate, scn.channels)
+    if scn.noiseseed is not None:
+        o.set_noiseseed(scn.noiseseed)
+    build_engine(scn, o, ao)
+    out = o.render(scn.events(), scn.frames, scn.buffer)
+    o.close()
+    return out
