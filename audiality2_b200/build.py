@@ -1,0 +1,48 @@
+"""In-tree build of the CUDA libraries (sm_100a only).
+
+    python -m audiality2_b200.build            # liba2cu.so (engine + kernels)
+
+nvcc cross-compiles without a GPU; the resulting .so files are git-ignored but
+travel to the GPU box with the gpurun snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+ROOT = os.path.dirname(HERE)
+LIB = os.path.join(HERE, "liba2cu.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--expt-extended-lambda", "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared",
+]
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build_engine(force=False, verbose=False):
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)
+            if f.endswith((".cu", ".cuh", ".h"))]
+    srcs.append(os.path.join(ROOT, "include", "a2cu.h"))
+    if not force and not _stale(LIB, srcs):
+        return LIB
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+        "-I", os.path.join(ROOT, "include"), "-o", LIB,
+        os.path.join(CSRC, "a2cu_engine.cu")]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+def build_all(force=False, verbose=False):
+    return [build_engine(force, verbose)]
+
+
+if __name__ == "__main__":
+    print(build_all(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,735 @@
+// a2cu_device.cuh - device-side DSP primitives and voice-unit templates.
+//
+// One CUDA thread owns one voice. A voice structure ("chain") is a compile-time
+// list of unit templates; the scratch channels that the reference keeps in
+// st->scratch[nestlevel] (core.c:364-395) live in two registers. Per-voice
+// state is structure-of-arrays in HBM: word w of slot s is state[w * stride + s],
+// so a warp's load of one word is one coalesced 128-byte transaction.
+//
+// All audio arithmetic is integer and must match the reference bit for bit;
+// signed overflow is performed on unsigned operands (wraps like gcc/x86-64).
+// Reference file:line is cited at each function.
+#pragma once
+#include <stdint.h>
+
+namespace a2cu {
+
+#define A2CU_DEV __device__ __forceinline__
+
+constexpr int kMaxFrag = 64;      // A2_MAXFRAG, audiality2.h.cmake:50
+constexpr int kMipLevels = 10;    // a2_waves.h:33
+constexpr int kWavePre = 1;       // a2_waves.h:61
+constexpr int kMaxPhInc = 512;    // a2_waves.h:58
+
+// ---- wrapping helpers ------------------------------------------------------
+A2CU_DEV int wadd(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
+A2CU_DEV int wsub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
+A2CU_DEV int wmul(int a, int b) { return (int)((unsigned)a * (unsigned)b); }
+A2CU_DEV int mulshr(int a, int b, int sh) {       // (int64)a * b >> sh, truncated
+    return (int)(((long long)a * (long long)b) >> sh);
+}
+
+// ---- wave descriptors (read side of A2_wave, a2_waves.h:88-103) -------------
+enum WaveType { W_OFF = 0, W_NOISE = 1, W_WAVE = 2, W_MIPWAVE = 3 };
+constexpr unsigned kLooped = 0x100;               // A2_LOOPED, a2_waves.h:108
+
+struct WaveDesc {
+    int type;
+    unsigned flags;
+    unsigned period;
+    unsigned size[kMipLevels];      // excluding pads
+    unsigned offset[kMipLevels];    // index of data[level][A2_WAVEPRE] in the pool
+};
+
+// Everything a unit needs besides its own state.
+struct Ctx {
+    const WaveDesc *waves;
+    const int16_t *pool;            // all wave data, int16, pads included
+    const unsigned *ptab;           // 64 x {base, coeff}, pitch.c:70-96
+    const int16_t *fmsine;          // 2049-entry sine LUT (shared memory)
+    int samplerate;
+    unsigned *noisestate;           // per-voice LCG slot or nullptr
+};
+
+// ---- a2_dsp.h ---------------------------------------------------------------
+struct Ramp { int value, target, delta, timer; };
+
+// a2_dsp.h:128-149
+A2CU_DEV void ramp_prepare(Ramp &r, int frames) {
+    if (!r.timer) {
+        r.value = r.target;
+        r.delta = 0;
+    } else if (frames <= (r.timer >> 8)) {
+        r.delta = (int)(((long long)wsub(r.target, r.value) << 8) / r.timer);
+        r.timer -= frames << 8;
+    } else {
+        r.delta = wsub(r.target, r.value) / frames;
+        r.timer = 0;
+    }
+}
+// a2_dsp.h:152-155
+A2CU_DEV void ramp_run(Ramp &r, int frames) { r.value = wadd(r.value, wmul(r.delta, frames)); }
+// a2_dsp.h:161-170
+A2CU_DEV void ramp_set(Ramp &r, int target, int start, int dur) {
+    r.target = (int)((unsigned)target << 8);
+    r.timer = dur + start;
+    if (r.timer < 256)
+        r.value = r.target;
+    else
+        r.value = wadd(r.value, wmul(r.delta, start) >> 8);
+}
+// a2_dsp.h:121-125
+A2CU_DEV void ramp_init(Ramp &r, int v) {
+    r.value = r.target = (int)((unsigned)v << 8);
+    r.delta = r.timer = 0;
+}
+
+// a2_dsp.h:37-42
+A2CU_DEV int noise_next(unsigned &st) {
+    st = st * 1566083941u + 1u;
+    return (int)((st * (st >> 16)) >> 16);
+}
+
+// a2_dsp.h:50-55
+A2CU_DEV int lerp16(const int16_t *d, unsigned ph) {
+    int i = ph >> 8;
+    int x = ph & 0xff;
+    return (d[i] * (256 - x) + d[i + 1] * x) >> 8;
+}
+
+// a2_dsp.h:64-74 on raw taps
+A2CU_DEV int hermite4(int dm, int d0, int d1, int d2, unsigned ph) {
+    int x = (int)((ph & 0xff) << 7);
+    int c = (d1 - dm) >> 1;
+    int a = (3 * (d0 - d1) + d2 - dm) >> 1;
+    int b = dm - d0 + c - a;
+    a = wmul(a, x) >> 15;
+    a = wmul(a + b, x) >> 15;
+    return d0 + (wmul(a + c, x) >> 15);
+}
+A2CU_DEV int hermite(const int16_t *d, unsigned ph) {
+    int i = (int)(ph >> 8);
+    return hermite4(d[i - 1], d[i], d[i + 1], d[i + 2], ph);
+}
+
+// pitch.c:57-67; the shift count is taken & 31 like the x86-64 build does
+A2CU_DEV unsigned p2i(const unsigned *ptab, int pitch) {
+    int n = pitch & 0xffff;
+    int oct = pitch >> 16;
+    unsigned base = __ldg(ptab + 2 * (n >> 10));
+    unsigned coeff = __ldg(ptab + 2 * (n >> 10) + 1);
+    unsigned dph = coeff * (unsigned)(n & 0x3ff);
+    dph >>= 2;
+    dph += base;
+    return dph >> ((7 - oct) & 31);
+}
+
+// filter12.c:65-72: float multiply, double sin. The float/double operations
+// are IEEE-exact (no contraction); sin() is CUDA's (<= 2 ulp), glibc's on the
+// host is <= 1 ulp: after the truncation to int the two differ with
+// probability ~1e-8 per evaluation (DESIGN.md "filter12 coefficient").
+A2CU_DEV int f12_coeff(const unsigned *ptab, int cutoff_value, int samplerate) {
+    float f = __fmul_rn(__uint2float_rn(p2i(ptab, cutoff_value >> 8)), 261.626f / 16777216.0f);
+    if (f > (float)(samplerate >> 2))
+        return 362 << 16;
+    double x = __ddiv_rn(__dmul_rn(3.14159265358979323846, (double)f), (double)samplerate);
+    return (int)__dmul_rn(33554432.0, sin(x));
+}
+
+// ---- state I/O --------------------------------------------------------------
+struct StatePtr {
+    int *base;          // word 0 of this voice (already offset by slot)
+    size_t stride;      // slots per word row
+    A2CU_DEV int ld(int w) const { return base[(size_t)w * stride]; }
+    A2CU_DEV void st(int w, int v) const { base[(size_t)w * stride] = v; }
+    A2CU_DEV void ld_ramp(int w, Ramp &r) const {
+        r.value = ld(w); r.target = ld(w + 1); r.delta = ld(w + 2); r.timer = ld(w + 3);
+    }
+    A2CU_DEV void st_ramp(int w, const Ramp &r) const {
+        st(w, r.value); st(w + 1, r.target); st(w + 2, r.delta); st(w + 3, r.timer);
+    }
+};
+
+// =============================================================================
+// wtosc (src/units/wtosc.c)
+// =============================================================================
+enum OscMode { OSC_OFF = 0, OSC_NOISE = 1, OSC_NOMIP = 2, OSC_MIP = 3 };
+// per-segment inner loop variants
+enum OscRun { RUN_SILENT = 0, RUN_TABLE = 1, RUN_NOISE = 2, RUN_CHECK_LOOP = 3, RUN_CHECK_END = 4 };
+
+template <bool ADD, bool WIREOUT>
+struct WtOsc {
+    static constexpr int kWords = 14;
+    static constexpr int kNIn = 0, kNOut = 1;
+    static constexpr bool kUsesFm = false;
+    // persistent state (wtosc.c:66-80)
+    Ramp p, a;
+    unsigned dphase;
+    unsigned long long phase;
+    int noise, p_ramping;
+    int wave;           // index into Ctx::waves or -1
+    int mode;           // OscMode
+    // segment-local
+    const int16_t *d;
+    unsigned long long ph;
+    unsigned dph;
+    unsigned wsize;
+    int astep;
+    int mm, run;
+
+    A2CU_DEV void load(const StatePtr &s, int w) {
+        s.ld_ramp(w, p); s.ld_ramp(w + 4, a);
+        dphase = (unsigned)s.ld(w + 8);
+        phase = (unsigned)s.ld(w + 9) | ((unsigned long long)(unsigned)s.ld(w + 10) << 32);
+        noise = s.ld(w + 11);
+        int x = s.ld(w + 12);
+        p_ramping = s.ld(w + 13);
+        wave = x >> 8; mode = x & 0xff;
+        run = RUN_SILENT; astep = 0; mm = 0; d = nullptr; ph = 0; dph = 0; wsize = 0;
+    }
+    A2CU_DEV void store(const StatePtr &s, int w) const {
+        s.st_ramp(w, p); s.st_ramp(w + 4, a);
+        s.st(w + 8, (int)dphase);
+        s.st(w + 9, (int)(unsigned)phase); s.st(w + 10, (int)(unsigned)(phase >> 32));
+        s.st(w + 11, noise);
+        s.st(w + 12, (wave << 8) | mode);
+        s.st(w + 13, p_ramping);
+    }
+
+    // wtosc.c:378-387
+    A2CU_DEV void set_phase(const Ctx &c, int phv, unsigned sst) {
+        if (wave < 0) { phase = 0; return; }
+        phv = wadd(phv, (int)((sst * (dphase >> 8)) >> 8));
+        phase = (unsigned long long)(((long long)phv * (long long)c.waves[wave].period) << 8);
+    }
+    // wtosc.c:390-423; arg = transpose + basepitch, sst = waketime & 0xff
+    A2CU_DEV void init(const Ctx &c, int arg, unsigned sst) {
+        noise = 0; wave = -1;
+        ramp_init(a, 0);
+        ramp_init(p, arg);
+        dphase = p2i(c.ptab, p.value >> 8);
+        p_ramping = 0;
+        set_phase(c, 0, sst);
+        mode = OSC_OFF;
+    }
+    // wtosc.c:433-504. Values are pre-cooked by the host: reg 0 carries the
+    // device wave index (-1 = off/invalid), reg 1 the pitch incl. transpose
+    // and basepitch.
+    A2CU_DEV void write(const Ctx &c, int reg, int v, int start, int dur) {
+        switch (reg) {
+        case 0:
+            wave = v;
+            if (v < 0) mode = OSC_OFF;
+            else {
+                int t = c.waves[v].type;
+                mode = t == W_NOISE ? OSC_NOISE : t == W_WAVE ? OSC_NOMIP :
+                       t == W_MIPWAVE ? OSC_MIP : OSC_OFF;
+                if (mode == OSC_OFF) wave = -1;
+            }
+            break;
+        case 1:
+            ramp_set(p, v, start, dur);
+            if (!dur) p_ramping = 1;
+            break;
+        case 2: ramp_set(a, v, start, dur); break;
+        case 3: set_phase(c, v, (unsigned)start); break;
+        }
+    }
+    // wtosc.c:89-105
+    A2CU_DEV void run_pitch(const Ctx &c, int frames) {
+        ramp_prepare(p, frames);
+        if (dphase && (!p.timer && !p_ramping)) return;
+        unsigned lastv = (unsigned)p.value;
+        ramp_run(p, frames);
+        p_ramping = p.delta;
+        dphase = p2i(c.ptab, (int)((lastv + (unsigned)p.value) >> 9));
+    }
+    // Segment prologue: everything the reference does per Process() call
+    // before/around the sample loop (wtosc.c:108-126, 129-137, 239-286, 301-358)
+    A2CU_DEV void prepare(const Ctx &c, int frames) {
+        run = RUN_SILENT; astep = 0; mm = 0;
+        if (mode == OSC_MIP || mode == OSC_NOMIP) {
+            const WaveDesc &w = c.waves[wave];
+            if (!w.size[0]) {           // unloaded while playing, wtosc.c:168-183
+                wave = -1; mode = OSC_OFF;
+                return;
+            }
+        }
+        switch (mode) {
+        case OSC_OFF:
+            ramp_prepare(p, frames); ramp_prepare(a, frames);
+            ramp_run(p, frames); ramp_run(a, frames);
+            return;
+        case OSC_NOISE:
+            run_pitch(c, frames);
+            ramp_prepare(a, frames);
+            run = RUN_NOISE; astep = a.delta;
+            return;
+        case OSC_MIP: {
+            const WaveDesc &w = c.waves[wave];
+            run_pitch(c, frames);
+            unsigned e = ((dphase + 255) >> 8) * w.period;
+            ramp_prepare(a, frames);
+            int m = 0;
+            for (; (e > (unsigned)(kMaxPhInc << 8)) && (m < kMipLevels - 1); ++m) e >>= 1;
+            mm = m;
+            ph = phase >> m;
+            dph = (unsigned)(((unsigned long long)dphase * w.period) >> m);
+            if (w.flags & kLooped)
+                ph %= (unsigned long long)w.size[m] << 24;
+            else if ((ph >> 24) > (unsigned long long)(w.size[m] + kWavePre))
+                return;                 // all played: silence, nothing advances
+            if (dph > (unsigned)(kMaxPhInc << 16)) {
+                ph += (unsigned long long)dph * (unsigned)frames;
+                phase = ph << m;
+                ramp_run(a, frames);
+                return;                 // out of range: muted
+            }
+            d = c.pool + w.offset[m];
+            run = RUN_TABLE; astep = a.delta; wsize = 0;
+            return;
+        }
+        case OSC_NOMIP: {
+            const WaveDesc &w = c.waves[wave];
+            run_pitch(c, frames);
+            unsigned long long dp = (unsigned long long)dphase * w.period;
+            ramp_prepare(a, frames);
+            d = c.pool + w.offset[0];
+            if (dp >> 32) {
+                phase += dp * (unsigned)frames;
+                ramp_run(a, frames);
+                return;
+            }
+            dph = (unsigned)dp;
+            if (dp > (unsigned long long)(kMaxPhInc << 16)) {
+                ph = phase;
+                wsize = w.size[0];
+                run = (w.flags & kLooped) ? RUN_CHECK_LOOP : RUN_CHECK_END;
+                astep = a.delta;
+                return;
+            }
+            if (w.flags & kLooped) {
+                unsigned m32 = w.size[0] << 24;     // 32-bit, as written (wtosc.c:346)
+                if (m32) phase %= m32;              // (reference divides by zero here)
+            } else if ((phase >> 24) > (unsigned long long)(w.size[0] + kWavePre))
+                return;
+            ph = phase;
+            run = RUN_TABLE; astep = a.delta; wsize = 0;
+            return;
+        }
+        }
+    }
+    // One output sample. wtosc.c:200-236 (table), :139-151 (noise)
+    A2CU_DEV void sample(const Ctx &c, int &s0, int &s1, int &o0, int &o1) {
+        int v = 0;
+        if (run == RUN_TABLE || run >= RUN_CHECK_LOOP) {
+            bool live = true;
+            if (run == RUN_CHECK_LOOP)
+                ph %= (unsigned long long)wsize << 24;
+            else if (run == RUN_CHECK_END && (ph >> 24) >= wsize) {
+                run = RUN_SILENT; astep = 0; live = false;
+                phase = ph;
+            }
+            if (live) {
+                unsigned p16 = (unsigned)(ph >> 16);
+                unsigned dp16 = dph >> 16;
+                int h = hermite(d, p16) + hermite(d, p16 + (dp16 >> 1));
+                v = mulshr(h, a.value, 17);
+                ph += dph;
+                a.value = wadd(a.value, astep);
+            }
+        } else if (run == RUN_NOISE) {
+            unsigned long long nph = phase + dphase;
+            if ((dphase >= (1u << 23)) || ((nph ^ phase) >> 23))
+                noise = noise_next(*c.noisestate) - 32767;
+            phase = nph;
+            v = wmul(noise, a.value >> 10) >> 6;
+            a.value = wadd(a.value, astep);
+        }
+        if (WIREOUT) o0 = wadd(o0, v);
+        else if (ADD) s0 = wadd(s0, v);
+        else s0 = v;
+    }
+    // Segment epilogue: write the phase accumulator back (wtosc.c:283-285)
+    A2CU_DEV void finish() {
+        if (run == RUN_TABLE || run >= RUN_CHECK_LOOP) phase = ph << mm;
+        run = RUN_SILENT; astep = 0;
+    }
+};
+
+// =============================================================================
+// panmix (src/units/panmix.c)
+// =============================================================================
+template <int NIN, int NOUT, bool ADD, bool WIREOUT>
+struct PanMix {
+    static constexpr int kWords = 8;
+    static constexpr bool kUsesFm = false;
+    Ramp vol, pan;
+    int vstep, pstep;
+    bool clamp;
+
+    A2CU_DEV void load(const StatePtr &s, int w) {
+        s.ld_ramp(w, vol); s.ld_ramp(w + 4, pan);
+        vstep = pstep = 0; clamp = false;
+    }
+    A2CU_DEV void store(const StatePtr &s, int w) const { s.st_ramp(w, vol); s.st_ramp(w + 4, pan); }
+    A2CU_DEV void init(const Ctx &, int, unsigned) { ramp_init(vol, 65536); ramp_init(pan, 0); }
+    A2CU_DEV void write(const Ctx &, int reg, int v, int start, int dur) {
+        ramp_set(reg == 0 ? vol : pan, v, start, dur);
+    }
+    A2CU_DEV void prepare(const Ctx &, int frames) {
+        if (NIN == 1 && NOUT == 1) {        // panmix.c:49-64: pan untouched
+            ramp_prepare(vol, frames);
+            vstep = vol.delta; pstep = 0;
+            return;
+        }
+        // clamp variant is picked per call, before Prepare (panmix.c:117-135)
+        clamp = pan.target > 0xffffff || pan.target < -0xffffff ||
+                pan.value > 0xffffff || pan.value < -0xffffff;
+        ramp_prepare(vol, frames);
+        ramp_prepare(pan, frames);
+        vstep = vol.delta; pstep = pan.delta;
+    }
+    A2CU_DEV void sample(const Ctx &, int &s0, int &s1, int &o0, int &o1) {
+        int r0, r1 = 0;
+        if (NIN == 1 && NOUT == 1) {
+            r0 = mulshr(s0, vol.value, 24);
+        } else {
+            int v = vol.value;
+            int vp = mulshr(pan.value, v, 24);
+            int v0 = wsub(v, vp), v1 = wadd(v, vp);
+            if (clamp) {
+                int lim = (int)((unsigned)v << 1);
+                if (v0 > lim) v0 = lim;
+                if (v1 > lim) v1 = lim;
+            }
+            if (NIN == 1) {
+                r0 = mulshr(s0, v0, 24); r1 = mulshr(s0, v1, 24);
+            } else if (NOUT == 1) {
+                r0 = (int)(((long long)s0 * v0 + (long long)s1 * v1) >> 25);
+            } else {
+                r0 = mulshr(s0, v0, 24); r1 = mulshr(s1, v1, 24);
+            }
+            pan.value = wadd(pan.value, pstep);
+        }
+        vol.value = wadd(vol.value, vstep);
+        if (WIREOUT) { o0 = wadd(o0, r0); if (NOUT == 2) o1 = wadd(o1, r1); }
+        else if (ADD) { s0 = wadd(s0, r0); if (NOUT == 2) s1 = wadd(s1, r1); }
+        else { s0 = r0; if (NOUT == 2) s1 = r1; }
+    }
+    A2CU_DEV void finish() { vstep = pstep = 0; }
+};
+
+// =============================================================================
+// filter12 (src/units/filter12.c)
+// =============================================================================
+template <int CH, bool ADD, bool WIREOUT>
+struct Filter12 {
+    static constexpr int kWords = 12 + 2 * CH;
+    static constexpr bool kUsesFm = false;
+    Ramp cutoff, q;
+    int lp, bp, hp, f1;
+    int d1[CH], d2[CH];
+    int f0, df, qstep;
+
+    A2CU_DEV void load(const StatePtr &s, int w) {
+        s.ld_ramp(w, cutoff); s.ld_ramp(w + 4, q);
+        lp = s.ld(w + 8); bp = s.ld(w + 9); hp = s.ld(w + 10); f1 = s.ld(w + 11);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) { d1[c] = s.ld(w + 12 + c); d2[c] = s.ld(w + 12 + CH + c); }
+        f0 = f1; df = 0; qstep = 0;
+    }
+    A2CU_DEV void store(const StatePtr &s, int w) const {
+        s.st_ramp(w, cutoff); s.st_ramp(w + 4, q);
+        s.st(w + 8, lp); s.st(w + 9, bp); s.st(w + 10, hp); s.st(w + 11, f1);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) { s.st(w + 12 + c, d1[c]); s.st(w + 12 + CH + c, d2[c]); }
+    }
+    // filter12.c:180-221; arg = transpose
+    A2CU_DEV void init(const Ctx &c, int arg, unsigned) {
+        ramp_init(cutoff, 0); ramp_init(q, 0);
+        write(c, 0, arg, 0, 0);
+        write(c, 1, 32768, 0, 0);
+        lp = 65536 >> 8; bp = hp = 0;
+#pragma unroll
+        for (int ch = 0; ch < CH; ++ch) d1[ch] = d2[ch] = 0;
+    }
+    // filter12.c:141-177. Cooked by the host: cutoff includes transpose, q is
+    // the ramper target (32768 or (65536 << 8) / v), lp/bp/hp are >> 8.
+    // reg 5 = exact coefficient computed by the host's libm (see engine).
+    A2CU_DEV void write(const Ctx &c, int reg, int v, int start, int dur) {
+        switch (reg) {
+        case 0:
+            ramp_set(cutoff, v, start, dur);
+            if ((unsigned)dur < 256u) f1 = f12_coeff(c.ptab, cutoff.value, c.samplerate);
+            break;
+        case 1: ramp_set(q, v, start, dur); break;
+        case 2: lp = v; break;
+        case 3: bp = v; break;
+        case 4: hp = v; break;
+        case 5: f1 = v; break;
+        }
+    }
+    // filter12.c:74-96
+    A2CU_DEV void prepare(const Ctx &c, int frames) {
+        f0 = f1;
+        ramp_prepare(q, frames);
+        ramp_prepare(cutoff, frames);
+        if (cutoff.delta) {
+            ramp_run(cutoff, frames);
+            f1 = f12_coeff(c.ptab, cutoff.value, c.samplerate);
+            df = (wsub(f1, f0) + (frames >> 1)) / frames;
+        } else
+            df = 0;
+        qstep = q.delta;
+    }
+    // filter12.c:97-118
+    A2CU_DEV void sample(const Ctx &, int &s0, int &s1, int &o0, int &o1) {
+        int f = f0 >> 12;
+        int qq = q.value >> 12;
+        int in[2] = { s0, s1 };
+        int out[2] = { 0, 0 };
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            int d1s = d1[c] >> 4;
+            int l = wadd(d2[c], wmul(f, d1s) >> 8);
+            int h = wsub(wsub(in[c] >> 5, l), wmul(qq, d1s) >> 8);
+            int b = wadd(wmul(f, h >> 4) >> 8, d1[c]);
+            out[c] = wadd(wadd(wmul(l, lp), wmul(b, bp)), wmul(h, hp)) >> 3;
+            d1[c] = b; d2[c] = l;
+        }
+        f0 = wadd(f0, df);
+        q.value = wadd(q.value, qstep);
+        if (WIREOUT) { o0 = wadd(o0, out[0]); if (CH == 2) o1 = wadd(o1, out[1]); }
+        else if (ADD) { s0 = wadd(s0, out[0]); if (CH == 2) s1 = wadd(s1, out[1]); }
+        else { s0 = out[0]; if (CH == 2) s1 = out[1]; }
+    }
+    A2CU_DEV void finish() { qstep = 0; df = 0; }
+};
+
+// =============================================================================
+// waveshaper (src/units/waveshaper.c:55-108)
+// =============================================================================
+template <int CH, bool ADD, bool WIREOUT>
+struct WaveShaper {
+    static constexpr int kWords = 4;
+    static constexpr bool kUsesFm = false;
+    Ramp amount;
+    int step;
+    A2CU_DEV void load(const StatePtr &s, int w) { s.ld_ramp(w, amount); step = 0; }
+    A2CU_DEV void store(const StatePtr &s, int w) const { s.st_ramp(w, amount); }
+    A2CU_DEV void init(const Ctx &, int, unsigned) { ramp_init(amount, 0); }
+    A2CU_DEV void write(const Ctx &, int, int v, int start, int dur) { ramp_set(amount, v, start, dur); }
+    A2CU_DEV void prepare(const Ctx &, int frames) { ramp_prepare(amount, frames); step = amount.delta; }
+    A2CU_DEV int shape(int v, int a, int a3p1, int asqr) {
+        int vsqr = (int)(((long long)v * v) >> 22);
+        long long vout = (long long)v * a3p1;
+        long long sqrsub = (long long)a * vsqr;
+        if (v >= 0) vout -= sqrsub; else vout += sqrsub;
+        vout /= (((long long)asqr * vsqr) >> 16) + (1 << 24);
+        return (int)vout;
+    }
+    A2CU_DEV void sample(const Ctx &, int &s0, int &s1, int &o0, int &o1) {
+        int a = amount.value;
+        int a3p1 = wadd(wadd((int)((unsigned)a << 1), a), 1 << 24);
+        int asqr = (int)(((long long)(a >> 4) * (a >> 4)) >> 24);
+        int r0 = shape(s0, a, a3p1, asqr);
+        int r1 = CH == 2 ? shape(s1, a, a3p1, asqr) : 0;
+        amount.value = wadd(amount.value, step);
+        if (WIREOUT) { o0 = wadd(o0, r0); if (CH == 2) o1 = wadd(o1, r1); }
+        else if (ADD) { s0 = wadd(s0, r0); if (CH == 2) s1 = wadd(s1, r1); }
+        else { s0 = r0; if (CH == 2) s1 = r1; }
+    }
+    A2CU_DEV void finish() { step = 0; }
+};
+
+// =============================================================================
+// fm1..fm4r (src/units/fm.c). NOPS operators, OSBITS oversampling bits,
+// PAR 0 = chain, 1 = parallel modulators, 2 = ring modulator pair.
+// As built, fm.c does not see A2_HIFI: fm1 1x, fm2/fm2r 2x, the rest 4x.
+// =============================================================================
+struct FmOp {
+    Ramp a, fb, p;
+    int last_pitch;
+    unsigned phase, dphase;
+    int last;
+};
+
+template <int NOPS, int OSBITS, int PAR, bool ADD, bool WIREOUT>
+struct Fm {
+    static constexpr int kWords = 16 * NOPS;
+    static constexpr bool kUsesFm = true;
+    FmOp op[NOPS];
+    int astep[NOPS], fbstep[NOPS];
+
+    A2CU_DEV void load(const StatePtr &s, int w) {
+#pragma unroll
+        for (int i = 0; i < NOPS; ++i) {
+            int b = w + 16 * i;
+            s.ld_ramp(b, op[i].a); s.ld_ramp(b + 4, op[i].fb); s.ld_ramp(b + 8, op[i].p);
+            op[i].last_pitch = s.ld(b + 12);
+            op[i].phase = (unsigned)s.ld(b + 13);
+            op[i].dphase = (unsigned)s.ld(b + 14);
+            op[i].last = s.ld(b + 15);
+            astep[i] = fbstep[i] = 0;
+        }
+    }
+    A2CU_DEV void store(const StatePtr &s, int w) const {
+#pragma unroll
+        for (int i = 0; i < NOPS; ++i) {
+            int b = w + 16 * i;
+            s.st_ramp(b, op[i].a); s.st_ramp(b + 4, op[i].fb); s.st_ramp(b + 8, op[i].p);
+            s.st(b + 12, op[i].last_pitch);
+            s.st(b + 13, (int)op[i].phase);
+            s.st(b + 14, (int)op[i].dphase);
+            s.st(b + 15, op[i].last);
+        }
+    }
+    // fm.c:328-336
+    A2CU_DEV void set_phase(int ph, unsigned sst) {
+#pragma unroll
+        for (int i = 0; i < NOPS; ++i) {
+            int ssph = wadd(ph, (int)((sst * (op[i].dphase >> 8)) >> 8));
+            op[i].phase = (unsigned)(wmul(ssph, 2048) >> 8);
+        }
+    }
+    // fm.c:339-408; arg = transpose + basepitch
+    A2CU_DEV void init(const Ctx &c, int arg, unsigned sst) {
+#pragma unroll
+        for (int i = 0; i < NOPS; ++i) {
+            ramp_init(op[i].a, 0); ramp_init(op[i].fb, 0); ramp_init(op[i].p, arg);
+            op[i].last_pitch = 0; op[i].last = 0;
+        }
+        op[0].dphase = p2i(c.ptab, op[0].p.value >> 8);
+#pragma unroll
+        for (int i = 1; i < NOPS; ++i) op[i].dphase = op[0].dphase;
+        set_phase(0, sst);
+    }
+    // fm.c:411-483; op0 pitch is cooked (incl. transpose + basepitch)
+    A2CU_DEV void write(const Ctx &, int reg, int v, int start, int dur) {
+        if (reg == 0) { set_phase(v, (unsigned)start); return; }
+        int o = (reg - 1) / 3, which = (reg - 1) % 3;
+#pragma unroll
+        for (int i = 0; i < NOPS; ++i)
+            if (i == o) {
+                if (which == 0) ramp_set(op[i].p, v, start, dur);
+                else if (which == 1) ramp_set(op[i].a, v, start, dur);
+                else ramp_set(op[i].fb, v, start, dur);
+            }
+    }
+    // fm.c:194-210 with fm_run_pitch :125-140
+    A2CU_DEV void prepare(const Ctx &c, int frames) {
+        int detune = 0;
+#pragma unroll
+        for (int i = 0; i < NOPS; ++i) {
+            ramp_prepare(op[i].a, frames);
+            ramp_prepare(op[i].fb, frames);
+            ramp_prepare(op[i].p, frames);
+            ramp_run(op[i].p, frames >> 1);
+            int np = wadd(op[i].p.value, detune) >> 8;
+            if (np != op[i].last_pitch) {
+                op[i].dphase = p2i(c.ptab, np);
+                op[i].last_pitch = np;
+            }
+            detune = op[0].p.value;
+            astep[i] = op[i].a.delta; fbstep[i] = op[i].fb.delta;
+        }
+    }
+    // fm.c:111-122
+    A2CU_DEV int osc(const Ctx &c, FmOp &o, int mod) {
+        int fb = mulshr(o.last, o.fb.value, 17);
+        unsigned ph = (o.phase + (unsigned)mod + (unsigned)fb) >> 5;
+        o.last = lerp16(c.fmsine, ph & ((2048u << 8) - 1));
+        return mulshr(o.last, o.a.value, 16);
+    }
+    // fm.c:150-163 / :170-192
+    A2CU_DEV int subsample(const Ctx &c) {
+        if (PAR == 2) {
+            int v[2];
+            if (NOPS == 2) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    v[i] = osc(c, op[i], 0);
+                    op[i].phase += op[i].dphase >> OSBITS;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    constexpr int dummy = 0; (void)dummy;
+                    int m = osc(c, op[(i + 2) % NOPS], 0);
+                    v[i] = osc(c, op[i], m);
+                    op[i].phase += op[i].dphase >> OSBITS;
+                    op[(i + 2) % NOPS].phase += op[(i + 2) % NOPS].dphase >> OSBITS;
+                }
+            }
+            return (int)(((long long)v[0] * v[1]) >> 23);
+        }
+        int v = 0;
+#pragma unroll
+        for (int i = NOPS - 1; i >= 0; --i) {
+            if (i && PAR == 1) v = wadd(v, osc(c, op[i], 0));
+            else v = osc(c, op[i], v);
+            op[i].phase += op[i].dphase >> OSBITS;
+        }
+        return v;
+    }
+    // fm.c:211-232
+    A2CU_DEV void sample(const Ctx &c, int &s0, int &s1, int &o0, int &o1) {
+        int vsum = 0;
+#pragma unroll
+        for (int os = 0; os < (1 << OSBITS); ++os) vsum = wadd(vsum, subsample(c));
+#pragma unroll
+        for (int i = 0; i < NOPS; ++i) {
+            op[i].a.value = wadd(op[i].a.value, astep[i]);
+            op[i].fb.value = wadd(op[i].fb.value, fbstep[i]);
+            op[i].phase += op[i].dphase & ((1u << OSBITS) - 1);
+        }
+        int v = vsum >> OSBITS;
+        if (WIREOUT) o0 = wadd(o0, v);
+        else if (ADD) s0 = wadd(s0, v);
+        else s0 = v;
+    }
+    A2CU_DEV void finish() {
+#pragma unroll
+        for (int i = 0; i < NOPS; ++i) astep[i] = fbstep[i] = 0;
+    }
+};
+
+// =============================================================================
+// Chain: compile-time list of units
+// =============================================================================
+template <class... Us> struct Chain;
+
+template <> struct Chain<> {
+    static constexpr int kWords = 0;
+    static constexpr bool kUsesFm = false;
+    A2CU_DEV void load(const StatePtr &, int) {}
+    A2CU_DEV void store(const StatePtr &, int) const {}
+    A2CU_DEV void init_unit(const Ctx &, int, int, unsigned) {}
+    A2CU_DEV void write(const Ctx &, int, int, int, int, int) {}
+    A2CU_DEV void prepare(const Ctx &, int) {}
+    A2CU_DEV void sample(const Ctx &, int &, int &, int &, int &) {}
+    A2CU_DEV void finish() {}
+};
+
+template <class U, class... Rest> struct Chain<U, Rest...> {
+    static constexpr int kWords = U::kWords + Chain<Rest...>::kWords;
+    static constexpr bool kUsesFm = U::kUsesFm || Chain<Rest...>::kUsesFm;
+    U u;
+    Chain<Rest...> rest;
+    A2CU_DEV void load(const StatePtr &s, int w) { u.load(s, w); rest.load(s, w + U::kWords); }
+    A2CU_DEV void store(const StatePtr &s, int w) const { u.store(s, w); rest.store(s, w + U::kWords); }
+    A2CU_DEV void init_unit(const Ctx &c, int unit, int arg, unsigned sst) {
+        if (unit == 0) u.init(c, arg, sst); else rest.init_unit(c, unit - 1, arg, sst);
+    }
+    A2CU_DEV void write(const Ctx &c, int unit, int reg, int v, int start, int dur) {
+        if (unit == 0) u.write(c, reg, v, start, dur); else rest.write(c, unit - 1, reg, v, start, dur);
+    }
+    A2CU_DEV void prepare(const Ctx &c, int frames) { u.prepare(c, frames); rest.prepare(c, frames); }
+    A2CU_DEV void sample(const Ctx &c, int &s0, int &s1, int &o0, int &o1) {
+        u.sample(c, s0, s1, o0, o1); rest.sample(c, s0, s1, o0, o1);
+    }
+    A2CU_DEV void finish() { u.finish(); rest.finish(); }
+};
+
+}  // namespace a2cu

@@ -1,0 +1,937 @@
+// a2cu_engine.cu - host side of the voice engine and the C ABI of include/a2cu.h.
+//
+// The host owns: wave preparation (waves.c:59-151 semantics), the pitch and FM
+// sine tables (built with the host libm exactly like pitch.c:70-96 and
+// fm.c:486-501, then uploaded - never recomputed with device libm), event
+// queues, and the launch sequence per window:
+//
+//   H2D event CSR -> memset bus accumulators -> render_bank<Chain> per bank
+//   -> mix_buses -> (D2H master)
+//
+// No CPU fallback exists: every sample is produced by the kernels.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/a2cu.h"
+#include "a2cu_kernels.cuh"
+
+using namespace a2cu;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, const char *detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+#define CK(call)                                                              \
+    do {                                                                      \
+        cudaError_t err__ = (call);                                           \
+        if (err__ != cudaSuccess)                                             \
+            return fail(A2CU_ECUDA, #call ": %s", cudaGetErrorString(err__)); \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// Chain registry: signature string -> kernel
+// ---------------------------------------------------------------------------
+typedef void (*render_fn)(const RenderParams);
+struct KernelEntry {
+    render_fn fn;
+    int words;      // incl. the flags word
+    const char *name;
+};
+static std::map<std::string, KernelEntry> &registry() {
+    static std::map<std::string, KernelEntry> r;
+    return r;
+}
+static std::string sig_of(const a2cu_unitspec *c, int n) {
+    std::string s;
+    char b[32];
+    for (int i = 0; i < n; ++i) {
+        snprintf(b, sizeof(b), "%d:%d%d%d%d;", c[i].kind, c[i].ninputs, c[i].noutputs,
+                 c[i].add ? 1 : 0, c[i].wireout ? 1 : 0);
+        s += b;
+    }
+    return s;
+}
+template <class CH>
+static void reg_chain(std::vector<a2cu_unitspec> specs, const char *name) {
+    KernelEntry e;
+    e.fn = render_bank<CH>;
+    e.words = CH::kWords + 1;
+    e.name = name;
+    registry()[sig_of(specs.data(), (int)specs.size())] = e;
+}
+
+// spec helpers: {kind, nin, nout, add, wireout}
+#define S_OSC0 {A2CU_WTOSC, 0, 1, 0, 0}       /* first generator: replaces scratch */
+#define S_OSCA {A2CU_WTOSC, 0, 1, 1, 0}       /* further generators: add */
+#define S_OSCW {A2CU_WTOSC, 0, 1, 1, 1}       /* lone wtosc, straight to the bus */
+#define S_PM12W {A2CU_PANMIX, 1, 2, 1, 1}
+#define S_F11 {A2CU_FILTER12, 1, 1, 0, 0}
+#define S_F11W {A2CU_FILTER12, 1, 1, 1, 1}
+#define S_WS11 {A2CU_WAVESHAPER, 1, 1, 0, 0}
+#define S_FM(k) {k, 0, 1, 0, 0}
+
+typedef WtOsc<false, false> Osc0;
+typedef WtOsc<true, false> OscA;
+typedef WtOsc<true, true> OscW;
+typedef PanMix<1, 2, true, true> Pm12W;
+typedef Filter12<1, false, false> F11;
+typedef Filter12<1, true, true> F11W;
+typedef WaveShaper<1, false, false> Ws11;
+typedef Fm<1, 0, 0, false, false> Fm1;
+typedef Fm<2, 1, 0, false, false> Fm2;
+typedef Fm<3, 2, 0, false, false> Fm3;
+typedef Fm<4, 2, 0, false, false> Fm4;
+typedef Fm<3, 2, 1, false, false> Fm3p;
+typedef Fm<4, 2, 1, false, false> Fm4p;
+typedef Fm<2, 1, 2, false, false> Fm2r;
+typedef Fm<4, 2, 2, false, false> Fm4r;
+
+static void register_all() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    reg_chain<Chain<OscW>>({S_OSCW}, "wtosc");
+    reg_chain<Chain<Osc0, Pm12W>>({S_OSC0, S_PM12W}, "wtosc_panmix");
+    reg_chain<Chain<Osc0, F11, Pm12W>>({S_OSC0, S_F11, S_PM12W}, "wtosc_filter12_panmix");
+    reg_chain<Chain<Osc0, F11W>>({S_OSC0, S_F11W}, "wtosc_filter12");
+    reg_chain<Chain<Osc0, OscA, Pm12W>>({S_OSC0, S_OSCA, S_PM12W}, "wtosc2_panmix");
+    reg_chain<Chain<Osc0, OscA, OscA, Pm12W>>({S_OSC0, S_OSCA, S_OSCA, S_PM12W}, "wtosc3_panmix");
+    reg_chain<Chain<Osc0, OscA, OscA, OscA, Pm12W>>({S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_PM12W}, "wtosc4_panmix");
+    reg_chain<Chain<Osc0, OscA, OscA, OscA, OscA, OscA, OscA, OscA, Pm12W>>(
+        {S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_PM12W}, "wtosc8_panmix");
+    reg_chain<Chain<Osc0, OscA, F11W>>({S_OSC0, S_OSCA, S_F11W}, "wtosc2_filter12");
+    reg_chain<Chain<Osc0, OscA, F11, Pm12W>>({S_OSC0, S_OSCA, S_F11, S_PM12W}, "wtosc2_filter12_panmix");
+    reg_chain<Chain<Osc0, OscA, OscA, F11, Pm12W>>({S_OSC0, S_OSCA, S_OSCA, S_F11, S_PM12W},
+                                                  "wtosc3_filter12_panmix");
+    reg_chain<Chain<Osc0, Ws11, Pm12W>>({S_OSC0, S_WS11, S_PM12W}, "wtosc_waveshaper_panmix");
+    reg_chain<Chain<Fm1, Pm12W>>({S_FM(A2CU_FM1), S_PM12W}, "fm1_panmix");
+    reg_chain<Chain<Fm2, Pm12W>>({S_FM(A2CU_FM2), S_PM12W}, "fm2_panmix");
+    reg_chain<Chain<Fm3, Pm12W>>({S_FM(A2CU_FM3), S_PM12W}, "fm3_panmix");
+    reg_chain<Chain<Fm4, Pm12W>>({S_FM(A2CU_FM4), S_PM12W}, "fm4_panmix");
+    reg_chain<Chain<Fm3p, Pm12W>>({S_FM(A2CU_FM3P), S_PM12W}, "fm3p_panmix");
+    reg_chain<Chain<Fm4p, Pm12W>>({S_FM(A2CU_FM4P), S_PM12W}, "fm4p_panmix");
+    reg_chain<Chain<Fm2r, Pm12W>>({S_FM(A2CU_FM2R), S_PM12W}, "fm2r_panmix");
+    reg_chain<Chain<Fm4r, Pm12W>>({S_FM(A2CU_FM4R), S_PM12W}, "fm4r_panmix");
+    reg_chain<Chain<Fm2, Ws11, Pm12W>>({S_FM(A2CU_FM2), S_WS11, S_PM12W}, "fm2_waveshaper_panmix");
+}
+
+// ---------------------------------------------------------------------------
+// Host-side tables (same libm calls as the reference, uploaded as integers)
+// ---------------------------------------------------------------------------
+struct HostTables {
+    unsigned ptab[128];     // {base, coeff} x 64, pitch.c:70-96
+    int16_t fmsine[2049];   // fm.c:486-501
+    HostTables() {
+        unsigned b = 0x80000000u;
+        for (unsigned i = 0; i < 64; ++i) {
+            unsigned b2 = (unsigned)(long long)((double)0x80000000u * powf(2.0f, (i + 1) * (1.0f / 64)) + 0.5f);
+            ptab[2 * i] = b;
+            ptab[2 * i + 1] = (b2 - b + 128) >> 8;
+            b = b2;
+        }
+        for (int s = 0; s < 2049; ++s) fmsine[s] = (int16_t)(sin(s * 2.0f * M_PI / 2048) * 32767.0f);
+    }
+    unsigned p2i(int pitch) const {     // pitch.c:57-67 (shift count & 31 as on x86-64)
+        int n = pitch & 0xffff;
+        int oct = pitch >> 16;
+        unsigned dph = ptab[2 * (n >> 10) + 1] * (unsigned)(n & 0x3ff);
+        dph >>= 2;
+        dph += ptab[2 * (n >> 10)];
+        return dph >> ((7 - oct) & 31);
+    }
+    int f12_coeff(int cutoff_value, int samplerate) const {    // filter12.c:65-72
+        float f = p2i(cutoff_value >> 8) * (261.626f / 16777216.0f);
+        if (f > (samplerate >> 2)) return 362 << 16;
+        return (int)(512.0f * 65536.0f * sin(M_PI * f / samplerate));
+    }
+};
+static const HostTables &tables() {
+    static HostTables t;
+    return t;
+}
+
+// ---------------------------------------------------------------------------
+// Engine objects
+// ---------------------------------------------------------------------------
+struct HostWave {
+    int type;
+    unsigned flags, period;
+    std::vector<int16_t> data[kMipLevels];  // incl. pads
+    unsigned size[kMipLevels];
+    std::string name;
+};
+
+struct HostEvent {
+    uint64_t time;
+    uint32_t seq;
+    int voice;
+    uint32_t y;     // kind | unit << 8 | reg << 16
+    int value;
+    uint32_t dur;
+};
+
+struct Bank {
+    std::vector<a2cu_unitspec> chain;
+    KernelEntry k;
+    int nvoices = 0;
+    size_t stride = 0;
+    int *d_state = nullptr;
+    int *d_bus = nullptr;
+    unsigned *d_noise = nullptr;
+    std::vector<int> transpose, group;
+    std::vector<HostEvent> events;
+    uint32_t seq = 0;
+    // per-window device buffers (grown on demand)
+    unsigned *d_evoff = nullptr;
+    uint4 *d_ev = nullptr;
+    size_t ev_cap = 0;
+    bool has_noise = false;
+};
+
+struct MixHostEvent {
+    uint64_t time;
+    uint32_t seq;
+    int target, reg, value;
+    uint32_t dur;
+};
+
+struct a2cu_engine {
+    int device = 0, samplerate = 48000, channels = 2;
+    int basepitch = 0;
+    uint32_t msdur = 0;
+    uint64_t now = 0;           // 24:8
+    uint32_t root_wake = 1000000;
+    uint32_t noiseseed = 324357;
+    cudaStream_t stream = 0;
+    bool post_root = true;
+    std::vector<HostWave> waves;
+    bool waves_dirty = true;
+    WaveDesc *d_waves = nullptr;
+    int16_t *d_pool = nullptr;
+    size_t pool_cap = 0, waves_cap = 0;
+    unsigned *d_ptab = nullptr;
+    int16_t *d_fmsine = nullptr;
+    std::vector<Bank *> banks;
+    int ngroups = 0;
+    int *d_gstate = nullptr;
+    int gstate_cap = 0;
+    int *d_rstate = nullptr;
+    std::vector<MixHostEvent> mixev;
+    uint32_t mixseq = 0;
+    MixEvent *d_mixev = nullptr;
+    size_t mixev_cap = 0;
+    int *d_acc = nullptr;
+    size_t acc_cap = 0;
+    int *d_master = nullptr;
+    size_t master_cap = 0;
+    // pinned staging
+    void *h_stage = nullptr;
+    size_t stage_cap = 0;
+    int32_t *h_out = nullptr;
+    size_t hout_cap = 0;
+    uint64_t launches = 0;
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    // last window (for a2cu_apply_root_stage)
+    MixParams last_mix;
+};
+
+static int ensure_stage(a2cu_engine *e, size_t bytes) {
+    if (bytes <= e->stage_cap) return 0;
+    if (e->h_stage) cudaFreeHost(e->h_stage);
+    e->stage_cap = std::max(bytes * 2, (size_t)1 << 20);
+    CK(cudaMallocHost(&e->h_stage, e->stage_cap));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Waves (host preparation; semantics of waves.c:59-151 and :629-708)
+// ---------------------------------------------------------------------------
+static const int kPost = 132;   // A2_WAVEPOST, a2_waves.h:63-64
+
+static void wave_pad(HostWave &w, int lvl) {
+    std::vector<int16_t> &d = w.data[lvl];
+    unsigned n = w.size[lvl];
+    if ((w.flags & A2CU_LOOPED) && n) {
+        d[0] = d[n];                                   // pre pad = last sample
+        for (int i = 0; i < kPost; ++i) d[kWavePre + n + i] = d[kWavePre + i % n];
+    } else {
+        d[0] = 0;
+        for (int i = 0; i < kPost; ++i) d[kWavePre + n + i] = 0;
+    }
+}
+
+static void wave_build(HostWave &w, const int16_t *src, unsigned length) {
+    int levels = w.type == A2CU_WMIPWAVE ? kMipLevels : (w.type == A2CU_WWAVE ? 1 : 0);
+    for (int l = 0; l < kMipLevels; ++l) w.size[l] = 0;
+    for (int l = 0; l < levels; ++l) {
+        w.size[l] = (length + (1u << l) - 1) >> l;
+        w.data[l].assign(kWavePre + w.size[l] + kPost, 0);
+    }
+    if (!levels) return;
+    std::copy(src, src + length, w.data[0].begin() + kWavePre);
+    wave_pad(w, 0);
+    for (int l = 1; l < levels; ++l) {
+        const int16_t *sd = w.data[l - 1].data() + kWavePre;
+        int16_t *d = w.data[l].data() + kWavePre;
+        for (int s = 0; s < (int)w.size[l]; ++s)
+            d[s] = (int16_t)((((int)sd[s * 2] << 1) + sd[s * 2 - 1] + sd[s * 2 + 1]) >> 2);
+        wave_pad(w, l);
+    }
+}
+
+static int upload_waves(a2cu_engine *e) {
+    if (!e->waves_dirty) return 0;
+    size_t total = 0;
+    for (auto &w : e->waves)
+        for (int l = 0; l < kMipLevels; ++l) total += w.data[l].size();
+    std::vector<WaveDesc> desc(e->waves.size());
+    std::vector<int16_t> pool(total ? total : 1);
+    size_t pos = 0;
+    for (size_t i = 0; i < e->waves.size(); ++i) {
+        HostWave &w = e->waves[i];
+        desc[i].type = w.type; desc[i].flags = w.flags; desc[i].period = w.period;
+        for (int l = 0; l < kMipLevels; ++l) {
+            desc[i].size[l] = w.size[l];
+            desc[i].offset[l] = (unsigned)(pos + kWavePre);
+            if (!w.data[l].empty()) {
+                std::copy(w.data[l].begin(), w.data[l].end(), pool.begin() + pos);
+                pos += w.data[l].size();
+            }
+        }
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    if (pool.size() > e->pool_cap) {
+        if (e->d_pool) cudaFree(e->d_pool);
+        e->pool_cap = pool.size() * 2;
+        CK(cudaMalloc(&e->d_pool, e->pool_cap * sizeof(int16_t)));
+    }
+    if (desc.size() > e->waves_cap) {
+        if (e->d_waves) cudaFree(e->d_waves);
+        e->waves_cap = desc.size() * 2 + 8;
+        CK(cudaMalloc(&e->d_waves, e->waves_cap * sizeof(WaveDesc)));
+    }
+    CK(cudaMemcpy(e->d_pool, pool.data(), pool.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+    if (!desc.empty())
+        CK(cudaMemcpy(e->d_waves, desc.data(), desc.size() * sizeof(WaveDesc), cudaMemcpyHostToDevice));
+    e->waves_dirty = false;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char *a2cu_last_error(void) { return g_err; }
+
+a2cu_engine *a2cu_open(int device, int samplerate, int channels) {
+    register_all();
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        fail(A2CU_ENODEVICE, "no CUDA device %s (this library has no CPU fallback)", "");
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        fail(A2CU_ENODEVICE, "cudaSetDevice failed%s", "");
+        return nullptr;
+    }
+    a2cu_engine *e = new a2cu_engine();
+    e->device = device;
+    e->samplerate = samplerate;
+    e->channels = channels < 2 ? 1 : 2;
+    // audiality2.c:398-399 (a2_F2Pf: pitch.c:45-48) and :499
+    e->basepitch = (int)((float)log2(261.626f / (float)samplerate) * 65536.0f + 0.5f);
+    e->msdur = (uint32_t)(samplerate * 65.536f + .5f);
+    const HostTables &t = tables();
+    bool ok = cudaMalloc(&e->d_ptab, sizeof(t.ptab)) == cudaSuccess &&
+              cudaMalloc(&e->d_fmsine, sizeof(t.fmsine)) == cudaSuccess &&
+              cudaMalloc(&e->d_rstate, 8 * sizeof(int)) == cudaSuccess &&
+              cudaMemcpy(e->d_ptab, t.ptab, sizeof(t.ptab), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(e->d_fmsine, t.fmsine, sizeof(t.fmsine), cudaMemcpyHostToDevice) == cudaSuccess;
+    // root panmix: vol 1.0, pan 0 (panmix.c:252-262)
+    int rs[8] = {65536 << 8, 65536 << 8, 0, 0, 0, 0, 0, 0};
+    ok = ok && cudaMemcpy(e->d_rstate, rs, sizeof(rs), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess;
+    if (!ok) {
+        fail(A2CU_ECUDA, "a2cu_open: %s", cudaGetErrorString(cudaGetLastError()));
+        delete e;
+        return nullptr;
+    }
+    return e;
+}
+
+void a2cu_close(a2cu_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (Bank *b : e->banks) {
+        cudaFree(b->d_state); cudaFree(b->d_bus); cudaFree(b->d_noise);
+        cudaFree(b->d_evoff); cudaFree(b->d_ev);
+        delete b;
+    }
+    cudaFree(e->d_waves); cudaFree(e->d_pool); cudaFree(e->d_ptab); cudaFree(e->d_fmsine);
+    cudaFree(e->d_gstate); cudaFree(e->d_rstate); cudaFree(e->d_mixev);
+    cudaFree(e->d_acc); cudaFree(e->d_master);
+    if (e->h_stage) cudaFreeHost(e->h_stage);
+    if (e->h_out) cudaFreeHost(e->h_out);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    delete e;
+}
+
+int a2cu_set_stream(a2cu_engine *e, void *s) {
+    if (!e) return A2CU_EINVAL;
+    e->stream = (cudaStream_t)s;
+    return A2CU_OK;
+}
+int a2cu_basepitch(const a2cu_engine *e) { return e->basepitch; }
+uint32_t a2cu_msdur(const a2cu_engine *e) { return e->msdur; }
+uint64_t a2cu_now(const a2cu_engine *e) { return e->now; }
+int a2cu_set_root_wake_period(a2cu_engine *e, uint32_t p) { e->root_wake = p; return A2CU_OK; }
+int a2cu_set_noiseseed(a2cu_engine *e, uint32_t s) { e->noiseseed = s; return A2CU_OK; }
+uint64_t a2cu_launch_count(const a2cu_engine *e) { return e->launches; }
+int a2cu_set_timing(a2cu_engine *e, int on) { e->timing = on != 0; return A2CU_OK; }
+float a2cu_last_render_ms(a2cu_engine *e) { return e->last_ms; }
+int a2cu_set_post_root_stage(a2cu_engine *e, int on) { e->post_root = on != 0; return A2CU_OK; }
+
+// ---- waves -----------------------------------------------------------------
+int a2cu_wave_upload(a2cu_engine *e, int type, unsigned period, unsigned flags, const int16_t *data,
+                     unsigned length) {
+    if (!e || type < A2CU_WOFF || type > A2CU_WMIPWAVE) return fail(A2CU_EINVAL, "bad wave type%s");
+    if ((type == A2CU_WWAVE || type == A2CU_WMIPWAVE) && !data && length) return fail(A2CU_EINVAL, "no data%s");
+    HostWave w;
+    w.type = type; w.flags = flags; w.period = period;
+    wave_build(w, data, length);
+    e->waves.push_back(std::move(w));
+    e->waves_dirty = true;
+    return (int)e->waves.size() - 1;
+}
+
+int a2cu_wave_upload_prepared(a2cu_engine *e, int type, unsigned period, unsigned flags,
+                              const int16_t *const *data, const unsigned *size) {
+    if (!e) return A2CU_EINVAL;
+    HostWave w;
+    w.type = type; w.flags = flags; w.period = period;
+    int levels = type == A2CU_WMIPWAVE ? kMipLevels : (type == A2CU_WWAVE ? 1 : 0);
+    for (int l = 0; l < kMipLevels; ++l) w.size[l] = 0;
+    for (int l = 0; l < levels; ++l) {
+        w.size[l] = size[l];
+        w.data[l].assign(data[l], data[l] + kWavePre + size[l] + kPost);
+    }
+    e->waves.push_back(std::move(w));
+    e->waves_dirty = true;
+    return (int)e->waves.size() - 1;
+}
+
+int a2cu_wave_builtin(a2cu_engine *e, const char *name) {
+    if (!e || !name) return A2CU_EINVAL;
+    for (size_t i = 0; i < e->waves.size(); ++i)
+        if (e->waves[i].name == name) return (int)i;
+    const int N = 2048;                     // A2_WAVEPERIOD, a2_waves.h:71
+    std::vector<int16_t> buf(N, 0);
+    int h;
+    std::string n(name);
+    if (n == "off") h = a2cu_wave_upload(e, A2CU_WOFF, 0, 0, nullptr, 0);
+    else if (n == "noise") h = a2cu_wave_upload(e, A2CU_WNOISE, 256, A2CU_LOOPED, nullptr, 0);
+    else {
+        int duty = n == "square" ? 50 : (n.compare(0, 5, "pulse") == 0 ? atoi(name + 5) : 0);
+        if (duty > 0 && duty <= 50) {
+            // waves.c:637-651; index s1 keeps the previous duty cycle's -32767
+            int s1 = (N * duty + 50) / 100;
+            for (int s = 0; s < N; ++s) buf[s] = s < s1 ? 32767 : -32767;
+        } else if (n == "saw") {
+            for (int s = 0; s < N; ++s) buf[s] = (int16_t)(s * 65534 / N - 32767);
+        } else if (n == "triangle") {
+            for (int s = 0; s < N; ++s) buf[s] = (int16_t)(s * 65534 / N - 32767);
+            for (int s = 0; s < N / 2; ++s)
+                buf[(5 * N / 4 - s - 1) % N] = buf[s + N / 4] = (int16_t)(s * 65534 * 2 / N - 32767);
+        } else if (n == "sine" || n == "asine" || n == "hsine" || n == "qsine") {
+            for (int s = 0; s < N; ++s) buf[s] = (int16_t)(sin(s * 2.0f * M_PI / N) * 32767.0f);
+            if (n != "sine")
+                for (int s = N / 2; s < N; ++s) buf[s] = (int16_t)-buf[s];
+            if (n == "hsine" || n == "qsine")
+                for (int s = N / 2; s < N; ++s) buf[s] = 0;
+            if (n == "qsine")
+                for (int s = 0; s < N / 4; ++s) buf[s + N / 2] = buf[s];
+        } else
+            return fail(A2CU_EINVAL, "unknown builtin wave '%s'", name);
+        h = a2cu_wave_upload(e, A2CU_WMIPWAVE, N, A2CU_LOOPED, buf.data(), N);
+    }
+    if (h >= 0) e->waves[h].name = n;
+    return h;
+}
+
+int a2cu_wave_unload(a2cu_engine *e, int wave) {
+    if (!e || wave < 0 || wave >= (int)e->waves.size()) return A2CU_EINVAL;
+    e->waves[wave].size[0] = 0;
+    e->waves_dirty = true;
+    return A2CU_OK;
+}
+
+int a2cu_wave_read(a2cu_engine *e, int wave, int level, int16_t *out, unsigned cap, unsigned *size) {
+    if (!e || wave < 0 || wave >= (int)e->waves.size() || level < 0 || level >= kMipLevels) return A2CU_EINVAL;
+    const std::vector<int16_t> &d = e->waves[wave].data[level];
+    if (size) *size = e->waves[wave].size[level];
+    unsigned n = (unsigned)std::min((size_t)cap, d.size());
+    if (out) memcpy(out, d.data(), n * sizeof(int16_t));
+    return (int)n;
+}
+
+// ---- groups and banks ------------------------------------------------------
+int a2cu_group_new(a2cu_engine *e) {
+    if (!e) return A2CU_EINVAL;
+    cudaSetDevice(e->device);
+    if (e->ngroups + 1 > e->gstate_cap) {
+        int ncap = std::max(64, e->gstate_cap * 2);
+        int *n = nullptr;
+        CK(cudaMalloc(&n, (size_t)ncap * 8 * sizeof(int)));
+        CK(cudaStreamSynchronize(e->stream));
+        if (e->d_gstate) {
+            CK(cudaMemcpy(n, e->d_gstate, (size_t)e->ngroups * 8 * sizeof(int), cudaMemcpyDeviceToDevice));
+            cudaFree(e->d_gstate);
+        }
+        e->d_gstate = n;
+        e->gstate_cap = ncap;
+    }
+    int gs[8] = {65536 << 8, 65536 << 8, 0, 0, 0, 0, 0, 0};
+    CK(cudaMemcpy(e->d_gstate + (size_t)e->ngroups * 8, gs, sizeof(gs), cudaMemcpyHostToDevice));
+    return e->ngroups++;
+}
+
+int a2cu_chain_supported(const a2cu_unitspec *chain, int nunits) {
+    register_all();
+    return registry().count(sig_of(chain, nunits)) ? 1 : 0;
+}
+
+static void push_event(Bank *b, uint64_t time, int voice, int kind, int unit, int reg, int value, uint32_t dur) {
+    HostEvent ev;
+    ev.time = time; ev.seq = b->seq++; ev.voice = voice;
+    ev.y = (uint32_t)kind | ((uint32_t)unit << 8) | ((uint32_t)(reg & 0xff) << 16);
+    ev.value = value; ev.dur = dur;
+    b->events.push_back(ev);
+}
+
+int a2cu_bank_new(a2cu_engine *e, const a2cu_unitspec *chain, int nunits, int nvoices,
+                  const int32_t *transpose, const int32_t *group, unsigned substart) {
+    if (!e || !chain || nunits < 1 || nvoices < 1) return fail(A2CU_EINVAL, "a2cu_bank_new: bad args%s");
+    auto it = registry().find(sig_of(chain, nunits));
+    if (it == registry().end())
+        return fail(A2CU_ENOTIMPL, "no kernel for voice structure %s", sig_of(chain, nunits).c_str());
+    cudaSetDevice(e->device);
+    Bank *b = new Bank();
+    b->chain.assign(chain, chain + nunits);
+    b->k = it->second;
+    b->nvoices = nvoices;
+    b->stride = ((size_t)nvoices + kThreads - 1) / kThreads * kThreads;
+    b->transpose.assign(nvoices, 0);
+    b->group.assign(nvoices, -1);
+    if (transpose) b->transpose.assign(transpose, transpose + nvoices);
+    if (group) b->group.assign(group, group + nvoices);
+    std::vector<int> bus(b->stride, 0);
+    for (int i = 0; i < nvoices; ++i) {
+        if (b->group[i] >= e->ngroups) { delete b; return fail(A2CU_EINVAL, "bad group index%s"); }
+        bus[i] = b->group[i] < 0 ? 0 : 1 + b->group[i];
+    }
+    for (int u = 0; u < nunits; ++u)
+        if (chain[u].kind == A2CU_WTOSC) b->has_noise = true;   // may select the noise wave later
+    size_t sbytes = (size_t)b->k.words * b->stride * sizeof(int);
+    if (cudaMalloc(&b->d_state, sbytes) != cudaSuccess || cudaMalloc(&b->d_bus, b->stride * sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&b->d_noise, b->stride * sizeof(unsigned)) != cudaSuccess ||
+        cudaMalloc(&b->d_evoff, (b->stride + 1) * sizeof(unsigned)) != cudaSuccess) {
+        delete b;
+        return fail(A2CU_ENOMEM, "cudaMalloc bank state: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    CK(cudaMemset(b->d_state, 0, sbytes));
+    CK(cudaMemset(b->d_noise, 0, b->stride * sizeof(unsigned)));
+    CK(cudaMemcpy(b->d_bus, bus.data(), b->stride * sizeof(int), cudaMemcpyHostToDevice));
+    // Initialize() of every unit, in chain order, at the current time
+    uint64_t t = (e->now & ~(uint64_t)0xff) | (substart & 0xff);
+    const HostTables &tb = tables();
+    for (int i = 0; i < nvoices; ++i) {
+        push_event(b, t, i, EV_START, 0, 0, 0, 0);
+        for (int u = 0; u < nunits; ++u) {
+            int kind = chain[u].kind;
+            int arg = 0;
+            if (kind == A2CU_WTOSC || kind >= A2CU_FM1) arg = b->transpose[i] + e->basepitch;
+            else if (kind == A2CU_FILTER12) arg = b->transpose[i];
+            push_event(b, t, i, EV_INIT, u, 0, arg, 0);
+            if (kind == A2CU_FILTER12)      // exact coefficient from the host libm
+                push_event(b, t, i, EV_WRITE, u, 5,
+                           tb.f12_coeff((int)((unsigned)arg << 8), e->samplerate), 0);
+        }
+    }
+    e->banks.push_back(b);
+    return (int)e->banks.size() - 1;
+}
+
+static Bank *get_bank(a2cu_engine *e, int bank) {
+    if (!e || bank < 0 || bank >= (int)e->banks.size()) return nullptr;
+    return e->banks[bank];
+}
+
+const char *a2cu_bank_kernel_name(a2cu_engine *e, int bank) {
+    Bank *b = get_bank(e, bank);
+    return b ? b->k.name : "";
+}
+int a2cu_bank_state_bytes(a2cu_engine *e, int bank) {
+    Bank *b = get_bank(e, bank);
+    return b ? b->k.words * (int)sizeof(int) : A2CU_EINVAL;
+}
+
+// Translate a VM-level register write into the device-level record(s)
+// (the host half of each unit's A2_write_cb; see a2cu_device.cuh write()).
+static int cook_write(a2cu_engine *e, Bank *b, int voice, int unit, int reg, int value, uint64_t when, uint32_t dur) {
+    if (unit < 0 || unit >= (int)b->chain.size() || reg < 0) return fail(A2CU_EINVAL, "bad unit/register%s");
+    int kind = b->chain[unit].kind;
+    int start = (int)(when & 0xff);
+    switch (kind) {
+    case A2CU_WTOSC:
+        if (reg > 3) return fail(A2CU_EINVAL, "wtosc has 4 registers%s");
+        if (reg == 0) {                 // wtosc.c:433-483
+            int h = value >> 16;
+            int w = (h >= 0 && h < (int)e->waves.size()) ? h : -1;
+            if (w >= 0) {
+                const HostWave &hw = e->waves[w];
+                if ((hw.type == A2CU_WWAVE || hw.type == A2CU_WMIPWAVE) && hw.size[0] > 0x01000000u - 1 - kPost)
+                    w = -1;
+                if (hw.type == A2CU_WOFF) w = -1;
+            }
+            value = w;
+        } else if (reg == 1)            // wtosc.c:486-492
+            value = value + b->transpose[voice] + e->basepitch;
+        break;
+    case A2CU_PANMIX:
+        if (reg > 1) return fail(A2CU_EINVAL, "panmix has 2 registers%s");
+        break;
+    case A2CU_WAVESHAPER:
+        if (reg > 0) return fail(A2CU_EINVAL, "waveshaper has 1 register%s");
+        break;
+    case A2CU_FILTER12:
+        if (reg > 4) return fail(A2CU_EINVAL, "filter12 has 5 registers%s");
+        if (reg == 0) {                 // filter12.c:141-147
+            value = value + b->transpose[voice];
+            push_event(b, when, voice, EV_WRITE, unit, 0, value, dur);
+            if ((uint64_t)dur + (uint64_t)start < 256)
+                push_event(b, when, voice, EV_WRITE, unit, 5,
+                           tables().f12_coeff((int)((unsigned)value << 8), e->samplerate), 0);
+            return A2CU_OK;
+        } else if (reg == 1)            // filter12.c:149-162
+            value = value < 512 ? 32768 : (65536 << 8) / value;
+        else
+            value >>= 8;                // filter12.c:164-177
+        break;
+    default: {
+        if (kind < A2CU_FM1 || kind > A2CU_FM4R) return fail(A2CU_EINVAL, "unknown unit kind%s");
+        static const int nops[8] = {1, 2, 3, 4, 3, 4, 2, 4};
+        if (reg > 3 * nops[kind - A2CU_FM1]) return fail(A2CU_EINVAL, "fm register out of range%s");
+        if (reg == 1) value = value + b->transpose[voice] + e->basepitch;   // fm.c:417-423
+        break;
+    }
+    }
+    push_event(b, when, voice, EV_WRITE, unit, reg, value, dur);
+    return A2CU_OK;
+}
+
+int a2cu_bank_write(a2cu_engine *e, int bank, int voice, int unit, int reg, int32_t value, uint64_t when,
+                    uint32_t dur) {
+    Bank *b = get_bank(e, bank);
+    if (!b || voice < 0 || voice >= b->nvoices) return fail(A2CU_EINVAL, "bad bank/voice%s");
+    if (when < e->now) return fail(A2CU_ELATE, "event time already rendered%s");
+    return cook_write(e, b, voice, unit, reg, value, when, dur);
+}
+
+int a2cu_bank_write_all(a2cu_engine *e, int bank, int unit, int reg, const int32_t *values, int stride,
+                        uint64_t when, uint32_t dur) {
+    Bank *b = get_bank(e, bank);
+    if (!b || !values) return fail(A2CU_EINVAL, "bad bank%s");
+    if (when < e->now) return fail(A2CU_ELATE, "event time already rendered%s");
+    b->events.reserve(b->events.size() + b->nvoices);
+    for (int i = 0; i < b->nvoices; ++i) {
+        int r = cook_write(e, b, i, unit, reg, values[(size_t)i * stride], when, dur);
+        if (r) return r;
+    }
+    return A2CU_OK;
+}
+
+int a2cu_bank_wake(a2cu_engine *e, int bank, int voice, uint64_t when) {
+    Bank *b = get_bank(e, bank);
+    if (!b || voice >= b->nvoices) return fail(A2CU_EINVAL, "bad bank/voice%s");
+    if (when < e->now) return fail(A2CU_ELATE, "event time already rendered%s");
+    if (voice >= 0) push_event(b, when, voice, EV_WAKE, 0, 0, 0, 0);
+    else
+        for (int i = 0; i < b->nvoices; ++i) push_event(b, when, i, EV_WAKE, 0, 0, 0, 0);
+    return A2CU_OK;
+}
+
+int a2cu_bank_kill(a2cu_engine *e, int bank, int voice, uint64_t when) {
+    Bank *b = get_bank(e, bank);
+    if (!b || voice < 0 || voice >= b->nvoices) return fail(A2CU_EINVAL, "bad bank/voice%s");
+    if (when < e->now) return fail(A2CU_ELATE, "event time already rendered%s");
+    push_event(b, when, voice, EV_STOP, 0, 0, 0, 0);
+    return A2CU_OK;
+}
+
+static int mix_write(a2cu_engine *e, int target, int reg, int value, uint64_t when, uint32_t dur) {
+    if (when < e->now) return fail(A2CU_ELATE, "event time already rendered%s");
+    if (reg > 1) return fail(A2CU_EINVAL, "panmix has 2 registers%s");
+    MixHostEvent m;
+    m.time = when; m.seq = e->mixseq++; m.target = target; m.reg = reg < 0 ? -1 : reg;
+    m.value = value; m.dur = dur;
+    e->mixev.push_back(m);
+    if (target >= 0) {
+        // the group's wake-up cuts its children's segments (core.c:1769-1776)
+        for (Bank *b : e->banks)
+            for (int i = 0; i < b->nvoices; ++i)
+                if (b->group[i] == target) push_event(b, when, i, EV_WAKE, 0, 0, 0, 0);
+    }
+    return A2CU_OK;
+}
+int a2cu_group_write(a2cu_engine *e, int group, int reg, int32_t value, uint64_t when, uint32_t dur) {
+    if (!e || group < 0 || group >= e->ngroups) return fail(A2CU_EINVAL, "bad group%s");
+    return mix_write(e, group, reg, value, when, dur);
+}
+int a2cu_root_write(a2cu_engine *e, int reg, int32_t value, uint64_t when, uint32_t dur) {
+    if (!e) return A2CU_EINVAL;
+    return mix_write(e, -1, reg, value, when, dur);
+}
+
+// ---- rendering ---------------------------------------------------------------
+static int collect_splits(a2cu_engine *e, uint64_t t0, uint64_t t1, int *splits, int *n) {
+    // Root-level segment cuts inside [t0, t1): periodic root wake-ups and root
+    // writes. They apply to every voice (the root's inline recursion).
+    std::vector<int> s;
+    if (e->root_wake) {
+        uint64_t k = t0 / e->root_wake;
+        for (uint64_t t = k * e->root_wake; t < t1; t += e->root_wake)
+            if (t > t0 && t < t1) s.push_back((int)((t - t0) >> 8));
+    }
+    for (auto &m : e->mixev)
+        if (m.target < 0 && m.time > t0 && m.time < t1) s.push_back((int)((m.time - t0) >> 8));
+    std::sort(s.begin(), s.end());
+    s.erase(std::unique(s.begin(), s.end()), s.end());
+    s.erase(std::remove(s.begin(), s.end(), 0), s.end());
+    if ((int)s.size() > kMaxSplits) return -1;
+    *n = (int)s.size();
+    for (int i = 0; i < *n; ++i) splits[i] = s[i];
+    return 0;
+}
+
+static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *dev_out) {
+    if (!frames) return A2CU_OK;
+    if (!buffer) buffer = frames;
+    const uint64_t t0 = e->now, t1 = e->now + ((uint64_t)frames << 8);
+    int splits[kMaxSplits], nsplits = 0;
+    if (collect_splits(e, t0, t1, splits, &nsplits)) {
+        // too many root-level cuts for one launch: render in two halves
+        if (frames <= buffer) return fail(A2CU_EINVAL, "too many root events in one buffer%s");
+        unsigned nb = (frames + buffer - 1) / buffer;
+        unsigned h = (nb / 2) * buffer;
+        int r = run_window(e, h, buffer, dev_out);
+        if (r) return r;
+        return run_window(e, frames - h, buffer, dev_out ? dev_out + (size_t)h * e->channels : nullptr);
+    }
+    int r = upload_waves(e);
+    if (r) return r;
+
+    const int W = (int)frames;
+    const int nbus = 1 + e->ngroups;
+    size_t acc_n = (size_t)nbus * W * 2;
+    if (acc_n > e->acc_cap) {
+        CK(cudaStreamSynchronize(e->stream));
+        if (e->d_acc) cudaFree(e->d_acc);
+        e->acc_cap = acc_n * 2;
+        CK(cudaMalloc(&e->d_acc, e->acc_cap * sizeof(int)));
+    }
+    size_t m_n = (size_t)W * 2;
+    if (m_n > e->master_cap) {
+        CK(cudaStreamSynchronize(e->stream));
+        if (e->d_master) cudaFree(e->d_master);
+        e->master_cap = m_n * 2;
+        CK(cudaMalloc(&e->d_master, e->master_cap * sizeof(int)));
+    }
+
+    // ---- stage events (host -> pinned -> device) ----
+    size_t stage_bytes = 0;
+    std::vector<std::vector<HostEvent>> due(e->banks.size());
+    for (size_t bi = 0; bi < e->banks.size(); ++bi) {
+        Bank *b = e->banks[bi];
+        std::vector<HostEvent> keep;
+        for (auto &ev : b->events)
+            (ev.time < t1 ? due[bi] : keep).push_back(ev);
+        b->events.swap(keep);
+        std::sort(due[bi].begin(), due[bi].end(), [](const HostEvent &a, const HostEvent &c) {
+            if (a.voice != c.voice) return a.voice < c.voice;
+            if ((a.time >> 8) != (c.time >> 8)) return a.time < c.time;
+            return a.seq < c.seq;
+        });
+        if (!due[bi].empty())
+            stage_bytes += (b->stride + 1) * sizeof(unsigned) + due[bi].size() * sizeof(uint4) + 64;
+    }
+    std::vector<MixHostEvent> mdue, mkeep;
+    for (auto &m : e->mixev) (m.time < t1 ? mdue : mkeep).push_back(m);
+    e->mixev.swap(mkeep);
+    std::sort(mdue.begin(), mdue.end(), [](const MixHostEvent &a, const MixHostEvent &c) {
+        if ((a.time >> 8) != (c.time >> 8)) return a.time < c.time;
+        return a.seq < c.seq;
+    });
+    stage_bytes += mdue.size() * sizeof(MixEvent) + 64;
+    if (stage_bytes > 128)
+        CK(cudaStreamSynchronize(e->stream));  // the pinned staging buffer is reused
+    r = ensure_stage(e, stage_bytes);
+    if (r) return r;
+    char *stage = (char *)e->h_stage;
+    size_t spos = 0;
+
+    CK(cudaMemsetAsync(e->d_acc, 0, acc_n * sizeof(int), e->stream));
+    if (e->timing) CK(cudaEventRecord(e->ev0, e->stream));
+
+    for (size_t bi = 0; bi < e->banks.size(); ++bi) {
+        Bank *b = e->banks[bi];
+        RenderParams P;
+        memset(&P, 0, sizeof(P));
+        P.state = b->d_state; P.stride = b->stride; P.nvoices = b->nvoices;
+        P.bus_of = b->d_bus; P.acc = e->d_acc; P.W = W; P.buffer = (int)buffer;
+        P.nsplits = nsplits;
+        for (int i = 0; i < nsplits; ++i) P.splits[i] = splits[i];
+        P.waves = e->d_waves; P.pool = e->d_pool; P.ptab = e->d_ptab; P.fmsine = e->d_fmsine;
+        P.samplerate = e->samplerate;
+        P.noise = b->d_noise;
+        if (!due[bi].empty()) {
+            size_t nev = due[bi].size();
+            if (nev > b->ev_cap) {
+                if (b->d_ev) cudaFree(b->d_ev);
+                b->ev_cap = nev * 2;
+                CK(cudaMalloc(&b->d_ev, b->ev_cap * sizeof(uint4)));
+            }
+            unsigned *off = (unsigned *)(stage + spos);
+            spos += (b->stride + 1) * sizeof(unsigned);
+            spos = (spos + 15) & ~(size_t)15;
+            uint4 *recs = (uint4 *)(stage + spos);
+            spos += nev * sizeof(uint4);
+            size_t k = 0;
+            for (size_t v = 0; v <= b->stride; ++v) {
+                while (k < nev && (size_t)due[bi][k].voice < v) ++k;
+                off[v] = (unsigned)k;
+            }
+            for (size_t i = 0; i < nev; ++i) {
+                const HostEvent &ev = due[bi][i];
+                uint64_t rel = ev.time - t0;                // >= 0: late writes are refused
+                recs[i] = make_uint4((unsigned)rel, ev.y, (unsigned)ev.value, ev.dur);
+            }
+            CK(cudaMemcpyAsync(b->d_evoff, off, (b->stride + 1) * sizeof(unsigned), cudaMemcpyHostToDevice,
+                               e->stream));
+            CK(cudaMemcpyAsync(b->d_ev, recs, nev * sizeof(uint4), cudaMemcpyHostToDevice, e->stream));
+            P.ev_off = b->d_evoff; P.ev = b->d_ev;
+        }
+        int grid = (b->nvoices + kThreads - 1) / kThreads;
+        b->k.fn<<<grid, kThreads, 0, e->stream>>>(P);
+        ++e->launches;
+    }
+    if (e->timing) CK(cudaEventRecord(e->ev1, e->stream));
+
+    MixParams M;
+    memset(&M, 0, sizeof(M));
+    M.acc = e->d_acc; M.W = W; M.buffer = (int)buffer; M.ngroups = e->ngroups; M.channels = e->channels;
+    M.nsplits = nsplits;
+    for (int i = 0; i < nsplits; ++i) M.splits[i] = splits[i];
+    M.gstate = e->d_gstate; M.rstate = e->d_rstate;
+    M.nev = (int)mdue.size();
+    if (M.nev) {
+        if (mdue.size() > e->mixev_cap) {
+            if (e->d_mixev) cudaFree(e->d_mixev);
+            e->mixev_cap = mdue.size() * 2;
+            CK(cudaMalloc(&e->d_mixev, e->mixev_cap * sizeof(MixEvent)));
+        }
+        spos = (spos + 15) & ~(size_t)15;
+        MixEvent *me = (MixEvent *)(stage + spos);
+        for (size_t i = 0; i < mdue.size(); ++i) {
+            uint64_t rel = mdue[i].time >= t0 ? mdue[i].time - t0 : (mdue[i].time & 0xff);
+            me[i].time = (unsigned)rel; me[i].target = mdue[i].target;
+            me[i].reg_dur_hi = mdue[i].reg & 0xff; me[i].value = mdue[i].value; me[i].dur = mdue[i].dur;
+        }
+        CK(cudaMemcpyAsync(e->d_mixev, me, mdue.size() * sizeof(MixEvent), cudaMemcpyHostToDevice, e->stream));
+        M.ev = e->d_mixev;
+    }
+    M.master = dev_out ? dev_out : e->d_master;
+    M.root_stage = e->post_root ? 1 : 0;
+    mix_buses<<<1, 256, 0, e->stream>>>(M);
+    ++e->launches;
+    CK(cudaGetLastError());
+    e->last_mix = M;
+    e->now = t1;
+    return A2CU_OK;
+}
+
+int a2cu_run_async(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *dev_out) {
+    if (!e) return A2CU_EINVAL;
+    cudaSetDevice(e->device);
+    return run_window(e, frames, buffer, dev_out);
+}
+
+int32_t *a2cu_master_devptr(a2cu_engine *e) { return e ? e->d_master : nullptr; }
+
+int a2cu_sync(a2cu_engine *e) {
+    if (!e) return A2CU_EINVAL;
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->timing) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_ms = ms;
+    }
+    return A2CU_OK;
+}
+
+int a2cu_run(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *out) {
+    if (!e) return A2CU_EINVAL;
+    cudaSetDevice(e->device);
+    const int och = e->post_root ? e->channels : 2;
+    size_t n = (size_t)frames * och;
+    // make sure the engine-owned master buffer is large enough before launching
+    if ((size_t)frames * 2 > e->master_cap) {
+        CK(cudaStreamSynchronize(e->stream));
+        if (e->d_master) cudaFree(e->d_master);
+        e->master_cap = (size_t)frames * 4;
+        CK(cudaMalloc(&e->d_master, e->master_cap * sizeof(int)));
+    }
+    int r = run_window(e, frames, buffer, nullptr);
+    if (r) return r;
+    if (out) {
+        if (n > e->hout_cap) {
+            if (e->h_out) cudaFreeHost(e->h_out);
+            e->hout_cap = n * 2;
+            CK(cudaMallocHost(&e->h_out, e->hout_cap * sizeof(int32_t)));
+        }
+        CK(cudaMemcpyAsync(e->h_out, e->d_master, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    }
+    r = a2cu_sync(e);
+    if (r) return r;
+    if (out) memcpy(out, e->h_out, n * sizeof(int32_t));
+    return A2CU_OK;
+}
+
+int a2cu_apply_root_stage(a2cu_engine *e, const int32_t *dev_rootbus, int32_t *dev_master, unsigned frames,
+                          unsigned buffer, uint64_t start_time) {
+    // Runs only the root panmix over an externally summed root bus.
+    if (!e || !dev_rootbus || !dev_master) return A2CU_EINVAL;
+    cudaSetDevice(e->device);
+    MixParams M = e->last_mix;
+    (void)start_time;
+    M.acc = (int *)dev_rootbus; M.W = (int)frames; M.buffer = (int)(buffer ? buffer : frames);
+    M.ngroups = 0; M.master = dev_master; M.root_stage = 1;
+    mix_buses<<<1, 256, 0, e->stream>>>(M);
+    ++e->launches;
+    CK(cudaGetLastError());
+    return A2CU_OK;
+}
+
+}  // extern "C"

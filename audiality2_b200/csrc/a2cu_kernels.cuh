@@ -1,0 +1,260 @@
+// a2cu_kernels.cuh - render kernels of the voice engine.
+//
+//   render_bank<Chain>   one thread = one voice, frame-synchronous over a
+//                        window of W frames; replays each voice's segment list
+//                        (core.c:1847-1880), runs the fused unit chain per
+//                        sample and reduces the warp's voices with
+//                        redux.sync (__reduce_add_sync) into a per-CTA shared
+//                        memory bus, flushed to the device bus with integer
+//                        atomics once per fragment.  Integer add is
+//                        associative, so any reduction order is bit-exact.
+//   mix_buses            group buses -> group panmix -> root bus -> root
+//                        panmix -> master (core.c:1763-1776, audiality2.c:
+//                        268-304, xinsert bypass xinsert.c:149-156)
+#pragma once
+#include "a2cu_device.cuh"
+
+namespace a2cu {
+
+constexpr int kThreads = 128;
+constexpr int kMaxSplits = 8;
+
+// Event record, 16 bytes. x = (frame_in_window << 8) | substart
+// y = kind | unit << 8 | reg << 16 ; z = value ; w = duration (24:8)
+enum EvKind { EV_WRITE = 0, EV_WAKE = 1, EV_INIT = 2, EV_START = 3, EV_STOP = 4 };
+
+struct RenderParams {
+    int *state;               // [words][stride]
+    size_t stride;
+    int nvoices;
+    const int *bus_of;        // per voice: 0 = root bus, 1 + g = group g
+    const unsigned *ev_off;   // CSR offsets [nvoices + 1] or nullptr
+    const uint4 *ev;
+    int *acc;                 // [nbus][W][2]
+    int W;                    // frames in this window
+    int buffer;               // driver buffer size
+    int nsplits;
+    int splits[kMaxSplits];   // forced split frames (root wake-ups / writes)
+    const WaveDesc *waves;
+    const int16_t *pool;
+    const unsigned *ptab;
+    const int16_t *fmsine;
+    int samplerate;
+    unsigned *noise;          // per-voice LCG scratch [stride] (noise oscillators)
+};
+
+// End of the fragment that contains frame f: fragments restart at every driver
+// buffer and are at most 64 frames (core.c:1964-1973).
+A2CU_DEV int frag_end(int f, int buffer, int W) {
+    int pos = f % buffer;
+    int e = f - pos + min(buffer, (pos / kMaxFrag + 1) * kMaxFrag);
+    return min(e, W);
+}
+
+template <class CH>
+__global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
+    __shared__ int sacc[kMaxFrag][2];
+    __shared__ int16_t s_sine[CH::kUsesFm ? 2049 : 1];
+    __shared__ int s_home;
+
+    const int tid = threadIdx.x;
+    const int v = blockIdx.x * kThreads + tid;
+    const bool valid = v < P.nvoices;
+
+    if (CH::kUsesFm)
+        for (int i = tid; i < 2049; i += kThreads) s_sine[i] = P.fmsine[i];
+    if (tid < kMaxFrag) { sacc[tid][0] = 0; sacc[tid][1] = 0; }
+    const int mybus = valid ? P.bus_of[v] : -1;
+    if (tid == 0) s_home = mybus;
+    __syncthreads();
+    const int home = s_home;
+
+    unsigned nstate = valid && P.noise ? P.noise[v] : 0u;
+    Ctx c;
+    c.waves = P.waves; c.pool = P.pool; c.ptab = P.ptab; c.fmsine = s_sine;
+    c.samplerate = P.samplerate; c.noisestate = &nstate;
+
+    CH ch;
+    StatePtr sp{P.state + (valid ? v : 0), P.stride};
+    int alive = 0;
+    if (valid) { alive = sp.ld(0) & 1; ch.load(sp, 1); }
+
+    unsigned evp = 0, eve = 0;
+    if (valid && P.ev_off) { evp = P.ev_off[v]; eve = P.ev_off[v + 1]; }
+    int next_ev = evp < eve ? (int)(P.ev[evp].x >> 8) : 0x7fffffff;
+
+    int seg_end = 0;
+    bool in_seg = false;
+    const int W = P.W;
+
+    for (int f0 = 0; f0 < W;) {
+        const int fe = frag_end(f0, P.buffer, W);
+        for (int f = f0; f < fe; ++f) {
+            if (valid && f == seg_end) {
+                if (in_seg) ch.finish();
+                while (next_ev <= f) {
+                    const uint4 e = P.ev[evp];
+                    const int kind = e.y & 0xff, unit = (e.y >> 8) & 0xff;
+                    const int reg = (e.y >> 16) & 0xff;
+                    switch (kind) {
+                    case EV_WRITE: ch.write(c, unit, reg, (int)e.z, (int)(e.x & 0xff), (int)e.w); break;
+                    case EV_INIT: ch.init_unit(c, unit, (int)e.z, e.x & 0xff); break;
+                    case EV_START: alive = 1; break;
+                    case EV_STOP: alive = 0; break;
+                    default: break;
+                    }
+                    ++evp;
+                    next_ev = evp < eve ? (int)(P.ev[evp].x >> 8) : 0x7fffffff;
+                }
+                int nxt = min(fe, next_ev);
+                for (int k = 0; k < P.nsplits; ++k)
+                    if (P.splits[k] > f) nxt = min(nxt, P.splits[k]);
+                seg_end = nxt;
+                in_seg = alive != 0;
+                if (in_seg) ch.prepare(c, nxt - f);
+            }
+            int s0 = 0, s1 = 0, o0 = 0, o1 = 0;
+            if (in_seg) ch.sample(c, s0, s1, o0, o1);
+            const bool athome = mybus == home;
+            int h0 = __reduce_add_sync(0xffffffffu, athome ? o0 : 0);
+            int h1 = __reduce_add_sync(0xffffffffu, athome ? o1 : 0);
+            if ((tid & 31) == 0) {
+                atomicAdd(&sacc[f - f0][0], h0);
+                atomicAdd(&sacc[f - f0][1], h1);
+            }
+            if (valid && !athome && in_seg) {
+                int *a = P.acc + ((size_t)mybus * W + f) * 2;
+                atomicAdd(a, o0);
+                atomicAdd(a + 1, o1);
+            }
+        }
+        __syncthreads();
+        if (tid < (fe - f0) * 2 && home >= 0) {
+            int val = sacc[tid >> 1][tid & 1];
+            if (val) atomicAdd(P.acc + ((size_t)home * W + f0) * 2 + tid, val);
+            sacc[tid >> 1][tid & 1] = 0;
+        }
+        __syncthreads();
+        f0 = fe;
+    }
+    if (valid) {
+        if (in_seg) ch.finish();
+        sp.st(0, alive);
+        ch.store(sp, 1);
+        if (P.noise) P.noise[v] = nstate;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Bus stage
+// ---------------------------------------------------------------------------
+struct MixEvent {           // 16 bytes
+    unsigned time;          // (frame_in_window << 8) | substart
+    int target;             // group index, or -1 for the root
+    int reg_dur_hi;         // reg (int8, -1 = wake) in low 8 bits
+    int value;
+    unsigned dur;
+    int pad[3];
+};
+
+struct MixParams {
+    int *acc;               // [nbus][W][2]; bus 0 = root
+    int W, buffer, ngroups, channels;
+    int nsplits;
+    int splits[kMaxSplits];
+    int *gstate;            // [ngroups][8] panmix rampers (vol, pan)
+    int *rstate;            // [8]
+    const MixEvent *ev;     // sorted by time
+    int nev;
+    int *master;            // [W][channels], or raw root bus [W][2] if !root_stage
+    int root_stage;
+};
+
+A2CU_DEV void pm_load(const int *s, Ramp &vol, Ramp &pan) {
+    vol.value = s[0]; vol.target = s[1]; vol.delta = s[2]; vol.timer = s[3];
+    pan.value = s[4]; pan.target = s[5]; pan.delta = s[6]; pan.timer = s[7];
+}
+A2CU_DEV void pm_store(int *s, const Ramp &vol, const Ramp &pan) {
+    s[0] = vol.value; s[1] = vol.target; s[2] = vol.delta; s[3] = vol.timer;
+    s[4] = pan.value; s[5] = pan.target; s[6] = pan.delta; s[7] = pan.timer;
+}
+
+// Sequential walk of one bus-level panmix over the window. OUT1: 2 -> 1.
+// Calls emit(f, r0, r1) per frame. panmix.c:137-229.
+template <class Emit>
+A2CU_DEV void pm_walk(const MixParams &P, int target, int *state, const int *in, bool mono, Emit emit) {
+    Ramp vol, pan;
+    pm_load(state, vol, pan);
+    int evp = 0;
+    auto next_time = [&]() {
+        while (evp < P.nev && P.ev[evp].target != target) ++evp;
+        return evp < P.nev ? (int)(P.ev[evp].time >> 8) : 0x7fffffff;
+    };
+    int next_ev = next_time();
+    int seg_end = 0;
+    bool clamp = false;
+    for (int f = 0; f < P.W; ++f) {
+        if (f == seg_end) {
+            while (next_ev <= f) {
+                const MixEvent &e = P.ev[evp];
+                int reg = (int)(signed char)(e.reg_dur_hi & 0xff);
+                if (reg >= 0) ramp_set(reg == 0 ? vol : pan, e.value, (int)(e.time & 0xff), (int)e.dur);
+                ++evp;
+                next_ev = next_time();
+            }
+            int nxt = min(frag_end(f, P.buffer, P.W), next_ev);
+            // a group's segments are additionally cut by its parent's (the root's)
+            for (int k = 0; k < P.nsplits; ++k)
+                if (P.splits[k] > f) nxt = min(nxt, P.splits[k]);
+            seg_end = nxt;
+            clamp = pan.target > 0xffffff || pan.target < -0xffffff ||
+                    pan.value > 0xffffff || pan.value < -0xffffff;
+            ramp_prepare(vol, nxt - f);
+            ramp_prepare(pan, nxt - f);
+        }
+        int v = vol.value;
+        int vp = mulshr(pan.value, v, 24);
+        int v0 = wsub(v, vp), v1 = wadd(v, vp);
+        if (clamp) {
+            int lim = (int)((unsigned)v << 1);
+            if (v0 > lim) v0 = lim;
+            if (v1 > lim) v1 = lim;
+        }
+        int i0 = in[f * 2], i1 = in[f * 2 + 1];
+        if (mono)
+            emit(f, (int)(((long long)i0 * v0 + (long long)i1 * v1) >> 25), 0);
+        else
+            emit(f, mulshr(i0, v0, 24), mulshr(i1, v1, 24));
+        vol.value = wadd(vol.value, vol.delta);
+        pan.value = wadd(pan.value, pan.delta);
+    }
+    pm_store(state, vol, pan);
+}
+
+__global__ void __launch_bounds__(256) mix_buses(const MixParams P) {
+    const int tid = threadIdx.x;
+    int *root = P.acc;
+    // groups: { inline 0 *; panmix * *; xinsert * > } -> add into the root bus
+    for (int g = tid; g < P.ngroups; g += blockDim.x) {
+        const int *in = P.acc + (size_t)(1 + g) * P.W * 2;
+        pm_walk(P, g, P.gstate + g * 8, in, false, [&](int f, int r0, int r1) {
+            atomicAdd(root + f * 2, r0);
+            atomicAdd(root + f * 2 + 1, r1);
+        });
+    }
+    __syncthreads();
+    if (!P.root_stage) {
+        for (int i = tid; i < P.W * 2; i += blockDim.x) P.master[i] = root[i];
+        return;
+    }
+    // root: { inline 0 *|2; panmix * *|2 1; xinsert * > } into the cleared master
+    if (tid == 0) {
+        const bool mono = P.channels == 1;
+        pm_walk(P, -1, P.rstate, root, mono, [&](int f, int r0, int r1) {
+            if (mono) P.master[f] = r0;
+            else { P.master[f * 2] = r0; P.master[f * 2 + 1] = r1; }
+        });
+    }
+}
+
+}  // namespace a2cu

@@ -1,0 +1,217 @@
+/*
+ * a2cu.h - C ABI of the B200 voice-render engine ("bank mode").
+ *
+ * This is the device engine underneath the drop-in unit plug-in
+ * (include/a2cu_units.h) and the entry point for hosts that batch voices
+ * themselves.  Plain C: opaque handle, pointers and sizes, no torch or CUDA
+ * types in the signatures (a CUDA stream travels as void *).
+ *
+ * Relation to the reference (paths relative to the Audiality 2 tree):
+ *
+ *   a2cu_open / a2cu_close     a2_Open / a2_Close for the render path only:
+ *                              sample rate, channel count, basepitch
+ *                              (src/audiality2.c:398-399, 406-511)
+ *   a2cu_wave_*                read side of the wave store: a2_InitWaves
+ *                              (src/waves.c:629-708), pad + mip preparation
+ *                              (src/waves.c:59-151), a2_GetWave (:759-772)
+ *   a2cu_bank_new              a2_PopulateVoice / a2_AddUnit + each unit's
+ *                              Initialize() (src/core.c:163-420) for N voices
+ *                              of one struct at once
+ *   a2cu_bank_write[_all]      A2_write_cb of the unit's A2_crdesc
+ *                              (include/a2_units.h:115), i.e. what
+ *                              a2_VoiceControl delivers (src/core.c:143-149)
+ *   a2cu_bank_wake             a VM wake-up that writes nothing but still
+ *                              splits the Process() segment (core.c:1847-1880)
+ *   a2cu_group_new/_write      a2_NewGroup's a2_groupdriver voice:
+ *                              inline; panmix; xinsert (audiality2.c:294-304)
+ *   a2cu_root_write            the root driver's panmix (audiality2.c:268-292)
+ *   a2cu_run                   a2_Run(): a2_AudioCallback's fragment loop,
+ *                              a2_ProcessVoices, every unit's Process() and
+ *                              the bus mix-down (src/core.c:1847-2011); output
+ *                              is what the driver's int32 8:24 buffers hold
+ *                              (include/a2_drivers.h:301), interleaved
+ *
+ * Values are 16:16 fixed point exactly as the VM registers hold them; times
+ * are 24:8 fixed point sample frames since a2cu_open (A2_timestamp units).
+ * Every function returns 0 (A2CU_OK) or a negative a2cu_error unless stated.
+ * There is NO CPU fallback: without a usable CUDA device a2cu_open fails.
+ */
+#ifndef A2CU_H
+#define A2CU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct a2cu_engine a2cu_engine;
+
+typedef enum a2cu_error {
+	A2CU_OK = 0,
+	A2CU_ENODEVICE = -1,	/* no CUDA device / wrong architecture */
+	A2CU_ECUDA = -2,	/* CUDA runtime error, see a2cu_last_error() */
+	A2CU_EINVAL = -3,	/* bad argument */
+	A2CU_ENOTIMPL = -4,	/* voice structure has no kernel (A2_NOTIMPLEMENTED) */
+	A2CU_ENOMEM = -5,
+	A2CU_ELATE = -6		/* event time already rendered */
+} a2cu_error;
+
+/* Unit kinds (a2_core_units[], src/audiality2.c:183-207) */
+enum {
+	A2CU_WTOSC = 1, A2CU_PANMIX = 2, A2CU_FILTER12 = 3, A2CU_WAVESHAPER = 4,
+	A2CU_FM1 = 16, A2CU_FM2, A2CU_FM3, A2CU_FM4,
+	A2CU_FM3P, A2CU_FM4P, A2CU_FM2R, A2CU_FM4R
+};
+
+/* Wave types and flags (include/a2_waves.h:78-84, :108) */
+enum { A2CU_WOFF = 0, A2CU_WNOISE = 1, A2CU_WWAVE = 2, A2CU_WMIPWAVE = 3 };
+#define A2CU_LOOPED	0x100
+#define A2CU_MIPLEVELS	10
+
+/*
+ * One unit of a voice structure after the compiler's autowiring
+ * (src/compiler.c:3036-3138) and instantiation (src/core.c:163-243).
+ */
+typedef struct a2cu_unitspec {
+	int32_t kind;
+	int32_t ninputs;
+	int32_t noutputs;
+	int32_t add;		/* A2_PROCADD */
+	int32_t wireout;	/* A2_IO_WIREOUT: outputs are the voice's bus */
+} a2cu_unitspec;
+
+/* ---- engine ---------------------------------------------------------- */
+
+/* device: CUDA ordinal. channels: 1 or 2. Returns NULL on failure. */
+a2cu_engine *a2cu_open(int device, int samplerate, int channels);
+void a2cu_close(a2cu_engine *e);
+const char *a2cu_last_error(void);
+
+/* Use an existing CUDA stream (cudaStream_t passed as void *); default 0. */
+int a2cu_set_stream(a2cu_engine *e, void *cuda_stream);
+
+int a2cu_basepitch(const a2cu_engine *e);		/* audiality2.c:398 */
+uint32_t a2cu_msdur(const a2cu_engine *e);		/* audiality2.c:499 */
+uint64_t a2cu_now(const a2cu_engine *e);		/* 24:8 frames rendered */
+
+/*
+ * The reference's root voice re-arms a wake-up every 1000000 time units
+ * (src/core.c:1191-1216), which splits every voice's segments there.  On by
+ * default so that output equals the reference's offline render; 0 disables.
+ */
+int a2cu_set_root_wake_period(a2cu_engine *e, uint32_t period_24_8);
+
+/* Seed of the shared noise LCG (A2_PNOISESEED, src/properties.c:298). */
+int a2cu_set_noiseseed(a2cu_engine *e, uint32_t seed);
+
+/* ---- waves ----------------------------------------------------------- */
+
+/* Builtin wave by its A2S name ("sine", "saw", "pulse25", ...). Returns id. */
+int a2cu_wave_builtin(a2cu_engine *e, const char *name);
+
+/* Upload raw int16 samples; pads and mip levels are prepared here. Returns id. */
+int a2cu_wave_upload(a2cu_engine *e, int type, unsigned period, unsigned flags,
+		const int16_t *data, unsigned length);
+
+/*
+ * Upload a wave the host already prepared (A2_wave, include/a2_waves.h:88-103):
+ * data[l] points at the FIRST PAD sample of level l (A2_wave_wave.data[l]),
+ * size[l] excludes the pads. Used by the drop-in plug-in. Returns id.
+ */
+int a2cu_wave_upload_prepared(a2cu_engine *e, int type, unsigned period,
+		unsigned flags, const int16_t *const *data, const unsigned *size);
+
+/* Mark a wave unloaded (size[0] = 0, src/waves.c:718-724). */
+int a2cu_wave_unload(a2cu_engine *e, int wave);
+
+/* Copy level 'level' incl. pads to 'out' (capacity in samples); returns count. */
+int a2cu_wave_read(a2cu_engine *e, int wave, int level, int16_t *out,
+		unsigned capacity, unsigned *size);
+
+/* ---- groups and banks -------------------------------------------------- */
+
+/* New group bus with its own panmix, mixing into the root bus. Returns id. */
+int a2cu_group_new(a2cu_engine *e);
+
+/* 1 if a kernel exists for this voice structure. */
+int a2cu_chain_supported(const a2cu_unitspec *chain, int nunits);
+
+/*
+ * Create a bank: nvoices voices of one structure, started at the current time
+ * with sub-sample offset 'substart' (waketime & 0xff). transpose / group may
+ * be NULL (0 / root bus) or arrays of nvoices entries. Returns bank id.
+ */
+int a2cu_bank_new(a2cu_engine *e, const a2cu_unitspec *chain, int nunits,
+		int nvoices, const int32_t *transpose, const int32_t *group,
+		unsigned substart);
+
+/* Stop a voice at 'when' (a2_VoiceFree at a segment start, core.c:1891). */
+int a2cu_bank_kill(a2cu_engine *e, int bank, int voice, uint64_t when);
+
+/* One control write to one voice. 'when' >= a2cu_now(). */
+int a2cu_bank_write(a2cu_engine *e, int bank, int voice, int unit, int reg,
+		int32_t value, uint64_t when, uint32_t dur);
+
+/*
+ * The same register of every voice of the bank: values[i * stride] for voice
+ * i (stride 0 broadcasts values[0]).
+ */
+int a2cu_bank_write_all(a2cu_engine *e, int bank, int unit, int reg,
+		const int32_t *values, int stride, uint64_t when, uint32_t dur);
+
+/* Bare wake-up (segment split) of one voice, or of all with voice < 0. */
+int a2cu_bank_wake(a2cu_engine *e, int bank, int voice, uint64_t when);
+
+/* reg: 0 = vol, 1 = pan (src/units/panmix.c:29-33); reg < 0: bare wake-up */
+int a2cu_group_write(a2cu_engine *e, int group, int reg, int32_t value,
+		uint64_t when, uint32_t dur);
+int a2cu_root_write(a2cu_engine *e, int reg, int32_t value, uint64_t when,
+		uint32_t dur);
+
+/* ---- rendering ----------------------------------------------------------- */
+
+/*
+ * Render 'frames' frames as driver buffers of 'buffer' frames (fragments of at
+ * most 64 inside each buffer, src/core.c:1964-1973) and copy the interleaved
+ * int32 8:24 master output [frame][channel] to HOST memory 'out'. Blocks
+ * until the copy is complete. 'out' may be NULL (render only).
+ */
+int a2cu_run(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *out);
+
+/*
+ * Same, but leaves the result in DEVICE memory 'dev_out' (or in the engine's
+ * own buffer when NULL; see a2cu_master_devptr) and does not synchronise: work
+ * is queued on the engine's stream.
+ */
+int a2cu_run_async(a2cu_engine *e, unsigned frames, unsigned buffer,
+		int32_t *dev_out);
+int32_t *a2cu_master_devptr(a2cu_engine *e);
+int a2cu_sync(a2cu_engine *e);
+
+/*
+ * Multi-GPU cut: with post_root_stage 0 the engine stops
+ * before the root panmix and outputs the raw 2-channel root bus, so partial
+ * buses of several engines can be summed (integer add, order-free) before ONE
+ * engine applies the truncating root stage with a2cu_apply_root_stage().
+ */
+int a2cu_set_post_root_stage(a2cu_engine *e, int enabled);
+int a2cu_apply_root_stage(a2cu_engine *e, const int32_t *dev_rootbus,
+		int32_t *dev_master, unsigned frames, unsigned buffer,
+		uint64_t start_time);
+
+/* Kernel launches issued by this engine so far (bench's gpu_launches). */
+uint64_t a2cu_launch_count(const a2cu_engine *e);
+/* Name of the render kernel a bank uses (for profiles/). */
+const char *a2cu_bank_kernel_name(a2cu_engine *e, int bank);
+/* Bytes of per-voice state a bank keeps in HBM (roofline arithmetic). */
+int a2cu_bank_state_bytes(a2cu_engine *e, int bank);
+/* CUDA-event time (ms) of the last a2cu_run*'s render kernels only. */
+float a2cu_last_render_ms(a2cu_engine *e);
+/* Turn the event timing above on/off (adds two event records per run). */
+int a2cu_set_timing(a2cu_engine *e, int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* A2CU_H */

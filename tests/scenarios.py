@@ -320,3 +320,53 @@ def run_oracle(scn):
     out = o.render(scn.events(), scn.frames, scn.buffer)
     o.close()
     return out
+
+
+def run_cuda(scn, window=None):
+    """Render `scn` with the CUDA engine through its C ABI (ctypes).
+    window: frames per a2cu_run call (multiple of scn.buffer), default all."""
+    from audiality2_b200 import engine as eng
+    from oracle import a2oracle as ao
+    e = eng.Engine(scn.samplerate, scn.channels)
+    try:
+        if scn.noiseseed is not None:
+            e.set_noiseseed(scn.noiseseed)
+        for w in scn.waves:
+            e.builtin_wave(w)
+        for _ in range(scn.ngroups):
+            e.new_group()
+        # one bank per distinct voice structure, slots in voice order
+        chains, where = {}, []
+        for v in scn.voices:
+            key = tuple(v.kinds)
+            chains.setdefault(key, []).append(v)
+            where.append((key, len(chains[key]) - 1))
+        bank_of = {}
+        for key, vs in chains.items():
+            bank_of[key] = e.new_bank(autowire(list(key)), len(vs),
+                                      transpose=[v.transpose for v in vs],
+                                      group=[v.group for v in vs])
+        for ev in scn.events():
+            t, kind, tgt = int(ev["time"]), int(ev["kind"]), int(ev["voice"])
+            if kind == ao.EV_WRITE:
+                key, slot = where[tgt]
+                e.write(bank_of[key], slot, int(ev["unit"]), int(ev["reg"]),
+                        int(ev["value"]), t, int(ev["dur"]))
+            elif kind == ao.EV_WAKE:
+                key, slot = where[tgt]
+                e.wake(bank_of[key], slot, t)
+            elif kind == ao.EV_GROUPWRITE:
+                e.group_write(tgt, int(ev["reg"]), int(ev["value"]), t, int(ev["dur"]))
+            elif kind == ao.EV_ROOTWRITE and int(ev["reg"]) >= 0:
+                e.root_write(int(ev["reg"]), int(ev["value"]), t, int(ev["dur"]))
+            # root wake-ups (reg < 0) are the engine's own root_wake_period
+        if window is None:
+            return e.run(scn.frames, scn.buffer)
+        parts, done = [], 0
+        while done < scn.frames:
+            n = min(window, scn.frames - done)
+            parts.append(e.run(n, scn.buffer))
+            done += n
+        return np.concatenate(parts, axis=0)
+    finally:
+        e.close()
