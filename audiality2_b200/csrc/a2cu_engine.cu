@@ -238,10 +238,10 @@ struct a2cu_engine {
     size_t stage_cap = 0;
     int32_t *h_out = nullptr;
     size_t hout_cap = 0;
-    uint64_t launches = 0;
+    uint64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
     bool timing = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    float last_ms = 0.f;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    float last_ms = 0.f, last_mix_ms = 0.f;
     // last window (for a2cu_apply_root_stage)
     MixParams last_mix;
 };
@@ -362,7 +362,8 @@ a2cu_engine *a2cu_open(int device, int samplerate, int channels) {
     // root panmix: vol 1.0, pan 0 (panmix.c:252-262)
     int rs[8] = {65536 << 8, 65536 << 8, 0, 0, 0, 0, 0, 0};
     ok = ok && cudaMemcpy(e->d_rstate, rs, sizeof(rs), cudaMemcpyHostToDevice) == cudaSuccess;
-    ok = ok && cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess;
+    ok = ok && cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess &&
+         cudaEventCreate(&e->ev2) == cudaSuccess;
     if (!ok) {
         fail(A2CU_ECUDA, "a2cu_open: %s", cudaGetErrorString(cudaGetLastError()));
         delete e;
@@ -387,6 +388,7 @@ void a2cu_close(a2cu_engine *e) {
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev2) cudaEventDestroy(e->ev2);
     delete e;
 }
 
@@ -401,8 +403,11 @@ uint64_t a2cu_now(const a2cu_engine *e) { return e->now; }
 int a2cu_set_root_wake_period(a2cu_engine *e, uint32_t p) { e->root_wake = p; return A2CU_OK; }
 int a2cu_set_noiseseed(a2cu_engine *e, uint32_t s) { e->noiseseed = s; return A2CU_OK; }
 uint64_t a2cu_launch_count(const a2cu_engine *e) { return e->launches; }
+uint64_t a2cu_h2d_bytes(const a2cu_engine *e) { return e->h2d_bytes; }
+uint64_t a2cu_d2h_bytes(const a2cu_engine *e) { return e->d2h_bytes; }
 int a2cu_set_timing(a2cu_engine *e, int on) { e->timing = on != 0; return A2CU_OK; }
 float a2cu_last_render_ms(a2cu_engine *e) { return e->last_ms; }
+float a2cu_last_mix_ms(a2cu_engine *e) { return e->last_mix_ms; }
 int a2cu_set_post_root_stage(a2cu_engine *e, int on) { e->post_root = on != 0; return A2CU_OK; }
 
 // ---- waves -----------------------------------------------------------------
@@ -794,11 +799,11 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     size_t spos = 0;
 
     CK(cudaMemsetAsync(e->d_acc, 0, acc_n * sizeof(int), e->stream));
-    if (e->timing) CK(cudaEventRecord(e->ev0, e->stream));
 
+    std::vector<RenderParams> params(e->banks.size());
     for (size_t bi = 0; bi < e->banks.size(); ++bi) {
         Bank *b = e->banks[bi];
-        RenderParams P;
+        RenderParams &P = params[bi];
         memset(&P, 0, sizeof(P));
         P.state = b->d_state; P.stride = b->stride; P.nvoices = b->nvoices;
         P.bus_of = b->d_bus; P.acc = e->d_acc; P.W = W; P.buffer = (int)buffer;
@@ -832,10 +837,16 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             CK(cudaMemcpyAsync(b->d_evoff, off, (b->stride + 1) * sizeof(unsigned), cudaMemcpyHostToDevice,
                                e->stream));
             CK(cudaMemcpyAsync(b->d_ev, recs, nev * sizeof(uint4), cudaMemcpyHostToDevice, e->stream));
+            e->h2d_bytes += (b->stride + 1) * sizeof(unsigned) + nev * sizeof(uint4);
             P.ev_off = b->d_evoff; P.ev = b->d_ev;
         }
+    }
+    // inputs are resident from here on: ev0 .. ev1 brackets the render kernels
+    if (e->timing) CK(cudaEventRecord(e->ev0, e->stream));
+    for (size_t bi = 0; bi < e->banks.size(); ++bi) {
+        Bank *b = e->banks[bi];
         int grid = (b->nvoices + kThreads - 1) / kThreads;
-        b->k.fn<<<grid, kThreads, 0, e->stream>>>(P);
+        b->k.fn<<<grid, kThreads, 0, e->stream>>>(params[bi]);
         ++e->launches;
     }
     if (e->timing) CK(cudaEventRecord(e->ev1, e->stream));
@@ -861,6 +872,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             me[i].reg_dur_hi = mdue[i].reg & 0xff; me[i].value = mdue[i].value; me[i].dur = mdue[i].dur;
         }
         CK(cudaMemcpyAsync(e->d_mixev, me, mdue.size() * sizeof(MixEvent), cudaMemcpyHostToDevice, e->stream));
+        e->h2d_bytes += mdue.size() * sizeof(MixEvent);
         M.ev = e->d_mixev;
     }
     M.master = dev_out ? dev_out : e->d_master;
@@ -868,6 +880,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     mix_buses<<<1, 256, 0, e->stream>>>(M);
     ++e->launches;
     CK(cudaGetLastError());
+    if (e->timing) CK(cudaEventRecord(e->ev2, e->stream));
     e->last_mix = M;
     e->now = t1;
     return A2CU_OK;
@@ -887,6 +900,7 @@ int a2cu_sync(a2cu_engine *e) {
     if (e->timing) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_ms = ms;
+        if (cudaEventElapsedTime(&ms, e->ev1, e->ev2) == cudaSuccess) e->last_mix_ms = ms;
     }
     return A2CU_OK;
 }
@@ -912,6 +926,7 @@ int a2cu_run(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *out) {
             CK(cudaMallocHost(&e->h_out, e->hout_cap * sizeof(int32_t)));
         }
         CK(cudaMemcpyAsync(e->h_out, e->d_master, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+        e->d2h_bytes += n * sizeof(int32_t);
     }
     r = a2cu_sync(e);
     if (r) return r;

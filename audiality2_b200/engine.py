@@ -68,6 +68,9 @@ SYMBOLS = {
     "a2cu_bank_kernel_name": (C.c_char_p, [_VP, _I]),
     "a2cu_bank_state_bytes": (_I, [_VP, _I]),
     "a2cu_last_render_ms": (C.c_float, [_VP]),
+    "a2cu_last_mix_ms": (C.c_float, [_VP]),
+    "a2cu_h2d_bytes": (_U64, [_VP]),
+    "a2cu_d2h_bytes": (_U64, [_VP]),
     "a2cu_set_timing": (_I, [_VP, _I]),
 }
 
@@ -152,6 +155,17 @@ class Engine:
 
     def last_render_ms(self):
         return float(self.L.a2cu_last_render_ms(self.h))
+
+    def last_mix_ms(self):
+        return float(self.L.a2cu_last_mix_ms(self.h))
+
+    @property
+    def h2d_bytes(self):
+        return self.L.a2cu_h2d_bytes(self.h)
+
+    @property
+    def d2h_bytes(self):
+        return self.L.a2cu_d2h_bytes(self.h)
 
     def set_post_root_stage(self, on):
         self.post_root = bool(on)

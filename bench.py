@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py - voice-samples/s of the voice-render hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path
+
+Workload (config.workload "cfg2"): 4 096 voices wtosc -> filter12 -> panmix on
+the shared 2 048-point saw, 48 kHz, 64-frame blocks, plus ONE control write
+per voice per step (amplitude re-targeted and ramped across the step) so that
+every step has real host->device input.  One step = one a2cu_run call of 960
+frames (20 ms = 15 blocks of 64) = voices x 960 voice-samples.
+
+Numbers on the JSON line:
+  value   voice-samples/s over the CUDA-event spans of the kernels (render +
+          bus stage [+ NCCL reduce and root stage for N > 1]); the step's
+          events are already in HBM when the span starts.  L2 is flushed
+          between steps, outside the spans.
+  e2e     the same metric through a2cu_run() with HOST buffers: event staging,
+          H2D, kernels, D2H of the int32 master block, synchronise - host wall
+          time per call, max over ranks.
+  roofline  HBM roofline of the dominant kernel (render_bank<...>).
+  cpu_baseline  the reference's own CPU render (oracle/_ref) on a bounded
+          sample of the same workload, 1 core, rank 0, N = 1 only.
+Multi-GPU (weak scaling): every rank renders its own bank; the raw stereo root
+bus is summed with one NCCL all-reduce (int32) before the truncating root stage.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+STEP_MS = 20
+RATE = 48000
+STEP_FRAMES = STEP_MS * RATE // 1000     # 960 = 15 blocks of 64
+BLOCK = 64
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown",
+                                  "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------
+# reference / cpu baseline (oracle/_ref: the unmodified reference, CPU)
+# ---------------------------------------------------------------------------
+def _write_script(nvoices, steps, seed, path):
+    from cases import bench_bank
+    scn = bench_bank(nvoices, steps=steps, step_ms=STEP_MS, seed=seed)
+    with open(path, "w") as f:
+        f.write(scn.to_a2s())
+
+
+def ref_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "a2render")
+    return p if os.path.exists(p) else None
+
+
+def run_reference_sample(nvoices, frames, shards, seed=324357):
+    """Render `frames` frames of the cfg2 bench bank with the reference on
+    `shards` host processes (one engine state is single-threaded, so the only
+    legal parallelism is independent states on disjoint voice shards,
+    audiality2.h.cmake:163-166). Returns (voice_samples, seconds, kind)."""
+    exe = ref_binary()
+    steps = (frames + STEP_FRAMES - 1) // STEP_FRAMES
+    if exe is None:
+        # plain-C port (single thread)
+        from cases import bench_bank
+        from scenarios import run_oracle
+        scn = bench_bank(nvoices, steps=steps, step_ms=STEP_MS, seed=seed)
+        scn.frames = frames
+        t0 = time.perf_counter()
+        run_oracle(scn)
+        return nvoices * frames, time.perf_counter() - t0, "port", 1
+    per = (nvoices + shards - 1) // shards
+    tmp = tempfile.mkdtemp(prefix="a2ref_")
+    procs = []
+    for s in range(shards):
+        n = min(per, nvoices - s * per)
+        if n <= 0:
+            break
+        path = os.path.join(tmp, "shard%d.a2s" % s)
+        _write_script(n, steps, seed + s, path)
+        procs.append(subprocess.Popen(
+            [exe, "-r", str(RATE), "-b", str(BLOCK), "-c", "2", "-n", str(frames),
+             "-p", "Song", path], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    secs = []
+    for p in procs:
+        out, err = p.communicate()
+        if p.returncode:
+            raise RuntimeError("a2render failed: " + err[-500:])
+        secs.append(json.loads(out.strip().splitlines()[-1])["seconds"])
+    return nvoices * frames, max(secs), "reference", len(procs)
+
+
+def bench_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    frames = RATE          # one second of audio per step (bounded sample)
+    times = []
+    for i in range(args.warmup + args.steps):
+        vs, sec, kind, used = run_reference_sample(args.voices, frames, cores)
+        if i >= args.warmup:
+            times.append(sec)
+    total = args.voices * frames * len(times)
+    T = sum(times)
+    value = total / T
+    sample = "%d voices x %d frames per step, %d independent engine states on %d host threads" % (
+        args.voices, frames, used, used)
+    line = {
+        "impl": "reference", "metric": "voice-samples/sec at 64-frame blocks",
+        "value": value, "unit": "voice-samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * T / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "cfg2: %d voices wtosc->filter12->panmix, saw 2048-pt, 48 kHz, "
+                               "64-frame blocks, 1 amplitude write/voice/20 ms" % args.voices},
+        "cpu_baseline": {"value": value, "unit": "voice-samples/s", "cores": used,
+                         "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "voice-samples/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def bench_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from audiality2_b200 import engine as eng
+    from audiality2_b200.workloads import cfg2_bank
+    from scenarios import autowire
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    e = eng.Engine(RATE, 2, device=local)
+    stream = torch.cuda.current_stream()
+    e.set_stream(stream.cuda_stream)
+    e.set_timing(True)
+    b = cfg2_bank(args.voices, seed=324357 + rank)
+    w = e.builtin_wave(b["wave"])
+    chain = autowire(list(b["kinds"]))
+    bank = e.new_bank(chain, args.voices)
+    e.write_all(bank, 0, 0, [w << 16], dur=STEP_FRAMES << 8)
+    e.write_all(bank, 0, 1, b["pitch"])
+    e.write_all(bank, 0, 2, [b["amp"]])
+    e.write_all(bank, 1, 0, b["cutoff"])
+    e.write_all(bank, 1, 1, [b["q"]])
+    e.write_all(bank, 2, 1, b["pan"])
+    multi = world > 1
+    if multi:
+        e.set_post_root_stage(False)
+    rootbus = torch.zeros((STEP_FRAMES, 2), dtype=torch.int32, device=dev)
+    master = torch.zeros((STEP_FRAMES, 2), dtype=torch.int32, device=dev)
+    host_out = torch.zeros((STEP_FRAMES, 2), dtype=torch.int32).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    amp = [b["amp"] // 2, b["amp"]]
+
+    ev_a = torch.cuda.Event(enable_timing=True)
+    ev_b = torch.cuda.Event(enable_timing=True)
+    dev_ms, host_s, render_ms = [], [], []
+    state = {"step": 0}
+
+    def one_step(timed):
+        flush.zero_()                       # L2 flush, outside every span
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        # --- the step, through the public API, host buffers in and out ---
+        e.write_all(bank, 0, 2, [amp[state["step"] & 1]], dur=STEP_FRAMES << 8)
+        if not multi:
+            out = e.run(STEP_FRAMES, BLOCK)            # H2D + kernels + D2H + sync
+            span = e.last_render_ms() + e.last_mix_ms()
+        else:
+            e.run_async(STEP_FRAMES, BLOCK, rootbus.data_ptr())
+            ev_a.record(stream)
+            dist.all_reduce(rootbus)                   # NCCL int32 sum over NVLink
+            e.apply_root_stage(rootbus.data_ptr(), master.data_ptr(), STEP_FRAMES, BLOCK)
+            ev_b.record(stream)
+            host_out.copy_(master, non_blocking=True)
+            e.sync()
+            torch.cuda.synchronize()
+            span = e.last_render_ms() + e.last_mix_ms() + ev_a.elapsed_time(ev_b)
+        t1 = time.perf_counter()
+        state["step"] += 1
+        if timed:
+            dev_ms.append(span)
+            host_s.append(t1 - t0)
+            render_ms.append(e.last_render_ms())
+
+    for _ in range(max(3, args.warmup)):
+        one_step(False)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    if multi:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0, h0, d0 = e.launches, e.h2d_bytes, e.d2h_bytes
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step(True)
+    torch.cuda.synchronize()
+    if multi:
+        dist.barrier()
+    wall1 = time.perf_counter()
+    launches = e.launches - l0
+    h2d = (e.h2d_bytes - h0) / args.steps
+    d2h = (e.d2h_bytes - d0) / args.steps
+    if multi:
+        d2h = STEP_FRAMES * 2 * 4 if rank == 0 else 0
+    clk = clocks.stop() if rank == 0 else None
+
+    tot = torch.tensor([sum(dev_ms), sum(host_s) * 1000.0], dtype=torch.float64, device=dev)
+    if multi:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    dev_total_ms, host_total_ms = [float(x) for x in tot.tolist()]
+    vs_total = float(args.voices) * STEP_FRAMES * args.steps * world
+    value = vs_total / (dev_total_ms / 1000.0)
+    e2e = vs_total / (host_total_ms / 1000.0)
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        state_bytes = e.bank_state_bytes(bank)
+        cmd_bytes = 16 + 4                          # one event record + CSR offset per voice
+        alg_bytes = args.voices * (2 * state_bytes + cmd_bytes) + STEP_FRAMES * 2 * 4
+        k_ms = statistics.mean(render_ms)
+        achieved = alg_bytes / (k_ms / 1000.0) / 1e9
+        line = {
+            "metric": "voice-samples/sec at 64-frame blocks",
+            "value": value, "unit": "voice-samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": dev_total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {
+                "workload": "cfg2: %d voices/GPU wtosc->filter12->panmix, saw 2048-pt, 48 kHz, "
+                            "64-frame blocks, 1 amplitude write/voice/20 ms" % args.voices,
+                "step": "%d frames (15 blocks of 64) per a2cu_run call" % STEP_FRAMES,
+                "l2": "flushed (256 MiB memset) between steps, outside the timed spans",
+                "timing": "value: CUDA-event spans of kernels summed over steps; "
+                          "e2e: host wall time of each a2cu_run incl. H2D/D2H; max over ranks",
+                "multi_gpu": "voices sharded, one NCCL int32 all-reduce of the root bus per step"
+                             if multi else "single GPU",
+            },
+            "wall_ms_per_step_incl_flush": 1000.0 * (wall1 - wall0) / args.steps,
+            "e2e": {"value": e2e, "unit": "voice-samples/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": host_total_ms / args.steps},
+            "gpu_launches": int(launches),
+            "kernel": "render_bank<%s> + mix_buses" % e.bank_kernel_name(bank),
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel": "render_bank<%s>" % e.bank_kernel_name(bank),
+                "kernel_ms": k_ms,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "note": "state is read and written once per 960-frame launch and the wavetable "
+                        "is L1/L2 resident: the kernel is INT32-issue/latency bound, not HBM "
+                        "bound (DESIGN.md, profiles/)",
+            },
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            frames = args.cpu_frames
+            vs, sec, kind, used = run_reference_sample(args.voices, frames, 1)
+            line["cpu_baseline"] = {
+                "value": vs / sec, "unit": "voice-samples/s", "cores": 1, "kind": kind,
+                "sample": "%d voices x %d frames of the same workload, one engine state "
+                          "(single-threaded by design), a2_Run loop only" % (args.voices, frames)}
+        print(json.dumps(line), flush=True)
+    e.close()
+    if multi:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--voices", type=int, default=4096)
+    ap.add_argument("--cpu-frames", type=int, default=96000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        bench_reference(args)
+    else:
+        bench_ours(args)
+
+
+if __name__ == "__main__":
+    main()

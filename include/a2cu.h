@@ -208,7 +208,12 @@ const char *a2cu_bank_kernel_name(a2cu_engine *e, int bank);
 int a2cu_bank_state_bytes(a2cu_engine *e, int bank);
 /* CUDA-event time (ms) of the last a2cu_run*'s render kernels only. */
 float a2cu_last_render_ms(a2cu_engine *e);
-/* Turn the event timing above on/off (adds two event records per run). */
+/* Same for the bus stage (mix_buses) of the last run. */
+float a2cu_last_mix_ms(a2cu_engine *e);
+/* Bytes this engine copied host->device / device->host so far. */
+uint64_t a2cu_h2d_bytes(const a2cu_engine *e);
+uint64_t a2cu_d2h_bytes(const a2cu_engine *e);
+/* Turn the event timing above on/off (adds three event records per run). */
 int a2cu_set_timing(a2cu_engine *e, int enabled);
 
 #ifdef __cplusplus

@@ -269,6 +269,28 @@ def bank(nvoices=256, kinds=("wtosc", "filter12", "panmix"), wave="saw",
     return s
 
 
+def bench_bank(nvoices=4096, steps=4, step_ms=20, seed=324357):
+    """The bench.py workload (BASELINE config 2 + one control write per voice
+    per step): static pitch/cutoff/pan, amplitude re-targeted every step_ms
+    and ramped across the step, 48 kHz, 64-frame blocks."""
+    from audiality2_b200.workloads import cfg2_bank
+    b = cfg2_bank(nvoices, seed)
+    s = Scenario(48000, 2, 64, steps * step_ms * 48)
+    w = s.wave(b["wave"])
+    a0 = b["amp"]
+    for v in range(nvoices):
+        s.add_voice(list(b["kinds"]), [
+            ("ramp", 0, W, w << 16), ("set", 0, P, int(b["pitch"][v])),
+            ("set", 0, A, a0),
+            ("set", 1, CUT, int(b["cutoff"][v])), ("set", 1, Q, b["q"]),
+            ("set", 2, PAN, int(b["pan"][v])),
+            ("loop", (steps + 1) // 2, [
+                ("ramp", 0, A, a0 // 2), ("d", fx(step_ms)),
+                ("ramp", 0, A, a0), ("d", fx(step_ms))]),
+        ])
+    return s
+
+
 def fm_bank(nvoices=64, frames=1280):
     """BASELINE config 4 shape: voices cycling fm3/fm3p/fm2r/fm4r."""
     s = Scenario(48000, 2, 64, frames)
@@ -297,4 +319,5 @@ CASES = {
     "noise": noise,
     "bank256": bank,
     "fm_bank64": fm_bank,
+    "bench_bank200": lambda: bench_bank(200, steps=3),
 }

@@ -172,7 +172,17 @@ class Scenario:
         ev = []
         t = 0
         pending = []
-        for st in steps:
+
+        def flat(steps):
+            for st in steps:
+                if st[0] == "loop":
+                    for _ in range(st[1]):
+                        for x in flat(st[2]):
+                            yield x
+                else:
+                    yield st
+
+        for st in flat(steps):
             if st[0] == "set":
                 _, u, r, v = st
                 pending = [p for p in pending if (p[0], p[1]) != (u, r)]
@@ -227,22 +237,27 @@ class Scenario:
         """Script whose Song() spawns every group and voice at time 0."""
         L = ['def title "generated"', 'def a2sversion "1.9"', ""]
 
-        def body(kinds, steps, names):
+        def body(kinds, steps, names, indent="\t", final=True):
             out = []
             for st in steps:
-                if st[0] == "set":
+                if st[0] == "loop":
+                    out.append("%s%d {" % (indent, st[1]))
+                    out += body(kinds, st[2], names, indent + "\t", False)
+                    out.append("%s}" % indent)
+                elif st[0] == "set":
                     rn = self._regname(kinds, names, st[1], st[2])
                     val = self.waves[st[3] >> 16] if st[2] == 0 and \
                         kinds[st[1]] == "wtosc" else lit(st[3])
-                    out.append("\t@%s %s" % (rn, val))
+                    out.append("%s@%s %s" % (indent, rn, val))
                 elif st[0] == "ramp":
                     rn = self._regname(kinds, names, st[1], st[2])
                     val = self.waves[st[3] >> 16] if st[2] == 0 and \
                         kinds[st[1]] == "wtosc" else lit(st[3])
-                    out.append("\t%s %s" % (rn, val))
+                    out.append("%s%s %s" % (indent, rn, val))
                 elif st[0] == "d":
-                    out.append("\td %s" % lit(st[1]))
-            out.append("\tfor { d 30000 }")
+                    out.append("%sd %s" % (indent, lit(st[1])))
+            if final:
+                out.append("\tfor { d 30000 }")
             return out
 
         for vi, v in enumerate(self.voices):
@@ -280,10 +295,32 @@ class Scenario:
         for vi, v in enumerate(self.voices):
             if v.group < 0:
                 items.append(("v", vi))
-        for kind, idx in items:
-            L.append("\t%s%d" % ("G" if kind == "g" else "V", idx))
+        if len(items) <= 100:
+            for kind, idx in items:
+                L.append("\t%s%d" % ("G" if kind == "g" else "V", idx))
+        else:
+            # One program may run at most A2_INSLIMIT = 1000 VM instructions
+            # between timing points (config.h:119): spawn through helper
+            # voices without units (their children inherit the root bus).
+            nsp = (len(items) + 63) // 64
+            for k in range(nsp):
+                L.append("\tS%d" % k)
         L.append("\tfor { d 30000 }")
         L.append("}")
+        if len(items) > 100:
+            head = L[:3]
+            sp = []
+            for k in range(nsp):
+                sp.append("S%d()" % k)
+                sp.append("{")
+                for kind, idx in items[k * 64:(k + 1) * 64]:
+                    sp.append("\t%s%d" % ("G" if kind == "g" else "V", idx))
+                sp.append("\tfor { d 30000 }")
+                sp.append("}")
+                sp.append("")
+            # programs must be defined before use: voices, groups, spawners, Song
+            song_at = L.index("export Song()")
+            L = L[:song_at] + sp + L[song_at:]
         return "\n".join(L) + "\n"
 
 
