@@ -350,6 +350,20 @@ struct WtOsc {
         else if (ADD) s0 = wadd(s0, v);
         else s0 = v;
     }
+    // True when the current segment is the common unchecked wavetable loop.
+    A2CU_DEV bool plain() const { return run == RUN_TABLE; }
+    // sample() specialised for plain(): no mode tests, so the compiler can
+    // overlap the two Hermite gathers of consecutive frames (wtosc.c:226-233).
+    A2CU_DEV void sample_fast(const Ctx &, int &s0, int &s1, int &o0, int &o1) {
+        unsigned p16 = (unsigned)(ph >> 16);
+        int h = hermite(d, p16) + hermite(d, p16 + (dph >> 17));
+        int v = mulshr(h, a.value, 17);
+        ph += dph;
+        a.value = wadd(a.value, astep);
+        if (WIREOUT) o0 = wadd(o0, v);
+        else if (ADD) s0 = wadd(s0, v);
+        else s0 = v;
+    }
     // Segment epilogue: write the phase accumulator back (wtosc.c:283-285)
     A2CU_DEV void finish() {
         if (run == RUN_TABLE || run >= RUN_CHECK_LOOP) phase = ph << mm;
@@ -417,6 +431,8 @@ struct PanMix {
         else if (ADD) { s0 = wadd(s0, r0); if (NOUT == 2) s1 = wadd(s1, r1); }
         else { s0 = r0; if (NOUT == 2) s1 = r1; }
     }
+    A2CU_DEV bool plain() const { return true; }
+    A2CU_DEV void sample_fast(const Ctx &c, int &s0, int &s1, int &o0, int &o1) { sample(c, s0, s1, o0, o1); }
     A2CU_DEV void finish() { vstep = pstep = 0; }
 };
 
@@ -504,6 +520,8 @@ struct Filter12 {
         else if (ADD) { s0 = wadd(s0, out[0]); if (CH == 2) s1 = wadd(s1, out[1]); }
         else { s0 = out[0]; if (CH == 2) s1 = out[1]; }
     }
+    A2CU_DEV bool plain() const { return true; }
+    A2CU_DEV void sample_fast(const Ctx &c, int &s0, int &s1, int &o0, int &o1) { sample(c, s0, s1, o0, o1); }
     A2CU_DEV void finish() { qstep = 0; df = 0; }
 };
 
@@ -540,6 +558,8 @@ struct WaveShaper {
         else if (ADD) { s0 = wadd(s0, r0); if (CH == 2) s1 = wadd(s1, r1); }
         else { s0 = r0; if (CH == 2) s1 = r1; }
     }
+    A2CU_DEV bool plain() const { return true; }
+    A2CU_DEV void sample_fast(const Ctx &c, int &s0, int &s1, int &o0, int &o1) { sample(c, s0, s1, o0, o1); }
     A2CU_DEV void finish() { step = 0; }
 };
 
@@ -689,6 +709,8 @@ struct Fm {
         else if (ADD) s0 = wadd(s0, v);
         else s0 = v;
     }
+    A2CU_DEV bool plain() const { return true; }
+    A2CU_DEV void sample_fast(const Ctx &c, int &s0, int &s1, int &o0, int &o1) { sample(c, s0, s1, o0, o1); }
     A2CU_DEV void finish() {
 #pragma unroll
         for (int i = 0; i < NOPS; ++i) astep[i] = fbstep[i] = 0;
@@ -709,6 +731,8 @@ template <> struct Chain<> {
     A2CU_DEV void write(const Ctx &, int, int, int, int, int) {}
     A2CU_DEV void prepare(const Ctx &, int) {}
     A2CU_DEV void sample(const Ctx &, int &, int &, int &, int &) {}
+    A2CU_DEV void sample_fast(const Ctx &, int &, int &, int &, int &) {}
+    A2CU_DEV bool plain() const { return true; }
     A2CU_DEV void finish() {}
 };
 
@@ -729,6 +753,10 @@ template <class U, class... Rest> struct Chain<U, Rest...> {
     A2CU_DEV void sample(const Ctx &c, int &s0, int &s1, int &o0, int &o1) {
         u.sample(c, s0, s1, o0, o1); rest.sample(c, s0, s1, o0, o1);
     }
+    A2CU_DEV void sample_fast(const Ctx &c, int &s0, int &s1, int &o0, int &o1) {
+        u.sample_fast(c, s0, s1, o0, o1); rest.sample_fast(c, s0, s1, o0, o1);
+    }
+    A2CU_DEV bool plain() const { return u.plain() && rest.plain(); }
     A2CU_DEV void finish() { u.finish(); rest.finish(); }
 };
 

@@ -6,7 +6,7 @@
 // queues, and the launch sequence per window:
 //
 //   H2D event CSR -> memset bus accumulators -> render_bank<Chain> per bank
-//   -> mix_buses -> (D2H master)
+//   -> mix_groups -> mix_root -> (D2H master)
 //
 // No CPU fallback exists: every sample is produced by the kernels.
 #include <cuda_runtime.h>
@@ -877,7 +877,11 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     }
     M.master = dev_out ? dev_out : e->d_master;
     M.root_stage = e->post_root ? 1 : 0;
-    mix_buses<<<1, 256, 0, e->stream>>>(M);
+    if (e->ngroups) {
+        mix_groups<<<e->ngroups, 256, 0, e->stream>>>(M);
+        ++e->launches;
+    }
+    mix_root<<<1, 256, 0, e->stream>>>(M);
     ++e->launches;
     CK(cudaGetLastError());
     if (e->timing) CK(cudaEventRecord(e->ev2, e->stream));
@@ -943,7 +947,7 @@ int a2cu_apply_root_stage(a2cu_engine *e, const int32_t *dev_rootbus, int32_t *d
     (void)start_time;
     M.acc = (int *)dev_rootbus; M.W = (int)frames; M.buffer = (int)(buffer ? buffer : frames);
     M.ngroups = 0; M.master = dev_master; M.root_stage = 1;
-    mix_buses<<<1, 256, 0, e->stream>>>(M);
+    mix_root<<<1, 256, 0, e->stream>>>(M);
     ++e->launches;
     CK(cudaGetLastError());
     return A2CU_OK;

@@ -8,7 +8,7 @@
 //                        memory bus, flushed to the device bus with integer
 //                        atomics once per fragment.  Integer add is
 //                        associative, so any reduction order is bit-exact.
-//   mix_buses            group buses -> group panmix -> root bus -> root
+//   mix_groups/mix_root  group buses -> group panmix -> root bus -> root
 //                        panmix -> master (core.c:1763-1776, audiality2.c:
 //                        268-304, xinsert bypass xinsert.c:149-156)
 #pragma once
@@ -89,33 +89,58 @@ __global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
 
     for (int f0 = 0; f0 < W;) {
         const int fe = frag_end(f0, P.buffer, W);
-        for (int f = f0; f < fe; ++f) {
-            if (valid && f == seg_end) {
-                if (in_seg) ch.finish();
-                while (next_ev <= f) {
-                    const uint4 e = P.ev[evp];
-                    const int kind = e.y & 0xff, unit = (e.y >> 8) & 0xff;
-                    const int reg = (e.y >> 16) & 0xff;
-                    switch (kind) {
-                    case EV_WRITE: ch.write(c, unit, reg, (int)e.z, (int)(e.x & 0xff), (int)e.w); break;
-                    case EV_INIT: ch.init_unit(c, unit, (int)e.z, e.x & 0xff); break;
-                    case EV_START: alive = 1; break;
-                    case EV_STOP: alive = 0; break;
-                    default: break;
-                    }
-                    ++evp;
-                    next_ev = evp < eve ? (int)(P.ev[evp].x >> 8) : 0x7fffffff;
+        const bool athome = mybus == home;
+        int f = f0;
+        // Segment boundary work for the first frame of the fragment
+        auto boundary = [&](int fr) {
+            if (in_seg) ch.finish();
+            while (next_ev <= fr) {
+                const uint4 e = P.ev[evp];
+                const int kind = e.y & 0xff, unit = (e.y >> 8) & 0xff;
+                const int reg = (e.y >> 16) & 0xff;
+                switch (kind) {
+                case EV_WRITE: ch.write(c, unit, reg, (int)e.z, (int)(e.x & 0xff), (int)e.w); break;
+                case EV_INIT: ch.init_unit(c, unit, (int)e.z, e.x & 0xff); break;
+                case EV_START: alive = 1; break;
+                case EV_STOP: alive = 0; break;
+                default: break;
                 }
-                int nxt = min(fe, next_ev);
-                for (int k = 0; k < P.nsplits; ++k)
-                    if (P.splits[k] > f) nxt = min(nxt, P.splits[k]);
-                seg_end = nxt;
-                in_seg = alive != 0;
-                if (in_seg) ch.prepare(c, nxt - f);
+                ++evp;
+                next_ev = evp < eve ? (int)(P.ev[evp].x >> 8) : 0x7fffffff;
             }
+            int nxt = min(fe, next_ev);
+            for (int k = 0; k < P.nsplits; ++k)
+                if (P.splits[k] > fr) nxt = min(nxt, P.splits[k]);
+            seg_end = nxt;
+            in_seg = alive != 0;
+            if (in_seg) ch.prepare(c, nxt - fr);
+        };
+        if (valid && f == seg_end) boundary(f);
+        // Fast path: every voice of the warp runs one plain segment across the
+        // whole fragment -> straight-line sample loop, unrolled for ILP.
+        const bool ok = !valid || (seg_end == fe && (!in_seg || ch.plain()));
+        if (__all_sync(0xffffffffu, ok)) {
+#pragma unroll 4
+            for (; f < fe; ++f) {
+                int s0 = 0, s1 = 0, o0 = 0, o1 = 0;
+                if (in_seg) ch.sample_fast(c, s0, s1, o0, o1);
+                int h0 = __reduce_add_sync(0xffffffffu, athome ? o0 : 0);
+                int h1 = __reduce_add_sync(0xffffffffu, athome ? o1 : 0);
+                if ((tid & 31) == 0) {
+                    atomicAdd(&sacc[f - f0][0], h0);
+                    atomicAdd(&sacc[f - f0][1], h1);
+                }
+                if (valid && !athome && in_seg) {
+                    int *a = P.acc + ((size_t)mybus * W + f) * 2;
+                    atomicAdd(a, o0);
+                    atomicAdd(a + 1, o1);
+                }
+            }
+        }
+        for (; f < fe; ++f) {
+            if (valid && f == seg_end && f != f0) boundary(f);
             int s0 = 0, s1 = 0, o0 = 0, o1 = 0;
             if (in_seg) ch.sample(c, s0, s1, o0, o1);
-            const bool athome = mybus == home;
             int h0 = __reduce_add_sync(0xffffffffu, athome ? o0 : 0);
             int h1 = __reduce_add_sync(0xffffffffu, athome ? o1 : 0);
             if ((tid & 31) == 0) {
@@ -179,82 +204,125 @@ A2CU_DEV void pm_store(int *s, const Ramp &vol, const Ramp &pan) {
     s[4] = pan.value; s[5] = pan.target; s[6] = pan.delta; s[7] = pan.timer;
 }
 
-// Sequential walk of one bus-level panmix over the window. OUT1: 2 -> 1.
-// Calls emit(f, r0, r1) per frame. panmix.c:137-229.
-template <class Emit>
-A2CU_DEV void pm_walk(const MixParams &P, int target, int *state, const int *in, bool mono, Emit emit) {
-    Ramp vol, pan;
-    pm_load(state, vol, pan);
-    int evp = 0;
-    auto next_time = [&]() {
-        while (evp < P.nev && P.ev[evp].target != target) ++evp;
-        return evp < P.nev ? (int)(P.ev[evp].time >> 8) : 0x7fffffff;
-    };
-    int next_ev = next_time();
-    int seg_end = 0;
-    bool clamp = false;
-    for (int f = 0; f < P.W; ++f) {
-        if (f == seg_end) {
-            while (next_ev <= f) {
-                const MixEvent &e = P.ev[evp];
-                int reg = (int)(signed char)(e.reg_dur_hi & 0xff);
-                if (reg >= 0) ramp_set(reg == 0 ? vol : pan, e.value, (int)(e.time & 0xff), (int)e.dur);
-                ++evp;
-                next_ev = next_time();
-            }
-            int nxt = min(frag_end(f, P.buffer, P.W), next_ev);
-            // a group's segments are additionally cut by its parent's (the root's)
-            for (int k = 0; k < P.nsplits; ++k)
-                if (P.splits[k] > f) nxt = min(nxt, P.splits[k]);
-            seg_end = nxt;
-            clamp = pan.target > 0xffffff || pan.target < -0xffffff ||
-                    pan.value > 0xffffff || pan.value < -0xffffff;
-            ramp_prepare(vol, nxt - f);
-            ramp_prepare(pan, nxt - f);
-        }
-        int v = vol.value;
-        int vp = mulshr(pan.value, v, 24);
-        int v0 = wsub(v, vp), v1 = wadd(v, vp);
-        if (clamp) {
-            int lim = (int)((unsigned)v << 1);
-            if (v0 > lim) v0 = lim;
-            if (v1 > lim) v1 = lim;
-        }
-        int i0 = in[f * 2], i1 = in[f * 2 + 1];
-        if (mono)
-            emit(f, (int)(((long long)i0 * v0 + (long long)i1 * v1) >> 25), 0);
-        else
-            emit(f, mulshr(i0, v0, 24), mulshr(i1, v1, 24));
-        vol.value = wadd(vol.value, vol.delta);
-        pan.value = wadd(pan.value, pan.delta);
-    }
-    pm_store(state, vol, pan);
-}
+// One bus-level panmix (panmix.c:137-229) over the window, one CTA per bus.
+// Thread 0 replays the control-rate part (events, a2_PrepareRamper per
+// segment) into per-segment records; the ramps are linear inside a segment,
+// so every frame is then evaluated independently by the whole CTA.
+struct MixSeg {
+    int f0, f1;         // [f0, f1)
+    int vol, dvol, pan, dpan;
+    int clamp;
+};
+constexpr int kMixSegs = 128;
 
-__global__ void __launch_bounds__(256) mix_buses(const MixParams P) {
+template <class Emit>
+A2CU_DEV void pm_bus(const MixParams &P, int target, int *state, const int *in, bool mono, Emit emit) {
+    __shared__ MixSeg seg[kMixSegs];
+    __shared__ int s_nseg, s_next, s_evp;
+    __shared__ int s_state[8];
     const int tid = threadIdx.x;
-    int *root = P.acc;
-    // groups: { inline 0 *; panmix * *; xinsert * > } -> add into the root bus
-    for (int g = tid; g < P.ngroups; g += blockDim.x) {
-        const int *in = P.acc + (size_t)(1 + g) * P.W * 2;
-        pm_walk(P, g, P.gstate + g * 8, in, false, [&](int f, int r0, int r1) {
-            atomicAdd(root + f * 2, r0);
-            atomicAdd(root + f * 2 + 1, r1);
-        });
+    if (tid == 0) {
+        s_next = 0; s_evp = 0;
+        for (int i = 0; i < 8; ++i) s_state[i] = state[i];
     }
     __syncthreads();
+    while (true) {
+        const int c0 = s_next;
+        if (c0 >= P.W) break;
+        if (tid == 0) {
+            Ramp vol, pan;
+            pm_load(s_state, vol, pan);
+            int evp = s_evp;
+            auto next_time = [&]() {
+                while (evp < P.nev && P.ev[evp].target != target) ++evp;
+                return evp < P.nev ? (int)(P.ev[evp].time >> 8) : 0x7fffffff;
+            };
+            int next_ev = next_time();
+            int f = c0, n = 0;
+            while (f < P.W && n < kMixSegs) {
+                while (next_ev <= f) {
+                    const MixEvent &e = P.ev[evp];
+                    int reg = (int)(signed char)(e.reg_dur_hi & 0xff);
+                    if (reg >= 0) ramp_set(reg == 0 ? vol : pan, e.value, (int)(e.time & 0xff), (int)e.dur);
+                    ++evp;
+                    next_ev = next_time();
+                }
+                int nxt = min(frag_end(f, P.buffer, P.W), next_ev);
+                // a group's segments are additionally cut by its parent's (the root's)
+                for (int k = 0; k < P.nsplits; ++k)
+                    if (P.splits[k] > f) nxt = min(nxt, P.splits[k]);
+                MixSeg sg;
+                sg.clamp = pan.target > 0xffffff || pan.target < -0xffffff ||
+                           pan.value > 0xffffff || pan.value < -0xffffff;
+                ramp_prepare(vol, nxt - f);
+                ramp_prepare(pan, nxt - f);
+                sg.f0 = f; sg.f1 = nxt;
+                sg.vol = vol.value; sg.dvol = vol.delta; sg.pan = pan.value; sg.dpan = pan.delta;
+                seg[n++] = sg;
+                ramp_run(vol, nxt - f);
+                ramp_run(pan, nxt - f);
+                f = nxt;
+            }
+            pm_store(s_state, vol, pan);
+            s_nseg = n; s_next = f; s_evp = evp;
+        }
+        __syncthreads();
+        const int c1 = s_next, nseg = s_nseg;
+        for (int f = c0 + tid; f < c1; f += blockDim.x) {
+            int lo = 0, hi = nseg - 1;
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (seg[mid].f1 <= f) lo = mid + 1; else hi = mid;
+            }
+            const MixSeg sg = seg[lo];
+            int k = f - sg.f0;
+            int v = wadd(sg.vol, wmul(sg.dvol, k));
+            int pn = wadd(sg.pan, wmul(sg.dpan, k));
+            int vp = mulshr(pn, v, 24);
+            int v0 = wsub(v, vp), v1 = wadd(v, vp);
+            if (sg.clamp) {
+                int lim = (int)((unsigned)v << 1);
+                if (v0 > lim) v0 = lim;
+                if (v1 > lim) v1 = lim;
+            }
+            int i0 = in[f * 2], i1 = in[f * 2 + 1];
+            if (mono)
+                emit(f, (int)(((long long)i0 * v0 + (long long)i1 * v1) >> 25), 0);
+            else
+                emit(f, mulshr(i0, v0, 24), mulshr(i1, v1, 24));
+        }
+        __syncthreads();
+    }
+    if (tid == 0)
+        for (int i = 0; i < 8; ++i) state[i] = s_state[i];
+}
+
+// groups: { inline 0 *; panmix * *; xinsert * > } -> add into the root bus.
+// grid = ngroups
+__global__ void __launch_bounds__(256) mix_groups(const MixParams P) {
+    const int g = blockIdx.x;
+    int *root = P.acc;
+    const int *in = P.acc + (size_t)(1 + g) * P.W * 2;
+    pm_bus(P, g, P.gstate + g * 8, in, false, [&](int f, int r0, int r1) {
+        atomicAdd(root + f * 2, r0);
+        atomicAdd(root + f * 2 + 1, r1);
+    });
+}
+
+// root: { inline 0 *|2; panmix * *|2 1; xinsert * > } into the cleared master;
+// with root_stage == 0 the raw root bus is copied out (multi-GPU cut).
+__global__ void __launch_bounds__(256) mix_root(const MixParams P) {
+    const int tid = threadIdx.x;
+    const int *root = P.acc;
     if (!P.root_stage) {
         for (int i = tid; i < P.W * 2; i += blockDim.x) P.master[i] = root[i];
         return;
     }
-    // root: { inline 0 *|2; panmix * *|2 1; xinsert * > } into the cleared master
-    if (tid == 0) {
-        const bool mono = P.channels == 1;
-        pm_walk(P, -1, P.rstate, root, mono, [&](int f, int r0, int r1) {
-            if (mono) P.master[f] = r0;
-            else { P.master[f * 2] = r0; P.master[f * 2 + 1] = r1; }
-        });
-    }
+    const bool mono = P.channels == 1;
+    pm_bus(P, -1, P.rstate, root, mono, [&](int f, int r0, int r1) {
+        if (mono) P.master[f] = r0;
+        else { P.master[f * 2] = r0; P.master[f * 2 + 1] = r1; }
+    });
 }
 
 }  // namespace a2cu

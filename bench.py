@@ -324,7 +324,7 @@ def bench_ours(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": host_total_ms / args.steps},
             "gpu_launches": int(launches),
-            "kernel": "render_bank<%s> + mix_buses" % e.bank_kernel_name(bank),
+            "kernel": "render_bank<%s> + mix_root" % e.bank_kernel_name(bank),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
