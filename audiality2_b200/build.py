@@ -40,8 +40,20 @@ def build_engine(force=False, verbose=False):
     return LIB
 
 
+def build_plugin():
+    """Drop-in unit library + its check harness. They compile against the
+    reference's headers where they lie, so this only works where
+    /root/reference exists (the dev container); the .so files travel."""
+    if not os.path.isdir("/root/reference/src"):
+        return None
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "plugin")])
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "dropin"])
+    return os.path.join(HERE, "liba2cu_units.so")
+
+
 def build_all(force=False, verbose=False):
-    return [build_engine(force, verbose)]
+    return [build_engine(force, verbose), build_plugin()]
 
 
 if __name__ == "__main__":

@@ -195,6 +195,15 @@ struct Bank {
     uint4 *d_ev = nullptr;
     size_t ev_cap = 0;
     bool has_noise = false;
+    // drop-in ("block") mode: dynamic slots + per-flush recording
+    bool dynamic = false;
+    std::vector<int> free_slots, deferred_free;   // freed slots are reusable from the next block
+    int used = 0;
+    std::vector<uint4> bev;
+    std::vector<VoiceRun> bruns;
+    int cur_slot = -1;
+    VoiceRun *d_runs = nullptr;
+    size_t runs_cap = 0;
 };
 
 struct MixHostEvent {
@@ -244,6 +253,16 @@ struct a2cu_engine {
     float last_ms = 0.f, last_mix_ms = 0.f;
     // last window (for a2cu_apply_root_stage)
     MixParams last_mix;
+    // drop-in ("block") mode
+    std::vector<BusCmd> buscmds;
+    BusCmd *d_buscmds = nullptr;
+    size_t buscmds_cap = 0;
+    int *d_bacc = nullptr;          // [bus][64][2]
+    int bacc_cap = 0, nbbus = 0, prev_nbbus = 0;
+    int *d_pmstate = nullptr;       // [pm][8]
+    int pm_cap = 0, pm_used = 0;
+    std::vector<int> pm_free, pm_deferred;
+    int32_t *h_xfer = nullptr;      // pinned, 64 x 2
 };
 
 static int ensure_stage(a2cu_engine *e, size_t bytes) {
@@ -378,12 +397,14 @@ void a2cu_close(a2cu_engine *e) {
     cudaStreamSynchronize(e->stream);
     for (Bank *b : e->banks) {
         cudaFree(b->d_state); cudaFree(b->d_bus); cudaFree(b->d_noise);
-        cudaFree(b->d_evoff); cudaFree(b->d_ev);
+        cudaFree(b->d_evoff); cudaFree(b->d_ev); cudaFree(b->d_runs);
         delete b;
     }
     cudaFree(e->d_waves); cudaFree(e->d_pool); cudaFree(e->d_ptab); cudaFree(e->d_fmsine);
     cudaFree(e->d_gstate); cudaFree(e->d_rstate); cudaFree(e->d_mixev);
     cudaFree(e->d_acc); cudaFree(e->d_master);
+    cudaFree(e->d_buscmds); cudaFree(e->d_bacc); cudaFree(e->d_pmstate);
+    if (e->h_xfer) cudaFreeHost(e->h_xfer);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -594,12 +615,14 @@ int a2cu_bank_state_bytes(a2cu_engine *e, int bank) {
     return b ? b->k.words * (int)sizeof(int) : A2CU_EINVAL;
 }
 
-// Translate a VM-level register write into the device-level record(s)
-// (the host half of each unit's A2_write_cb; see a2cu_device.cuh write()).
-static int cook_write(a2cu_engine *e, Bank *b, int voice, int unit, int reg, int value, uint64_t when, uint32_t dur) {
-    if (unit < 0 || unit >= (int)b->chain.size() || reg < 0) return fail(A2CU_EINVAL, "bad unit/register%s");
-    int kind = b->chain[unit].kind;
-    int start = (int)(when & 0xff);
+// Translate a VM-level register write into the device-level record(s): the
+// host half of each unit's A2_write_cb (see a2cu_device.cuh write()). Returns
+// the number of (reg, value, dur) records produced (1 or 2) or a negative error.
+struct Cooked { int reg, value; uint32_t dur; };
+static int cook(a2cu_engine *e, int kind, int reg, int value, int start, uint32_t dur, int transpose,
+                Cooked out[2]) {
+    if (reg < 0) return fail(A2CU_EINVAL, "bad register%s");
+    int n = 1;
     switch (kind) {
     case A2CU_WTOSC:
         if (reg > 3) return fail(A2CU_EINVAL, "wtosc has 4 registers%s");
@@ -614,7 +637,7 @@ static int cook_write(a2cu_engine *e, Bank *b, int voice, int unit, int reg, int
             }
             value = w;
         } else if (reg == 1)            // wtosc.c:486-492
-            value = value + b->transpose[voice] + e->basepitch;
+            value = value + transpose + e->basepitch;
         break;
     case A2CU_PANMIX:
         if (reg > 1) return fail(A2CU_EINVAL, "panmix has 2 registers%s");
@@ -625,12 +648,15 @@ static int cook_write(a2cu_engine *e, Bank *b, int voice, int unit, int reg, int
     case A2CU_FILTER12:
         if (reg > 4) return fail(A2CU_EINVAL, "filter12 has 5 registers%s");
         if (reg == 0) {                 // filter12.c:141-147
-            value = value + b->transpose[voice];
-            push_event(b, when, voice, EV_WRITE, unit, 0, value, dur);
-            if ((uint64_t)dur + (uint64_t)start < 256)
-                push_event(b, when, voice, EV_WRITE, unit, 5,
-                           tables().f12_coeff((int)((unsigned)value << 8), e->samplerate), 0);
-            return A2CU_OK;
+            value = value + transpose;
+            if ((uint64_t)dur + (uint64_t)start < 256) {
+                // ramper snaps to the target: the coefficient is known here,
+                // computed with the host libm exactly like the reference
+                out[1].reg = 5;
+                out[1].value = tables().f12_coeff((int)((unsigned)value << 8), e->samplerate);
+                out[1].dur = 0;
+                n = 2;
+            }
         } else if (reg == 1)            // filter12.c:149-162
             value = value < 512 ? 32768 : (65536 << 8) / value;
         else
@@ -640,11 +666,20 @@ static int cook_write(a2cu_engine *e, Bank *b, int voice, int unit, int reg, int
         if (kind < A2CU_FM1 || kind > A2CU_FM4R) return fail(A2CU_EINVAL, "unknown unit kind%s");
         static const int nops[8] = {1, 2, 3, 4, 3, 4, 2, 4};
         if (reg > 3 * nops[kind - A2CU_FM1]) return fail(A2CU_EINVAL, "fm register out of range%s");
-        if (reg == 1) value = value + b->transpose[voice] + e->basepitch;   // fm.c:417-423
+        if (reg == 1) value = value + transpose + e->basepitch;   // fm.c:417-423
         break;
     }
     }
-    push_event(b, when, voice, EV_WRITE, unit, reg, value, dur);
+    out[0].reg = reg; out[0].value = value; out[0].dur = dur;
+    return n;
+}
+
+static int cook_write(a2cu_engine *e, Bank *b, int voice, int unit, int reg, int value, uint64_t when, uint32_t dur) {
+    if (unit < 0 || unit >= (int)b->chain.size()) return fail(A2CU_EINVAL, "bad unit%s");
+    Cooked c[2];
+    int n = cook(e, b->chain[unit].kind, reg, value, (int)(when & 0xff), dur, b->transpose[voice], c);
+    if (n < 0) return n;
+    for (int i = 0; i < n; ++i) push_event(b, when, voice, EV_WRITE, unit, c[i].reg, c[i].value, c[i].dur);
     return A2CU_OK;
 }
 
@@ -950,6 +985,342 @@ int a2cu_apply_root_stage(a2cu_engine *e, const int32_t *dev_rootbus, int32_t *d
     mix_root<<<1, 256, 0, e->stream>>>(M);
     ++e->launches;
     CK(cudaGetLastError());
+    return A2CU_OK;
+}
+
+// ===========================================================================
+// Drop-in ("block") mode: the API the unit plug-in (plugin/a2cu_units.c)
+// records into while the reference host walks its voice tree.
+// ===========================================================================
+int a2cu_pool_open(a2cu_engine *e, const a2cu_unitspec *chain, int nunits) {
+    if (!e || !chain || nunits < 1) return fail(A2CU_EINVAL, "a2cu_pool_open: bad args%s");
+    std::string sig = sig_of(chain, nunits);
+    for (size_t i = 0; i < e->banks.size(); ++i)
+        if (e->banks[i]->dynamic && sig_of(e->banks[i]->chain.data(), (int)e->banks[i]->chain.size()) == sig)
+            return (int)i;
+    auto it = registry().find(sig);
+    if (it == registry().end()) return fail(A2CU_ENOTIMPL, "no kernel for voice structure %s", sig.c_str());
+    cudaSetDevice(e->device);
+    Bank *b = new Bank();
+    b->chain.assign(chain, chain + nunits);
+    b->k = it->second;
+    b->dynamic = true;
+    b->nvoices = 0;
+    b->stride = 1024;
+    size_t sbytes = (size_t)b->k.words * b->stride * sizeof(int);
+    if (cudaMalloc(&b->d_state, sbytes) != cudaSuccess || cudaMalloc(&b->d_noise, b->stride * sizeof(unsigned)) != cudaSuccess) {
+        delete b;
+        return fail(A2CU_ENOMEM, "cudaMalloc pool: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    CK(cudaMemset(b->d_state, 0, sbytes));
+    CK(cudaMemset(b->d_noise, 0, b->stride * sizeof(unsigned)));
+    e->banks.push_back(b);
+    return (int)e->banks.size() - 1;
+}
+
+static int pool_grow(a2cu_engine *e, Bank *b) {
+    size_t ns = b->stride * 2;
+    int *nstate = nullptr;
+    unsigned *nnoise = nullptr;
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMalloc(&nstate, (size_t)b->k.words * ns * sizeof(int)));
+    CK(cudaMalloc(&nnoise, ns * sizeof(unsigned)));
+    CK(cudaMemset(nstate, 0, (size_t)b->k.words * ns * sizeof(int)));
+    CK(cudaMemset(nnoise, 0, ns * sizeof(unsigned)));
+    CK(cudaMemcpy2D(nstate, ns * sizeof(int), b->d_state, b->stride * sizeof(int), b->stride * sizeof(int),
+                    b->k.words, cudaMemcpyDeviceToDevice));
+    cudaFree(b->d_state); cudaFree(b->d_noise);
+    b->d_state = nstate; b->d_noise = nnoise; b->stride = ns;
+    return A2CU_OK;
+}
+
+int a2cu_pool_alloc(a2cu_engine *e, int pool) {
+    Bank *b = get_bank(e, pool);
+    if (!b || !b->dynamic) return fail(A2CU_EINVAL, "bad pool%s");
+    cudaSetDevice(e->device);
+    if (!b->free_slots.empty()) {
+        int s = b->free_slots.back();
+        b->free_slots.pop_back();
+        return s;
+    }
+    if ((size_t)b->used >= b->stride) {
+        int r = pool_grow(e, b);
+        if (r) return r;
+    }
+    return b->used++;
+}
+
+int a2cu_pool_free(a2cu_engine *e, int pool, int slot) {
+    Bank *b = get_bank(e, pool);
+    if (!b || !b->dynamic || slot < 0 || slot >= b->used) return fail(A2CU_EINVAL, "bad pool/slot%s");
+    b->deferred_free.push_back(slot);     // still referenced by records of this block
+    return A2CU_OK;
+}
+
+int a2cu_block_begin(a2cu_engine *e) {
+    if (!e) return A2CU_EINVAL;
+    cudaSetDevice(e->device);
+    int fr = a2cu_block_flush(e);           // nothing of the previous block may be left
+    if (fr) return fr;
+    for (Bank *b : e->banks) {
+        b->free_slots.insert(b->free_slots.end(), b->deferred_free.begin(), b->deferred_free.end());
+        b->deferred_free.clear();
+    }
+    e->pm_free.insert(e->pm_free.end(), e->pm_deferred.begin(), e->pm_deferred.end());
+    e->pm_deferred.clear();
+    if (e->prev_nbbus < e->nbbus) e->prev_nbbus = e->nbbus;
+    if (e->prev_nbbus && e->d_bacc)
+        CK(cudaMemsetAsync(e->d_bacc, 0, (size_t)e->prev_nbbus * kMaxFrag * 2 * sizeof(int), e->stream));
+    e->prev_nbbus = 0;
+    e->nbbus = 0;
+    e->buscmds.clear();
+    for (Bank *b : e->banks) { b->bev.clear(); b->bruns.clear(); b->cur_slot = -1; }
+    int r = upload_waves(e);
+    return r;
+}
+
+int a2cu_block_bus(a2cu_engine *e) {
+    if (!e) return A2CU_EINVAL;
+    if (e->nbbus + 1 > e->bacc_cap) {
+        int ncap = std::max(256, e->bacc_cap * 2);
+        int *n = nullptr;
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaMalloc(&n, (size_t)ncap * kMaxFrag * 2 * sizeof(int)));
+        CK(cudaMemset(n, 0, (size_t)ncap * kMaxFrag * 2 * sizeof(int)));
+        if (e->d_bacc) {
+            CK(cudaMemcpy(n, e->d_bacc, (size_t)e->bacc_cap * kMaxFrag * 2 * sizeof(int), cudaMemcpyDeviceToDevice));
+            cudaFree(e->d_bacc);
+        }
+        e->d_bacc = n;
+        e->bacc_cap = ncap;
+    }
+    return e->nbbus++;
+}
+
+static void block_rec(Bank *b, int slot, unsigned x, unsigned y, int z, unsigned w) {
+    if (b->cur_slot != slot || b->bruns.empty()) {
+        VoiceRun r;
+        r.slot = slot; r.ev_begin = (unsigned)b->bev.size(); r.ev_count = 0;
+        b->bruns.push_back(r);
+        b->cur_slot = slot;
+    }
+    b->bev.push_back(make_uint4(x, y, (unsigned)z, w));
+    ++b->bruns.back().ev_count;
+}
+
+int a2cu_block_init(a2cu_engine *e, int pool, int slot, int unit, int transpose, unsigned frame, unsigned substart) {
+    Bank *b = get_bank(e, pool);
+    if (!b || !b->dynamic || unit < 0 || unit >= (int)b->chain.size()) return fail(A2CU_EINVAL, "bad pool/unit%s");
+    int kind = b->chain[unit].kind;
+    int arg = 0;
+    if (kind == A2CU_WTOSC || kind >= A2CU_FM1) arg = transpose + e->basepitch;
+    else if (kind == A2CU_FILTER12) arg = transpose;
+    unsigned x = (frame << 8) | (substart & 0xff);
+    block_rec(b, slot, x, EV_INIT | ((unsigned)unit << 8), arg, 0);
+    if (kind == A2CU_FILTER12)
+        block_rec(b, slot, x, EV_WRITE | ((unsigned)unit << 8) | (5u << 16),
+                  tables().f12_coeff((int)((unsigned)arg << 8), e->samplerate), 0);
+    return A2CU_OK;
+}
+
+int a2cu_block_write(a2cu_engine *e, int pool, int slot, int unit, int reg, int32_t value, int transpose,
+                     unsigned frame, unsigned start, uint32_t dur) {
+    Bank *b = get_bank(e, pool);
+    if (!b || !b->dynamic || unit < 0 || unit >= (int)b->chain.size()) return fail(A2CU_EINVAL, "bad pool/unit%s");
+    Cooked c[2];
+    int n = cook(e, b->chain[unit].kind, reg, value, (int)(start & 0xff), dur, transpose, c);
+    if (n < 0) return n;
+    unsigned x = (frame << 8) | (start & 0xff);
+    for (int i = 0; i < n; ++i)
+        block_rec(b, slot, x, EV_WRITE | ((unsigned)unit << 8) | ((unsigned)(c[i].reg & 0xff) << 16), c[i].value,
+                  c[i].dur);
+    return A2CU_OK;
+}
+
+int a2cu_block_proc(a2cu_engine *e, int pool, int slot, unsigned frame, unsigned frames, int bus) {
+    Bank *b = get_bank(e, pool);
+    if (!b || !b->dynamic || frames < 1 || frame + frames > (unsigned)kMaxFrag || bus < 0 || bus >= e->nbbus)
+        return fail(A2CU_EINVAL, "a2cu_block_proc: bad args%s");
+    block_rec(b, slot, frame << 8, EV_PROC | (frames << 8), bus, 0);
+    return A2CU_OK;
+}
+
+int a2cu_pm_alloc(a2cu_engine *e) {
+    if (!e) return A2CU_EINVAL;
+    cudaSetDevice(e->device);
+    int id;
+    if (!e->pm_free.empty()) { id = e->pm_free.back(); e->pm_free.pop_back(); }
+    else {
+        if (e->pm_used + 1 > e->pm_cap) {
+            int ncap = std::max(256, e->pm_cap * 2);
+            int *n = nullptr;
+            CK(cudaStreamSynchronize(e->stream));
+            CK(cudaMalloc(&n, (size_t)ncap * 8 * sizeof(int)));
+            if (e->d_pmstate) {
+                CK(cudaMemcpy(n, e->d_pmstate, (size_t)e->pm_cap * 8 * sizeof(int), cudaMemcpyDeviceToDevice));
+                cudaFree(e->d_pmstate);
+            }
+            e->d_pmstate = n; e->pm_cap = ncap;
+        }
+        id = e->pm_used++;
+    }
+    int st[8] = {65536 << 8, 65536 << 8, 0, 0, 0, 0, 0, 0};     // panmix.c:252-262
+    CK(cudaMemcpyAsync(e->d_pmstate + (size_t)id * 8, st, sizeof(st), cudaMemcpyHostToDevice, e->stream));
+    return id;
+}
+
+int a2cu_pm_free(a2cu_engine *e, int pm) {
+    if (!e || pm < 0 || pm >= e->pm_used) return A2CU_EINVAL;
+    e->pm_deferred.push_back(pm);
+    return A2CU_OK;
+}
+
+int a2cu_block_pm_write(a2cu_engine *e, int pm, int reg, int32_t value, unsigned start, uint32_t dur) {
+    if (!e || pm < 0 || pm >= e->pm_used || reg < 0 || reg > 1) return fail(A2CU_EINVAL, "bad panmix write%s");
+    BusCmd c;
+    memset(&c, 0, sizeof(c));
+    c.op = BUS_PM_WRITE; c.pm = pm; c.reg = reg; c.value = value; c.start = (int)(start & 0xff); c.dur = (int)dur;
+    e->buscmds.push_back(c);
+    return A2CU_OK;
+}
+
+int a2cu_block_pm_proc(a2cu_engine *e, int pm, int nin, int nout, int add, int in_bus, int out_bus, unsigned frame,
+                       unsigned frames) {
+    if (!e || pm < 0 || pm >= e->pm_used || in_bus < 0 || in_bus >= e->nbbus || out_bus < 0 || out_bus >= e->nbbus ||
+        frames < 1 || frame + frames > (unsigned)kMaxFrag || nin < 1 || nin > 2 || nout < 1 || nout > 2)
+        return fail(A2CU_EINVAL, "a2cu_block_pm_proc: bad args%s");
+    BusCmd c;
+    memset(&c, 0, sizeof(c));
+    c.op = BUS_PM_PROC; c.pm = pm; c.nin = nin; c.nout = nout; c.add = add ? 1 : 0;
+    c.in_bus = in_bus; c.out_bus = out_bus; c.frame = (int)frame; c.frames = (int)frames;
+    e->buscmds.push_back(c);
+    return A2CU_OK;
+}
+
+int a2cu_block_flush(a2cu_engine *e) {
+    if (!e) return A2CU_EINVAL;
+    cudaSetDevice(e->device);
+    {
+        int wr = upload_waves(e);           // waves first seen in this block
+        if (wr) return wr;
+    }
+    for (Bank *b : e->banks) {
+        if (!b->dynamic || b->bruns.empty()) continue;
+        // One thread per voice: merge the runs of a slot (a voice is visited
+        // once per segment of its parent) keeping record order.
+        {
+            bool dup = false;
+            std::vector<VoiceRun> sorted(b->bruns);
+            std::stable_sort(sorted.begin(), sorted.end(),
+                             [](const VoiceRun &a, const VoiceRun &c) { return a.slot < c.slot; });
+            for (size_t i = 1; i < sorted.size(); ++i)
+                if (sorted[i].slot == sorted[i - 1].slot) { dup = true; break; }
+            if (dup) {
+                std::vector<uint4> ev;
+                std::vector<VoiceRun> runs;
+                ev.reserve(b->bev.size());
+                for (const VoiceRun &r : sorted) {
+                    if (runs.empty() || runs.back().slot != r.slot) {
+                        VoiceRun n;
+                        n.slot = r.slot; n.ev_begin = (unsigned)ev.size(); n.ev_count = 0;
+                        runs.push_back(n);
+                    }
+                    ev.insert(ev.end(), b->bev.begin() + r.ev_begin, b->bev.begin() + r.ev_begin + r.ev_count);
+                    runs.back().ev_count += r.ev_count;
+                }
+                b->bev.swap(ev);
+                b->bruns.swap(runs);
+            }
+        }
+        size_t nev = b->bev.size(), nr = b->bruns.size();
+        if (nev > b->ev_cap) {
+            CK(cudaStreamSynchronize(e->stream));
+            if (b->d_ev) cudaFree(b->d_ev);
+            b->ev_cap = nev * 2;
+            CK(cudaMalloc(&b->d_ev, b->ev_cap * sizeof(uint4)));
+        }
+        if (nr > b->runs_cap) {
+            CK(cudaStreamSynchronize(e->stream));
+            if (b->d_runs) cudaFree(b->d_runs);
+            b->runs_cap = nr * 2;
+            CK(cudaMalloc(&b->d_runs, b->runs_cap * sizeof(VoiceRun)));
+        }
+        CK(cudaMemcpyAsync(b->d_ev, b->bev.data(), nev * sizeof(uint4), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(b->d_runs, b->bruns.data(), nr * sizeof(VoiceRun), cudaMemcpyHostToDevice, e->stream));
+        e->h2d_bytes += nev * sizeof(uint4) + nr * sizeof(VoiceRun);
+        RenderParams P;
+        memset(&P, 0, sizeof(P));
+        P.state = b->d_state; P.stride = b->stride; P.nvoices = (int)nr;
+        P.acc = e->d_bacc; P.W = kMaxFrag; P.buffer = kMaxFrag;
+        P.waves = e->d_waves; P.pool = e->d_pool; P.ptab = e->d_ptab; P.fmsine = e->d_fmsine;
+        P.samplerate = e->samplerate; P.noise = b->d_noise;
+        P.ev = b->d_ev; P.runs = b->d_runs; P.explicit_ = 1;
+        int grid = ((int)nr + kThreads - 1) / kThreads;
+        b->k.fn<<<grid, kThreads, 0, e->stream>>>(P);
+        ++e->launches;
+        b->bev.clear(); b->bruns.clear(); b->cur_slot = -1;
+    }
+    if (!e->buscmds.empty()) {
+        size_t n = e->buscmds.size();
+        if (n > e->buscmds_cap) {
+            CK(cudaStreamSynchronize(e->stream));
+            if (e->d_buscmds) cudaFree(e->d_buscmds);
+            e->buscmds_cap = n * 2;
+            CK(cudaMalloc(&e->d_buscmds, e->buscmds_cap * sizeof(BusCmd)));
+        }
+        CK(cudaMemcpyAsync(e->d_buscmds, e->buscmds.data(), n * sizeof(BusCmd), cudaMemcpyHostToDevice, e->stream));
+        e->h2d_bytes += n * sizeof(BusCmd);
+        bus_vm<<<1, kMaxFrag, 0, e->stream>>>(e->d_buscmds, (int)n, e->d_bacc, e->d_pmstate);
+        ++e->launches;
+        e->buscmds.clear();
+    }
+    CK(cudaGetLastError());
+    return A2CU_OK;
+}
+
+static int ensure_xfer(a2cu_engine *e) {
+    if (!e->h_xfer) CK(cudaMallocHost(&e->h_xfer, kMaxFrag * 2 * sizeof(int32_t)));
+    return A2CU_OK;
+}
+
+int a2cu_block_upload(a2cu_engine *e, int bus, int nch, unsigned frame, unsigned frames, const int32_t *const *src) {
+    if (!e || bus < 0 || bus >= e->nbbus || frames < 1 || frame + frames > (unsigned)kMaxFrag || nch < 1 || nch > 2)
+        return fail(A2CU_EINVAL, "a2cu_block_upload: bad args%s");
+    cudaSetDevice(e->device);
+    int r = a2cu_block_flush(e);            // keep device order == host walk order
+    if (r) return r;
+    r = ensure_xfer(e);
+    if (r) return r;
+    CK(cudaStreamSynchronize(e->stream));   // h_xfer reuse
+    for (unsigned i = 0; i < frames; ++i) {
+        e->h_xfer[i * 2] = src[0][frame + i];
+        e->h_xfer[i * 2 + 1] = nch > 1 ? src[1][frame + i] : 0;
+    }
+    CK(cudaMemcpyAsync(e->d_bacc + ((size_t)bus * kMaxFrag + frame) * 2, e->h_xfer, frames * 2 * sizeof(int32_t),
+                       cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->h2d_bytes += frames * 2 * sizeof(int32_t);
+    return A2CU_OK;
+}
+
+int a2cu_block_download(a2cu_engine *e, int bus, int nch, unsigned frame, unsigned frames, int32_t *const *dst,
+                        int add) {
+    if (!e || bus < 0 || bus >= e->nbbus || frames < 1 || frame + frames > (unsigned)kMaxFrag || nch < 1 || nch > 2)
+        return fail(A2CU_EINVAL, "a2cu_block_download: bad args%s");
+    cudaSetDevice(e->device);
+    int r = a2cu_block_flush(e);
+    if (r) return r;
+    r = ensure_xfer(e);
+    if (r) return r;
+    CK(cudaMemcpyAsync(e->h_xfer, e->d_bacc + ((size_t)bus * kMaxFrag + frame) * 2, frames * 2 * sizeof(int32_t),
+                       cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->d2h_bytes += frames * 2 * sizeof(int32_t);
+    for (int c = 0; c < nch; ++c)
+        for (unsigned i = 0; i < frames; ++i) {
+            if (add) dst[c][frame + i] += e->h_xfer[i * 2 + c];
+            else dst[c][frame + i] = e->h_xfer[i * 2 + c];
+        }
     return A2CU_OK;
 }
 

@@ -21,7 +21,12 @@ constexpr int kMaxSplits = 8;
 
 // Event record, 16 bytes. x = (frame_in_window << 8) | substart
 // y = kind | unit << 8 | reg << 16 ; z = value ; w = duration (24:8)
-enum EvKind { EV_WRITE = 0, EV_WAKE = 1, EV_INIT = 2, EV_START = 3, EV_STOP = 4 };
+// EV_PROC (drop-in mode): y = kind | frames << 8, z = device bus index: one
+// Process() call of the voice's units, exactly as the host walked it.
+enum EvKind { EV_WRITE = 0, EV_WAKE = 1, EV_INIT = 2, EV_START = 3, EV_STOP = 4, EV_PROC = 5 };
+
+// One active voice of a drop-in block: slot and its run of event records.
+struct VoiceRun { int slot; unsigned ev_begin, ev_count; };
 
 struct RenderParams {
     int *state;               // [words][stride]
@@ -41,6 +46,10 @@ struct RenderParams {
     const int16_t *fmsine;
     int samplerate;
     unsigned *noise;          // per-voice LCG scratch [stride] (noise oscillators)
+    // drop-in ("block") mode: thread i renders runs[i]; segments are the
+    // host's explicit EV_PROC records and carry their own target bus
+    const VoiceRun *runs;
+    int explicit_;
 };
 
 // End of the fragment that contains frame f: fragments restart at every driver
@@ -58,14 +67,16 @@ __global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
     __shared__ int s_home;
 
     const int tid = threadIdx.x;
-    const int v = blockIdx.x * kThreads + tid;
-    const bool valid = v < P.nvoices;
+    const int idx = blockIdx.x * kThreads + tid;
+    const bool valid = idx < P.nvoices;
+    const bool expl = P.explicit_ != 0;
+    const int v = (valid && P.runs) ? P.runs[idx].slot : idx;
 
     if (CH::kUsesFm)
         for (int i = tid; i < 2049; i += kThreads) s_sine[i] = P.fmsine[i];
     if (tid < kMaxFrag) { sacc[tid][0] = 0; sacc[tid][1] = 0; }
-    const int mybus = valid ? P.bus_of[v] : -1;
-    if (tid == 0) s_home = mybus;
+    int mybus = (valid && !expl) ? P.bus_of[v] : -1;
+    if (tid == 0) s_home = expl ? -2 : mybus;
     __syncthreads();
     const int home = s_home;
 
@@ -80,7 +91,8 @@ __global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
     if (valid) { alive = sp.ld(0) & 1; ch.load(sp, 1); }
 
     unsigned evp = 0, eve = 0;
-    if (valid && P.ev_off) { evp = P.ev_off[v]; eve = P.ev_off[v + 1]; }
+    if (valid && P.runs) { evp = P.runs[idx].ev_begin; eve = evp + P.runs[idx].ev_count; }
+    else if (valid && P.ev_off) { evp = P.ev_off[v]; eve = P.ev_off[v + 1]; }
     int next_ev = evp < eve ? (int)(P.ev[evp].x >> 8) : 0x7fffffff;
 
     int seg_end = 0;
@@ -89,12 +101,12 @@ __global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
 
     for (int f0 = 0; f0 < W;) {
         const int fe = frag_end(f0, P.buffer, W);
-        const bool athome = mybus == home;
         int f = f0;
         // Segment boundary work for the first frame of the fragment
         auto boundary = [&](int fr) {
             if (in_seg) ch.finish();
-            while (next_ev <= fr) {
+            int proc_n = 0;
+            while (next_ev <= fr && !proc_n) {
                 const uint4 e = P.ev[evp];
                 const int kind = e.y & 0xff, unit = (e.y >> 8) & 0xff;
                 const int reg = (e.y >> 16) & 0xff;
@@ -103,19 +115,28 @@ __global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
                 case EV_INIT: ch.init_unit(c, unit, (int)e.z, e.x & 0xff); break;
                 case EV_START: alive = 1; break;
                 case EV_STOP: alive = 0; break;
+                case EV_PROC: proc_n = (e.y >> 8) & 0xff; mybus = (int)e.z; break;
                 default: break;
                 }
                 ++evp;
                 next_ev = evp < eve ? (int)(P.ev[evp].x >> 8) : 0x7fffffff;
             }
-            int nxt = min(fe, next_ev);
-            for (int k = 0; k < P.nsplits; ++k)
-                if (P.splits[k] > fr) nxt = min(nxt, P.splits[k]);
+            int nxt;
+            if (expl) {
+                // the host decided the segment: [fr, fr + proc_n), or idle
+                nxt = proc_n ? min(fe, fr + proc_n) : min(fe, next_ev);
+                in_seg = proc_n != 0;
+            } else {
+                nxt = min(fe, next_ev);
+                for (int k = 0; k < P.nsplits; ++k)
+                    if (P.splits[k] > fr) nxt = min(nxt, P.splits[k]);
+                in_seg = alive != 0;
+            }
             seg_end = nxt;
-            in_seg = alive != 0;
             if (in_seg) ch.prepare(c, nxt - fr);
         };
         if (valid && f == seg_end) boundary(f);
+        const bool athome0 = mybus == home;
         // Fast path: every voice of the warp runs one plain segment across the
         // whole fragment -> straight-line sample loop, unrolled for ILP.
         const bool ok = !valid || (seg_end == fe && (!in_seg || ch.plain()));
@@ -124,6 +145,7 @@ __global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
             for (; f < fe; ++f) {
                 int s0 = 0, s1 = 0, o0 = 0, o1 = 0;
                 if (in_seg) ch.sample_fast(c, s0, s1, o0, o1);
+                const bool athome = athome0;
                 int h0 = __reduce_add_sync(0xffffffffu, athome ? o0 : 0);
                 int h1 = __reduce_add_sync(0xffffffffu, athome ? o1 : 0);
                 if ((tid & 31) == 0) {
@@ -141,6 +163,7 @@ __global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
             if (valid && f == seg_end && f != f0) boundary(f);
             int s0 = 0, s1 = 0, o0 = 0, o1 = 0;
             if (in_seg) ch.sample(c, s0, s1, o0, o1);
+            const bool athome = mybus == home;
             int h0 = __reduce_add_sync(0xffffffffu, athome ? o0 : 0);
             int h1 = __reduce_add_sync(0xffffffffu, athome ? o1 : 0);
             if ((tid & 31) == 0) {
@@ -323,6 +346,80 @@ __global__ void __launch_bounds__(256) mix_root(const MixParams P) {
         if (mono) P.master[f] = r0;
         else { P.master[f * 2] = r0; P.master[f * 2 + 1] = r1; }
     });
+}
+
+// ---------------------------------------------------------------------------
+// Drop-in mode bus stage: the bus-level Process()/write calls the host made
+// during its tree walk, replayed in order by one CTA (panmix.c, all variants).
+// ---------------------------------------------------------------------------
+enum BusOp { BUS_PM_PROC = 0, BUS_PM_WRITE = 1 };
+struct BusCmd {
+    int op, pm;             // pm: index of the panmix instance state
+    int nin, nout, add;
+    int in_bus, out_bus;    // device bus indices (stereo rows of acc)
+    int frame, frames;
+    int reg, value, start, dur;
+    int pad[3];
+};
+
+__global__ void __launch_bounds__(kMaxFrag) bus_vm(const BusCmd *cmds, int ncmd, int *acc, int *pmstate) {
+    __shared__ MixSeg sg;
+    const int tid = threadIdx.x;
+    for (int i = 0; i < ncmd; ++i) {
+        const BusCmd c = cmds[i];
+        int *st = pmstate + (size_t)c.pm * 8;
+        if (c.op == BUS_PM_WRITE) {
+            if (tid == 0) {
+                Ramp vol, pan;
+                pm_load(st, vol, pan);
+                ramp_set(c.reg == 0 ? vol : pan, c.value, c.start, c.dur);
+                pm_store(st, vol, pan);
+            }
+            __syncthreads();
+            continue;
+        }
+        if (tid == 0) {
+            Ramp vol, pan;
+            pm_load(st, vol, pan);
+            const bool one = c.nin == 1 && c.nout == 1;     // panmix.c:49-64
+            sg.clamp = !one && (pan.target > 0xffffff || pan.target < -0xffffff ||
+                                pan.value > 0xffffff || pan.value < -0xffffff);
+            ramp_prepare(vol, c.frames);
+            if (!one) ramp_prepare(pan, c.frames);
+            sg.vol = vol.value; sg.dvol = vol.delta;
+            sg.pan = pan.value; sg.dpan = one ? 0 : pan.delta;
+            ramp_run(vol, c.frames);
+            if (!one) ramp_run(pan, c.frames);
+            pm_store(st, vol, pan);
+        }
+        __syncthreads();
+        if (tid < c.frames) {
+            const int f = c.frame + tid;
+            const int *in = acc + ((size_t)c.in_bus * kMaxFrag + f) * 2;
+            int *out = acc + ((size_t)c.out_bus * kMaxFrag + f) * 2;
+            const int i0 = in[0], i1 = in[1];
+            const int v = wadd(sg.vol, wmul(sg.dvol, tid));
+            int r0, r1 = 0;
+            if (c.nin == 1 && c.nout == 1) {
+                r0 = mulshr(i0, v, 24);
+            } else {
+                const int pn = wadd(sg.pan, wmul(sg.dpan, tid));
+                const int vp = mulshr(pn, v, 24);
+                int v0 = wsub(v, vp), v1 = wadd(v, vp);
+                if (sg.clamp) {
+                    const int lim = (int)((unsigned)v << 1);
+                    if (v0 > lim) v0 = lim;
+                    if (v1 > lim) v1 = lim;
+                }
+                if (c.nin == 1) { r0 = mulshr(i0, v0, 24); r1 = mulshr(i0, v1, 24); }
+                else if (c.nout == 1) r0 = (int)(((long long)i0 * v0 + (long long)i1 * v1) >> 25);
+                else { r0 = mulshr(i0, v0, 24); r1 = mulshr(i1, v1, 24); }
+            }
+            if (c.add) { out[0] = wadd(out[0], r0); if (c.nout == 2) out[1] = wadd(out[1], r1); }
+            else { out[0] = r0; if (c.nout == 2) out[1] = r1; }
+        }
+        __syncthreads();
+    }
 }
 
 }  // namespace a2cu

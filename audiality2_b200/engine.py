@@ -72,6 +72,22 @@ SYMBOLS = {
     "a2cu_h2d_bytes": (_U64, [_VP]),
     "a2cu_d2h_bytes": (_U64, [_VP]),
     "a2cu_set_timing": (_I, [_VP, _I]),
+    # drop-in ("block") mode, used by the unit plug-in
+    "a2cu_pool_open": (_I, [_VP, C.POINTER(UnitSpec), _I]),
+    "a2cu_pool_alloc": (_I, [_VP, _I]),
+    "a2cu_pool_free": (_I, [_VP, _I, _I]),
+    "a2cu_block_begin": (_I, [_VP]),
+    "a2cu_block_bus": (_I, [_VP]),
+    "a2cu_block_init": (_I, [_VP, _I, _I, _I, _I, _U, _U]),
+    "a2cu_block_write": (_I, [_VP, _I, _I, _I, _I, C.c_int32, _I, _U, _U, C.c_uint32]),
+    "a2cu_block_proc": (_I, [_VP, _I, _I, _U, _U, _I]),
+    "a2cu_pm_alloc": (_I, [_VP]),
+    "a2cu_pm_free": (_I, [_VP, _I]),
+    "a2cu_block_pm_write": (_I, [_VP, _I, _I, C.c_int32, _U, C.c_uint32]),
+    "a2cu_block_pm_proc": (_I, [_VP, _I, _I, _I, _I, _I, _I, _U, _U]),
+    "a2cu_block_flush": (_I, [_VP]),
+    "a2cu_block_upload": (_I, [_VP, _I, _I, _U, _U, _VP]),
+    "a2cu_block_download": (_I, [_VP, _I, _I, _U, _U, _VP, _I]),
 }
 
 

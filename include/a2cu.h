@@ -216,6 +216,51 @@ uint64_t a2cu_d2h_bytes(const a2cu_engine *e);
 /* Turn the event timing above on/off (adds three event records per run). */
 int a2cu_set_timing(a2cu_engine *e, int enabled);
 
+/* ---- drop-in ("block") mode ------------------------------------------------
+ *
+ * What the unit plug-in (include/a2cu_units.h, plugin/a2cu_units.c) records
+ * while the UNMODIFIED reference host walks its voice tree, one fragment of at
+ * most 64 frames at a time (a2_AudioCallback, src/core.c:1964-1973):
+ *
+ *   Initialize()  of a voice's units  -> a2cu_pool_alloc + a2cu_block_init
+ *   A2_write_cb                       -> a2cu_block_write   (leaf voices)
+ *                                        a2cu_block_pm_write (bus-level panmix)
+ *   Process(u, offset, frames)        -> a2cu_block_proc     (one per voice and
+ *                                        segment, src/core.c:1875-1876)
+ *                                        a2cu_block_pm_proc  (bus-level panmix)
+ *   inline's Process (src/core.c:1763-1776) -> a2cu_block_bus: a fresh device
+ *                                        bus for the sub-tree being walked
+ *   a unit whose successor is a host unit -> a2cu_block_download (flushes the
+ *                                        recorded work, then copies the bus)
+ *   a unit whose input was written by a host unit -> a2cu_block_upload
+ *   Deinitialize()                    -> a2cu_pool_free / a2cu_pm_free
+ *
+ * 'frame' arguments are fragment-relative (0..63).
+ */
+int a2cu_pool_open(a2cu_engine *e, const a2cu_unitspec *chain, int nunits);
+int a2cu_pool_alloc(a2cu_engine *e, int pool);
+int a2cu_pool_free(a2cu_engine *e, int pool, int slot);
+int a2cu_block_begin(a2cu_engine *e);
+int a2cu_block_bus(a2cu_engine *e);
+int a2cu_block_init(a2cu_engine *e, int pool, int slot, int unit, int transpose,
+		unsigned frame, unsigned substart);
+int a2cu_block_write(a2cu_engine *e, int pool, int slot, int unit, int reg,
+		int32_t value, int transpose, unsigned frame, unsigned start,
+		uint32_t dur);
+int a2cu_block_proc(a2cu_engine *e, int pool, int slot, unsigned frame,
+		unsigned frames, int bus);
+int a2cu_pm_alloc(a2cu_engine *e);
+int a2cu_pm_free(a2cu_engine *e, int pm);
+int a2cu_block_pm_write(a2cu_engine *e, int pm, int reg, int32_t value,
+		unsigned start, uint32_t dur);
+int a2cu_block_pm_proc(a2cu_engine *e, int pm, int nin, int nout, int add,
+		int in_bus, int out_bus, unsigned frame, unsigned frames);
+int a2cu_block_flush(a2cu_engine *e);
+int a2cu_block_upload(a2cu_engine *e, int bus, int nch, unsigned frame,
+		unsigned frames, const int32_t *const *src);
+int a2cu_block_download(a2cu_engine *e, int bus, int nch, unsigned frame,
+		unsigned frames, int32_t *const *dst, int add);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,837 @@
+/*
+ * a2cu_units.c - drop-in replacements for Audiality 2's hot-path voice units.
+ *
+ * Exports the A2_unitdesc symbols the reference's a2_core_units[] table
+ * (src/audiality2.c:183-207) links against:
+ *
+ *     a2_wtosc_unitdesc  a2_panmix_unitdesc  a2_filter12_unitdesc
+ *     a2_waveshaper_unitdesc  a2_fm1 .. a2_fm4, a2_fm3p, a2_fm4p, a2_fm2r,
+ *     a2_fm4r _unitdesc,  and  a2_inline_unitdesc (bus bracketing)
+ *
+ * The host (A2S compiler, VM, event scheduler, voice tree, drivers) is the
+ * reference's own code, unmodified; it calls Initialize / write / Process /
+ * Deinitialize exactly as it calls its built-in units (src/core.c:163-308,
+ * 143-149, 1875-1876, 318-327). These callbacks do NO DSP: they record what
+ * the host asked for into the CUDA engine (include/a2cu.h, block mode) and
+ * make the result visible in host buffers only where an un-replaced host unit
+ * is about to read it. There is no CPU fallback: a voice structure without a
+ * kernel fails to instantiate (A2_NOTIMPLEMENTED), it is never rendered on
+ * the host.
+ *
+ * This file compiles against the reference's own headers where they lie
+ * (include/ for the public plug-in API, src/internals.h + src/units/inline.h
+ * for the two private structs the reference's own inline unit also uses:
+ * A2_voice and A2_inline) - see plugin/Makefile. Nothing is copied.
+ *
+ * Classification of a voice (at its first Process call, when the unit chain
+ * is complete; chains never change afterwards, src/core.c:155-161):
+ *   LEAF  first unit is a generator of ours and every unit is ours:
+ *         one device voice slot, the whole chain runs fused in one kernel
+ *   BUS   first unit is our inline: sub-voices mix into a fresh device bus;
+ *         our panmix units after it run on the device bus; host units in the
+ *         chain (xinsert, fbdelay, ...) see materialised host buffers
+ *   anything else involving our units is not supported yet (RT error).
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include "internals.h"
+#include "inline.h"
+#include "a2cu.h"
+#include "a2cu_units.h"
+
+#define A2CU_MAXCHAIN	12
+
+typedef struct A2CU_ctx A2CU_ctx;
+typedef struct A2CU_voice A2CU_voice;
+
+/* Our instance data; the A2_inline layout must stay first for core.c:1763 */
+typedef struct A2CU_unit
+{
+	A2_inline	il;		/* header (+ voice, state for inline) */
+	A2CU_ctx	*cx;
+	A2CU_voice	*voice;
+	int		kind;		/* A2CU_* or 0 for inline */
+	int		index;		/* position among the voice's units */
+	unsigned	flags;		/* A2_PROCADD */
+	unsigned	substart;
+	int		init_transpose;
+	int		*transpose;
+	int		pm;		/* device panmix instance (BUS voices) */
+	int		bus;		/* inline: device bus of this fragment */
+	unsigned	bus_serial;
+} A2CU_unit;
+
+typedef struct A2CU_pending
+{
+	int		unit, reg, value;
+	unsigned	start, dur;
+} A2CU_pending;
+
+enum { VC_NEW = 0, VC_LEAF, VC_BUS, VC_BAD };
+
+struct A2CU_voice
+{
+	A2_vmstate	*vms;
+	int		refs;
+	int		nunits;
+	A2CU_unit	*units[A2CU_MAXCHAIN];
+	int		cls;
+	int		pool, slot;
+	A2CU_pending	*pend;
+	int		npend, cpend;
+	/* BUS voices: where the scratch data currently lives */
+	int		cur_bus;
+	int		on_device;
+};
+
+typedef struct A2CU_wavemap { A2_wave *w; int id; } A2CU_wavemap;
+typedef struct A2CU_owner { int32_t **outputs; A2CU_unit *il; } A2CU_owner;
+/* Host-only bus (no inline of ours owns it, e.g. the master) fed by voices */
+typedef struct A2CU_orphan { int32_t **outputs; int bus, nch; } A2CU_orphan;
+#define A2CU_MAXORPHANS	16
+
+struct A2CU_ctx
+{
+	A2_config	*cfg;
+	A2_state	*st;
+	a2cu_engine	*eng;
+	int		refs;
+	unsigned	serial;		/* fragment counter */
+	unsigned	last_fragstart;
+	int		started;
+	A2CU_wavemap	*waves;
+	int		nwaves;
+	A2CU_owner	owners[A2_NESTLIMIT];
+	int		nowners;
+	A2CU_orphan	orphans[A2CU_MAXORPHANS];
+	int		norphans;
+	A2CU_voice	*last_voice;	/* voice being populated */
+	A2CU_ctx	*next;
+};
+
+static A2CU_ctx *contexts = NULL;
+static int a2cu_device = 0;
+static int a2cu_trace = -1;
+#define TRACE(...)							\
+	do {								\
+		if(a2cu_trace < 0)					\
+			a2cu_trace = getenv("A2CU_TRACE") ? 1 : 0;	\
+		if(a2cu_trace)						\
+			fprintf(stderr, "a2cu: " __VA_ARGS__);		\
+	} while(0)
+
+static int is_ours(const A2_unitdesc *d);
+
+
+/*---------------------------------------------------------
+	Context (one per engine state), OpenState/CloseState
+---------------------------------------------------------*/
+
+static A2_errors a2cu_OpenState(A2_config *cfg, void **statedata)
+{
+	A2CU_ctx *cx;
+	for(cx = contexts; cx; cx = cx->next)
+		if(cx->cfg == cfg)
+			break;
+	if(!cx)
+	{
+		const char *dev = getenv("A2CU_DEVICE");
+		if(dev)
+			a2cu_device = atoi(dev);
+		if(!(cx = (A2CU_ctx *)calloc(1, sizeof(A2CU_ctx))))
+			return A2_OOMEMORY;
+		cx->cfg = cfg;
+		cx->st = ((A2_interface_i *)cfg->interface)->state;
+		cx->eng = a2cu_open(a2cu_device, cfg->samplerate, 2);
+		if(!cx->eng)
+		{
+			fprintf(stderr, "a2cu_units: %s\n", a2cu_last_error());
+			free(cx);
+			return A2_DEVICEOPEN;
+		}
+		cx->next = contexts;
+		contexts = cx;
+	}
+	++cx->refs;
+	*statedata = cx;
+	return A2_OK;
+}
+
+static void a2cu_CloseState(void *statedata)
+{
+	A2CU_ctx *cx = (A2CU_ctx *)statedata, **p;
+	if(!cx || --cx->refs)
+		return;
+	for(p = &contexts; *p; p = &(*p)->next)
+		if(*p == cx)
+		{
+			*p = cx->next;
+			break;
+		}
+	a2cu_close(cx->eng);
+	free(cx->waves);
+	free(cx);
+}
+
+/* New fragment? (a2_AudioCallback advances now_fragstart, core.c:1964-1973) */
+static inline void frag_check(A2CU_ctx *cx)
+{
+	if(cx->started && (cx->last_fragstart == cx->st->now_fragstart))
+		return;
+	cx->started = 1;
+	cx->last_fragstart = cx->st->now_fragstart;
+	++cx->serial;
+	cx->nowners = 0;
+	cx->norphans = 0;
+	a2cu_block_begin(cx->eng);
+}
+
+static A2CU_unit *owner_find(A2CU_ctx *cx, int32_t **outputs)
+{
+	int i;
+	for(i = cx->nowners - 1; i >= 0; --i)
+		if(cx->owners[i].outputs == outputs)
+			return cx->owners[i].il;
+	return NULL;
+}
+
+static int wave_id(A2CU_ctx *cx, int handle)
+{
+	int i;
+	A2_wave *w = a2_GetWave(cx->cfg->interface, handle);
+	if(!w)
+		return -1;
+	for(i = 0; i < cx->nwaves; ++i)
+		if(cx->waves[i].w == w)
+			return cx->waves[i].id;
+	{
+		A2CU_wavemap *nw = (A2CU_wavemap *)realloc(cx->waves,
+				sizeof(A2CU_wavemap) * (cx->nwaves + 1));
+		int id;
+		if(!nw)
+			return -1;
+		cx->waves = nw;
+		id = a2cu_wave_upload_prepared(cx->eng, w->type, w->period,
+				w->flags & A2_LOOPED,
+				(const int16_t *const *)w->d.wave.data,
+				w->d.wave.size);
+		if(id < 0)
+			return -1;
+		cx->waves[cx->nwaves].w = w;
+		cx->waves[cx->nwaves].id = id;
+		++cx->nwaves;
+		return id;
+	}
+}
+
+
+/*---------------------------------------------------------
+	Voice records
+---------------------------------------------------------*/
+
+static A2CU_voice *voice_for(A2CU_ctx *cx, A2_vmstate *vms, int first)
+{
+	A2CU_voice *v = cx->last_voice;
+	if(!first && v && (v->vms == vms) && (v->cls == VC_NEW))
+		return v;
+	if(!(v = (A2CU_voice *)calloc(1, sizeof(A2CU_voice))))
+		return NULL;
+	v->vms = vms;
+	v->pool = v->slot = -1;
+	cx->last_voice = v;
+	return v;
+}
+
+static void voice_release(A2CU_ctx *cx, A2CU_voice *v)
+{
+	if(--v->refs)
+		return;
+	if(v->cls == VC_LEAF && v->slot >= 0)
+		a2cu_pool_free(cx->eng, v->pool, v->slot);
+	if(cx->last_voice == v)
+		cx->last_voice = NULL;
+	free(v->pend);
+	free(v);
+}
+
+static void emit_write(A2CU_ctx *cx, A2CU_voice *v, A2CU_unit *au, int reg,
+		int value, unsigned frame, unsigned start, unsigned dur)
+{
+	if(v->cls == VC_LEAF)
+	{
+		if(au->kind == A2CU_WTOSC && reg == 0)
+			value = wave_id(cx, value >> 16) << 16;
+		a2cu_block_write(cx->eng, v->pool, v->slot, au->index, reg,
+				value, *au->transpose, frame, start, dur);
+	}
+	else if(v->cls == VC_BUS && au->kind == A2CU_PANMIX && au->pm >= 0)
+		a2cu_block_pm_write(cx->eng, au->pm, reg, value, start, dur);
+}
+
+/* Decide what this voice is, now that its unit chain is complete. */
+static void classify(A2CU_ctx *cx, A2CU_voice *v, unsigned frame)
+{
+	A2_voice *hv = a2_voice_from_vms(v->vms);
+	A2_unit *u;
+	a2cu_unitspec chain[A2CU_MAXCHAIN];
+	int n = 0, all_ours = 1, i;
+	for(u = hv->units; u; u = u->next)
+		if(!is_ours(u->descriptor))
+			all_ours = 0;
+	v->cls = VC_BAD;
+	if(hv->units && hv->units->descriptor == &a2_inline_unitdesc)
+	{
+		/* BUS voice: our panmix units get device instances */
+		for(i = 0; i < v->nunits; ++i)
+		{
+			A2CU_unit *au = v->units[i];
+			if(au->kind == 0)
+				continue;
+			if(au->kind != A2CU_PANMIX)
+			{
+				a2r_Error(cx->st, A2_NOTIMPLEMENTED,
+						"a2cu: bus-level unit");
+				return;
+			}
+			au->pm = a2cu_pm_alloc(cx->eng);
+		}
+		v->cls = VC_BUS;
+	}
+	else if(all_ours && v->nunits && v->units[0]->kind != A2CU_PANMIX &&
+			v->units[0]->kind != A2CU_FILTER12 &&
+			v->units[0]->kind != A2CU_WAVESHAPER)
+	{
+		for(i = 0; i < v->nunits && n < A2CU_MAXCHAIN; ++i, ++n)
+		{
+			A2_unit *h = &v->units[i]->il.header;
+			chain[n].kind = v->units[i]->kind;
+			chain[n].ninputs = h->ninputs;
+			chain[n].noutputs = h->noutputs;
+			chain[n].add = (v->units[i]->flags & A2_PROCADD) ? 1 : 0;
+			chain[n].wireout = h->outputs == hv->outputs;
+		}
+		v->pool = a2cu_pool_open(cx->eng, chain, n);
+		if(v->pool < 0)
+		{
+			a2r_Error(cx->st, A2_NOTIMPLEMENTED, a2cu_last_error());
+			return;
+		}
+		v->slot = a2cu_pool_alloc(cx->eng, v->pool);
+		if(v->slot < 0)
+		{
+			a2r_Error(cx->st, A2_OOMEMORY, "a2cu: voice slot");
+			return;
+		}
+		v->cls = VC_LEAF;
+		for(i = 0; i < v->nunits; ++i)
+			a2cu_block_init(cx->eng, v->pool, v->slot, i,
+					v->units[i]->init_transpose, frame,
+					v->units[i]->substart);
+	}
+	else
+	{
+		a2r_Error(cx->st, A2_NOTIMPLEMENTED,
+				"a2cu: mixed host/device leaf voice");
+		return;
+	}
+	/* Control writes that arrived before the first Process() call */
+	for(i = 0; i < v->npend; ++i)
+		emit_write(cx, v, v->units[v->pend[i].unit], v->pend[i].reg,
+				v->pend[i].value, frame, v->pend[i].start,
+				v->pend[i].dur);
+	v->npend = 0;
+}
+
+
+/*---------------------------------------------------------
+	Callbacks shared by all replaced units
+---------------------------------------------------------*/
+
+static A2_errors unit_init(A2_unit *u, A2_vmstate *vms, void *statedata,
+		unsigned flags, int kind)
+{
+	A2CU_unit *au = (A2CU_unit *)u;
+	A2CU_ctx *cx = (A2CU_ctx *)statedata;
+	A2_voice *hv = a2_voice_from_vms(vms);
+	A2CU_voice *v;
+	int j, nregs = 0;
+	if(!cx)
+		return A2_INTERNAL + 900;
+	/* First unit of a voice: v->units is still empty (core.c:299-303) */
+	if(!(v = voice_for(cx, vms, hv->units == NULL)))
+		return A2_OOMEMORY;
+	if(v->nunits >= A2CU_MAXCHAIN)
+		return A2_NOTIMPLEMENTED;
+	au->cx = cx;
+	au->voice = v;
+	au->kind = kind;
+	au->index = v->nunits;
+	au->flags = flags;
+	au->substart = vms->waketime & 0xff;
+	au->transpose = vms->r + R_TRANSPOSE;
+	au->init_transpose = *au->transpose;
+	au->pm = -1;
+	au->bus = -1;
+	au->bus_serial = 0;
+	v->units[v->nunits++] = au;
+	++v->refs;
+	/* Register defaults, as each unit's Initialize() leaves them */
+	if(u->descriptor->registers)
+		while(u->descriptor->registers[nregs].name)
+			++nregs;
+	for(j = 0; j < nregs; ++j)
+		u->registers[j] = 0;
+	if(kind == A2CU_PANMIX)
+		u->registers[0] = 65536;	/* panmix.c:264 */
+	else if(kind == A2CU_FILTER12)
+		u->registers[2] = 65536;	/* filter12.c:194 */
+	return A2_OK;
+}
+
+static void unit_deinit(A2_unit *u)
+{
+	A2CU_unit *au = (A2CU_unit *)u;
+	if(au->pm >= 0)
+		a2cu_pm_free(au->cx->eng, au->pm);
+	if(au->voice)
+		voice_release(au->cx, au->voice);
+}
+
+static void unit_write(A2_unit *u, int reg, int value, unsigned start,
+		unsigned dur)
+{
+	A2CU_unit *au = (A2CU_unit *)u;
+	A2CU_voice *v = au->voice;
+	A2CU_ctx *cx = au->cx;
+	if(v->cls == VC_NEW)
+	{
+		if(v->npend == v->cpend)
+		{
+			int nc = v->cpend ? v->cpend * 2 : 16;
+			A2CU_pending *np = (A2CU_pending *)realloc(v->pend,
+					sizeof(A2CU_pending) * nc);
+			if(!np)
+				return;
+			v->pend = np;
+			v->cpend = nc;
+		}
+		v->pend[v->npend].unit = au->index;
+		v->pend[v->npend].reg = reg;
+		v->pend[v->npend].value = value;
+		v->pend[v->npend].start = start;
+		v->pend[v->npend].dur = dur;
+		++v->npend;
+		return;
+	}
+	frag_check(cx);
+	/* The VM runs at "now": the frame of the next Process() segment */
+	emit_write(cx, v, au, reg, value,
+			(unsigned)(v->vms->waketime - cx->st->now_fragstart) >> 8,
+			start, dur);
+}
+
+#define	WRITE_CB(n)							\
+static void unit_write##n(A2_unit *u, int v, unsigned s, unsigned d)	\
+{									\
+	unit_write(u, n, v, s, d);					\
+}
+WRITE_CB(0) WRITE_CB(1) WRITE_CB(2) WRITE_CB(3) WRITE_CB(4) WRITE_CB(5)
+WRITE_CB(6) WRITE_CB(7) WRITE_CB(8) WRITE_CB(9) WRITE_CB(10) WRITE_CB(11)
+WRITE_CB(12)
+
+/* Make 'bus' visible in the host buffers 'bufs' (before a host unit runs) */
+static void materialize(A2CU_ctx *cx, int bus, int nch, unsigned offset,
+		unsigned frames, int32_t **bufs, int add)
+{
+	TRACE("materialize bus %d nch %d [%u,+%u) add %d\n", bus, nch, offset,
+			frames, add);
+	if(a2cu_block_download(cx->eng, bus, nch > 2 ? 2 : nch, offset, frames,
+			bufs, add))
+	{
+		TRACE("download failed: %s\n", a2cu_last_error());
+		a2r_Error(cx->st, A2_READ, a2cu_last_error());
+	}
+}
+
+/* Process() of every replaced DSP unit (never inline) */
+static void unit_process(A2_unit *u, unsigned offset, unsigned frames)
+{
+	A2CU_unit *au = (A2CU_unit *)u;
+	A2CU_voice *v = au->voice;
+	A2CU_ctx *cx = au->cx;
+	frag_check(cx);
+	if(v->cls == VC_NEW)
+	{
+		classify(cx, v, offset);
+		TRACE("classified voice %p: cls %d pool %d slot %d units %d\n",
+				(void *)v, v->cls, v->pool, v->slot, v->nunits);
+	}
+	if(v->cls == VC_LEAF)
+	{
+		A2CU_unit *last, *owner;
+		if(au->index)
+			return;		/* one record per voice and segment */
+		last = v->units[v->nunits - 1];
+		owner = owner_find(cx, last->il.header.outputs);
+		TRACE("leaf proc slot %d [%u,+%u) owner %p\n", v->slot, offset,
+				frames, (void *)owner);
+		if(owner)
+			a2cu_block_proc(cx->eng, v->pool, v->slot, offset,
+					frames, owner->bus);
+		else
+		{
+			/*
+			 * The voice mixes into a bus no inline of ours owns
+			 * (a voice started before the root driver's INITV
+			 * inherits the master bus, core.c:479-480): give that
+			 * host bus a device shadow, added back when the
+			 * outermost inline returns.
+			 */
+			int i, bus = -1;
+			int32_t **outs = last->il.header.outputs;
+			for(i = 0; i < cx->norphans; ++i)
+				if(cx->orphans[i].outputs == outs)
+					bus = cx->orphans[i].bus;
+			if(bus < 0)
+			{
+				if(cx->norphans >= A2CU_MAXORPHANS)
+				{
+					a2r_Error(cx->st, A2_NOTIMPLEMENTED,
+							"a2cu: too many host buses");
+					return;
+				}
+				bus = a2cu_block_bus(cx->eng);
+				cx->orphans[cx->norphans].outputs = outs;
+				cx->orphans[cx->norphans].bus = bus;
+				cx->orphans[cx->norphans].nch = 0;
+				i = cx->norphans++;
+			}
+			else
+				for(i = 0; cx->orphans[i].outputs != outs; ++i)
+					;
+			if(last->il.header.noutputs > cx->orphans[i].nch)
+				cx->orphans[i].nch = last->il.header.noutputs;
+			a2cu_block_proc(cx->eng, v->pool, v->slot, offset,
+					frames, bus);
+		}
+		return;
+	}
+	if(v->cls != VC_BUS || au->kind != A2CU_PANMIX || au->pm < 0)
+		return;
+	/* Bus-level panmix */
+	TRACE("bus panmix pm %d [%u,+%u) on_device %d bus %d\n", au->pm, offset,
+			frames, v->on_device, v->cur_bus);
+	{
+		int in_bus, out_bus, wireout, add;
+		A2CU_unit *owner;
+		wireout = u->outputs != u->inputs;
+		add = (au->flags & A2_PROCADD) ? 1 : 0;
+		if(v->on_device)
+			in_bus = v->cur_bus;
+		else
+		{
+			/* A host unit wrote our input: bring it over */
+			in_bus = a2cu_block_bus(cx->eng);
+			a2cu_block_upload(cx->eng, in_bus,
+					u->ninputs > 2 ? 2 : u->ninputs,
+					offset, frames,
+					(const int32_t *const *)u->inputs);
+		}
+		if(wireout && (owner = owner_find(cx, u->outputs)))
+		{
+			a2cu_block_pm_proc(cx->eng, au->pm, u->ninputs,
+					u->noutputs, add, in_bus, owner->bus,
+					offset, frames);
+			return;
+		}
+		if(wireout)
+		{
+			/* Output is a host-only bus (e.g. the master) */
+			out_bus = a2cu_block_bus(cx->eng);
+			a2cu_block_pm_proc(cx->eng, au->pm, u->ninputs,
+					u->noutputs, 0, in_bus, out_bus,
+					offset, frames);
+			materialize(cx, out_bus, u->noutputs, offset, frames,
+					u->outputs, 1);
+			return;
+		}
+		out_bus = in_bus;
+		a2cu_block_pm_proc(cx->eng, au->pm, u->ninputs, u->noutputs,
+				add, in_bus, out_bus, offset, frames);
+		v->cur_bus = out_bus;
+		v->on_device = 1;
+		if(!u->next || !is_ours(u->next->descriptor))
+		{
+			materialize(cx, out_bus, u->noutputs, offset, frames,
+					u->outputs, 0);
+			v->on_device = 0;
+		}
+	}
+}
+
+
+/*---------------------------------------------------------
+	inline (src/units/inline.c, src/core.c:1763-1776)
+---------------------------------------------------------*/
+
+static void inline_process(A2_unit *u, unsigned offset, unsigned frames,
+		int add)
+{
+	A2CU_unit *au = (A2CU_unit *)u;
+	A2CU_voice *v = au->voice;
+	A2CU_ctx *cx = au->cx;
+	int i;
+	frag_check(cx);
+	if(v->cls == VC_NEW)
+		classify(cx, v, offset);
+	if(au->bus_serial != cx->serial)
+	{
+		au->bus = a2cu_block_bus(cx->eng);
+		au->bus_serial = cx->serial;
+	}
+	TRACE("inline %p [%u,+%u) add %d bus %d cls %d\n", (void *)au, offset,
+			frames, add, au->bus, v->cls);
+	if(!add)
+		for(i = 0; i < u->noutputs; ++i)
+			memset(u->outputs[i] + offset, 0, frames * sizeof(int));
+	/* Sub-voices that mix into u->outputs now mix into our device bus */
+	if(cx->nowners < A2_NESTLIMIT)
+	{
+		cx->owners[cx->nowners].outputs = u->outputs;
+		cx->owners[cx->nowners].il = au;
+		++cx->nowners;
+	}
+	a2_inline_ProcessAdd(u, offset, frames);	/* the host's recursion */
+	if(cx->nowners)
+		--cx->nowners;
+	frag_check(cx);
+	if(!cx->nowners)
+		for(i = 0; i < cx->norphans; ++i)	/* outermost inline */
+			materialize(cx, cx->orphans[i].bus, cx->orphans[i].nch,
+					offset, frames, cx->orphans[i].outputs,
+					1);
+	v->cur_bus = au->bus;
+	v->on_device = 1;
+	if(v->cls != VC_BUS || !u->next || !is_ours(u->next->descriptor))
+	{
+		/* A host unit (or nothing of ours) follows: hand the sum over */
+		materialize(cx, au->bus, u->noutputs, offset, frames,
+				u->outputs, 1);
+		v->on_device = 0;
+	}
+}
+
+static void inline_Process(A2_unit *u, unsigned offset, unsigned frames)
+{
+	inline_process(u, offset, frames, 0);
+}
+
+static void inline_ProcessAdd(A2_unit *u, unsigned offset, unsigned frames)
+{
+	inline_process(u, offset, frames, 1);
+}
+
+static A2_errors inline_Initialize(A2_unit *u, A2_vmstate *vms,
+		void *statedata, unsigned flags)
+{
+	A2CU_unit *au = (A2CU_unit *)u;
+	A2_errors res = unit_init(u, vms, statedata, flags, 0);
+	if(res)
+		return res;
+	/* units/inline.c:26-39 */
+	au->il.state = au->cx->st;
+	au->il.voice = a2_voice_from_vms(vms);
+	au->il.voice->noutputs = u->noutputs;
+	au->il.voice->outputs = u->outputs;
+	u->Process = (flags & A2_PROCADD) ? inline_ProcessAdd : inline_Process;
+	return A2_OK;
+}
+
+
+/*---------------------------------------------------------
+	Unit descriptors
+---------------------------------------------------------*/
+
+#define	INIT_CB(name, kind)						\
+static A2_errors name##_Initialize(A2_unit *u, A2_vmstate *vms,	\
+		void *statedata, unsigned flags)			\
+{									\
+	A2_errors res = unit_init(u, vms, statedata, flags, kind);	\
+	u->Process = unit_process;					\
+	return res;							\
+}
+
+INIT_CB(wtosc, A2CU_WTOSC)
+INIT_CB(panmix, A2CU_PANMIX)
+INIT_CB(filter12, A2CU_FILTER12)
+INIT_CB(waveshaper, A2CU_WAVESHAPER)
+INIT_CB(fm1, A2CU_FM1)
+INIT_CB(fm2, A2CU_FM2)
+INIT_CB(fm3, A2CU_FM3)
+INIT_CB(fm4, A2CU_FM4)
+INIT_CB(fm3p, A2CU_FM3P)
+INIT_CB(fm4p, A2CU_FM4P)
+INIT_CB(fm2r, A2CU_FM2R)
+INIT_CB(fm4r, A2CU_FM4R)
+
+/* Register names and order: the reference's A2_crdesc tables */
+static const A2_crdesc wtosc_regs[] = {		/* wtosc.c:507-514 */
+	{ "w", unit_write0 }, { "p", unit_write1 }, { "a", unit_write2 },
+	{ "phase", unit_write3 }, { NULL, NULL }
+};
+static const A2_crdesc panmix_regs[] = {	/* panmix.c:298-303 */
+	{ "vol", unit_write0 }, { "pan", unit_write1 }, { NULL, NULL }
+};
+static const A2_constdesc panmix_constants[] = {	/* panmix.c:305-311 */
+	{ "CENTER", 0 }, { "LEFT", (-1) << 16 }, { "RIGHT", 1 << 16 },
+	{ NULL, 0 }
+};
+static const A2_crdesc filter12_regs[] = {	/* filter12.c:231-239 */
+	{ "cutoff", unit_write0 }, { "q", unit_write1 }, { "lp", unit_write2 },
+	{ "bp", unit_write3 }, { "hp", unit_write4 }, { NULL, NULL }
+};
+static const A2_crdesc waveshaper_regs[] = {	/* waveshaper.c:166-170 */
+	{ "amount", unit_write0 }, { NULL, NULL }
+};
+/* fm.c:519-530 etc: phase, then (p, a, fb) per operator */
+static const A2_crdesc fm_regs[] = {
+	{ "phase", unit_write0 },
+	{ "p", unit_write1 }, { "a", unit_write2 }, { "fb", unit_write3 },
+	{ "p1", unit_write4 }, { "a1", unit_write5 }, { "fb1", unit_write6 },
+	{ "p2", unit_write7 }, { "a2", unit_write8 }, { "fb2", unit_write9 },
+	{ "p3", unit_write10 }, { "a3", unit_write11 }, { "fb3", unit_write12 },
+	{ NULL, NULL }
+};
+static const A2_crdesc fm1_regs[] = {
+	{ "phase", unit_write0 },
+	{ "p", unit_write1 }, { "a", unit_write2 }, { "fb", unit_write3 },
+	{ NULL, NULL }
+};
+static const A2_crdesc fm2_regs[] = {
+	{ "phase", unit_write0 },
+	{ "p", unit_write1 }, { "a", unit_write2 }, { "fb", unit_write3 },
+	{ "p1", unit_write4 }, { "a1", unit_write5 }, { "fb1", unit_write6 },
+	{ NULL, NULL }
+};
+static const A2_crdesc fm3_regs[] = {
+	{ "phase", unit_write0 },
+	{ "p", unit_write1 }, { "a", unit_write2 }, { "fb", unit_write3 },
+	{ "p1", unit_write4 }, { "a1", unit_write5 }, { "fb1", unit_write6 },
+	{ "p2", unit_write7 }, { "a2", unit_write8 }, { "fb2", unit_write9 },
+	{ NULL, NULL }
+};
+
+#define	UNITDESC(sym, uname, uflags, regs, consts, mini, maxi, mino, maxo, init) \
+const A2_unitdesc sym = {						\
+	uname, uflags, regs, NULL, consts,				\
+	mini, maxi, mino, maxo,						\
+	sizeof(A2CU_unit), init, unit_deinit,				\
+	a2cu_OpenState, a2cu_CloseState					\
+};
+
+/* I/O limits and flags as in the reference descriptors */
+UNITDESC(a2_wtosc_unitdesc, "wtosc", 0, wtosc_regs, NULL, 0, 0, 1, 1,
+		wtosc_Initialize)			/* wtosc.c:516-536 */
+UNITDESC(a2_panmix_unitdesc, "panmix", 0, panmix_regs, panmix_constants,
+		1, 2, 1, 2, panmix_Initialize)		/* panmix.c:313-333 */
+UNITDESC(a2_filter12_unitdesc, "filter12", A2_MATCHIO, filter12_regs, NULL,
+		1, 2, 1, 2, filter12_Initialize)	/* filter12.c:241-261 */
+UNITDESC(a2_waveshaper_unitdesc, "waveshaper", A2_MATCHIO, waveshaper_regs,
+		NULL, 1, 2, 1, 2, waveshaper_Initialize) /* waveshaper.c:173-193 */
+UNITDESC(a2_fm1_unitdesc, "fm1", 0, fm1_regs, NULL, 0, 0, 1, 1, fm1_Initialize)
+UNITDESC(a2_fm2_unitdesc, "fm2", 0, fm2_regs, NULL, 0, 0, 1, 1, fm2_Initialize)
+UNITDESC(a2_fm3_unitdesc, "fm3", 0, fm3_regs, NULL, 0, 0, 1, 1, fm3_Initialize)
+UNITDESC(a2_fm4_unitdesc, "fm4", 0, fm_regs, NULL, 0, 0, 1, 1, fm4_Initialize)
+UNITDESC(a2_fm3p_unitdesc, "fm3p", 0, fm3_regs, NULL, 0, 0, 1, 1,
+		fm3p_Initialize)
+UNITDESC(a2_fm4p_unitdesc, "fm4p", 0, fm_regs, NULL, 0, 0, 1, 1,
+		fm4p_Initialize)
+UNITDESC(a2_fm2r_unitdesc, "fm2r", 0, fm2_regs, NULL, 0, 0, 1, 1,
+		fm2r_Initialize)
+UNITDESC(a2_fm4r_unitdesc, "fm4r", 0, fm_regs, NULL, 0, 0, 1, 1,
+		fm4r_Initialize)
+/* units/inline.c:49-69 */
+UNITDESC(a2_inline_unitdesc, "inline", 0, NULL, NULL, 0, 0, 1, A2_MAXCHANNELS,
+		inline_Initialize)
+
+static int is_ours(const A2_unitdesc *d)
+{
+	return d->OpenState == a2cu_OpenState;
+}
+
+
+/*---------------------------------------------------------
+	"cuda" audio driver (mirrors drivers/bufferdrv.c:28-110)
+---------------------------------------------------------*/
+
+static A2_errors cudad_Run(A2_audiodriver *driver, unsigned frames)
+{
+	A2_config *cfg = driver->driver.config;
+	if(driver->Process)
+		driver->Process(driver, frames);	/* a2_AudioCallback */
+	else
+	{
+		int c;
+		for(c = 0; c < cfg->channels; ++c)
+			memset(driver->buffers[c], 0, sizeof(int32_t) * frames);
+	}
+	return A2_OK;
+}
+
+static void cudad_Lock(A2_audiodriver *driver) { }
+static void cudad_Unlock(A2_audiodriver *driver) { }
+
+static void cudad_Close(A2_driver *driver)
+{
+	A2_audiodriver *ad = (A2_audiodriver *)driver;
+	A2_config *cfg = driver->config;
+	if(ad->buffers)
+	{
+		int c;
+		for(c = 0; c < cfg->channels; ++c)
+			free(ad->buffers[c]);
+		free(ad->buffers);
+		ad->buffers = NULL;
+	}
+	ad->Run = NULL;
+	ad->Lock = NULL;
+	ad->Unlock = NULL;
+}
+
+static A2_errors cudad_Open(A2_driver *driver)
+{
+	A2_audiodriver *ad = (A2_audiodriver *)driver;
+	A2_config *cfg = driver->config;
+	int c;
+	ad->Run = cudad_Run;
+	ad->Lock = cudad_Lock;
+	ad->Unlock = cudad_Unlock;
+	if(!(ad->buffers = (int32_t **)calloc(cfg->channels, sizeof(int32_t *))))
+		return A2_OOMEMORY;
+	for(c = 0; c < cfg->channels; ++c)
+		if(!(ad->buffers[c] = (int32_t *)calloc(cfg->buffer,
+				sizeof(int32_t))))
+		{
+			cudad_Close(driver);
+			return A2_OOMEMORY;
+		}
+	return A2_OK;
+}
+
+static A2_driver *cudad_new(A2_drivertypes type, const char *nameopts)
+{
+	A2_audiodriver *d = (A2_audiodriver *)calloc(1, sizeof(A2_audiodriver));
+	if(!d)
+		return NULL;
+	d->driver.type = A2_AUDIODRIVER;
+	d->driver.name = "cuda";
+	d->driver.Open = cudad_Open;
+	d->driver.Close = cudad_Close;
+	return &d->driver;
+}
+
+int a2cu_RegisterDriver(void)
+{
+	return a2_RegisterDriver(A2_AUDIODRIVER, "cuda", cudad_new);
+}
