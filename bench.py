@@ -268,14 +268,21 @@ def bench_ours(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    nwarm = 0
+    # >= max(3, W) warm-up steps, then as many more as it takes to keep the GPU
+    # under this load for ~1.5 s so nvidia-smi (100 ms period) samples clocks
+    # under load; the count is decided on rank 0 and broadcast (all ranks must
+    # run the same number of collective steps).
+    nwarm = max(3, args.warmup)
     t_w = time.perf_counter()
-    # >= max(3, W) warm-up steps, and enough of them (>= 1.5 s) for nvidia-smi
-    # (100 ms period) to sample clocks under this load before and during the
-    # timed region
-    while nwarm < max(3, args.warmup) or time.perf_counter() - t_w < 1.5:
+    for _ in range(nwarm):
         one_step(False)
-        nwarm += 1
+    per_step = (time.perf_counter() - t_w) / nwarm
+    extra = torch.tensor([int(min(20000, max(0, 1.5 / max(per_step, 1e-6))))], device=dev)
+    if multi:
+        dist.broadcast(extra, 0)
+    for _ in range(int(extra.item())):
+        one_step(False)
+    nwarm += int(extra.item())
     if multi:
         dist.barrier()
     torch.cuda.synchronize()
