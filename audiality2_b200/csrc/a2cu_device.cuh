@@ -48,7 +48,6 @@ struct Ctx {
     const unsigned *ptab;           // 64 x {base, coeff}, pitch.c:70-96
     const int16_t *fmsine;          // 2049-entry sine LUT (shared memory)
     int samplerate;
-    unsigned *noisestate;           // per-voice LCG slot or nullptr
 };
 
 // ---- a2_dsp.h ---------------------------------------------------------------
@@ -174,6 +173,7 @@ struct WtOsc {
     unsigned long long ph;
     unsigned dph;
     unsigned wsize;
+    unsigned nstate;    // LCG state for this segment's noise draws (EV_SEED)
     int astep;
     int mm, run;
 
@@ -185,7 +185,7 @@ struct WtOsc {
         int x = s.ld(w + 12);
         p_ramping = s.ld(w + 13);
         wave = x >> 8; mode = x & 0xff;
-        run = RUN_SILENT; astep = 0; mm = 0; d = nullptr; ph = 0; dph = 0; wsize = 0;
+        run = RUN_SILENT; astep = 0; mm = 0; d = nullptr; ph = 0; dph = 0; wsize = 0; nstate = 0;
     }
     A2CU_DEV void store(const StatePtr &s, int w) const {
         s.st_ramp(w, p); s.st_ramp(w + 4, a);
@@ -341,7 +341,7 @@ struct WtOsc {
         } else if (run == RUN_NOISE) {
             unsigned long long nph = phase + dphase;
             if ((dphase >= (1u << 23)) || ((nph ^ phase) >> 23))
-                noise = noise_next(*c.noisestate) - 32767;
+                noise = noise_next(nstate) - 32767;
             phase = nph;
             v = wmul(noise, a.value >> 10) >> 6;
             a.value = wadd(a.value, astep);
@@ -350,6 +350,9 @@ struct WtOsc {
         else if (ADD) s0 = wadd(s0, v);
         else s0 = v;
     }
+    // The shared noise LCG (a2_dsp.h:37-42, wtosc.c:135-144) is advanced in
+    // tree-walk order on the host; each noise segment gets its start state.
+    A2CU_DEV void seed(unsigned s) { nstate = s; }
     // True when the current segment is the common unchecked wavetable loop.
     A2CU_DEV bool plain() const { return run == RUN_TABLE; }
     // sample() specialised for plain(): no mode tests, so the compiler can
@@ -433,6 +436,7 @@ struct PanMix {
     }
     A2CU_DEV bool plain() const { return true; }
     A2CU_DEV void sample_fast(const Ctx &c, int &s0, int &s1, int &o0, int &o1) { sample(c, s0, s1, o0, o1); }
+    A2CU_DEV void seed(unsigned) {}
     A2CU_DEV void finish() { vstep = pstep = 0; }
 };
 
@@ -522,6 +526,7 @@ struct Filter12 {
     }
     A2CU_DEV bool plain() const { return true; }
     A2CU_DEV void sample_fast(const Ctx &c, int &s0, int &s1, int &o0, int &o1) { sample(c, s0, s1, o0, o1); }
+    A2CU_DEV void seed(unsigned) {}
     A2CU_DEV void finish() { qstep = 0; df = 0; }
 };
 
@@ -560,6 +565,7 @@ struct WaveShaper {
     }
     A2CU_DEV bool plain() const { return true; }
     A2CU_DEV void sample_fast(const Ctx &c, int &s0, int &s1, int &o0, int &o1) { sample(c, s0, s1, o0, o1); }
+    A2CU_DEV void seed(unsigned) {}
     A2CU_DEV void finish() { step = 0; }
 };
 
@@ -709,6 +715,7 @@ struct Fm {
         else if (ADD) s0 = wadd(s0, v);
         else s0 = v;
     }
+    A2CU_DEV void seed(unsigned) {}
     A2CU_DEV bool plain() const { return true; }
     A2CU_DEV void sample_fast(const Ctx &c, int &s0, int &s1, int &o0, int &o1) { sample(c, s0, s1, o0, o1); }
     A2CU_DEV void finish() {
@@ -729,6 +736,7 @@ template <> struct Chain<> {
     A2CU_DEV void store(const StatePtr &, int) const {}
     A2CU_DEV void init_unit(const Ctx &, int, int, unsigned) {}
     A2CU_DEV void write(const Ctx &, int, int, int, int, int) {}
+    A2CU_DEV void seed_unit(int, unsigned) {}
     A2CU_DEV void prepare(const Ctx &, int) {}
     A2CU_DEV void sample(const Ctx &, int &, int &, int &, int &) {}
     A2CU_DEV void sample_fast(const Ctx &, int &, int &, int &, int &) {}
@@ -748,6 +756,9 @@ template <class U, class... Rest> struct Chain<U, Rest...> {
     }
     A2CU_DEV void write(const Ctx &c, int unit, int reg, int v, int start, int dur) {
         if (unit == 0) u.write(c, reg, v, start, dur); else rest.write(c, unit - 1, reg, v, start, dur);
+    }
+    A2CU_DEV void seed_unit(int unit, unsigned sd) {
+        if (unit == 0) u.seed(sd); else rest.seed_unit(unit - 1, sd);
     }
     A2CU_DEV void prepare(const Ctx &c, int frames) { u.prepare(c, frames); rest.prepare(c, frames); }
     A2CU_DEV void sample(const Ctx &c, int &s0, int &s1, int &o0, int &o1) {

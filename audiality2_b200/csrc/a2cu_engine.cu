@@ -159,6 +159,82 @@ static const HostTables &tables() {
     return t;
 }
 
+
+// ---------------------------------------------------------------------------
+// Noise planner: host-side control-rate twin of the wtosc unit.
+//
+// The noise wave draws from ONE LCG shared by every voice (and the VM's RAND)
+// in tree-walk order (wtosc.c:135-144, core.c:1401-1409), so the start state of
+// each noise segment depends on how many draws every earlier voice made. Voices
+// that select the noise wave get a host "mirror" of their oscillators' control
+// state (pitch ramper, dphase, phase, mode) - created by reading the device
+// state back once - which replays exactly the per-Process()-call logic of
+// a2cu_device.cuh WtOsc::prepare/finish with the sample loop in closed form.
+// It yields the draw count per segment; the LCG start state is delivered to the
+// device as an EV_SEED record. No audio is computed on the host.
+// ---------------------------------------------------------------------------
+struct HRamp { int value, target, delta, timer; };
+static inline int h_add(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
+static inline int h_sub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
+static inline int h_mul(int a, int b) { return (int)((unsigned)a * (unsigned)b); }
+static void hramp_prepare(HRamp &r, int frames) {      // a2_dsp.h:128-149
+    if (!r.timer) { r.value = r.target; r.delta = 0; }
+    else if (frames <= (r.timer >> 8)) {
+        r.delta = (int)(((long long)h_sub(r.target, r.value) << 8) / r.timer);
+        r.timer -= frames << 8;
+    } else { r.delta = h_sub(r.target, r.value) / frames; r.timer = 0; }
+}
+static void hramp_run(HRamp &r, int frames) { r.value = h_add(r.value, h_mul(r.delta, frames)); }
+static void hramp_set(HRamp &r, int target, int start, int dur) {   // a2_dsp.h:161-170
+    r.target = (int)((unsigned)target << 8);
+    r.timer = dur + start;
+    if (r.timer < 256) r.value = r.target;
+    else r.value = h_add(r.value, h_mul(r.delta, start) >> 8);
+}
+
+struct OscMirror {
+    HRamp p;
+    int p_ramping;
+    unsigned dphase;
+    unsigned long long phase;
+    int wave, mode;     // OscMode
+
+    void load(const int *w) {       // word layout of WtOsc::store
+        p.value = w[0]; p.target = w[1]; p.delta = w[2]; p.timer = w[3];
+        dphase = (unsigned)w[8];
+        phase = (unsigned)w[9] | ((unsigned long long)(unsigned)w[10] << 32);
+        wave = w[12] >> 8; mode = w[12] & 0xff;
+        p_ramping = w[13];
+    }
+    void set_phase(const a2cu_engine *e, int phv, unsigned sst);
+    void init(const a2cu_engine *e, int arg, unsigned sst) {
+        wave = -1;
+        p.value = p.target = (int)((unsigned)arg << 8); p.delta = p.timer = 0;
+        dphase = tables().p2i(p.value >> 8);
+        p_ramping = 0;
+        set_phase(e, 0, sst);
+        mode = OSC_OFF;
+    }
+    void write(const a2cu_engine *e, int reg, int v, int start, int dur);
+    void run_pitch(int frames) {        // wtosc.c:89-105
+        hramp_prepare(p, frames);
+        if (dphase && (!p.timer && !p_ramping)) return;
+        unsigned lastv = (unsigned)p.value;
+        hramp_run(p, frames);
+        p_ramping = p.delta;
+        dphase = tables().p2i((int)((lastv + (unsigned)p.value) >> 9));
+    }
+    // One Process() call: returns the number of LCG draws (noise mode) and
+    // whether the segment is a noise segment at all.
+    int segment(const a2cu_engine *e, int frames, bool *is_noise);
+};
+
+struct VoiceMirror {
+    int alive = 0;
+    std::vector<std::pair<int, OscMirror>> osc;     // (unit index, twin)
+    size_t cursor = 0;                              // planner scratch
+};
+
 // ---------------------------------------------------------------------------
 // Engine objects
 // ---------------------------------------------------------------------------
@@ -195,6 +271,7 @@ struct Bank {
     uint4 *d_ev = nullptr;
     size_t ev_cap = 0;
     bool has_noise = false;
+    uint32_t stamp = 0;
     // drop-in ("block") mode: dynamic slots + per-flush recording
     bool dynamic = false;
     std::vector<int> free_slots, deferred_free;   // freed slots are reusable from the next block
@@ -253,6 +330,11 @@ struct a2cu_engine {
     float last_ms = 0.f, last_mix_ms = 0.f;
     // last window (for a2cu_apply_root_stage)
     MixParams last_mix;
+    // noise planner
+    std::map<uint64_t, VoiceMirror> mirrors;    // key: bank << 32 | slot
+    uint32_t *noise_ptr = nullptr;              // shared LCG (host's st->noisestate in drop-in mode)
+    uint32_t stamp = 0;                         // creation order (tree-walk order is newest first)
+    std::vector<uint32_t> gstamp;
     // drop-in ("block") mode
     std::vector<BusCmd> buscmds;
     BusCmd *d_buscmds = nullptr;
@@ -264,6 +346,139 @@ struct a2cu_engine {
     std::vector<int> pm_free, pm_deferred;
     int32_t *h_xfer = nullptr;      // pinned, 64 x 2
 };
+
+
+void OscMirror::set_phase(const a2cu_engine *e, int phv, unsigned sst) {   // wtosc.c:378-387
+    if (wave < 0) { phase = 0; return; }
+    phv = h_add(phv, (int)((sst * (dphase >> 8)) >> 8));
+    phase = (unsigned long long)(((long long)phv * (long long)e->waves[wave].period) << 8);
+}
+
+void OscMirror::write(const a2cu_engine *e, int reg, int v, int start, int dur) {    // WtOsc::write
+    switch (reg) {
+    case 0:
+        wave = v;
+        if (v < 0) mode = OSC_OFF;
+        else {
+            int t = e->waves[v].type;
+            mode = t == A2CU_WNOISE ? OSC_NOISE : t == A2CU_WWAVE ? OSC_NOMIP : t == A2CU_WMIPWAVE ? OSC_MIP : OSC_OFF;
+            if (mode == OSC_OFF) wave = -1;
+        }
+        break;
+    case 1:
+        hramp_set(p, v, start, dur);
+        if (!dur) p_ramping = 1;
+        break;
+    case 3: set_phase(e, v, (unsigned)start); break;
+    default: break;     // amplitude does not influence phase or draw count
+    }
+}
+
+int OscMirror::segment(const a2cu_engine *e, int frames, bool *is_noise) {     // WtOsc::prepare + loop + finish
+    *is_noise = false;
+    if (mode == OSC_MIP || mode == OSC_NOMIP) {
+        if (!e->waves[wave].size[0]) { wave = -1; mode = OSC_OFF; return 0; }
+    }
+    switch (mode) {
+    case OSC_OFF:
+        hramp_prepare(p, frames); hramp_run(p, frames);
+        return 0;
+    case OSC_NOISE: {
+        run_pitch(frames);
+        int draws = 0;
+        for (int i = 0; i < frames; ++i) {      // wtosc.c:140-145
+            unsigned long long nph = phase + dphase;
+            if ((dphase >= (1u << 23)) || ((nph ^ phase) >> 23)) ++draws;
+            phase = nph;
+        }
+        *is_noise = true;
+        return draws;
+    }
+    case OSC_MIP: {
+        const HostWave &w = e->waves[wave];
+        run_pitch(frames);
+        unsigned est = ((dphase + 255) >> 8) * w.period;
+        int m = 0;
+        for (; (est > (unsigned)(kMaxPhInc << 8)) && (m < kMipLevels - 1); ++m) est >>= 1;
+        unsigned long long ph = phase >> m;
+        unsigned dph = (unsigned)(((unsigned long long)dphase * w.period) >> m);
+        if (w.flags & A2CU_LOOPED) ph %= (unsigned long long)w.size[m] << 24;
+        else if ((ph >> 24) > (unsigned long long)(w.size[m] + kWavePre)) return 0;
+        ph += (unsigned long long)dph * (unsigned)frames;      // muted or played: same advance
+        phase = ph << m;
+        return 0;
+    }
+    case OSC_NOMIP: {
+        const HostWave &w = e->waves[wave];
+        run_pitch(frames);
+        unsigned long long dp = (unsigned long long)dphase * w.period;
+        if (dp >> 32) { phase += dp * (unsigned)frames; return 0; }
+        unsigned dph = (unsigned)dp;
+        if (dp > (unsigned long long)(kMaxPhInc << 16)) {
+            unsigned long long ph = phase;
+            for (int i = 0; i < frames; ++i) {
+                if (w.flags & A2CU_LOOPED) ph %= (unsigned long long)w.size[0] << 24;
+                else if ((ph >> 24) >= w.size[0]) break;
+                ph += dph;
+            }
+            phase = ph;
+            return 0;
+        }
+        if (w.flags & A2CU_LOOPED) {
+            unsigned m32 = w.size[0] << 24;
+            if (m32) phase %= m32;
+        } else if ((phase >> 24) > (unsigned long long)(w.size[0] + kWavePre)) return 0;
+        phase += (unsigned long long)dph * (unsigned)frames;
+        return 0;
+    }
+    }
+    return 0;
+}
+
+static inline void lcg_advance(uint32_t *st, int draws) {     // a2_dsp.h:39-40
+    for (int i = 0; i < draws; ++i) *st = *st * 1566083941u + 1u;
+}
+
+static int unit_words(const a2cu_unitspec &u) {
+    switch (u.kind) {
+    case A2CU_WTOSC: return 14;
+    case A2CU_PANMIX: return 8;
+    case A2CU_FILTER12: return 12 + 2 * u.ninputs;
+    case A2CU_WAVESHAPER: return 4;
+    default: {
+        static const int nops[8] = {1, 2, 3, 4, 3, 4, 2, 4};
+        return 16 * nops[u.kind - A2CU_FM1];
+    }
+    }
+}
+
+// Read the control state of a voice's oscillators back from the device.
+static int mirror_create(a2cu_engine *e, int bank, int slot, VoiceMirror **out) {
+    Bank *b = e->banks[bank];
+    uint64_t key = ((uint64_t)bank << 32) | (uint32_t)slot;
+    auto it = e->mirrors.find(key);
+    if (it != e->mirrors.end()) { *out = &it->second; return A2CU_OK; }
+    VoiceMirror vm;
+    CK(cudaStreamSynchronize(e->stream));
+    int flags = 0;
+    CK(cudaMemcpy(&flags, b->d_state + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    vm.alive = flags & 1;
+    int base = 1;
+    for (size_t u = 0; u < b->chain.size(); ++u) {
+        if (b->chain[u].kind == A2CU_WTOSC) {
+            int w[14];
+            CK(cudaMemcpy2D(w, sizeof(int), b->d_state + (size_t)base * b->stride + slot, b->stride * sizeof(int),
+                            sizeof(int), 14, cudaMemcpyDeviceToHost));
+            OscMirror m;
+            m.load(w);
+            vm.osc.push_back(std::make_pair((int)u, m));
+        }
+        base += unit_words(b->chain[u]);
+    }
+    e->mirrors[key] = vm;
+    *out = &e->mirrors[key];
+    return A2CU_OK;
+}
 
 static int ensure_stage(a2cu_engine *e, size_t bytes) {
     if (bytes <= e->stage_cap) return 0;
@@ -366,6 +581,7 @@ a2cu_engine *a2cu_open(int device, int samplerate, int channels) {
         return nullptr;
     }
     a2cu_engine *e = new a2cu_engine();
+    e->noise_ptr = &e->noiseseed;
     e->device = device;
     e->samplerate = samplerate;
     e->channels = channels < 2 ? 1 : 2;
@@ -422,7 +638,12 @@ int a2cu_basepitch(const a2cu_engine *e) { return e->basepitch; }
 uint32_t a2cu_msdur(const a2cu_engine *e) { return e->msdur; }
 uint64_t a2cu_now(const a2cu_engine *e) { return e->now; }
 int a2cu_set_root_wake_period(a2cu_engine *e, uint32_t p) { e->root_wake = p; return A2CU_OK; }
-int a2cu_set_noiseseed(a2cu_engine *e, uint32_t s) { e->noiseseed = s; return A2CU_OK; }
+int a2cu_set_noiseseed(a2cu_engine *e, uint32_t s) { *e->noise_ptr = s; return A2CU_OK; }
+int a2cu_set_noise_state_ptr(a2cu_engine *e, uint32_t *p) {
+    if (!e) return A2CU_EINVAL;
+    e->noise_ptr = p ? p : &e->noiseseed;
+    return A2CU_OK;
+}
 uint64_t a2cu_launch_count(const a2cu_engine *e) { return e->launches; }
 uint64_t a2cu_h2d_bytes(const a2cu_engine *e) { return e->h2d_bytes; }
 uint64_t a2cu_d2h_bytes(const a2cu_engine *e) { return e->d2h_bytes; }
@@ -532,6 +753,7 @@ int a2cu_group_new(a2cu_engine *e) {
     }
     int gs[8] = {65536 << 8, 65536 << 8, 0, 0, 0, 0, 0, 0};
     CK(cudaMemcpy(e->d_gstate + (size_t)e->ngroups * 8, gs, sizeof(gs), cudaMemcpyHostToDevice));
+    e->gstamp.push_back(e->stamp++);
     return e->ngroups++;
 }
 
@@ -559,6 +781,7 @@ int a2cu_bank_new(a2cu_engine *e, const a2cu_unitspec *chain, int nunits, int nv
     b->chain.assign(chain, chain + nunits);
     b->k = it->second;
     b->nvoices = nvoices;
+    b->stamp = e->stamp++;
     b->stride = ((size_t)nvoices + kThreads - 1) / kThreads * kThreads;
     b->transpose.assign(nvoices, 0);
     b->group.assign(nvoices, -1);
@@ -767,6 +990,120 @@ static int collect_splits(a2cu_engine *e, uint64_t t0, uint64_t t1, int *splits,
     return 0;
 }
 
+// Bank-mode noise planner: seeds for every noise segment of the window, in
+// tree-walk order (newest bank / highest voice index first, like the
+// reference's head insertion in a2_VoiceNew, core.c:476-477).
+static int plan_noise(a2cu_engine *e, uint64_t t0, int W, int buffer, const int *splits, int nsplits,
+                      std::vector<std::vector<HostEvent>> &due) {
+    // 1. new mirrors for voices that select the noise wave in this window
+    for (size_t bi = 0; bi < e->banks.size(); ++bi) {
+        Bank *b = e->banks[bi];
+        if (b->dynamic) continue;
+        for (const HostEvent &ev : due[bi]) {
+            int kind = ev.y & 0xff, unit = (ev.y >> 8) & 0xff, reg = (ev.y >> 16) & 0xff;
+            if (kind != EV_WRITE || b->chain[unit].kind != A2CU_WTOSC || reg != 0) continue;
+            if (ev.value < 0 || e->waves[ev.value].type != A2CU_WNOISE) continue;
+            VoiceMirror *vm;
+            int r = mirror_create(e, (int)bi, ev.voice, &vm);
+            if (r) return r;
+        }
+    }
+    if (e->mirrors.empty()) return A2CU_OK;
+    // 2. mirrored voices in walk order
+    struct Item { uint32_t rootkey, bstamp; int bank, slot; VoiceMirror *vm; size_t lo, hi; };
+    std::vector<Item> items;
+    for (auto &kv : e->mirrors) {
+        Item it;
+        it.bank = (int)(kv.first >> 32); it.slot = (int)(uint32_t)kv.first; it.vm = &kv.second;
+        Bank *b = e->banks[it.bank];
+        if (b->dynamic) continue;
+        int g = b->group[it.slot];
+        it.bstamp = b->stamp;
+        it.rootkey = g >= 0 ? e->gstamp[g] : b->stamp;
+        auto cmp = [](const HostEvent &a, int v) { return a.voice < v; };
+        it.lo = std::lower_bound(due[it.bank].begin(), due[it.bank].end(), it.slot, cmp) - due[it.bank].begin();
+        it.hi = std::lower_bound(due[it.bank].begin(), due[it.bank].end(), it.slot + 1, cmp) - due[it.bank].begin();
+        it.vm->cursor = it.lo;
+        items.push_back(it);
+    }
+    std::sort(items.begin(), items.end(), [](const Item &a, const Item &c) {
+        if (a.rootkey != c.rootkey) return a.rootkey > c.rootkey;
+        if (a.bstamp != c.bstamp) return a.bstamp > c.bstamp;
+        return a.slot > c.slot;
+    });
+    std::vector<std::vector<HostEvent>> seeds(e->banks.size());
+    // 3. pieces = fragments cut by the root-level splits; voices inside a piece
+    for (int a = 0; a < W;) {
+        int pos = a % buffer;
+        int pe = a - pos + std::min(buffer, (pos / kMaxFrag + 1) * kMaxFrag);
+        pe = std::min(pe, W);
+        for (int k = 0; k < nsplits; ++k)
+            if (splits[k] > a) pe = std::min(pe, splits[k]);
+        for (Item &it : items) {
+            Bank *b = e->banks[it.bank];
+            std::vector<HostEvent> &ev = due[it.bank];
+            VoiceMirror *vm = it.vm;
+            int sfr = a;
+            while (sfr < pe) {
+                while (vm->cursor < it.hi && (int)((ev[vm->cursor].time - t0) >> 8) <= sfr) {
+                    const HostEvent &x = ev[vm->cursor++];
+                    int kind = x.y & 0xff, unit = (x.y >> 8) & 0xff, reg = (x.y >> 16) & 0xff;
+                    int start = (int)(x.time & 0xff);
+                    if (kind == EV_START) vm->alive = 1;
+                    else if (kind == EV_STOP) vm->alive = 0;
+                    else if (kind == EV_INIT || kind == EV_WRITE)
+                        for (auto &om : vm->osc)
+                            if (om.first == unit) {
+                                if (kind == EV_INIT) om.second.init(e, x.value, (unsigned)start);
+                                else om.second.write(e, reg, x.value, start, (int)x.dur);
+                            }
+                }
+                int nxt = pe;
+                if (vm->cursor < it.hi) nxt = std::min(nxt, (int)((ev[vm->cursor].time - t0) >> 8));
+                if (nxt <= sfr) nxt = sfr + 1;      // defensive: never stall
+                if (vm->alive)
+                    for (auto &om : vm->osc) {
+                        bool is_noise;
+                        int draws = om.second.segment(e, nxt - sfr, &is_noise);
+                        if (is_noise) {
+                            HostEvent sd;
+                            sd.time = t0 + ((uint64_t)sfr << 8);
+                            sd.seq = 0xf0000000u + (uint32_t)om.first;  // after the writes of this frame
+                            sd.voice = it.slot;
+                            sd.y = EV_SEED | ((uint32_t)om.first << 8);
+                            sd.value = (int)*e->noise_ptr;
+                            sd.dur = 0;
+                            seeds[it.bank].push_back(sd);
+                            lcg_advance(e->noise_ptr, draws);
+                        }
+                    }
+                sfr = nxt;
+            }
+            (void)b;
+        }
+        a = pe;
+    }
+    // 4. merge the seed records, drop mirrors that are no longer needed
+    for (size_t bi = 0; bi < e->banks.size(); ++bi) {
+        if (seeds[bi].empty()) continue;
+        due[bi].insert(due[bi].end(), seeds[bi].begin(), seeds[bi].end());
+        std::sort(due[bi].begin(), due[bi].end(), [](const HostEvent &a, const HostEvent &c) {
+            if (a.voice != c.voice) return a.voice < c.voice;
+            if ((a.time >> 8) != (c.time >> 8)) return a.time < c.time;
+            return a.seq < c.seq;
+        });
+    }
+    for (auto it = e->mirrors.begin(); it != e->mirrors.end();) {
+        bool keep = false;
+        if (it->second.alive)
+            for (auto &om : it->second.osc)
+                if (om.second.mode == OSC_NOISE) keep = true;
+        if (e->banks[(int)(it->first >> 32)]->dynamic) keep = true;
+        if (keep) ++it; else it = e->mirrors.erase(it);
+    }
+    return A2CU_OK;
+}
+
 static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *dev_out) {
     if (!frames) return A2CU_OK;
     if (!buffer) buffer = frames;
@@ -818,6 +1155,12 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         if (!due[bi].empty())
             stage_bytes += (b->stride + 1) * sizeof(unsigned) + due[bi].size() * sizeof(uint4) + 64;
     }
+    r = plan_noise(e, t0, W, (int)buffer, splits, nsplits, due);
+    if (r) return r;
+    stage_bytes = 0;
+    for (size_t bi = 0; bi < e->banks.size(); ++bi)
+        if (!due[bi].empty())
+            stage_bytes += (e->banks[bi]->stride + 1) * sizeof(unsigned) + due[bi].size() * sizeof(uint4) + 64;
     std::vector<MixHostEvent> mdue, mkeep;
     for (auto &m : e->mixev) (m.time < t1 ? mdue : mkeep).push_back(m);
     e->mixev.swap(mkeep);
@@ -846,7 +1189,6 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         for (int i = 0; i < nsplits; ++i) P.splits[i] = splits[i];
         P.waves = e->d_waves; P.pool = e->d_pool; P.ptab = e->d_ptab; P.fmsine = e->d_fmsine;
         P.samplerate = e->samplerate;
-        P.noise = b->d_noise;
         if (!due[bi].empty()) {
             size_t nev = due[bi].size();
             if (nev > b->ev_cap) {
@@ -1054,6 +1396,7 @@ int a2cu_pool_free(a2cu_engine *e, int pool, int slot) {
     Bank *b = get_bank(e, pool);
     if (!b || !b->dynamic || slot < 0 || slot >= b->used) return fail(A2CU_EINVAL, "bad pool/slot%s");
     b->deferred_free.push_back(slot);     // still referenced by records of this block
+    e->mirrors.erase(((uint64_t)pool << 32) | (uint32_t)slot);
     return A2CU_OK;
 }
 
@@ -1116,6 +1459,7 @@ int a2cu_block_init(a2cu_engine *e, int pool, int slot, int unit, int transpose,
     if (kind == A2CU_WTOSC || kind >= A2CU_FM1) arg = transpose + e->basepitch;
     else if (kind == A2CU_FILTER12) arg = transpose;
     unsigned x = (frame << 8) | (substart & 0xff);
+    if (unit == 0) e->mirrors.erase(((uint64_t)pool << 32) | (uint32_t)slot);   // slot reused by a new voice
     block_rec(b, slot, x, EV_INIT | ((unsigned)unit << 8), arg, 0);
     if (kind == A2CU_FILTER12)
         block_rec(b, slot, x, EV_WRITE | ((unsigned)unit << 8) | (5u << 16),
@@ -1131,6 +1475,25 @@ int a2cu_block_write(a2cu_engine *e, int pool, int slot, int unit, int reg, int3
     int n = cook(e, b->chain[unit].kind, reg, value, (int)(start & 0xff), dur, transpose, c);
     if (n < 0) return n;
     unsigned x = (frame << 8) | (start & 0xff);
+    if (b->chain[unit].kind == A2CU_WTOSC) {
+        uint64_t key = ((uint64_t)pool << 32) | (uint32_t)slot;
+        auto mi = e->mirrors.find(key);
+        if (mi == e->mirrors.end() && c[0].reg == 0 && c[0].value >= 0 &&
+            e->waves[c[0].value].type == A2CU_WNOISE) {
+            // first noise selection of this voice: run what is recorded, then
+            // read the oscillators' control state back once
+            int r = a2cu_block_flush(e);
+            if (r) return r;
+            VoiceMirror *vm;
+            r = mirror_create(e, pool, slot, &vm);
+            if (r) return r;
+            vm->alive = 1;
+            mi = e->mirrors.find(key);
+        }
+        if (mi != e->mirrors.end())
+            for (auto &om : mi->second.osc)
+                if (om.first == unit) om.second.write(e, c[0].reg, c[0].value, (int)(start & 0xff), (int)c[0].dur);
+    }
     for (int i = 0; i < n; ++i)
         block_rec(b, slot, x, EV_WRITE | ((unsigned)unit << 8) | ((unsigned)(c[i].reg & 0xff) << 16), c[i].value,
                   c[i].dur);
@@ -1141,6 +1504,16 @@ int a2cu_block_proc(a2cu_engine *e, int pool, int slot, unsigned frame, unsigned
     Bank *b = get_bank(e, pool);
     if (!b || !b->dynamic || frames < 1 || frame + frames > (unsigned)kMaxFrag || bus < 0 || bus >= e->nbbus)
         return fail(A2CU_EINVAL, "a2cu_block_proc: bad args%s");
+    auto mi = e->mirrors.find(((uint64_t)pool << 32) | (uint32_t)slot);
+    if (mi != e->mirrors.end())
+        for (auto &om : mi->second.osc) {      // units run in chain order inside one segment
+            bool is_noise;
+            int draws = om.second.segment(e, (int)frames, &is_noise);
+            if (is_noise) {
+                block_rec(b, slot, frame << 8, EV_SEED | ((unsigned)om.first << 8), (int)*e->noise_ptr, 0);
+                lcg_advance(e->noise_ptr, draws);
+            }
+        }
     block_rec(b, slot, frame << 8, EV_PROC | (frames << 8), bus, 0);
     return A2CU_OK;
 }
@@ -1253,7 +1626,7 @@ int a2cu_block_flush(a2cu_engine *e) {
         P.state = b->d_state; P.stride = b->stride; P.nvoices = (int)nr;
         P.acc = e->d_bacc; P.W = kMaxFrag; P.buffer = kMaxFrag;
         P.waves = e->d_waves; P.pool = e->d_pool; P.ptab = e->d_ptab; P.fmsine = e->d_fmsine;
-        P.samplerate = e->samplerate; P.noise = b->d_noise;
+        P.samplerate = e->samplerate;
         P.ev = b->d_ev; P.runs = b->d_runs; P.explicit_ = 1;
         int grid = ((int)nr + kThreads - 1) / kThreads;
         b->k.fn<<<grid, kThreads, 0, e->stream>>>(P);

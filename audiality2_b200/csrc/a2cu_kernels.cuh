@@ -23,7 +23,9 @@ constexpr int kMaxSplits = 8;
 // y = kind | unit << 8 | reg << 16 ; z = value ; w = duration (24:8)
 // EV_PROC (drop-in mode): y = kind | frames << 8, z = device bus index: one
 // Process() call of the voice's units, exactly as the host walked it.
-enum EvKind { EV_WRITE = 0, EV_WAKE = 1, EV_INIT = 2, EV_START = 3, EV_STOP = 4, EV_PROC = 5 };
+// EV_SEED: z = start state of the shared noise LCG for the next segment of unit
+// 'unit' (computed on the host in tree-walk order, wtosc.c:135-144)
+enum EvKind { EV_WRITE = 0, EV_WAKE = 1, EV_INIT = 2, EV_START = 3, EV_STOP = 4, EV_PROC = 5, EV_SEED = 6 };
 
 // One active voice of a drop-in block: slot and its run of event records.
 struct VoiceRun { int slot; unsigned ev_begin, ev_count; };
@@ -45,7 +47,6 @@ struct RenderParams {
     const unsigned *ptab;
     const int16_t *fmsine;
     int samplerate;
-    unsigned *noise;          // per-voice LCG scratch [stride] (noise oscillators)
     // drop-in ("block") mode: thread i renders runs[i]; segments are the
     // host's explicit EV_PROC records and carry their own target bus
     const VoiceRun *runs;
@@ -80,10 +81,9 @@ __global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
     __syncthreads();
     const int home = s_home;
 
-    unsigned nstate = valid && P.noise ? P.noise[v] : 0u;
     Ctx c;
     c.waves = P.waves; c.pool = P.pool; c.ptab = P.ptab; c.fmsine = s_sine;
-    c.samplerate = P.samplerate; c.noisestate = &nstate;
+    c.samplerate = P.samplerate;
 
     CH ch;
     StatePtr sp{P.state + (valid ? v : 0), P.stride};
@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
                 case EV_INIT: ch.init_unit(c, unit, (int)e.z, e.x & 0xff); break;
                 case EV_START: alive = 1; break;
                 case EV_STOP: alive = 0; break;
+                case EV_SEED: ch.seed_unit(unit, e.z); break;
                 case EV_PROC: proc_n = (e.y >> 8) & 0xff; mybus = (int)e.z; break;
                 default: break;
                 }
@@ -189,7 +190,6 @@ __global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
         if (in_seg) ch.finish();
         sp.st(0, alive);
         ch.store(sp, 1);
-        if (P.noise) P.noise[v] = nstate;
     }
 }
 

@@ -44,6 +44,7 @@ SYMBOLS = {
     "a2cu_now": (_U64, [_VP]),
     "a2cu_set_root_wake_period": (_I, [_VP, C.c_uint32]),
     "a2cu_set_noiseseed": (_I, [_VP, C.c_uint32]),
+    "a2cu_set_noise_state_ptr": (_I, [_VP, C.POINTER(C.c_uint32)]),
     "a2cu_wave_builtin": (_I, [_VP, C.c_char_p]),
     "a2cu_wave_upload": (_I, [_VP, _I, _U, _U, _VP, _U]),
     "a2cu_wave_upload_prepared": (_I, [_VP, _I, _U, _U, _VP, _VP]),

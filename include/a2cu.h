@@ -104,6 +104,12 @@ int a2cu_set_root_wake_period(a2cu_engine *e, uint32_t period_24_8);
 
 /* Seed of the shared noise LCG (A2_PNOISESEED, src/properties.c:298). */
 int a2cu_set_noiseseed(a2cu_engine *e, uint32_t seed);
+/*
+ * Drop-in mode: use the host's own LCG word (st->noisestate, src/internals.h:
+ * 682) so the VM's RAND instructions and the noise oscillators keep sharing one
+ * sequence (src/core.c:1401-1409, src/units/wtosc.c:135-144).
+ */
+int a2cu_set_noise_state_ptr(a2cu_engine *e, uint32_t *state);
 
 /* ---- waves ----------------------------------------------------------- */
 

@@ -150,6 +150,7 @@ static A2_errors a2cu_OpenState(A2_config *cfg, void **statedata)
 			free(cx);
 			return A2_DEVICEOPEN;
 		}
+		a2cu_set_noise_state_ptr(cx->eng, &cx->st->noisestate);
 		cx->next = contexts;
 		contexts = cx;
 	}

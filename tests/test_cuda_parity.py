@@ -78,8 +78,9 @@ def test_linearity_of_bus():
     assert np.array_equal(whole, parts)
 
 
-@pytest.mark.xfail(reason="shared-LCG noise planner not implemented yet", strict=False)
 def test_noise_oscillator():
+    """Shared-LCG noise (wtosc.c:129-152): seeds come from the host planner in
+    tree-walk order; three noise voices + pitch ramps + a plain voice."""
     scn = CASES["noise"]()
     out = run_cuda(scn)
     ref = np.load(GOLDEN)["noise"]

@@ -16,8 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = os.path.join(HERE, "golden", "ref_outputs.npz")
 HARNESS = os.path.join(ao.REF_DIR, "a2render_cuda")
 
-# noise: the shared LCG needs the noise planner (not in the plug-in yet)
-DROPIN_CASES = [n for n in sorted(CASES) if n != "noise"]
+DROPIN_CASES = sorted(CASES)
 
 
 @pytest.mark.skipif(not os.path.exists(HARNESS), reason="drop-in harness not built")
@@ -28,6 +27,7 @@ def test_dropin_matches_reference(name, driver):
     out, info = ao.ref_render(os.path.join(HERE, "golden", name + ".a2s"), "Song",
                               samplerate=scn.samplerate, channels=scn.channels,
                               buffer=scn.buffer, frames=scn.frames,
+                              noiseseed=scn.noiseseed,
                               binary="a2render_cuda", driver=driver)
     assert info["rt_error"] == 0
     ref = np.load(GOLDEN)[name]
