@@ -39,12 +39,14 @@ struct WaveDesc {
     unsigned period;
     unsigned size[kMipLevels];      // excluding pads
     unsigned offset[kMipLevels];    // index of data[level][A2_WAVEPRE] in the pool
+    int coff[kMipLevels];           // index of sample 0's entry in the Hermite coefficient pool, -1: none
 };
 
 // Everything a unit needs besides its own state.
 struct Ctx {
     const WaveDesc *waves;
     const int16_t *pool;            // all wave data, int16, pads included
+    const int4 *cpool;              // two-stage Hermite coefficients {d0, a, b, c} per sample
     const unsigned *ptab;           // 64 x {base, coeff}, pitch.c:70-96
     const int16_t *fmsine;          // 2049-entry sine LUT (shared memory)
     int samplerate;
@@ -110,6 +112,16 @@ A2CU_DEV int hermite(const int16_t *d, unsigned ph) {
     int i = (int)(ph >> 8);
     return hermite4(d[i - 1], d[i], d[i + 1], d[i + 2], ph);
 }
+// a2_Hermite2 (a2_dsp.h:91-98) on precomputed a2_Hermite2c coefficients
+// (a2_dsp.h:83-89): term for term the same integers as a2_Hermite, but one
+// 16-byte load instead of four unaligned int16 loads.
+A2CU_DEV int hermite_cf(const int4 *cf, unsigned ph) {
+    const int4 e = __ldg(cf + (int)(ph >> 8));      // {d0, a, b, c}
+    int x = (int)((ph & 0xff) << 7);
+    int a = wmul(e.y, x) >> 15;
+    a = wmul(a + e.z, x) >> 15;
+    return e.x + (wmul(a + e.w, x) >> 15);
+}
 
 // pitch.c:57-67; the shift count is taken & 31 like the x86-64 build does
 A2CU_DEV unsigned p2i(const unsigned *ptab, int pitch) {
@@ -170,6 +182,7 @@ struct WtOsc {
     int mode;           // OscMode
     // segment-local
     const int16_t *d;
+    const int4 *cf;     // coefficient table of the current level or nullptr
     unsigned long long ph;
     unsigned dph;
     unsigned wsize;
@@ -185,7 +198,7 @@ struct WtOsc {
         int x = s.ld(w + 12);
         p_ramping = s.ld(w + 13);
         wave = x >> 8; mode = x & 0xff;
-        run = RUN_SILENT; astep = 0; mm = 0; d = nullptr; ph = 0; dph = 0; wsize = 0; nstate = 0;
+        run = RUN_SILENT; astep = 0; mm = 0; d = nullptr; cf = nullptr; ph = 0; dph = 0; wsize = 0; nstate = 0;
     }
     A2CU_DEV void store(const StatePtr &s, int w) const {
         s.st_ramp(w, p); s.st_ramp(w + 4, a);
@@ -286,6 +299,7 @@ struct WtOsc {
                 return;                 // out of range: muted
             }
             d = c.pool + w.offset[m];
+            cf = w.coff[m] >= 0 ? c.cpool + w.coff[m] : nullptr;
             run = RUN_TABLE; astep = a.delta; wsize = 0;
             return;
         }
@@ -295,6 +309,7 @@ struct WtOsc {
             unsigned long long dp = (unsigned long long)dphase * w.period;
             ramp_prepare(a, frames);
             d = c.pool + w.offset[0];
+            cf = w.coff[0] >= 0 ? c.cpool + w.coff[0] : nullptr;
             if (dp >> 32) {
                 phase += dp * (unsigned)frames;
                 ramp_run(a, frames);
@@ -333,7 +348,8 @@ struct WtOsc {
             if (live) {
                 unsigned p16 = (unsigned)(ph >> 16);
                 unsigned dp16 = dph >> 16;
-                int h = hermite(d, p16) + hermite(d, p16 + (dp16 >> 1));
+                int h = cf ? hermite_cf(cf, p16) + hermite_cf(cf, p16 + (dp16 >> 1))
+                           : hermite(d, p16) + hermite(d, p16 + (dp16 >> 1));
                 v = mulshr(h, a.value, 17);
                 ph += dph;
                 a.value = wadd(a.value, astep);
@@ -359,7 +375,8 @@ struct WtOsc {
     // overlap the two Hermite gathers of consecutive frames (wtosc.c:226-233).
     A2CU_DEV void sample_fast(const Ctx &, int &s0, int &s1, int &o0, int &o1) {
         unsigned p16 = (unsigned)(ph >> 16);
-        int h = hermite(d, p16) + hermite(d, p16 + (dph >> 17));
+        int h = cf ? hermite_cf(cf, p16) + hermite_cf(cf, p16 + (dph >> 17))
+                   : hermite(d, p16) + hermite(d, p16 + (dph >> 17));
         int v = mulshr(h, a.value, 17);
         ph += dph;
         a.value = wadd(a.value, astep);

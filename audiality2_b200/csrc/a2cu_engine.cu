@@ -22,6 +22,7 @@
 
 #include "../../include/a2cu.h"
 #include "a2cu_kernels.cuh"
+#include "a2cu_split.cuh"
 
 using namespace a2cu;
 
@@ -45,6 +46,8 @@ struct KernelEntry {
     render_fn fn;
     int words;      // incl. the flags word
     const char *name;
+    render_fn split_fn;     // warp-specialised variant (a2cu_split.cuh) or nullptr
+    size_t split_smem;
 };
 static std::map<std::string, KernelEntry> &registry() {
     static std::map<std::string, KernelEntry> r;
@@ -66,7 +69,17 @@ static void reg_chain(std::vector<a2cu_unitspec> specs, const char *name) {
     e.fn = render_bank<CH>;
     e.words = CH::kWords + 1;
     e.name = name;
+    e.split_fn = nullptr;
+    e.split_smem = 0;
     registry()[sig_of(specs.data(), (int)specs.size())] = e;
+}
+template <int NOSC, bool FILT>
+static void reg_split(std::vector<a2cu_unitspec> specs) {
+    KernelEntry &e = registry()[sig_of(specs.data(), (int)specs.size())];
+    e.split_fn = render_split<NOSC, FILT>;
+    e.split_smem = SplitLayout<NOSC, FILT>::bytes;
+    cudaFuncSetAttribute(render_split<NOSC, FILT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)SplitLayout<NOSC, FILT>::bytes);
 }
 
 // spec helpers: {kind, nin, nout, add, wireout}
@@ -122,6 +135,18 @@ static void register_all() {
     reg_chain<Chain<Fm2r, Pm12W>>({S_FM(A2CU_FM2R), S_PM12W}, "fm2r_panmix");
     reg_chain<Chain<Fm4r, Pm12W>>({S_FM(A2CU_FM4R), S_PM12W}, "fm4r_panmix");
     reg_chain<Chain<Fm2, Ws11, Pm12W>>({S_FM(A2CU_FM2), S_WS11, S_PM12W}, "fm2_waveshaper_panmix");
+}
+
+// Warp-specialised variants; needs a current device (function attributes).
+static void register_split() {
+    reg_split<1, false>({S_OSC0, S_PM12W});
+    reg_split<2, false>({S_OSC0, S_OSCA, S_PM12W});
+    reg_split<3, false>({S_OSC0, S_OSCA, S_OSCA, S_PM12W});
+    reg_split<4, false>({S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_PM12W});
+    reg_split<8, false>({S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_PM12W});
+    reg_split<1, true>({S_OSC0, S_F11, S_PM12W});
+    reg_split<2, true>({S_OSC0, S_OSCA, S_F11, S_PM12W});
+    reg_split<3, true>({S_OSC0, S_OSCA, S_OSCA, S_F11, S_PM12W});
 }
 
 // ---------------------------------------------------------------------------
@@ -271,6 +296,7 @@ struct Bank {
     uint4 *d_ev = nullptr;
     size_t ev_cap = 0;
     bool has_noise = false;
+    bool exotic = false;    // selected a noise / non-mip / table-less wave: render_bank only
     uint32_t stamp = 0;
     // drop-in ("block") mode: dynamic slots + per-flush recording
     bool dynamic = false;
@@ -303,7 +329,8 @@ struct a2cu_engine {
     bool waves_dirty = true;
     WaveDesc *d_waves = nullptr;
     int16_t *d_pool = nullptr;
-    size_t pool_cap = 0, waves_cap = 0;
+    int4 *d_cpool = nullptr;
+    size_t pool_cap = 0, waves_cap = 0, cpool_cap = 0;
     unsigned *d_ptab = nullptr;
     int16_t *d_fmsine = nullptr;
     std::vector<Bank *> banks;
@@ -334,6 +361,8 @@ struct a2cu_engine {
     std::map<uint64_t, VoiceMirror> mirrors;    // key: bank << 32 | slot
     uint32_t *noise_ptr = nullptr;              // shared LCG (host's st->noisestate in drop-in mode)
     uint32_t stamp = 0;                         // creation order (tree-walk order is newest first)
+    bool use_split = true;                      // allow render_split where eligible
+    uint64_t split_launches = 0;
     std::vector<uint32_t> gstamp;
     // drop-in ("block") mode
     std::vector<BusCmd> buscmds;
@@ -531,16 +560,37 @@ static int upload_waves(a2cu_engine *e) {
         for (int l = 0; l < kMipLevels; ++l) total += w.data[l].size();
     std::vector<WaveDesc> desc(e->waves.size());
     std::vector<int16_t> pool(total ? total : 1);
+    // Two-stage Hermite coefficients (a2_Hermite2c, a2_dsp.h:83-89) for every
+    // sample position the oscillator can address: i in [0, size + kPost - 3].
+    // 16 bytes per sample, so only waves up to kCoefMaxSamples get a table;
+    // longer (sampled) waves are interpolated from the raw int16 data.
+    const size_t kCoefMaxSamples = 1u << 20;
+    std::vector<int4> cpool;
     size_t pos = 0;
     for (size_t i = 0; i < e->waves.size(); ++i) {
         HostWave &w = e->waves[i];
         desc[i].type = w.type; desc[i].flags = w.flags; desc[i].period = w.period;
+        size_t wave_total = 0;
+        for (int l = 0; l < kMipLevels; ++l) wave_total += w.data[l].size();
         for (int l = 0; l < kMipLevels; ++l) {
             desc[i].size[l] = w.size[l];
             desc[i].offset[l] = (unsigned)(pos + kWavePre);
+            desc[i].coff[l] = -1;
             if (!w.data[l].empty()) {
                 std::copy(w.data[l].begin(), w.data[l].end(), pool.begin() + pos);
                 pos += w.data[l].size();
+                if (wave_total <= kCoefMaxSamples) {
+                    const int16_t *d = w.data[l].data() + kWavePre;
+                    int n = (int)w.size[l] + kPost - 2;
+                    desc[i].coff[l] = (int)cpool.size();
+                    for (int k = 0; k < n; ++k) {
+                        int dm = d[k - 1], d0 = d[k], d1 = d[k + 1], d2 = d[k + 2];
+                        int c = (d1 - dm) >> 1;
+                        int a = (3 * (d0 - d1) + d2 - dm) >> 1;
+                        int b = dm - d0 + c - a;
+                        cpool.push_back(make_int4(d0, a, b, c));
+                    }
+                }
             }
         }
     }
@@ -555,6 +605,13 @@ static int upload_waves(a2cu_engine *e) {
         e->waves_cap = desc.size() * 2 + 8;
         CK(cudaMalloc(&e->d_waves, e->waves_cap * sizeof(WaveDesc)));
     }
+    if (cpool.size() > e->cpool_cap) {
+        if (e->d_cpool) cudaFree(e->d_cpool);
+        e->cpool_cap = cpool.size() * 2;
+        CK(cudaMalloc(&e->d_cpool, e->cpool_cap * sizeof(int4)));
+    }
+    if (!cpool.empty())
+        CK(cudaMemcpy(e->d_cpool, cpool.data(), cpool.size() * sizeof(int4), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(e->d_pool, pool.data(), pool.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
     if (!desc.empty())
         CK(cudaMemcpy(e->d_waves, desc.data(), desc.size() * sizeof(WaveDesc), cudaMemcpyHostToDevice));
@@ -580,7 +637,9 @@ a2cu_engine *a2cu_open(int device, int samplerate, int channels) {
         fail(A2CU_ENODEVICE, "cudaSetDevice failed%s", "");
         return nullptr;
     }
+    register_split();
     a2cu_engine *e = new a2cu_engine();
+    e->use_split = getenv("A2CU_NO_SPLIT") == nullptr;
     e->noise_ptr = &e->noiseseed;
     e->device = device;
     e->samplerate = samplerate;
@@ -616,7 +675,7 @@ void a2cu_close(a2cu_engine *e) {
         cudaFree(b->d_evoff); cudaFree(b->d_ev); cudaFree(b->d_runs);
         delete b;
     }
-    cudaFree(e->d_waves); cudaFree(e->d_pool); cudaFree(e->d_ptab); cudaFree(e->d_fmsine);
+    cudaFree(e->d_waves); cudaFree(e->d_pool); cudaFree(e->d_cpool); cudaFree(e->d_ptab); cudaFree(e->d_fmsine);
     cudaFree(e->d_gstate); cudaFree(e->d_rstate); cudaFree(e->d_mixev);
     cudaFree(e->d_acc); cudaFree(e->d_master);
     cudaFree(e->d_buscmds); cudaFree(e->d_bacc); cudaFree(e->d_pmstate);
@@ -645,6 +704,8 @@ int a2cu_set_noise_state_ptr(a2cu_engine *e, uint32_t *p) {
     return A2CU_OK;
 }
 uint64_t a2cu_launch_count(const a2cu_engine *e) { return e->launches; }
+uint64_t a2cu_split_launch_count(const a2cu_engine *e) { return e->split_launches; }
+int a2cu_set_split(a2cu_engine *e, int on) { e->use_split = on != 0; return A2CU_OK; }
 uint64_t a2cu_h2d_bytes(const a2cu_engine *e) { return e->h2d_bytes; }
 uint64_t a2cu_d2h_bytes(const a2cu_engine *e) { return e->d2h_bytes; }
 int a2cu_set_timing(a2cu_engine *e, int on) { e->timing = on != 0; return A2CU_OK; }
@@ -902,6 +963,12 @@ static int cook_write(a2cu_engine *e, Bank *b, int voice, int unit, int reg, int
     Cooked c[2];
     int n = cook(e, b->chain[unit].kind, reg, value, (int)(when & 0xff), dur, b->transpose[voice], c);
     if (n < 0) return n;
+    if (b->chain[unit].kind == A2CU_WTOSC && c[0].reg == 0 && c[0].value >= 0) {
+        const HostWave &hw = e->waves[c[0].value];
+        size_t total = 0;
+        for (int l = 0; l < kMipLevels; ++l) total += hw.data[l].size();
+        if (hw.type != A2CU_WMIPWAVE || total > ((size_t)1 << 20)) b->exotic = true;
+    }
     for (int i = 0; i < n; ++i) push_event(b, when, voice, EV_WRITE, unit, c[i].reg, c[i].value, c[i].dur);
     return A2CU_OK;
 }
@@ -1187,7 +1254,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         P.bus_of = b->d_bus; P.acc = e->d_acc; P.W = W; P.buffer = (int)buffer;
         P.nsplits = nsplits;
         for (int i = 0; i < nsplits; ++i) P.splits[i] = splits[i];
-        P.waves = e->d_waves; P.pool = e->d_pool; P.ptab = e->d_ptab; P.fmsine = e->d_fmsine;
+        P.waves = e->d_waves; P.pool = e->d_pool; P.cpool = e->d_cpool; P.ptab = e->d_ptab; P.fmsine = e->d_fmsine;
         P.samplerate = e->samplerate;
         if (!due[bi].empty()) {
             size_t nev = due[bi].size();
@@ -1222,8 +1289,33 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     if (e->timing) CK(cudaEventRecord(e->ev0, e->stream));
     for (size_t bi = 0; bi < e->banks.size(); ++bi) {
         Bank *b = e->banks[bi];
-        int grid = (b->nvoices + kThreads - 1) / kThreads;
-        b->k.fn<<<grid, kThreads, 0, e->stream>>>(params[bi]);
+        if (b->dynamic || !b->nvoices) continue;
+        bool split = e->use_split && b->k.split_fn && !b->exotic && nsplits <= 1;
+        if (split && (!due[bi].empty() || nsplits)) {
+            // at most kSplitSegs segments per voice and fragment
+            auto frag_start = [&](int f) { int pos = f % (int)buffer; return f - pos + (pos / kMaxFrag) * kMaxFrag; };
+            int split_frag = nsplits ? frag_start(splits[0]) : -1;
+            if (nsplits && splits[0] == split_frag) split_frag = -1;    // on a fragment boundary: no extra cut
+            int cur_voice = -1, cur_frag = -1, cnt = 0, last = -1;
+            for (const HostEvent &ev : due[bi]) {
+                int f = (int)((ev.time - t0) >> 8);
+                int fs = frag_start(f);
+                if (ev.voice != cur_voice || fs != cur_frag) {
+                    cur_voice = ev.voice; cur_frag = fs; last = -1;
+                    cnt = (fs == split_frag) ? 1 : 0;
+                }
+                if (f != fs && f != last && !(fs == split_frag && f == splits[0])) { ++cnt; last = f; }
+                if (cnt > kSplitSegs - 1) { split = false; break; }
+            }
+        }
+        if (split) {
+            int grid = (b->nvoices + 31) / 32;
+            b->k.split_fn<<<grid, kSplitThreads, b->k.split_smem, e->stream>>>(params[bi]);
+            ++e->split_launches;
+        } else {
+            int grid = (b->nvoices + kThreads - 1) / kThreads;
+            b->k.fn<<<grid, kThreads, 0, e->stream>>>(params[bi]);
+        }
         ++e->launches;
     }
     if (e->timing) CK(cudaEventRecord(e->ev1, e->stream));
@@ -1625,7 +1717,7 @@ int a2cu_block_flush(a2cu_engine *e) {
         memset(&P, 0, sizeof(P));
         P.state = b->d_state; P.stride = b->stride; P.nvoices = (int)nr;
         P.acc = e->d_bacc; P.W = kMaxFrag; P.buffer = kMaxFrag;
-        P.waves = e->d_waves; P.pool = e->d_pool; P.ptab = e->d_ptab; P.fmsine = e->d_fmsine;
+        P.waves = e->d_waves; P.pool = e->d_pool; P.cpool = e->d_cpool; P.ptab = e->d_ptab; P.fmsine = e->d_fmsine;
         P.samplerate = e->samplerate;
         P.ev = b->d_ev; P.runs = b->d_runs; P.explicit_ = 1;
         int grid = ((int)nr + kThreads - 1) / kThreads;

@@ -44,6 +44,7 @@ struct RenderParams {
     int splits[kMaxSplits];   // forced split frames (root wake-ups / writes)
     const WaveDesc *waves;
     const int16_t *pool;
+    const int4 *cpool;
     const unsigned *ptab;
     const int16_t *fmsine;
     int samplerate;
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
     const int home = s_home;
 
     Ctx c;
-    c.waves = P.waves; c.pool = P.pool; c.ptab = P.ptab; c.fmsine = s_sine;
+    c.waves = P.waves; c.pool = P.pool; c.cpool = P.cpool; c.ptab = P.ptab; c.fmsine = s_sine;
     c.samplerate = P.samplerate;
 
     CH ch;

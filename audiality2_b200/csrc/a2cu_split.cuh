@@ -1,0 +1,359 @@
+// a2cu_split.cuh - warp-specialised render kernel for wavetable voices.
+//
+// render_bank (a2cu_kernels.cuh) gives every voice one thread that walks the
+// window frame by frame. With a few thousand voices that leaves most of the
+// chip idle: 4 096 voices are 128 warps on 592 schedulers, each warp issuing a
+// dependent instruction every ~4 cycles. But only the filter12 recurrence is
+// truly serial in time. Inside one Process() segment
+//
+//   wtosc   sample k = Hermite(table, ph0 + k*dph) * (a0 + k*astep)   (closed form)
+//   panmix  gains at k = vol0 + k*vstep, pan0 + k*pstep                (closed form)
+//
+// (a2_RunRamper and "ph += dph" are exact modular recurrences, wtosc.c:231-232,
+// a2_dsp.h:152-155), so those two stages are evaluated per FRAME by helper
+// warps while one warp per 32 voices runs the control-rate code and another the
+// filter recurrence. One CTA = 32 voices (lane = voice everywhere, so the SoA
+// state stays coalesced and the bus reduce stays a warp redux.sync):
+//
+//   warp 0      control: events, per-segment prologues (the same unit code as
+//               render_bank: WtOsc/Filter12/PanMix ::write/prepare/finish),
+//               publishes per-segment parameters, advances state in closed form
+//   warp 1      serial: filter12 recurrence (filter12.c:97-118), frame by frame
+//   warps 2..   stage A: oscillator samples   -> tile A   (frames sliced)
+//               stage C: panmix + bus reduce  <- tile A/B (frames sliced)
+//
+// The stages form a software pipeline over the window's fragments (ring of 4
+// fragment slots in shared memory, one __syncthreads per fragment):
+//   iteration i:  control(i)  stageA(i-1)  serial(i-2)  stageC(i-3)
+//
+// Eligibility is decided by the host per launch (a2cu_engine.cu): at most
+// kSplitSegs segments per voice and fragment, only waves with a coefficient
+// table, no noise / non-mipmapped waves in the bank. Otherwise render_bank runs
+// on the same state layout. Results are bit-identical (tests).
+#pragma once
+#include "a2cu_kernels.cuh"
+
+namespace a2cu {
+
+constexpr int kSplitSegs = 2;
+constexpr int kRing = 4;
+constexpr int kHelpers = 6;
+constexpr int kSplitThreads = 32 * (2 + kHelpers);
+constexpr int kSlice = (kMaxFrag + kHelpers - 1) / kHelpers;    // frames per helper warp
+
+typedef WtOsc<true, false> SOsc;
+typedef Filter12<1, false, false> SFilt;
+typedef PanMix<1, 2, true, true> SPan;
+
+template <int NOSC, bool FILT>
+struct SplitLayout {
+    // int offsets into dynamic shared memory
+    static constexpr int oscp = 0;                                           // [ring][seg][osc][6][32]
+    static constexpr int fp = oscp + kRing * kSplitSegs * NOSC * 6 * 32;     // [ring][seg][7][32]
+    static constexpr int pmp = fp + (FILT ? kRing * kSplitSegs * 7 * 32 : 0);  // [ring][seg][5][32]
+    static constexpr int split = pmp + kRing * kSplitSegs * 5 * 32;          // [ring][32]
+    static constexpr int flags = split + kRing * 32;                         // [ring][32]
+    static constexpr int meta = flags + kRing * 32;                          // [ring][2]: f0, n
+    static constexpr int tileA = meta + kRing * 2 + 6;                       // [ring][64][32]
+    static constexpr int tileB = tileA + kRing * kMaxFrag * 32;              // [ring][64][32] (FILT)
+    static constexpr int total = tileB + (FILT ? kRing * kMaxFrag * 32 : 0);
+    static constexpr size_t bytes = (size_t)total * sizeof(int);
+    static constexpr int words = 1 + 14 * NOSC + (FILT ? 14 : 0) + 8;       // state words per voice
+    static constexpr int filt_w = 1 + 14 * NOSC;                             // first word of filter12
+    static constexpr int pm_w = filt_w + (FILT ? 14 : 0);
+};
+
+template <int NOSC, bool FILT>
+__global__ void __launch_bounds__(kSplitThreads) render_split(const RenderParams P) {
+    typedef SplitLayout<NOSC, FILT> L;
+    extern __shared__ int sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int v = blockIdx.x * 32 + lane;
+    const bool valid = v < P.nvoices;
+    const int W = P.W;
+
+    int nfrag = 0;
+    for (int f = 0; f < W; f = frag_end(f, P.buffer, W)) ++nfrag;
+    const int mybus = valid ? P.bus_of[v] : -1;
+    const int home = __shfl_sync(0xffffffffu, mybus, 0);
+
+    Ctx c;
+    c.waves = P.waves; c.pool = P.pool; c.cpool = P.cpool; c.ptab = P.ptab; c.fmsine = nullptr;
+    c.samplerate = P.samplerate;
+    StatePtr sp{P.state + (valid ? v : 0), P.stride};
+
+    // ---- control warp state ----
+    SOsc osc[NOSC];
+    SFilt filt;
+    SPan pm;
+    int alive = 0;
+    unsigned evp = 0, eve = 0;
+    int next_ev = 0x7fffffff, seg_end = 0;
+    bool in_seg = false;
+    int cf0 = 0;
+    // ---- serial warp state ----
+    int d1 = 0, d2 = 0;
+
+    if (warp == 0 && valid) {
+        alive = sp.ld(0) & 1;
+#pragma unroll
+        for (int i = 0; i < NOSC; ++i) osc[i].load(sp, 1 + 14 * i);
+        if (FILT) filt.load(sp, L::filt_w);
+        pm.load(sp, L::pm_w);
+        if (P.ev_off) { evp = P.ev_off[v]; eve = P.ev_off[v + 1]; }
+        next_ev = evp < eve ? (int)(P.ev[evp].x >> 8) : 0x7fffffff;
+    }
+    if (FILT && warp == 1 && valid) {
+        d1 = sp.ld(L::filt_w + 12);
+        d2 = sp.ld(L::filt_w + 13);
+    }
+
+    const int lag_c = FILT ? 3 : 2;     // stage C runs this many iterations behind control
+    for (int it = 0; it < nfrag + lag_c; ++it) {
+        // ================= control(it) =================
+        if (warp == 0 && it < nfrag) {
+            const int slot = it % kRing;
+            const int f0 = cf0;
+            const int fe = frag_end(f0, P.buffer, W);
+            int split = fe - f0, flags = 0;
+            if (valid) {
+                int f = f0, seg = 0;
+                while (f < fe) {
+                    // ---- segment boundary: identical to render_bank ----
+                    if (in_seg) {
+#pragma unroll
+                        for (int i = 0; i < NOSC; ++i) osc[i].finish();
+                        if (FILT) filt.finish();
+                        pm.finish();
+                    }
+                    while (next_ev <= f) {
+                        const uint4 e = P.ev[evp];
+                        const int kind = e.y & 0xff, unit = (e.y >> 8) & 0xff, reg = (e.y >> 16) & 0xff;
+                        const int st = (int)(e.x & 0xff);
+                        if (kind == EV_WRITE || kind == EV_INIT) {
+                            const bool init = kind == EV_INIT;
+#pragma unroll
+                            for (int i = 0; i < NOSC; ++i)
+                                if (unit == i) {
+                                    if (init) osc[i].init(c, (int)e.z, (unsigned)st);
+                                    else osc[i].write(c, reg, (int)e.z, st, (int)e.w);
+                                }
+                            if (FILT && unit == NOSC) {
+                                if (init) filt.init(c, (int)e.z, (unsigned)st);
+                                else filt.write(c, reg, (int)e.z, st, (int)e.w);
+                            }
+                            if (unit == NOSC + (FILT ? 1 : 0)) {
+                                if (init) pm.init(c, (int)e.z, (unsigned)st);
+                                else pm.write(c, reg, (int)e.z, st, (int)e.w);
+                            }
+                        } else if (kind == EV_START) alive = 1;
+                        else if (kind == EV_STOP) alive = 0;
+                        ++evp;
+                        next_ev = evp < eve ? (int)(P.ev[evp].x >> 8) : 0x7fffffff;
+                    }
+                    int nxt = min(fe, next_ev);
+                    for (int k = 0; k < P.nsplits; ++k)
+                        if (P.splits[k] > f) nxt = min(nxt, P.splits[k]);
+                    seg_end = nxt;
+                    in_seg = alive != 0;
+                    const int n = nxt - f;
+                    if (in_seg) {
+#pragma unroll
+                        for (int i = 0; i < NOSC; ++i) osc[i].prepare(c, n);
+                        if (FILT) filt.prepare(c, n);
+                        pm.prepare(c, n);
+                    }
+                    // ---- publish the segment, advance in closed form ----
+                    if (seg < kSplitSegs) {
+                        if (in_seg) flags |= 1 << seg;
+                        const int sb = (slot * kSplitSegs + seg);
+#pragma unroll
+                        for (int i = 0; i < NOSC; ++i) {
+                            int *q = sm + L::oscp + ((sb * NOSC + i) * 6) * 32 + lane;
+                            const bool live = in_seg && osc[i].run == RUN_TABLE && osc[i].cf;
+                            q[0] = live ? (int)(osc[i].cf - c.cpool) : -1;
+                            q[32] = (int)(unsigned)osc[i].ph;
+                            q[64] = (int)(unsigned)(osc[i].ph >> 32);
+                            q[96] = (int)osc[i].dph;
+                            q[128] = osc[i].a.value;
+                            q[160] = osc[i].astep;
+                            if (live) {     // wtosc.c:231-232 over n frames
+                                osc[i].ph += (unsigned long long)osc[i].dph * (unsigned)n;
+                                osc[i].a.value = wadd(osc[i].a.value, wmul(osc[i].astep, n));
+                            }
+                        }
+                        if (FILT) {
+                            int *q = sm + L::fp + (sb * 7) * 32 + lane;
+                            q[0] = filt.f0; q[32] = filt.df; q[64] = filt.q.value; q[96] = filt.qstep;
+                            q[128] = filt.lp; q[160] = filt.bp; q[192] = filt.hp;
+                            if (in_seg) filt.q.value = wadd(filt.q.value, wmul(filt.qstep, n));
+                        }
+                        {
+                            int *q = sm + L::pmp + (sb * 5) * 32 + lane;
+                            q[0] = pm.vol.value; q[32] = pm.vstep; q[64] = pm.pan.value; q[96] = pm.pstep;
+                            q[128] = pm.clamp ? 1 : 0;
+                            if (in_seg) {
+                                pm.vol.value = wadd(pm.vol.value, wmul(pm.vstep, n));
+                                pm.pan.value = wadd(pm.pan.value, wmul(pm.pstep, n));
+                            }
+                        }
+                        if (seg == 0) split = nxt - f0;
+                    }
+                    f = nxt;
+                    ++seg;
+                }
+            }
+            sm[L::split + slot * 32 + lane] = split;
+            sm[L::flags + slot * 32 + lane] = flags;
+            if (lane == 0) { sm[L::meta + slot * 2] = f0; sm[L::meta + slot * 2 + 1] = fe - f0; }
+            cf0 = fe;
+        }
+        // ================= serial(it - 2): filter12 recurrence =================
+        if (FILT && warp == 1 && it >= 2 && it - 2 < nfrag) {
+            const int slot = (it - 2) % kRing;
+            const int n = sm[L::meta + slot * 2 + 1];
+            const int split = sm[L::split + slot * 32 + lane];
+            const int flags = sm[L::flags + slot * 32 + lane];
+            const int *ta = sm + L::tileA + slot * kMaxFrag * 32 + lane;
+            int *tb = sm + L::tileB + slot * kMaxFrag * 32 + lane;
+            for (int seg = 0; seg < kSplitSegs; ++seg) {
+                const int a = seg ? split : 0, b = seg ? n : min(split, n);
+                if (a >= b) continue;
+                if (!((flags >> seg) & 1)) continue;    // inactive: state frozen, output unused
+                const int *q = sm + L::fp + ((slot * kSplitSegs + seg) * 7) * 32 + lane;
+                int f0v = q[0];
+                const int df = q[32];
+                int qv = q[64];
+                const int qstep = q[96], lp = q[128], bp = q[160], hp = q[192];
+#pragma unroll 4
+                for (int f = a; f < b; ++f) {           // filter12.c:97-118
+                    const int fc = f0v >> 12, qq = qv >> 12;
+                    const int in = ta[f * 32];
+                    const int d1s = d1 >> 4;
+                    const int l = wadd(d2, wmul(fc, d1s) >> 8);
+                    const int h = wsub(wsub(in >> 5, l), wmul(qq, d1s) >> 8);
+                    const int bb = wadd(wmul(fc, h >> 4) >> 8, d1);
+                    tb[f * 32] = wadd(wadd(wmul(l, lp), wmul(bb, bp)), wmul(h, hp)) >> 3;
+                    d1 = bb; d2 = l;
+                    f0v = wadd(f0v, df);
+                    qv = wadd(qv, qstep);
+                }
+            }
+        }
+        // ================= helpers: stageA(it - 1), stageC(it - lag_c) =================
+        if (warp >= 2) {
+            const int h = warp - 2;
+            if (it >= 1 && it - 1 < nfrag) {
+                const int slot = (it - 1) % kRing;
+                const int n = sm[L::meta + slot * 2 + 1];
+                const int split = sm[L::split + slot * 32 + lane];
+                const int flags = sm[L::flags + slot * 32 + lane];
+                int *ta = sm + L::tileA + slot * kMaxFrag * 32 + lane;
+                const int s0 = h * kSlice, s1 = min(n, s0 + kSlice);
+                for (int seg = 0; seg < kSplitSegs; ++seg) {
+                    const int sa = seg ? split : 0;
+                    const int a = max(s0, sa), b = min(s1, seg ? n : split);
+                    if (a >= b) continue;
+                    if (!((flags >> seg) & 1)) {
+                        for (int f = a; f < b; ++f) ta[f * 32] = 0;
+                        continue;
+                    }
+                    int acc[kSlice];
+#pragma unroll
+                    for (int k = 0; k < kSlice; ++k) acc[k] = 0;
+#pragma unroll
+                    for (int i = 0; i < NOSC; ++i) {
+                        const int *q = sm + L::oscp + (((slot * kSplitSegs + seg) * NOSC + i) * 6) * 32 + lane;
+                        const int cfo = q[0];
+                        if (cfo < 0) continue;          // silent segment of this oscillator
+                        const int4 *cf = c.cpool + cfo;
+                        const unsigned dph = (unsigned)q[96];
+                        unsigned long long ph = ((unsigned long long)(unsigned)q[64] << 32) | (unsigned)q[32];
+                        ph += (unsigned long long)dph * (unsigned)(a - sa);
+                        const int astep = q[160];
+                        int av = wadd(q[128], wmul(astep, a - sa));
+                        const unsigned half = dph >> 17;
+#pragma unroll
+                        for (int k = 0; k < kSlice; ++k) {
+                            if (a + k < b) {            // wtosc.c:226-233
+                                const unsigned p16 = (unsigned)(ph >> 16);
+                                const int hv = hermite_cf(cf, p16) + hermite_cf(cf, p16 + half);
+                                acc[k] = wadd(acc[k], mulshr(hv, av, 17));
+                                ph += dph;
+                                av = wadd(av, astep);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < kSlice; ++k)
+                        if (a + k < b) ta[(a + k) * 32] = acc[k];
+                }
+            }
+            if (it >= lag_c && it - lag_c < nfrag) {
+                const int slot = (it - lag_c) % kRing;
+                const int f0 = sm[L::meta + slot * 2];
+                const int n = sm[L::meta + slot * 2 + 1];
+                const int split = sm[L::split + slot * 32 + lane];
+                const int flags = sm[L::flags + slot * 32 + lane];
+                const int *tin = sm + (FILT ? L::tileB : L::tileA) + slot * kMaxFrag * 32 + lane;
+                const int s0 = h * kSlice, s1 = min(n, s0 + kSlice);
+                const bool athome = mybus == home;
+                for (int f = s0; f < s1; ++f) {
+                    const int seg = f >= split ? 1 : 0;
+                    int o0 = 0, o1 = 0;
+                    const bool act = (flags >> seg) & 1;
+                    if (act) {                          // panmix.c:78-115
+                        const int *q = sm + L::pmp + ((slot * kSplitSegs + seg) * 5) * 32 + lane;
+                        const int k = f - (seg ? split : 0);
+                        const int vol = wadd(q[0], wmul(q[32], k));
+                        const int pan = wadd(q[64], wmul(q[96], k));
+                        const int vp = mulshr(pan, vol, 24);
+                        int v0 = wsub(vol, vp), v1 = wadd(vol, vp);
+                        if (q[128]) {
+                            const int lim = (int)((unsigned)vol << 1);
+                            if (v0 > lim) v0 = lim;
+                            if (v1 > lim) v1 = lim;
+                        }
+                        const int in = tin[f * 32];
+                        o0 = mulshr(in, v0, 24);
+                        o1 = mulshr(in, v1, 24);
+                    }
+                    const int h0 = __reduce_add_sync(0xffffffffu, athome ? o0 : 0);
+                    const int h1 = __reduce_add_sync(0xffffffffu, athome ? o1 : 0);
+                    if (lane == 0 && home >= 0 && (h0 | h1)) {
+                        int *a = P.acc + ((size_t)home * W + f0 + f) * 2;
+                        if (h0) atomicAdd(a, h0);
+                        if (h1) atomicAdd(a + 1, h1);
+                    }
+                    if (valid && !athome && act) {
+                        int *a = P.acc + ((size_t)mybus * W + f0 + f) * 2;
+                        atomicAdd(a, o0);
+                        atomicAdd(a + 1, o1);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    if (warp == 0 && valid) {
+        if (in_seg) {
+#pragma unroll
+            for (int i = 0; i < NOSC; ++i) osc[i].finish();
+            if (FILT) filt.finish();
+            pm.finish();
+        }
+        sp.st(0, alive);
+#pragma unroll
+        for (int i = 0; i < NOSC; ++i) osc[i].store(sp, 1 + 14 * i);
+        if (FILT) filt.store(sp, L::filt_w);
+        pm.store(sp, L::pm_w);
+    }
+    __syncthreads();
+    if (FILT && warp == 1 && valid) {       // the recurrence state lives in the serial warp
+        sp.st(L::filt_w + 12, d1);
+        sp.st(L::filt_w + 13, d2);
+    }
+}
+
+}  // namespace a2cu

@@ -66,6 +66,8 @@ SYMBOLS = {
     "a2cu_set_post_root_stage": (_I, [_VP, _I]),
     "a2cu_apply_root_stage": (_I, [_VP, _VP, _VP, _U, _U, _U64]),
     "a2cu_launch_count": (_U64, [_VP]),
+    "a2cu_split_launch_count": (_U64, [_VP]),
+    "a2cu_set_split": (_I, [_VP, _I]),
     "a2cu_bank_kernel_name": (C.c_char_p, [_VP, _I]),
     "a2cu_bank_state_bytes": (_I, [_VP, _I]),
     "a2cu_last_render_ms": (C.c_float, [_VP]),
@@ -157,6 +159,13 @@ class Engine:
     @property
     def launches(self):
         return self.L.a2cu_launch_count(self.h)
+
+    @property
+    def split_launches(self):
+        return self.L.a2cu_split_launch_count(self.h)
+
+    def set_split(self, on):
+        self._ck(self.L.a2cu_set_split(self.h, int(on)))
 
     def set_stream(self, cuda_stream):
         self._ck(self.L.a2cu_set_stream(self.h, cuda_stream))

@@ -208,6 +208,14 @@ int a2cu_apply_root_stage(a2cu_engine *e, const int32_t *dev_rootbus,
 
 /* Kernel launches issued by this engine so far (bench's gpu_launches). */
 uint64_t a2cu_launch_count(const a2cu_engine *e);
+/*
+ * Wavetable voice structures have a second, warp-specialised kernel
+ * (render_split, csrc/a2cu_split.cuh) that the engine picks per launch when
+ * the window qualifies; a2cu_set_split(e, 0) forces the one-thread-per-voice
+ * kernel (same results, used for A/B tests). Also: env A2CU_NO_SPLIT.
+ */
+int a2cu_set_split(a2cu_engine *e, int enabled);
+uint64_t a2cu_split_launch_count(const a2cu_engine *e);
 /* Name of the render kernel a bank uses (for profiles/). */
 const char *a2cu_bank_kernel_name(a2cu_engine *e, int bank);
 /* Bytes of per-voice state a bank keeps in HBM (roofline arithmetic). */

@@ -359,13 +359,16 @@ def run_oracle(scn):
     return out
 
 
-def run_cuda(scn, window=None):
+def run_cuda(scn, window=None, split=True, stats=None):
     """Render `scn` with the CUDA engine through its C ABI (ctypes).
-    window: frames per a2cu_run call (multiple of scn.buffer), default all."""
+    window: frames per a2cu_run call (multiple of scn.buffer), default all.
+    split=False forces the one-thread-per-voice kernel (render_bank)."""
     from audiality2_b200 import engine as eng
     from oracle import a2oracle as ao
     e = eng.Engine(scn.samplerate, scn.channels)
     try:
+        if not split:
+            e.set_split(False)
         if scn.noiseseed is not None:
             e.set_noiseseed(scn.noiseseed)
         for w in scn.waves:
@@ -398,12 +401,17 @@ def run_cuda(scn, window=None):
                 e.root_write(int(ev["reg"]), int(ev["value"]), t, int(ev["dur"]))
             # root wake-ups (reg < 0) are the engine's own root_wake_period
         if window is None:
-            return e.run(scn.frames, scn.buffer)
-        parts, done = [], 0
-        while done < scn.frames:
-            n = min(window, scn.frames - done)
-            parts.append(e.run(n, scn.buffer))
-            done += n
-        return np.concatenate(parts, axis=0)
+            out = e.run(scn.frames, scn.buffer)
+        else:
+            parts, done = [], 0
+            while done < scn.frames:
+                n = min(window, scn.frames - done)
+                parts.append(e.run(n, scn.buffer))
+                done += n
+            out = np.concatenate(parts, axis=0)
+        if stats is not None:
+            stats["launches"] = e.launches
+            stats["split_launches"] = e.split_launches
+        return out
     finally:
         e.close()

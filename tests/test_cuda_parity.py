@@ -64,6 +64,20 @@ def test_fm_bank_1024():
     assert np.array_equal(out, ref), _diff(out, ref)
 
 
+@pytest.mark.parametrize("name", ["bank256", "bench_bank200", "additive8", "filter_sweep",
+                                  "osc_pan_ramps", "groups", "all_waves"])
+def test_split_kernel_equals_thread_per_voice_kernel(name):
+    """render_split (warp-specialised, closed-form oscillator/panmix stages)
+    and render_bank (one thread per voice) on the same state layout."""
+    scn = CASES[name]()
+    st = {}
+    a = run_cuda(scn, split=True, stats=st)
+    b = run_cuda(scn, split=False)
+    assert np.array_equal(a, b), _diff(a, b)
+    if name in ("bank256", "bench_bank200"):
+        assert st["split_launches"] > 0, "split kernel was expected to be eligible"
+
+
 def test_linearity_of_bus():
     """Size-independent property: the bus is an integer sum, so rendering two
     disjoint halves of a bank separately and adding equals rendering it whole
