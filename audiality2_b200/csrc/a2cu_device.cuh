@@ -52,6 +52,27 @@ struct Ctx {
     int samplerate;
 };
 
+// Exact C-style (truncating) num / den for |num| < 2^52, den > 0: a double
+// estimate corrected with the integer remainder. Replaces the ~100-instruction
+// software s64 division in the ramper prologue (a2_dsp.h:137).
+A2CU_DEV long long div_trunc(long long num, int den) {
+    long long q = (long long)((double)num / (double)den);
+    long long r = num - q * den;
+    if (num >= 0) {
+        if (r < 0) --q; else if (r >= den) ++q;
+    } else {
+        if (r > 0) ++q; else if (r <= -(long long)den) --q;
+    }
+    return q;
+}
+// x % m, cheap when x < 2m (the usual case for a looped phase accumulator)
+A2CU_DEV unsigned long long wrap_mod(unsigned long long x, unsigned long long m) {
+    if (x < m) return x;
+    x -= m;
+    if (x < m) return x;
+    return x % m;
+}
+
 // ---- a2_dsp.h ---------------------------------------------------------------
 struct Ramp { int value, target, delta, timer; };
 
@@ -61,7 +82,7 @@ A2CU_DEV void ramp_prepare(Ramp &r, int frames) {
         r.value = r.target;
         r.delta = 0;
     } else if (frames <= (r.timer >> 8)) {
-        r.delta = (int)(((long long)wsub(r.target, r.value) << 8) / r.timer);
+        r.delta = (int)div_trunc((long long)wsub(r.target, r.value) << 8, r.timer);
         r.timer -= frames << 8;
     } else {
         r.delta = wsub(r.target, r.value) / frames;
@@ -289,7 +310,7 @@ struct WtOsc {
             ph = phase >> m;
             dph = (unsigned)(((unsigned long long)dphase * w.period) >> m);
             if (w.flags & kLooped)
-                ph %= (unsigned long long)w.size[m] << 24;
+                ph = wrap_mod(ph, (unsigned long long)w.size[m] << 24);
             else if ((ph >> 24) > (unsigned long long)(w.size[m] + kWavePre))
                 return;                 // all played: silence, nothing advances
             if (dph > (unsigned)(kMaxPhInc << 16)) {

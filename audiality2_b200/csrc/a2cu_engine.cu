@@ -48,6 +48,7 @@ struct KernelEntry {
     const char *name;
     render_fn split_fn;     // warp-specialised variant (a2cu_split.cuh) or nullptr
     size_t split_smem;
+    int split_threads;
 };
 static std::map<std::string, KernelEntry> &registry() {
     static std::map<std::string, KernelEntry> r;
@@ -71,14 +72,16 @@ static void reg_chain(std::vector<a2cu_unitspec> specs, const char *name) {
     e.name = name;
     e.split_fn = nullptr;
     e.split_smem = 0;
+    e.split_threads = 0;
     registry()[sig_of(specs.data(), (int)specs.size())] = e;
 }
-template <int NOSC, bool FILT>
+template <int NOSC, bool FILT, int NA>
 static void reg_split(std::vector<a2cu_unitspec> specs) {
     KernelEntry &e = registry()[sig_of(specs.data(), (int)specs.size())];
-    e.split_fn = render_split<NOSC, FILT>;
+    e.split_fn = render_split<NOSC, FILT, NA>;
     e.split_smem = SplitLayout<NOSC, FILT>::bytes;
-    cudaFuncSetAttribute(render_split<NOSC, FILT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e.split_threads = SplitWarps<FILT, NA>::threads;
+    cudaFuncSetAttribute(render_split<NOSC, FILT, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)SplitLayout<NOSC, FILT>::bytes);
 }
 
@@ -139,14 +142,16 @@ static void register_all() {
 
 // Warp-specialised variants; needs a current device (function attributes).
 static void register_split() {
-    reg_split<1, false>({S_OSC0, S_PM12W});
-    reg_split<2, false>({S_OSC0, S_OSCA, S_PM12W});
-    reg_split<3, false>({S_OSC0, S_OSCA, S_OSCA, S_PM12W});
-    reg_split<4, false>({S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_PM12W});
-    reg_split<8, false>({S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_PM12W});
-    reg_split<1, true>({S_OSC0, S_F11, S_PM12W});
-    reg_split<2, true>({S_OSC0, S_OSCA, S_F11, S_PM12W});
-    reg_split<3, true>({S_OSC0, S_OSCA, S_OSCA, S_F11, S_PM12W});
+    // <oscillators, filter12, helper warps>: the control warp keeps the whole
+    // voice in registers, so wider voices get fewer warps per CTA
+    reg_split<1, false, 14>({S_OSC0, S_PM12W});
+    reg_split<2, false, 14>({S_OSC0, S_OSCA, S_PM12W});
+    reg_split<3, false, 10>({S_OSC0, S_OSCA, S_OSCA, S_PM12W});
+    reg_split<4, false, 10>({S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_PM12W});
+    reg_split<8, false, 6>({S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_PM12W});
+    reg_split<1, true, 14>({S_OSC0, S_F11, S_PM12W});
+    reg_split<2, true, 14>({S_OSC0, S_OSCA, S_F11, S_PM12W});
+    reg_split<3, true, 10>({S_OSC0, S_OSCA, S_OSCA, S_F11, S_PM12W});
 }
 
 // ---------------------------------------------------------------------------
@@ -362,6 +367,7 @@ struct a2cu_engine {
     uint32_t *noise_ptr = nullptr;              // shared LCG (host's st->noisestate in drop-in mode)
     uint32_t stamp = 0;                         // creation order (tree-walk order is newest first)
     bool use_split = true;                      // allow render_split where eligible
+    unsigned long long *d_prof = nullptr;       // render_split role counters (a2cu_split_profile)
     uint64_t split_launches = 0;
     std::vector<uint32_t> gstamp;
     // drop-in ("block") mode
@@ -605,6 +611,7 @@ static int upload_waves(a2cu_engine *e) {
         e->waves_cap = desc.size() * 2 + 8;
         CK(cudaMalloc(&e->d_waves, e->waves_cap * sizeof(WaveDesc)));
     }
+    for (int k = 0; k < 64; ++k) cpool.push_back(make_int4(0, 0, 0, 0));   // slack: render_split reads ahead
     if (cpool.size() > e->cpool_cap) {
         if (e->d_cpool) cudaFree(e->d_cpool);
         e->cpool_cap = cpool.size() * 2;
@@ -706,6 +713,20 @@ int a2cu_set_noise_state_ptr(a2cu_engine *e, uint32_t *p) {
 uint64_t a2cu_launch_count(const a2cu_engine *e) { return e->launches; }
 uint64_t a2cu_split_launch_count(const a2cu_engine *e) { return e->split_launches; }
 int a2cu_set_split(a2cu_engine *e, int on) { e->use_split = on != 0; return A2CU_OK; }
+int a2cu_split_profile(a2cu_engine *e, int enable, uint64_t out[8]) {
+    if (!e) return A2CU_EINVAL;
+    cudaSetDevice(e->device);
+    if (out && e->d_prof) {
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaMemcpy(out, e->d_prof, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    }
+    if (enable && !e->d_prof) {
+        CK(cudaMalloc(&e->d_prof, 8 * sizeof(uint64_t)));
+    }
+    if (e->d_prof) CK(cudaMemset(e->d_prof, 0, 8 * sizeof(uint64_t)));
+    if (!enable && e->d_prof) { cudaFree(e->d_prof); e->d_prof = nullptr; }
+    return A2CU_OK;
+}
 uint64_t a2cu_h2d_bytes(const a2cu_engine *e) { return e->h2d_bytes; }
 uint64_t a2cu_d2h_bytes(const a2cu_engine *e) { return e->d2h_bytes; }
 int a2cu_set_timing(a2cu_engine *e, int on) { e->timing = on != 0; return A2CU_OK; }
@@ -1309,8 +1330,9 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             }
         }
         if (split) {
+            params[bi].prof = e->d_prof;
             int grid = (b->nvoices + 31) / 32;
-            b->k.split_fn<<<grid, kSplitThreads, b->k.split_smem, e->stream>>>(params[bi]);
+            b->k.split_fn<<<grid, b->k.split_threads, b->k.split_smem, e->stream>>>(params[bi]);
             ++e->split_launches;
         } else {
             int grid = (b->nvoices + kThreads - 1) / kThreads;

@@ -52,6 +52,8 @@ struct RenderParams {
     // host's explicit EV_PROC records and carry their own target bus
     const VoiceRun *runs;
     int explicit_;
+    // optional per-role busy-cycle counters of render_split (debug/profiling)
+    unsigned long long *prof;
 };
 
 // End of the fragment that contains frame f: fragments restart at every driver

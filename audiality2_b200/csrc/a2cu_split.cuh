@@ -19,12 +19,15 @@
 //               render_bank: WtOsc/Filter12/PanMix ::write/prepare/finish),
 //               publishes per-segment parameters, advances state in closed form
 //   warp 1      serial: filter12 recurrence (filter12.c:97-118), frame by frame
-//   warps 2..   stage A: oscillator samples   -> tile A   (frames sliced)
-//               stage C: panmix + bus reduce  <- tile A/B (frames sliced)
+//   NH helpers  stage A: oscillator samples -> tile A; lane = voice, frames sliced
+//               stage C: panmix + bus sum <- tile A/B; lane = FRAME, each helper
+//               sums a few voices for 32 frames into a shared-memory bus
+//               (no cross-lane traffic); flushed with one coalesced atomic per
+//               frame and channel one iteration later (stage D)
 //
 // The stages form a software pipeline over the window's fragments (ring of 4
 // fragment slots in shared memory, one __syncthreads per fragment):
-//   iteration i:  control(i)  stageA(i-1)  serial(i-2)  stageC(i-3)
+//   iteration i:  control(i)  stageA(i-1)  serial(i-2)  stageC(i-3)  flush(i-4)
 //
 // Eligibility is decided by the host per launch (a2cu_engine.cu): at most
 // kSplitSegs segments per voice and fragment, only waves with a coefficient
@@ -37,9 +40,18 @@ namespace a2cu {
 
 constexpr int kSplitSegs = 2;
 constexpr int kRing = 4;
-constexpr int kHelpers = 6;
-constexpr int kSplitThreads = 32 * (2 + kHelpers);
-constexpr int kSlice = (kMaxFrag + kHelpers - 1) / kHelpers;    // frames per helper warp
+constexpr int kTileStride = 33;     // tile rows are voices; 33 keeps both access patterns conflict-free
+// Warp roles: 0 control, [1 serial if FILT], then NH helper warps. Every helper
+// runs a slice of stage A (lane = voice) and a part of stage C (lane = frame).
+template <bool FILT, int NH> struct SplitWarps {
+    static constexpr int serial = FILT ? 1 : -1;
+    static constexpr int c0 = FILT ? 2 : 1;                     // first helper warp
+    static constexpr int total = c0 + NH;
+    static constexpr int threads = total * 32;
+    static constexpr int slice = (kMaxFrag + NH - 1) / NH;      // stage A: frames per helper
+    static constexpr int groups = NH / 2;                       // stage C: voice groups (x 2 frame halves)
+    static constexpr int vpg = (32 + groups - 1) / groups;      // voices per group
+};
 
 typedef WtOsc<true, false> SOsc;
 typedef Filter12<1, false, false> SFilt;
@@ -54,18 +66,23 @@ struct SplitLayout {
     static constexpr int split = pmp + kRing * kSplitSegs * 5 * 32;          // [ring][32]
     static constexpr int flags = split + kRing * 32;                         // [ring][32]
     static constexpr int meta = flags + kRing * 32;                          // [ring][2]: f0, n
-    static constexpr int tileA = meta + kRing * 2 + 6;                       // [ring][64][32]
-    static constexpr int tileB = tileA + kRing * kMaxFrag * 32;              // [ring][64][32] (FILT)
-    static constexpr int total = tileB + (FILT ? kRing * kMaxFrag * 32 : 0);
+    static constexpr int bus = meta + kRing * 2;                             // [32] bus of each voice
+    static constexpr int sacc = bus + 32;                                    // [ring][64][2] home-bus sums
+    static constexpr int smeta = sacc + kRing * kMaxFrag * 2;                // [ring][2]: f0, n for the flush
+    static constexpr int tileA = smeta + kRing * 2;                          // [ring][64][33]
+    static constexpr int tileB = tileA + kRing * kMaxFrag * kTileStride;     // [ring][64][33] (FILT)
+    static constexpr int total = tileB + (FILT ? kRing * kMaxFrag * kTileStride : 0);
     static constexpr size_t bytes = (size_t)total * sizeof(int);
     static constexpr int words = 1 + 14 * NOSC + (FILT ? 14 : 0) + 8;       // state words per voice
     static constexpr int filt_w = 1 + 14 * NOSC;                             // first word of filter12
     static constexpr int pm_w = filt_w + (FILT ? 14 : 0);
 };
 
-template <int NOSC, bool FILT>
-__global__ void __launch_bounds__(kSplitThreads) render_split(const RenderParams P) {
+template <int NOSC, bool FILT, int NA>
+__global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(const RenderParams P) {
     typedef SplitLayout<NOSC, FILT> L;
+    typedef SplitWarps<FILT, NA> WR;
+    constexpr int kSlice = WR::slice;
     extern __shared__ int sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int v = blockIdx.x * 32 + lane;
@@ -76,6 +93,8 @@ __global__ void __launch_bounds__(kSplitThreads) render_split(const RenderParams
     for (int f = 0; f < W; f = frag_end(f, P.buffer, W)) ++nfrag;
     const int mybus = valid ? P.bus_of[v] : -1;
     const int home = __shfl_sync(0xffffffffu, mybus, 0);
+    if (warp == 0) sm[L::bus + lane] = mybus;
+    for (int i = tid; i < kRing * kMaxFrag * 2; i += WR::threads) sm[L::sacc + i] = 0;
 
     Ctx c;
     c.waves = P.waves; c.pool = P.pool; c.cpool = P.cpool; c.ptab = P.ptab; c.fmsine = nullptr;
@@ -103,13 +122,15 @@ __global__ void __launch_bounds__(kSplitThreads) render_split(const RenderParams
         if (P.ev_off) { evp = P.ev_off[v]; eve = P.ev_off[v + 1]; }
         next_ev = evp < eve ? (int)(P.ev[evp].x >> 8) : 0x7fffffff;
     }
-    if (FILT && warp == 1 && valid) {
+    if (FILT && warp == WR::serial && valid) {
         d1 = sp.ld(L::filt_w + 12);
         d2 = sp.ld(L::filt_w + 13);
     }
 
     const int lag_c = FILT ? 3 : 2;     // stage C runs this many iterations behind control
-    for (int it = 0; it < nfrag + lag_c; ++it) {
+    for (int it = 0; it < nfrag + lag_c + 1; ++it) {
+        long long t_begin = 0, t_mid = 0;
+        if (P.prof) t_begin = clock64();
         // ================= control(it) =================
         if (warp == 0 && it < nfrag) {
             const int slot = it % kRing;
@@ -209,13 +230,13 @@ __global__ void __launch_bounds__(kSplitThreads) render_split(const RenderParams
             cf0 = fe;
         }
         // ================= serial(it - 2): filter12 recurrence =================
-        if (FILT && warp == 1 && it >= 2 && it - 2 < nfrag) {
+        if (FILT && warp == WR::serial && it >= 2 && it - 2 < nfrag) {
             const int slot = (it - 2) % kRing;
             const int n = sm[L::meta + slot * 2 + 1];
             const int split = sm[L::split + slot * 32 + lane];
             const int flags = sm[L::flags + slot * 32 + lane];
-            const int *ta = sm + L::tileA + slot * kMaxFrag * 32 + lane;
-            int *tb = sm + L::tileB + slot * kMaxFrag * 32 + lane;
+            const int *ta = sm + L::tileA + slot * kMaxFrag * kTileStride + lane;
+            int *tb = sm + L::tileB + slot * kMaxFrag * kTileStride + lane;
             for (int seg = 0; seg < kSplitSegs; ++seg) {
                 const int a = seg ? split : 0, b = seg ? n : min(split, n);
                 if (a >= b) continue;
@@ -228,39 +249,35 @@ __global__ void __launch_bounds__(kSplitThreads) render_split(const RenderParams
 #pragma unroll 4
                 for (int f = a; f < b; ++f) {           // filter12.c:97-118
                     const int fc = f0v >> 12, qq = qv >> 12;
-                    const int in = ta[f * 32];
+                    const int in = ta[f * kTileStride];
                     const int d1s = d1 >> 4;
                     const int l = wadd(d2, wmul(fc, d1s) >> 8);
                     const int h = wsub(wsub(in >> 5, l), wmul(qq, d1s) >> 8);
                     const int bb = wadd(wmul(fc, h >> 4) >> 8, d1);
-                    tb[f * 32] = wadd(wadd(wmul(l, lp), wmul(bb, bp)), wmul(h, hp)) >> 3;
+                    tb[f * kTileStride] = wadd(wadd(wmul(l, lp), wmul(bb, bp)), wmul(h, hp)) >> 3;
                     d1 = bb; d2 = l;
                     f0v = wadd(f0v, df);
                     qv = wadd(qv, qstep);
                 }
             }
         }
-        // ================= helpers: stageA(it - 1), stageC(it - lag_c) =================
-        if (warp >= 2) {
-            const int h = warp - 2;
-            if (it >= 1 && it - 1 < nfrag) {
-                const int slot = (it - 1) % kRing;
-                const int n = sm[L::meta + slot * 2 + 1];
-                const int split = sm[L::split + slot * 32 + lane];
-                const int flags = sm[L::flags + slot * 32 + lane];
-                int *ta = sm + L::tileA + slot * kMaxFrag * 32 + lane;
-                const int s0 = h * kSlice, s1 = min(n, s0 + kSlice);
-                for (int seg = 0; seg < kSplitSegs; ++seg) {
-                    const int sa = seg ? split : 0;
-                    const int a = max(s0, sa), b = min(s1, seg ? n : split);
-                    if (a >= b) continue;
-                    if (!((flags >> seg) & 1)) {
-                        for (int f = a; f < b; ++f) ta[f * 32] = 0;
-                        continue;
-                    }
-                    int acc[kSlice];
+        // ================= stage A(it - 1): oscillators, lane = voice, frames sliced =================
+        if (warp >= WR::c0 && it >= 1 && it - 1 < nfrag) {
+            const int h = warp - WR::c0;
+            const int slot = (it - 1) % kRing;
+            const int n = sm[L::meta + slot * 2 + 1];
+            const int split = sm[L::split + slot * 32 + lane];
+            const int flags = sm[L::flags + slot * 32 + lane];
+            int *ta = sm + L::tileA + slot * kMaxFrag * kTileStride + lane;
+            const int s0 = h * kSlice, s1 = min(n, s0 + kSlice);
+            for (int seg = 0; seg < kSplitSegs; ++seg) {
+                const int sa = seg ? split : 0;
+                const int a = max(s0, sa), b = min(s1, seg ? n : split);
+                if (a >= b) continue;
+                int acc[kSlice];
 #pragma unroll
-                    for (int k = 0; k < kSlice; ++k) acc[k] = 0;
+                for (int k = 0; k < kSlice; ++k) acc[k] = 0;
+                if ((flags >> seg) & 1) {
 #pragma unroll
                     for (int i = 0; i < NOSC; ++i) {
                         const int *q = sm + L::oscp + (((slot * kSplitSegs + seg) * NOSC + i) * 6) * 32 + lane;
@@ -271,69 +288,100 @@ __global__ void __launch_bounds__(kSplitThreads) render_split(const RenderParams
                         unsigned long long ph = ((unsigned long long)(unsigned)q[64] << 32) | (unsigned)q[32];
                         ph += (unsigned long long)dph * (unsigned)(a - sa);
                         const int astep = q[160];
-                        int av = wadd(q[128], wmul(astep, a - sa));
+                        const int av0 = wadd(q[128], wmul(astep, a - sa));
                         const unsigned half = dph >> 17;
+                        // all kSlice frames are evaluated (independent chains the
+                        // scheduler can overlap); frames past the segment end read
+                        // table slack and are dropped at the store (wtosc.c:226-233)
 #pragma unroll
                         for (int k = 0; k < kSlice; ++k) {
-                            if (a + k < b) {            // wtosc.c:226-233
-                                const unsigned p16 = (unsigned)(ph >> 16);
-                                const int hv = hermite_cf(cf, p16) + hermite_cf(cf, p16 + half);
-                                acc[k] = wadd(acc[k], mulshr(hv, av, 17));
-                                ph += dph;
-                                av = wadd(av, astep);
-                            }
+                            const unsigned p16 = (unsigned)((ph + (unsigned long long)dph * (unsigned)k) >> 16);
+                            const int hv = hermite_cf(cf, p16) + hermite_cf(cf, p16 + half);
+                            acc[k] = wadd(acc[k], mulshr(hv, wadd(av0, wmul(astep, k)), 17));
                         }
                     }
-#pragma unroll
-                    for (int k = 0; k < kSlice; ++k)
-                        if (a + k < b) ta[(a + k) * 32] = acc[k];
                 }
+#pragma unroll
+                for (int k = 0; k < kSlice; ++k)
+                    if (a + k < b) ta[(a + k) * kTileStride] = acc[k];
             }
-            if (it >= lag_c && it - lag_c < nfrag) {
-                const int slot = (it - lag_c) % kRing;
-                const int f0 = sm[L::meta + slot * 2];
-                const int n = sm[L::meta + slot * 2 + 1];
-                const int split = sm[L::split + slot * 32 + lane];
-                const int flags = sm[L::flags + slot * 32 + lane];
-                const int *tin = sm + (FILT ? L::tileB : L::tileA) + slot * kMaxFrag * 32 + lane;
-                const int s0 = h * kSlice, s1 = min(n, s0 + kSlice);
-                const bool athome = mybus == home;
-                for (int f = s0; f < s1; ++f) {
+        }
+        if (P.prof) t_mid = clock64();
+        // ================= stage C(it - lag_c): panmix + bus sum, lane = frame =================
+        if (warp >= WR::c0 && warp < WR::c0 + 2 * WR::groups && it >= lag_c && it - lag_c < nfrag) {
+            const int h = warp - WR::c0;
+            const int slot = (it - lag_c) % kRing;
+            const int f0 = sm[L::meta + slot * 2];
+            const int n = sm[L::meta + slot * 2 + 1];
+            const int f = (h & 1) * 32 + lane;              // my frame of the fragment
+            const int vlo = (h >> 1) * WR::vpg;
+            if (h == 0 && lane == 0) {                      // the params slot is recycled before the flush
+                sm[L::smeta + slot * 2] = f0;
+                sm[L::smeta + slot * 2 + 1] = n;
+            }
+            const int *tin = sm + (FILT ? L::tileB : L::tileA) + slot * kMaxFrag * kTileStride + f * kTileStride;
+            int sum0 = 0, sum1 = 0;
+            if (f < n) {
+#pragma unroll
+                for (int j = 0; j < WR::vpg; ++j) {
+                    const int vv = vlo + j;
+                    if (vv >= 32) break;
+                    const int split = sm[L::split + slot * 32 + vv];
+                    const int flags = sm[L::flags + slot * 32 + vv];
                     const int seg = f >= split ? 1 : 0;
-                    int o0 = 0, o1 = 0;
-                    const bool act = (flags >> seg) & 1;
-                    if (act) {                          // panmix.c:78-115
-                        const int *q = sm + L::pmp + ((slot * kSplitSegs + seg) * 5) * 32 + lane;
-                        const int k = f - (seg ? split : 0);
-                        const int vol = wadd(q[0], wmul(q[32], k));
-                        const int pan = wadd(q[64], wmul(q[96], k));
-                        const int vp = mulshr(pan, vol, 24);
-                        int v0 = wsub(vol, vp), v1 = wadd(vol, vp);
-                        if (q[128]) {
-                            const int lim = (int)((unsigned)vol << 1);
-                            if (v0 > lim) v0 = lim;
-                            if (v1 > lim) v1 = lim;
-                        }
-                        const int in = tin[f * 32];
-                        o0 = mulshr(in, v0, 24);
-                        o1 = mulshr(in, v1, 24);
+                    if (!((flags >> seg) & 1)) continue;
+                    const int *q = sm + L::pmp + ((slot * kSplitSegs + seg) * 5) * 32 + vv;
+                    const int k = f - (seg ? split : 0);    // panmix.c:78-115
+                    const int vol = wadd(q[0], wmul(q[32], k));
+                    const int pan = wadd(q[64], wmul(q[96], k));
+                    const int vp = mulshr(pan, vol, 24);
+                    int v0 = wsub(vol, vp), v1 = wadd(vol, vp);
+                    if (q[128]) {
+                        const int lim = (int)((unsigned)vol << 1);
+                        if (v0 > lim) v0 = lim;
+                        if (v1 > lim) v1 = lim;
                     }
-                    const int h0 = __reduce_add_sync(0xffffffffu, athome ? o0 : 0);
-                    const int h1 = __reduce_add_sync(0xffffffffu, athome ? o1 : 0);
-                    if (lane == 0 && home >= 0 && (h0 | h1)) {
-                        int *a = P.acc + ((size_t)home * W + f0 + f) * 2;
-                        if (h0) atomicAdd(a, h0);
-                        if (h1) atomicAdd(a + 1, h1);
-                    }
-                    if (valid && !athome && act) {
-                        int *a = P.acc + ((size_t)mybus * W + f0 + f) * 2;
+                    const int in = tin[vv];
+                    const int o0 = mulshr(in, v0, 24), o1 = mulshr(in, v1, 24);
+                    const int vb = sm[L::bus + vv];
+                    if (vb == home) { sum0 = wadd(sum0, o0); sum1 = wadd(sum1, o1); }
+                    else {
+                        int *a = P.acc + ((size_t)vb * W + f0 + f) * 2;
                         atomicAdd(a, o0);
                         atomicAdd(a + 1, o1);
                     }
                 }
+                int *sa = sm + L::sacc + (slot * kMaxFrag + f) * 2;
+                if (sum0) atomicAdd(sa, sum0);
+                if (sum1) atomicAdd(sa + 1, sum1);
             }
         }
+        // ================= stage D(it - lag_c - 1): flush the fragment's bus sums =================
+        if (warp == WR::c0 && it >= lag_c + 1 && it - lag_c - 1 < nfrag && home >= 0) {
+            const int slot = (it - lag_c - 1) % kRing;
+            const int f0 = sm[L::smeta + slot * 2];
+            const int n = sm[L::smeta + slot * 2 + 1];
+            int *sa = sm + L::sacc + slot * kMaxFrag * 2;
+            int *ga = P.acc + ((size_t)home * W + f0) * 2;
+            for (int i = lane; i < n * 2; i += 32) {
+                const int val = sa[i];
+                if (val) { atomicAdd(ga + i, val); sa[i] = 0; }
+            }
+        }
+        long long t_done = 0;
+        if (P.prof) t_done = clock64();
         __syncthreads();
+        if (P.prof && lane == 0) {
+            // [0] control [1] serial [2] stage A [3] stage C [4] barrier wait, [5] iterations
+            if (warp == 0) atomicAdd(P.prof + 0, (unsigned long long)(t_done - t_begin));
+            else if (warp == WR::serial) atomicAdd(P.prof + 1, (unsigned long long)(t_done - t_begin));
+            else if (warp == WR::c0 + 1) {
+                atomicAdd(P.prof + 2, (unsigned long long)(t_mid - t_begin));
+                atomicAdd(P.prof + 3, (unsigned long long)(t_done - t_mid));
+                atomicAdd(P.prof + 4, (unsigned long long)(clock64() - t_done));
+                atomicAdd(P.prof + 5, 1ull);
+            }
+        }
     }
 
     if (warp == 0 && valid) {
@@ -350,7 +398,7 @@ __global__ void __launch_bounds__(kSplitThreads) render_split(const RenderParams
         pm.store(sp, L::pm_w);
     }
     __syncthreads();
-    if (FILT && warp == 1 && valid) {       // the recurrence state lives in the serial warp
+    if (FILT && warp == WR::serial && valid) {       // the recurrence state lives in the serial warp
         sp.st(L::filt_w + 12, d1);
         sp.st(L::filt_w + 13, d2);
     }

@@ -68,6 +68,7 @@ SYMBOLS = {
     "a2cu_launch_count": (_U64, [_VP]),
     "a2cu_split_launch_count": (_U64, [_VP]),
     "a2cu_set_split": (_I, [_VP, _I]),
+    "a2cu_split_profile": (_I, [_VP, _I, C.POINTER(C.c_uint64)]),
     "a2cu_bank_kernel_name": (C.c_char_p, [_VP, _I]),
     "a2cu_bank_state_bytes": (_I, [_VP, _I]),
     "a2cu_last_render_ms": (C.c_float, [_VP]),
@@ -166,6 +167,11 @@ class Engine:
 
     def set_split(self, on):
         self._ck(self.L.a2cu_set_split(self.h, int(on)))
+
+    def split_profile(self, enable=True, read=True):
+        out = (C.c_uint64 * 8)()
+        self._ck(self.L.a2cu_split_profile(self.h, int(enable), out if read else None))
+        return list(out)
 
     def set_stream(self, cuda_stream):
         self._ck(self.L.a2cu_set_stream(self.h, cuda_stream))
