@@ -367,6 +367,7 @@ struct a2cu_engine {
     uint32_t *noise_ptr = nullptr;              // shared LCG (host's st->noisestate in drop-in mode)
     uint32_t stamp = 0;                         // creation order (tree-walk order is newest first)
     bool use_split = true;                      // allow render_split where eligible
+    bool noise_seen = false;                    // some voice selected a noise wave (planner armed)
     unsigned long long *d_prof = nullptr;       // render_split role counters (a2cu_split_profile)
     uint64_t split_launches = 0;
     std::vector<uint32_t> gstamp;
@@ -989,6 +990,7 @@ static int cook_write(a2cu_engine *e, Bank *b, int voice, int unit, int reg, int
         size_t total = 0;
         for (int l = 0; l < kMipLevels; ++l) total += hw.data[l].size();
         if (hw.type != A2CU_WMIPWAVE || total > ((size_t)1 << 20)) b->exotic = true;
+        if (hw.type == A2CU_WNOISE) e->noise_seen = true;
     }
     for (int i = 0; i < n; ++i) push_event(b, when, voice, EV_WRITE, unit, c[i].reg, c[i].value, c[i].dur);
     return A2CU_OK;
@@ -1231,20 +1233,35 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     std::vector<std::vector<HostEvent>> due(e->banks.size());
     for (size_t bi = 0; bi < e->banks.size(); ++bi) {
         Bank *b = e->banks[bi];
-        std::vector<HostEvent> keep;
+        bool all_due = true;
         for (auto &ev : b->events)
-            (ev.time < t1 ? due[bi] : keep).push_back(ev);
-        b->events.swap(keep);
-        std::sort(due[bi].begin(), due[bi].end(), [](const HostEvent &a, const HostEvent &c) {
-            if (a.voice != c.voice) return a.voice < c.voice;
-            if ((a.time >> 8) != (c.time >> 8)) return a.time < c.time;
-            return a.seq < c.seq;
-        });
+            if (ev.time >= t1) { all_due = false; break; }
+        if (all_due) {
+            due[bi].swap(b->events);
+            b->events.clear();
+        } else {
+            std::vector<HostEvent> keep;
+            for (auto &ev : b->events)
+                (ev.time < t1 ? due[bi] : keep).push_back(ev);
+            b->events.swap(keep);
+        }
+        {
+            auto less = [](const HostEvent &a, const HostEvent &c) {
+                if (a.voice != c.voice) return a.voice < c.voice;
+                if ((a.time >> 8) != (c.time >> 8)) return a.time < c.time;
+                return a.seq < c.seq;
+            };
+            // bulk writes (a2cu_bank_write_all) arrive in voice order already
+            if (!std::is_sorted(due[bi].begin(), due[bi].end(), less))
+                std::sort(due[bi].begin(), due[bi].end(), less);
+        }
         if (!due[bi].empty())
             stage_bytes += (b->stride + 1) * sizeof(unsigned) + due[bi].size() * sizeof(uint4) + 64;
     }
-    r = plan_noise(e, t0, W, (int)buffer, splits, nsplits, due);
-    if (r) return r;
+    if (e->noise_seen || !e->mirrors.empty()) {
+        r = plan_noise(e, t0, W, (int)buffer, splits, nsplits, due);
+        if (r) return r;
+    }
     stage_bytes = 0;
     for (size_t bi = 0; bi < e->banks.size(); ++bi)
         if (!due[bi].empty())
@@ -1318,9 +1335,14 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             int split_frag = nsplits ? frag_start(splits[0]) : -1;
             if (nsplits && splits[0] == split_frag) split_frag = -1;    // on a fragment boundary: no extra cut
             int cur_voice = -1, cur_frag = -1, cnt = 0, last = -1;
+            uint64_t memo_time = ~(uint64_t)0;
+            int f = 0, fs = 0;
             for (const HostEvent &ev : due[bi]) {
-                int f = (int)((ev.time - t0) >> 8);
-                int fs = frag_start(f);
+                if (ev.time != memo_time) {     // bulk writes share one time stamp
+                    memo_time = ev.time;
+                    f = (int)((ev.time - t0) >> 8);
+                    fs = frag_start(f);
+                }
                 if (ev.voice != cur_voice || fs != cur_frag) {
                     cur_voice = ev.voice; cur_frag = fs; last = -1;
                     cnt = (fs == split_frag) ? 1 : 0;
