@@ -268,21 +268,23 @@ def bench_ours(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    # >= max(3, W) warm-up steps, then as many more as it takes to keep the GPU
-    # under this load for ~1.5 s so nvidia-smi (100 ms period) samples clocks
-    # under load; the count is decided on rank 0 and broadcast (all ranks must
-    # run the same number of collective steps).
+    # >= max(3, W) warm-up steps, then chunks of 50 more until the GPU has been
+    # under this load for ~1.5 s, so nvidia-smi (100 ms period) samples clocks
+    # under load. Rank 0 decides and broadcasts (all ranks must run the same
+    # number of collective steps).
     nwarm = max(3, args.warmup)
     t_w = time.perf_counter()
     for _ in range(nwarm):
         one_step(False)
-    per_step = (time.perf_counter() - t_w) / nwarm
-    extra = torch.tensor([int(min(20000, max(0, 1.5 / max(per_step, 1e-6))))], device=dev)
-    if multi:
-        dist.broadcast(extra, 0)
-    for _ in range(int(extra.item())):
-        one_step(False)
-    nwarm += int(extra.item())
+    while True:
+        go = torch.tensor([1 if time.perf_counter() - t_w < 1.5 and nwarm < 100000 else 0], device=dev)
+        if multi:
+            dist.broadcast(go, 0)
+        if not int(go.item()):
+            break
+        for _ in range(50):
+            one_step(False)
+        nwarm += 50
     if multi:
         dist.barrier()
     torch.cuda.synchronize()
@@ -311,6 +313,7 @@ def bench_ours(args):
 
     if rank == 0:
         peak, peak_src = peaks()
+        kname = "render_split" if e.split_launches else "render_bank"
         state_bytes = e.bank_state_bytes(bank)
         cmd_bytes = 16 + 4                          # one event record + CSR offset per voice
         alg_bytes = args.voices * (2 * state_bytes + cmd_bytes) + STEP_FRAMES * 2 * 4
@@ -338,16 +341,16 @@ def bench_ours(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": host_total_ms / args.steps},
             "gpu_launches": int(launches),
-            "kernel": "render_bank<%s> + mix_root" % e.bank_kernel_name(bank),
+            "kernel": "%s<%s> + mix_root" % (kname, e.bank_kernel_name(bank)),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel": "render_bank<%s>" % e.bank_kernel_name(bank),
+                "kernel": "%s<%s>" % (kname, e.bank_kernel_name(bank)),
                 "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "note": "state is read and written once per 960-frame launch and the wavetable "
-                        "is L1/L2 resident: the kernel is INT32-issue/latency bound, not HBM "
-                        "bound (DESIGN.md, profiles/)",
+                        "is L1/L2 resident: the kernel is bound by the filter12 recurrence "
+                        "latency and INT32 issue, not by HBM (DESIGN.md 4/6, profiles/)",
             },
             "clocks": clk,
         }
