@@ -321,3 +321,10 @@ CASES = {
     "fm_bank64": fm_bank,
     "bench_bank200": lambda: bench_bank(200, steps=3),
 }
+
+
+# Hand-written scripts rendered as whole songs: name -> (path, program, frames, rate, buffer)
+SCRIPTS = {
+    "hybrid_song": ("data/hybrid_song.a2s", "Song", 30000, 48000, 64),
+    "hybrid_song_44k_b256": ("data/hybrid_song.a2s", "Song", 20000, 44100, 256),
+}

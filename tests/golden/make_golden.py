@@ -21,8 +21,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-from cases import CASES            # noqa: E402
+from cases import CASES, SCRIPTS   # noqa: E402
 from scenarios import run_ref      # noqa: E402
+from oracle import a2oracle as ao  # noqa: E402
 
 
 def main():
@@ -35,6 +36,14 @@ def main():
         print("%-24s %s frames=%d sha256=%s" % (
             name, data.shape, scn.frames,
             hashlib.sha256(data.tobytes()).hexdigest()[:16]))
+    # hand-written scripts (tests/data/*.a2s): whole songs through the reference
+    for name, (path, program, frames, rate, buffer) in SCRIPTS.items():
+        data, info = ao.ref_render(os.path.join(os.path.dirname(HERE), path), program,
+                                   samplerate=rate, channels=2, buffer=buffer, frames=frames)
+        assert info["rt_error"] == 0
+        out["script_" + name] = data
+        print("%-24s %s frames=%d sha256=%s" % (
+            "script_" + name, data.shape, frames, hashlib.sha256(data.tobytes()).hexdigest()[:16]))
     np.savez_compressed(os.path.join(HERE, "ref_outputs.npz"), **out)
 
 

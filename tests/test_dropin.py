@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import CASES
+from cases import CASES, SCRIPTS
 from oracle import a2oracle as ao
 
 pytestmark = pytest.mark.gpu
@@ -44,3 +44,20 @@ def test_cuda_driver_registers():
     out, info = ao.ref_render(os.path.join(HERE, "golden", "osc_pan_ramps.a2s"), "Song",
                               frames=scn.frames, binary="a2render_cuda", driver="cuda")
     assert np.array_equal(out, np.load(GOLDEN)["osc_pan_ramps"])
+
+
+@pytest.mark.skipif(not os.path.exists(HARNESS), reason="drop-in harness not built")
+@pytest.mark.parametrize("name", sorted(SCRIPTS))
+def test_dropin_song_with_host_units(name):
+    """A song whose bus voice chains our inline, the HOST's fbdelay and our
+    panmix (download + upload materialisation), leaf voices incl. noise."""
+    path, program, frames, rate, buffer = SCRIPTS[name]
+    out, info = ao.ref_render(os.path.join(HERE, path), program, samplerate=rate,
+                              channels=2, buffer=buffer, frames=frames,
+                              binary="a2render_cuda")
+    assert info["rt_error"] == 0
+    ref = np.load(GOLDEN)["script_" + name]
+    if not np.array_equal(out, ref):
+        bad = np.nonzero((out != ref).any(axis=1))[0]
+        raise AssertionError("first diff at frame %d (%d differ, max abs %d)" % (
+            bad[0], len(bad), np.abs(out.astype(np.int64) - ref).max()))
