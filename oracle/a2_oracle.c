@@ -1246,6 +1246,16 @@ void a2o_write(a2o_engine *e, int vi, int ui, int reg, int value,
 	}
 }
 
+/* Bulk form of a2o_write for large banks: voice first + i gets values[i * stride] */
+void a2o_write_all(a2o_engine *e, int first, int count, int ui, int reg,
+		const int *values, int stride, unsigned start, unsigned dur)
+{
+	int i;
+	for(i = 0; i < count; ++i)
+		a2o_write(e, first + i, ui, reg, values[(long)i * stride],
+				start, dur);
+}
+
 /* ------------------------------------------------------------------ */
 /* Segment loop and bus semantics (core.c:1847-1896, 1749-1776)        */
 /* ------------------------------------------------------------------ */

@@ -5,7 +5,7 @@
  * cpu_baseline / --impl reference legs of bench.py may load this library.
  * The product (audiality2_b200/) never links, imports or executes it.
  *
- * Parity status: PINNED.  tests/test_oracle_vs_ref.py checks this port bit for
+ * Parity status: PINNED.  tests/test_oracle.py checks this port bit for
  * bit against outputs of the reference itself (oracle/_ref/libaudiality2.so,
  * built by oracle/Makefile from /root/reference) and against the golden
  * fixtures under tests/golden/ that were generated from that build with
@@ -121,6 +121,9 @@ void a2o_kill_voice(a2o_engine *e, int voice);
 /* Low level: immediate control write / one Process() round for one voice */
 void a2o_write(a2o_engine *e, int voice, int unit, int reg, int value,
 		unsigned start, unsigned dur);
+
+void a2o_write_all(a2o_engine *e, int first, int count, int unit, int reg,
+		const int *values, int stride, unsigned start, unsigned dur);
 
 /*
  * Render 'frames' frames in driver buffers of 'buffer' frames, fragments of

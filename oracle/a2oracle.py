@@ -65,6 +65,8 @@ def lib():
         L.a2o_kill_voice.argtypes = [C.c_void_p, C.c_int]
         L.a2o_write.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_uint, C.c_uint]
+        L.a2o_write_all.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_int, C.c_uint, C.c_uint]
         L.a2o_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                  C.c_long, C.c_int]
         L.a2o_p2i.restype = C.c_uint
@@ -142,6 +144,11 @@ class Oracle:
 
     def write(self, voice, unit, reg, value, start=0, dur=0):
         self.L.a2o_write(self.h, voice, unit, reg, value, start, dur)
+
+    def write_all(self, first, count, unit, reg, values, start=0, dur=0):
+        a = np.ascontiguousarray(values, dtype=np.int32)
+        self.L.a2o_write_all(self.h, first, count, unit, reg, a.ctypes.data,
+                             0 if a.size == 1 else 1, start, dur)
 
     def render(self, events, frames, buffer=64):
         ev = np.ascontiguousarray(events, dtype=EVENT_DTYPE)

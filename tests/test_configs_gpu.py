@@ -1,0 +1,99 @@
+"""GPU parity at BASELINE.json's full configuration sizes, driven through the
+bulk C-ABI calls (a2cu_bank_write_all) against the oracle port:
+
+  cfg 3  65 536 voices, 8 x wtosc + panmix per voice, sine, 256-frame buffers
+  cfg 4  the per-GPU shard (32 768 voices) of the 262 144-voice FM bank cycling
+         fm3 / fm3p / fm2r / fm4r + panmix, 64-frame blocks
+"""
+import numpy as np
+import pytest
+
+from cases import _FM_SETTINGS
+from scenarios import autowire, fx
+from oracle import a2oracle as ao
+
+pytestmark = pytest.mark.gpu
+
+
+def _diff(a, b):
+    bad = np.nonzero((a != b).any(axis=1))[0]
+    return "first diff at frame %d (%d frames differ, max abs %d)" % (
+        bad[0], len(bad), np.abs(a.astype(np.int64) - b).max())
+
+
+def test_cfg3_additive_65536_voices():
+    from audiality2_b200 import engine as eng
+    V, NOSC, frames, buffer = 65536, 8, 256, 256
+    r = np.random.RandomState(3)
+    pitch = r.randint(-2 * 65536, 2 * 65536, size=V).astype(np.int32)
+    pan = r.randint(-65536, 65536, size=V).astype(np.int32)
+    kinds = ["wtosc"] * NOSC + ["panmix"]
+    chain = autowire(kinds)
+
+    e = eng.Engine(48000, 2)
+    w = e.builtin_wave("sine")
+    bank = e.new_bank(chain, V)
+    o = ao.Oracle(48000, 2)
+    ow = o.builtin_wave("sine")
+    for _ in range(V):
+        o.new_voice(chain)
+    for k in range(NOSC):
+        pk = pitch + fx(np.log2(k + 1))
+        amp = fx(0.00002 / (k + 1))
+        e.write_all(bank, k, 1, pk)
+        e.write_all(bank, k, 2, [amp])
+        e.write_all(bank, k, 0, [w << 16])
+        o.write_all(0, V, k, 1, pk)
+        o.write_all(0, V, k, 2, [amp])
+        o.write_all(0, V, k, 0, [ow << 16])
+    e.write_all(bank, NOSC, 1, pan)
+    o.write_all(0, V, NOSC, 1, pan)
+    out = e.run(frames, buffer)
+    assert e.split_launches > 0          # warp-specialised kernel, 8 oscillators
+    ref = o.render(np.zeros(0, dtype=ao.EVENT_DTYPE), frames, buffer)
+    e.close()
+    o.close()
+    assert np.abs(ref).max() > 10000
+    assert np.array_equal(out, ref), _diff(out, ref)
+
+
+def test_cfg4_fm_shard_32768_voices():
+    from audiality2_b200 import engine as eng
+    V, frames = 32768, 256
+    kinds = ["fm3", "fm3p", "fm2r", "fm4r"]
+    r = np.random.RandomState(11)
+    pitch = r.randint(-2 * 65536, 2 * 65536, size=V).astype(np.int32)
+    pan = r.randint(-65536, 65536, size=V).astype(np.int32)
+
+    e = eng.Engine(48000, 2)
+    o = ao.Oracle(48000, 2)
+    first = 0
+    for ki, kind in enumerate(kinds):
+        idx = np.arange(ki, V, 4)
+        n = len(idx)
+        chain = autowire([kind, "panmix"])
+        bank = e.new_bank(chain, n)
+        for _ in range(n):
+            o.new_voice(chain)
+        st = _FM_SETTINGS[kind]
+
+        def both(unit, reg, values, dur=0):
+            e.write_all(bank, unit, reg, values, dur=dur)
+            o.write_all(first, n, unit, reg, values, 0, dur)
+
+        both(0, 1, pitch[idx])
+        both(0, 2, [fx(0.0005 * st[0][0])])
+        both(0, 3, [fx(st[0][1])])
+        for op in range(1, len(st)):
+            p, a, fb = st[op]
+            both(0, 1 + 3 * op, [fx(p)])
+            both(0, 2 + 3 * op, [fx(a)])
+            both(0, 3 + 3 * op, [fx(fb)], dur=100 << 8)     # one ramping feedback
+        both(1, 1, pan[idx])
+        first += n
+    out = e.run(frames, 64)
+    ref = o.render(np.zeros(0, dtype=ao.EVENT_DTYPE), frames, 64)
+    e.close()
+    o.close()
+    assert np.abs(ref).max() > 10000
+    assert np.array_equal(out, ref), _diff(out, ref)
