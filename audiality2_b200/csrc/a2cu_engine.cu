@@ -27,6 +27,16 @@
 using namespace a2cu;
 
 static thread_local char g_err[512] = "";
+
+// Optional host-side statistics of block mode (env A2CU_STATS=1, printed at close)
+#include <time.h>
+static inline double now_us() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
+}
+struct BlockStats { double flush_us = 0, download_us = 0, sync_us = 0, begin_us = 0; long flushes = 0, downloads = 0, begins = 0, procs = 0; };
+static BlockStats g_bs;
 static int fail(int code, const char *fmt, const char *detail = "") {
     snprintf(g_err, sizeof(g_err), fmt, detail);
     return code;
@@ -310,6 +320,9 @@ struct Bank {
     std::vector<uint4> bev;
     std::vector<VoiceRun> bruns;
     int cur_slot = -1;
+    std::vector<uint32_t> slot_mark;    // flush id in which a slot got its first run
+    uint32_t flush_id = 1;
+    bool dup_runs = false;              // some slot has more than one run in this flush
     VoiceRun *d_runs = nullptr;
     size_t runs_cap = 0;
 };
@@ -676,6 +689,10 @@ a2cu_engine *a2cu_open(int device, int samplerate, int channels) {
 
 void a2cu_close(a2cu_engine *e) {
     if (!e) return;
+    if (getenv("A2CU_STATS"))
+        fprintf(stderr, "a2cu stats: %ld flushes %.1f us avg (host side), %ld downloads, wait+copy %.1f us avg, "
+                        "%ld launches\n", g_bs.flushes, g_bs.flushes ? g_bs.flush_us / g_bs.flushes : 0.0,
+                g_bs.downloads, g_bs.downloads ? g_bs.sync_us / g_bs.downloads : 0.0, (long)e->launches);
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     for (Bank *b : e->banks) {
@@ -1582,6 +1599,9 @@ static void block_rec(Bank *b, int slot, unsigned x, unsigned y, int z, unsigned
         r.slot = slot; r.ev_begin = (unsigned)b->bev.size(); r.ev_count = 0;
         b->bruns.push_back(r);
         b->cur_slot = slot;
+        if (b->slot_mark.size() < b->stride) b->slot_mark.resize(b->stride, 0);
+        if (b->slot_mark[slot] == b->flush_id) b->dup_runs = true;
+        b->slot_mark[slot] = b->flush_id;
     }
     b->bev.push_back(make_uint4(x, y, (unsigned)z, w));
     ++b->bruns.back().ev_count;
@@ -1706,7 +1726,15 @@ int a2cu_block_pm_proc(a2cu_engine *e, int pm, int nin, int nout, int add, int i
     return A2CU_OK;
 }
 
+static int block_flush_impl(a2cu_engine *e);
 int a2cu_block_flush(a2cu_engine *e) {
+    double t0 = now_us();
+    int r = block_flush_impl(e);
+    g_bs.flush_us += now_us() - t0;
+    ++g_bs.flushes;
+    return r;
+}
+static int block_flush_impl(a2cu_engine *e) {
     if (!e) return A2CU_EINVAL;
     cudaSetDevice(e->device);
     {
@@ -1717,30 +1745,27 @@ int a2cu_block_flush(a2cu_engine *e) {
         if (!b->dynamic || b->bruns.empty()) continue;
         // One thread per voice: merge the runs of a slot (a voice is visited
         // once per segment of its parent) keeping record order.
-        {
-            bool dup = false;
+        if (b->dup_runs) {
             std::vector<VoiceRun> sorted(b->bruns);
             std::stable_sort(sorted.begin(), sorted.end(),
                              [](const VoiceRun &a, const VoiceRun &c) { return a.slot < c.slot; });
-            for (size_t i = 1; i < sorted.size(); ++i)
-                if (sorted[i].slot == sorted[i - 1].slot) { dup = true; break; }
-            if (dup) {
-                std::vector<uint4> ev;
-                std::vector<VoiceRun> runs;
-                ev.reserve(b->bev.size());
-                for (const VoiceRun &r : sorted) {
-                    if (runs.empty() || runs.back().slot != r.slot) {
-                        VoiceRun n;
-                        n.slot = r.slot; n.ev_begin = (unsigned)ev.size(); n.ev_count = 0;
-                        runs.push_back(n);
-                    }
-                    ev.insert(ev.end(), b->bev.begin() + r.ev_begin, b->bev.begin() + r.ev_begin + r.ev_count);
-                    runs.back().ev_count += r.ev_count;
+            std::vector<uint4> ev;
+            std::vector<VoiceRun> runs;
+            ev.reserve(b->bev.size());
+            for (const VoiceRun &r : sorted) {
+                if (runs.empty() || runs.back().slot != r.slot) {
+                    VoiceRun n;
+                    n.slot = r.slot; n.ev_begin = (unsigned)ev.size(); n.ev_count = 0;
+                    runs.push_back(n);
                 }
-                b->bev.swap(ev);
-                b->bruns.swap(runs);
+                ev.insert(ev.end(), b->bev.begin() + r.ev_begin, b->bev.begin() + r.ev_begin + r.ev_count);
+                runs.back().ev_count += r.ev_count;
             }
+            b->bev.swap(ev);
+            b->bruns.swap(runs);
         }
+        b->dup_runs = false;
+        ++b->flush_id;
         size_t nev = b->bev.size(), nr = b->bruns.size();
         if (nev > b->ev_cap) {
             CK(cudaStreamSynchronize(e->stream));
@@ -1821,9 +1846,12 @@ int a2cu_block_download(a2cu_engine *e, int bus, int nch, unsigned frame, unsign
     if (r) return r;
     r = ensure_xfer(e);
     if (r) return r;
+    double t0 = now_us();
     CK(cudaMemcpyAsync(e->h_xfer, e->d_bacc + ((size_t)bus * kMaxFrag + frame) * 2, frames * 2 * sizeof(int32_t),
                        cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
+    g_bs.sync_us += now_us() - t0;
+    ++g_bs.downloads;
     e->d2h_bytes += frames * 2 * sizeof(int32_t);
     for (int c = 0; c < nch; ++c)
         for (unsigned i = 0; i < frames; ++i) {

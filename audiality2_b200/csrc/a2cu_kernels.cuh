@@ -104,6 +104,44 @@ __global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
 
     for (int f0 = 0; f0 < W;) {
         const int fe = frag_end(f0, P.buffer, W);
+        // Bus mix-down of one frame (PROCADD "+=", wtosc.c:229, panmix.c:104-105):
+        // integer adds in any order. Bank mode: voices at the CTA's home bus are
+        // summed with redux.sync into the shared-memory bus. Drop-in mode: each
+        // segment names its own bus, so the warp sums the lanes that share the
+        // first active lane's bus; stragglers add directly.
+        auto accumulate = [&](int fr, bool athome, int o0, int o1) {
+            if (!expl) {
+                int h0 = __reduce_add_sync(0xffffffffu, athome ? o0 : 0);
+                int h1 = __reduce_add_sync(0xffffffffu, athome ? o1 : 0);
+                if ((tid & 31) == 0) {
+                    atomicAdd(&sacc[fr - f0][0], h0);
+                    atomicAdd(&sacc[fr - f0][1], h1);
+                }
+                if (valid && !athome && in_seg) {
+                    int *a = P.acc + ((size_t)mybus * W + fr) * 2;
+                    atomicAdd(a, o0);
+                    atomicAdd(a + 1, o1);
+                }
+                return;
+            }
+            const unsigned act = __ballot_sync(0xffffffffu, in_seg);
+            if (!act) return;
+            const int leader = __ffs(act) - 1;
+            const int lbus = __shfl_sync(0xffffffffu, mybus, leader);
+            const bool same = in_seg && mybus == lbus;
+            int h0 = __reduce_add_sync(0xffffffffu, same ? o0 : 0);
+            int h1 = __reduce_add_sync(0xffffffffu, same ? o1 : 0);
+            if ((tid & 31) == leader) {
+                int *a = P.acc + ((size_t)lbus * W + fr) * 2;
+                if (h0) atomicAdd(a, h0);
+                if (h1) atomicAdd(a + 1, h1);
+            }
+            if (in_seg && !same) {
+                int *a = P.acc + ((size_t)mybus * W + fr) * 2;
+                atomicAdd(a, o0);
+                atomicAdd(a + 1, o1);
+            }
+        };
         int f = f0;
         // Segment boundary work for the first frame of the fragment
         auto boundary = [&](int fr) {
@@ -149,36 +187,14 @@ __global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
             for (; f < fe; ++f) {
                 int s0 = 0, s1 = 0, o0 = 0, o1 = 0;
                 if (in_seg) ch.sample_fast(c, s0, s1, o0, o1);
-                const bool athome = athome0;
-                int h0 = __reduce_add_sync(0xffffffffu, athome ? o0 : 0);
-                int h1 = __reduce_add_sync(0xffffffffu, athome ? o1 : 0);
-                if ((tid & 31) == 0) {
-                    atomicAdd(&sacc[f - f0][0], h0);
-                    atomicAdd(&sacc[f - f0][1], h1);
-                }
-                if (valid && !athome && in_seg) {
-                    int *a = P.acc + ((size_t)mybus * W + f) * 2;
-                    atomicAdd(a, o0);
-                    atomicAdd(a + 1, o1);
-                }
+                accumulate(f, athome0, o0, o1);
             }
         }
         for (; f < fe; ++f) {
             if (valid && f == seg_end && f != f0) boundary(f);
             int s0 = 0, s1 = 0, o0 = 0, o1 = 0;
             if (in_seg) ch.sample(c, s0, s1, o0, o1);
-            const bool athome = mybus == home;
-            int h0 = __reduce_add_sync(0xffffffffu, athome ? o0 : 0);
-            int h1 = __reduce_add_sync(0xffffffffu, athome ? o1 : 0);
-            if ((tid & 31) == 0) {
-                atomicAdd(&sacc[f - f0][0], h0);
-                atomicAdd(&sacc[f - f0][1], h1);
-            }
-            if (valid && !athome && in_seg) {
-                int *a = P.acc + ((size_t)mybus * W + f) * 2;
-                atomicAdd(a, o0);
-                atomicAdd(a + 1, o1);
-            }
+            accumulate(f, mybus == home, o0, o1);
         }
         __syncthreads();
         if (tid < (fe - f0) * 2 && home >= 0) {
