@@ -168,6 +168,46 @@ A2CU_DEV int f12_coeff(const unsigned *ptab, int cutoff_value, int samplerate) {
     return (int)__dmul_rn(33554432.0, sin(x));
 }
 
+// Same interpolation through a generic pointer: the table staged in shared
+// memory by TMA, or the global pool (L1-cached)
+A2CU_DEV int hermite_cf_smem(const int4 *tab, unsigned ph) {
+    const int4 e = tab[(int)(ph >> 8)];
+    int x = (int)((ph & 0xff) << 7);
+    int a = wmul(e.y, x) >> 15;
+    a = wmul(a + e.z, x) >> 15;
+    return e.x + (wmul(a + e.w, x) >> 15);
+}
+
+// ---- TMA (1-D bulk copy) + mbarrier, inline PTX --------------------------------
+A2CU_DEV unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+A2CU_DEV void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+A2CU_DEV void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+// global -> shared, completion counted in bytes on the mbarrier (SASS: UBLKCP)
+A2CU_DEV void tma_bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+A2CU_DEV void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+
 // ---- state I/O --------------------------------------------------------------
 struct StatePtr {
     int *base;          // word 0 of this voice (already offset by slot)

@@ -85,6 +85,7 @@ static void reg_chain(std::vector<a2cu_unitspec> specs, const char *name) {
     e.split_threads = 0;
     registry()[sig_of(specs.data(), (int)specs.size())] = e;
 }
+static const size_t kMaxSplitSmem = 226 * 1024;   // dynamic part; the kernel also has a few static bytes
 template <int NOSC, bool FILT, int NA>
 static void reg_split(std::vector<a2cu_unitspec> specs) {
     KernelEntry &e = registry()[sig_of(specs.data(), (int)specs.size())];
@@ -92,7 +93,7 @@ static void reg_split(std::vector<a2cu_unitspec> specs) {
     e.split_smem = SplitLayout<NOSC, FILT>::bytes;
     e.split_threads = SplitWarps<FILT, NA>::threads;
     cudaFuncSetAttribute(render_split<NOSC, FILT, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)SplitLayout<NOSC, FILT>::bytes);
+                         (int)kMaxSplitSmem);
 }
 
 // spec helpers: {kind, nin, nout, add, wireout}
@@ -284,6 +285,7 @@ struct HostWave {
     std::vector<int16_t> data[kMipLevels];  // incl. pads
     unsigned size[kMipLevels];
     std::string name;
+    int cbegin = -1, ccount = 0;            // range in the Hermite coefficient pool
 };
 
 struct HostEvent {
@@ -312,6 +314,7 @@ struct Bank {
     size_t ev_cap = 0;
     bool has_noise = false;
     bool exotic = false;    // selected a noise / non-mip / table-less wave: render_bank only
+    int stage_wave = -1;    // wave whose coefficient table render_split stages in shared memory
     uint32_t stamp = 0;
     // drop-in ("block") mode: dynamic slots + per-flush recording
     bool dynamic = false;
@@ -592,6 +595,7 @@ static int upload_waves(a2cu_engine *e) {
         desc[i].type = w.type; desc[i].flags = w.flags; desc[i].period = w.period;
         size_t wave_total = 0;
         for (int l = 0; l < kMipLevels; ++l) wave_total += w.data[l].size();
+        w.cbegin = -1; w.ccount = 0;
         for (int l = 0; l < kMipLevels; ++l) {
             desc[i].size[l] = w.size[l];
             desc[i].offset[l] = (unsigned)(pos + kWavePre);
@@ -603,6 +607,8 @@ static int upload_waves(a2cu_engine *e) {
                     const int16_t *d = w.data[l].data() + kWavePre;
                     int n = (int)w.size[l] + kPost - 2;
                     desc[i].coff[l] = (int)cpool.size();
+                    if (w.cbegin < 0) w.cbegin = (int)cpool.size();
+                    w.ccount = (int)cpool.size() + n - w.cbegin;
                     for (int k = 0; k < n; ++k) {
                         int dm = d[k - 1], d0 = d[k], d1 = d[k + 1], d2 = d[k + 2];
                         int c = (d1 - dm) >> 1;
@@ -1008,6 +1014,7 @@ static int cook_write(a2cu_engine *e, Bank *b, int voice, int unit, int reg, int
         for (int l = 0; l < kMipLevels; ++l) total += hw.data[l].size();
         if (hw.type != A2CU_WMIPWAVE || total > ((size_t)1 << 20)) b->exotic = true;
         if (hw.type == A2CU_WNOISE) e->noise_seen = true;
+        if (hw.type == A2CU_WMIPWAVE) b->stage_wave = c[0].value;
     }
     for (int i = 0; i < n; ++i) push_event(b, when, voice, EV_WRITE, unit, c[i].reg, c[i].value, c[i].dur);
     return A2CU_OK;
@@ -1370,8 +1377,19 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         }
         if (split) {
             params[bi].prof = e->d_prof;
+            size_t smem = b->k.split_smem;
+            if (b->stage_wave >= 0 && e->waves[b->stage_wave].cbegin >= 0 && !getenv("A2CU_NO_STAGE")) {
+                // whole wave (all mip levels) + read-ahead slack, if it fits beside the pipeline buffers
+                const HostWave &hw = e->waves[b->stage_wave];
+                size_t tb = ((size_t)hw.ccount + 64) * sizeof(int4);
+                if (smem + tb <= kMaxSplitSmem) {
+                    params[bi].stage_begin = hw.cbegin;
+                    params[bi].stage_count = hw.ccount + 64;
+                    smem += tb;
+                }
+            }
             int grid = (b->nvoices + 31) / 32;
-            b->k.split_fn<<<grid, b->k.split_threads, b->k.split_smem, e->stream>>>(params[bi]);
+            b->k.split_fn<<<grid, b->k.split_threads, smem, e->stream>>>(params[bi]);
             ++e->split_launches;
         } else {
             int grid = (b->nvoices + kThreads - 1) / kThreads;

@@ -54,6 +54,9 @@ struct RenderParams {
     int explicit_;
     // optional per-role busy-cycle counters of render_split (debug/profiling)
     unsigned long long *prof;
+    // render_split: coefficient-pool range [stage_begin, stage_begin + stage_count)
+    // of the bank's wave, staged into shared memory with one TMA bulk copy
+    int stage_begin, stage_count;
 };
 
 // End of the fragment that contains frame f: fragments restart at every driver

@@ -72,7 +72,8 @@ struct SplitLayout {
     static constexpr int tileA = smeta + kRing * 2;                          // [ring][64][33]
     static constexpr int tileB = tileA + kRing * kMaxFrag * kTileStride;     // [ring][64][33] (FILT)
     static constexpr int total = tileB + (FILT ? kRing * kMaxFrag * kTileStride : 0);
-    static constexpr size_t bytes = (size_t)total * sizeof(int);
+    static constexpr int table = (total + 31) & ~31;                         // staged coefficient table (int4)
+    static constexpr size_t bytes = (size_t)table * sizeof(int);            // + 16 B per staged entry
     static constexpr int words = 1 + 14 * NOSC + (FILT ? 14 : 0) + 8;       // state words per voice
     static constexpr int filt_w = 1 + 14 * NOSC;                             // first word of filter12
     static constexpr int pm_w = filt_w + (FILT ? 14 : 0);
@@ -83,7 +84,8 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
     typedef SplitLayout<NOSC, FILT> L;
     typedef SplitWarps<FILT, NA> WR;
     constexpr int kSlice = WR::slice;
-    extern __shared__ int sm[];
+    extern __shared__ __align__(128) int sm[];
+    __shared__ __align__(8) unsigned long long s_mbar;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int v = blockIdx.x * 32 + lane;
     const bool valid = v < P.nvoices;
@@ -95,6 +97,24 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
     const int home = __shfl_sync(0xffffffffu, mybus, 0);
     if (warp == 0) sm[L::bus + lane] = mybus;
     for (int i = tid; i < kRing * kMaxFrag * 2; i += WR::threads) sm[L::sacc + i] = 0;
+    // Stage the bank's wavetable (Hermite coefficient form, all mip levels) into
+    // shared memory: one elected thread arms an mbarrier with the byte count and
+    // issues TMA bulk copies; the helper warps wait on it before their first gather.
+    const int4 *s_tab = reinterpret_cast<const int4 *>(sm + L::table);
+    const int stage_n = P.stage_count;
+    if (stage_n) {
+        if (tid == 0) mbar_init(&s_mbar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned total_b = (unsigned)stage_n * 16u;
+            mbar_expect_tx(&s_mbar, total_b);
+            const char *src = reinterpret_cast<const char *>(P.cpool + P.stage_begin);
+            char *dst = reinterpret_cast<char *>(sm + L::table);
+            for (unsigned off = 0; off < total_b; off += 32768u)
+                tma_bulk_g2s(dst + off, src + off, min(32768u, total_b - off), &s_mbar);
+        }
+    }
+    bool tab_ready = stage_n == 0;
 
     Ctx c;
     c.waves = P.waves; c.pool = P.pool; c.cpool = P.cpool; c.ptab = P.ptab; c.fmsine = nullptr;
@@ -278,12 +298,15 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
 #pragma unroll
                 for (int k = 0; k < kSlice; ++k) acc[k] = 0;
                 if ((flags >> seg) & 1) {
-#pragma unroll
-                    for (int i = 0; i < NOSC; ++i) {
+#pragma unroll 1
+                    for (int i = 0; i < NOSC; ++i) {    // not unrolled: keeps the hot loop in the I-cache
                         const int *q = sm + L::oscp + (((slot * kSplitSegs + seg) * NOSC + i) * 6) * 32 + lane;
                         const int cfo = q[0];
                         if (cfo < 0) continue;          // silent segment of this oscillator
-                        const int4 *cf = c.cpool + cfo;
+                        if (!tab_ready) { mbar_wait(&s_mbar, 0); tab_ready = true; }
+                        const int srel = cfo - P.stage_begin;
+                        // generic pointer: the staged copy in shared memory or the pool in global memory
+                        const int4 *cf = (srel >= 0 && srel < stage_n - 64) ? s_tab + srel : c.cpool + cfo;
                         const unsigned dph = (unsigned)q[96];
                         unsigned long long ph = ((unsigned long long)(unsigned)q[64] << 32) | (unsigned)q[32];
                         ph += (unsigned long long)dph * (unsigned)(a - sa);
@@ -296,7 +319,7 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
 #pragma unroll
                         for (int k = 0; k < kSlice; ++k) {
                             const unsigned p16 = (unsigned)((ph + (unsigned long long)dph * (unsigned)k) >> 16);
-                            const int hv = hermite_cf(cf, p16) + hermite_cf(cf, p16 + half);
+                            const int hv = hermite_cf_smem(cf, p16) + hermite_cf_smem(cf, p16 + half);
                             acc[k] = wadd(acc[k], mulshr(hv, wadd(av0, wmul(astep, k)), 17));
                         }
                     }
