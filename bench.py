@@ -44,6 +44,22 @@ STEP_FRAMES = STEP_MS * RATE // 1000     # 960 = 15 blocks of 64
 BLOCK = 64
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per
+    launch, from the committed `ncu --set full` summary of this workload."""
+    path = os.path.join(ROOT, "profiles", "r01_v3_render_split_ncu.txt")
+    try:
+        tot = 0.0
+        for ln in open(path):
+            f = ln.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(f[2], 1)
+                tot += float(f[1]) * mult
+        return tot or None
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -344,7 +360,8 @@ def bench_ours(args):
             "kernel": "%s<%s> + mix_root" % (kname, e.bank_kernel_name(bank)),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                "traffic_source": "profiles/r01_v3_render_split_ncu.txt (ncu --set full, per launch)",
                 "kernel": "%s<%s>" % (kname, e.bank_kernel_name(bank)),
                 "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,
