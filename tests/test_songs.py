@@ -1,0 +1,77 @@
+"""GPU parity on the reference's OWN songs and test scripts, through the
+drop-in boundary.
+
+The scripts are staged by `make -C oracle ref` under oracle/_ref/songs/ (git-
+ignored; they are reference inputs, never committed) and travel to the GPU box
+with the reference build. Each one is rendered twice on the box:
+
+  a2render       full reference, CPU            (the oracle, live)
+  a2render_cuda  UNMODIFIED reference host + audiality2_b200/liba2cu_units.so
+                 (VM, scheduler, fbdelay/env/dc/... on the host; wtosc,
+                 filter12, fm*, waveshaper, panmix, inline and the bus
+                 mix-down on the B200)
+
+with the settings of the reference's benchmark (benchmark/benchmark.sh:50:
+`a2play -dbuffer -r44100 <song> -pSong`, a2play's default 2 channels) and the
+int32 8:24 master output compared bit for bit. k2trance.a2s is BASELINE
+config 5's program.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import a2oracle as ao
+
+pytestmark = pytest.mark.gpu
+SONGS = os.path.join(ao.REF_DIR, "songs")
+HARNESS = os.path.join(ao.REF_DIR, "a2render_cuda")
+
+# (directory, file, program, frames, buffer)
+BENCH = [
+    ("benchmark", "k2trance.a2s", "Song", 441000, 500),
+    ("benchmark", "k2intro.a2s", "Song", 220500, 500),
+    ("benchmark", "k2epilogue.a2s", "Song", 220500, 500),
+    ("benchmark", "k2loader.a2s", "Song", 220500, 500),
+    ("benchmark", "pulsetronic.a2s", "Song", 220500, 500),
+    ("benchmark", "fmtest3.a2s", "Song", 220500, 500),
+    ("benchmark", "fmtest4.a2s", "Song", 220500, 500),
+    ("benchmark", "wstest.a2s", "Song", 220500, 500),
+    ("benchmark", "dctest.a2s", "Song", 110250, 500),
+]
+TESTDATA = [
+    ("testdata", n + ".a2s", "Song", 110250, 256) for n in (
+        "a2jingle", "envtest", "envtest2", "envtest3", "envtest4", "evilnoises",
+        "evtest", "fmtest", "fmtest2", "importtest", "importtest2", "microtonal",
+        "noisephase", "pitchenvtest", "ramptest", "ramptest2", "ramptestenv",
+        "recursetest")
+] + [("testdata", "octaves.a2s", "Octaves", 110250, 64)]
+
+
+def _render(path, program, frames, buffer, binary):
+    # scripts import their neighbours by relative name: run from their directory
+    cwd = os.getcwd()
+    os.chdir(os.path.dirname(path))
+    try:
+        return ao.ref_render(os.path.basename(path), program, samplerate=44100,
+                             channels=2, buffer=buffer, frames=frames, binary=binary)
+    finally:
+        os.chdir(cwd)
+
+
+@pytest.mark.skipif(not (os.path.isdir(SONGS) and os.path.exists(HARNESS)),
+                    reason="reference songs / drop-in harness not staged")
+@pytest.mark.parametrize("where,name,program,frames,buffer", BENCH + TESTDATA,
+                         ids=[w + "/" + n for w, n, _, _, _ in BENCH + TESTDATA])
+def test_song_dropin_matches_reference(where, name, program, frames, buffer):
+    path = os.path.join(SONGS, where, name)
+    ref, rinfo = _render(path, program, frames, buffer, "a2render")
+    out, info = _render(path, program, frames, buffer, "a2render_cuda")
+    assert np.abs(ref).max() > 0
+    assert info["rt_error"] == rinfo["rt_error"]
+    assert info["active_voices"] == rinfo["active_voices"]
+    assert out.shape == ref.shape
+    if not np.array_equal(out, ref):
+        bad = np.nonzero((out != ref).any(axis=1))[0]
+        raise AssertionError("%s: first diff at frame %d (%d frames differ, max abs %d)" % (
+            name, bad[0], len(bad), np.abs(out.astype(np.int64) - ref).max()))
