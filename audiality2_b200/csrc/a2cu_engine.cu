@@ -397,6 +397,13 @@ struct a2cu_engine {
     int pm_cap = 0, pm_used = 0;
     std::vector<int> pm_free, pm_deferred;
     int32_t *h_xfer = nullptr;      // pinned, 64 x 2
+    // generic units (any replaced unit outside a fused leaf voice, BUS_U_* ops)
+    struct GUnit { int kind = 0, nin = 0, nout = 0; bool live = false, has_osc = false; OscMirror osc; };
+    std::vector<GUnit> gunits;
+    std::vector<int> gunit_free, gunit_deferred;
+    int *d_ustate = nullptr;        // [unit][kUnitWords]
+    int ustate_cap = 0;
+    int32_t *d_upload = nullptr;    // staging row for a2cu_block_upload_add
 };
 
 
@@ -709,7 +716,7 @@ void a2cu_close(a2cu_engine *e) {
     cudaFree(e->d_waves); cudaFree(e->d_pool); cudaFree(e->d_cpool); cudaFree(e->d_ptab); cudaFree(e->d_fmsine);
     cudaFree(e->d_gstate); cudaFree(e->d_rstate); cudaFree(e->d_mixev);
     cudaFree(e->d_acc); cudaFree(e->d_master);
-    cudaFree(e->d_buscmds); cudaFree(e->d_bacc); cudaFree(e->d_pmstate);
+    cudaFree(e->d_buscmds); cudaFree(e->d_bacc); cudaFree(e->d_pmstate); cudaFree(e->d_ustate);
     if (e->h_xfer) cudaFreeHost(e->h_xfer);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->h_out) cudaFreeHost(e->h_out);
@@ -1582,6 +1589,8 @@ int a2cu_block_begin(a2cu_engine *e) {
     }
     e->pm_free.insert(e->pm_free.end(), e->pm_deferred.begin(), e->pm_deferred.end());
     e->pm_deferred.clear();
+    e->gunit_free.insert(e->gunit_free.end(), e->gunit_deferred.begin(), e->gunit_deferred.end());
+    e->gunit_deferred.clear();
     if (e->prev_nbbus < e->nbbus) e->prev_nbbus = e->nbbus;
     if (e->prev_nbbus && e->d_bacc)
         CK(cudaMemsetAsync(e->d_bacc, 0, (size_t)e->prev_nbbus * kMaxFrag * 2 * sizeof(int), e->stream));
@@ -1744,6 +1753,127 @@ int a2cu_block_pm_proc(a2cu_engine *e, int pm, int nin, int nout, int add, int i
     return A2CU_OK;
 }
 
+// ---- generic units: one replaced unit, called on its own (BUS_U_* ops) -------
+int a2cu_unit_alloc(a2cu_engine *e, int kind, int nin, int nout) {
+    if (!e) return A2CU_EINVAL;
+    a2cu_unitspec sp = {kind, nin, nout, 0, 0};
+    bool known = kind == A2CU_WTOSC || kind == A2CU_PANMIX || kind == A2CU_FILTER12 || kind == A2CU_WAVESHAPER ||
+                 (kind >= A2CU_FM1 && kind <= A2CU_FM4R);
+    if (!known || nin < 0 || nin > 2 || nout < 1 || nout > 2 || unit_words(sp) > kUnitWords)
+        return fail(A2CU_ENOTIMPL, "a2cu_unit_alloc: unsupported unit / channel count%s");
+    if ((kind == A2CU_FILTER12 || kind == A2CU_WAVESHAPER) && (nin != nout || nin < 1))
+        return fail(A2CU_EINVAL, "a2cu_unit_alloc: unit needs matching i/o%s");
+    cudaSetDevice(e->device);
+    int id;
+    if (!e->gunit_free.empty()) { id = e->gunit_free.back(); e->gunit_free.pop_back(); }
+    else {
+        if ((int)e->gunits.size() + 1 > e->ustate_cap) {
+            int ncap = std::max(256, e->ustate_cap * 2);
+            int *n = nullptr;
+            CK(cudaStreamSynchronize(e->stream));
+            CK(cudaMalloc(&n, (size_t)ncap * kUnitWords * sizeof(int)));
+            CK(cudaMemset(n, 0, (size_t)ncap * kUnitWords * sizeof(int)));
+            if (e->d_ustate) {
+                CK(cudaMemcpy(n, e->d_ustate, (size_t)e->ustate_cap * kUnitWords * sizeof(int),
+                              cudaMemcpyDeviceToDevice));
+                cudaFree(e->d_ustate);
+            }
+            e->d_ustate = n; e->ustate_cap = ncap;
+        }
+        id = (int)e->gunits.size();
+        e->gunits.emplace_back();
+    }
+    a2cu_engine::GUnit &g = e->gunits[id];
+    g.kind = kind; g.nin = nin; g.nout = nout; g.live = true; g.has_osc = false;
+    return id;
+}
+
+int a2cu_unit_free(a2cu_engine *e, int unit) {
+    if (!e || unit < 0 || unit >= (int)e->gunits.size() || !e->gunits[unit].live) return A2CU_EINVAL;
+    e->gunits[unit].live = false;
+    e->gunit_deferred.push_back(unit);      // still referenced by commands of this block
+    return A2CU_OK;
+}
+
+static a2cu_engine::GUnit *get_gunit(a2cu_engine *e, int unit) {
+    if (!e || unit < 0 || unit >= (int)e->gunits.size() || !e->gunits[unit].live) return nullptr;
+    return &e->gunits[unit];
+}
+
+static void gunit_cmd(a2cu_engine *e, int op, int unit, const a2cu_engine::GUnit &g, int reg, int value, int start,
+                      int dur) {
+    BusCmd c;
+    memset(&c, 0, sizeof(c));
+    c.op = op; c.pm = unit; c.kind = g.kind; c.nin = g.nin; c.nout = g.nout;
+    c.reg = reg; c.value = value; c.start = start; c.dur = dur;
+    e->buscmds.push_back(c);
+}
+
+int a2cu_block_unit_init(a2cu_engine *e, int unit, int transpose, unsigned substart) {
+    a2cu_engine::GUnit *g = get_gunit(e, unit);
+    if (!g) return fail(A2CU_EINVAL, "a2cu_block_unit_init: bad unit%s");
+    int arg = 0;
+    if (g->kind == A2CU_WTOSC || g->kind >= A2CU_FM1) arg = transpose + e->basepitch;
+    else if (g->kind == A2CU_FILTER12) arg = transpose;
+    gunit_cmd(e, BUS_U_INIT, unit, *g, 0, arg, (int)(substart & 0xff), 0);
+    if (g->kind == A2CU_FILTER12)
+        gunit_cmd(e, BUS_U_WRITE, unit, *g, 5, tables().f12_coeff((int)((unsigned)arg << 8), e->samplerate), 0, 0);
+    if (g->kind == A2CU_WTOSC) {
+        // host twin of the control-rate part from the start: yields the noise
+        // draw count of every Process() call (wtosc.c:135-144)
+        g->osc.init(e, arg, substart & 0xff);
+        g->has_osc = true;
+    }
+    return A2CU_OK;
+}
+
+int a2cu_block_unit_write(a2cu_engine *e, int unit, int reg, int32_t value, int transpose, unsigned start,
+                          uint32_t dur) {
+    a2cu_engine::GUnit *g = get_gunit(e, unit);
+    if (!g) return fail(A2CU_EINVAL, "a2cu_block_unit_write: bad unit%s");
+    Cooked c[2];
+    int n = cook(e, g->kind, reg, value, (int)(start & 0xff), dur, transpose, c);
+    if (n < 0) return n;
+    if (g->has_osc) g->osc.write(e, c[0].reg, c[0].value, (int)(start & 0xff), (int)c[0].dur);
+    for (int i = 0; i < n; ++i) gunit_cmd(e, BUS_U_WRITE, unit, *g, c[i].reg, c[i].value, (int)(start & 0xff), (int)c[i].dur);
+    return A2CU_OK;
+}
+
+int a2cu_block_unit_proc(a2cu_engine *e, int unit, int add, int wireout, int scratch_bus, int out_bus, unsigned frame,
+                         unsigned frames) {
+    a2cu_engine::GUnit *g = get_gunit(e, unit);
+    if (!g || scratch_bus < 0 || scratch_bus >= e->nbbus || frames < 1 || frame + frames > (unsigned)kMaxFrag ||
+        (wireout && (out_bus < 0 || out_bus >= e->nbbus)))
+        return fail(A2CU_EINVAL, "a2cu_block_unit_proc: bad args%s");
+    if (g->has_osc) {
+        bool is_noise;
+        int draws = g->osc.segment(e, (int)frames, &is_noise);
+        if (is_noise) {
+            gunit_cmd(e, BUS_U_SEED, unit, *g, 0, (int)*e->noise_ptr, 0, 0);
+            lcg_advance(e->noise_ptr, draws);
+        }
+    }
+    BusCmd c;
+    memset(&c, 0, sizeof(c));
+    c.op = BUS_U_RUN; c.pm = unit; c.kind = g->kind; c.nin = g->nin; c.nout = g->nout;
+    c.add = (add ? 1 : 0) | (wireout ? 2 : 0);
+    c.in_bus = scratch_bus; c.out_bus = wireout ? out_bus : scratch_bus;
+    c.frame = (int)frame; c.frames = (int)frames;
+    e->buscmds.push_back(c);
+    return A2CU_OK;
+}
+
+int a2cu_block_bus_add(a2cu_engine *e, int src_bus, int dst_bus, unsigned frame, unsigned frames) {
+    if (!e || src_bus < 0 || src_bus >= e->nbbus || dst_bus < 0 || dst_bus >= e->nbbus || frames < 1 ||
+        frame + frames > (unsigned)kMaxFrag)
+        return fail(A2CU_EINVAL, "a2cu_block_bus_add: bad args%s");
+    BusCmd c;
+    memset(&c, 0, sizeof(c));
+    c.op = BUS_ADD; c.in_bus = src_bus; c.out_bus = dst_bus; c.frame = (int)frame; c.frames = (int)frames;
+    e->buscmds.push_back(c);
+    return A2CU_OK;
+}
+
 static int block_flush_impl(a2cu_engine *e);
 int a2cu_block_flush(a2cu_engine *e) {
     double t0 = now_us();
@@ -1822,7 +1952,13 @@ static int block_flush_impl(a2cu_engine *e) {
         }
         CK(cudaMemcpyAsync(e->d_buscmds, e->buscmds.data(), n * sizeof(BusCmd), cudaMemcpyHostToDevice, e->stream));
         e->h2d_bytes += n * sizeof(BusCmd);
-        bus_vm<<<1, kMaxFrag, 0, e->stream>>>(e->d_buscmds, (int)n, e->d_bacc, e->d_pmstate);
+        BusVmParams BP;
+        memset(&BP, 0, sizeof(BP));
+        BP.cmds = e->d_buscmds; BP.ncmd = (int)n; BP.acc = e->d_bacc; BP.pmstate = e->d_pmstate;
+        BP.ustate = e->d_ustate;
+        BP.ctx.waves = e->d_waves; BP.ctx.pool = e->d_pool; BP.ctx.cpool = e->d_cpool; BP.ctx.ptab = e->d_ptab;
+        BP.ctx.fmsine = e->d_fmsine; BP.ctx.samplerate = e->samplerate;
+        bus_vm<<<1, kMaxFrag, 0, e->stream>>>(BP);
         ++e->launches;
         e->buscmds.clear();
     }
@@ -1835,7 +1971,8 @@ static int ensure_xfer(a2cu_engine *e) {
     return A2CU_OK;
 }
 
-int a2cu_block_upload(a2cu_engine *e, int bus, int nch, unsigned frame, unsigned frames, const int32_t *const *src) {
+static int block_upload(a2cu_engine *e, int bus, int nch, unsigned frame, unsigned frames,
+                        const int32_t *const *src, bool add) {
     if (!e || bus < 0 || bus >= e->nbbus || frames < 1 || frame + frames > (unsigned)kMaxFrag || nch < 1 || nch > 2)
         return fail(A2CU_EINVAL, "a2cu_block_upload: bad args%s");
     cudaSetDevice(e->device);
@@ -1848,11 +1985,30 @@ int a2cu_block_upload(a2cu_engine *e, int bus, int nch, unsigned frame, unsigned
         e->h_xfer[i * 2] = src[0][frame + i];
         e->h_xfer[i * 2 + 1] = nch > 1 ? src[1][frame + i] : 0;
     }
-    CK(cudaMemcpyAsync(e->d_bacc + ((size_t)bus * kMaxFrag + frame) * 2, e->h_xfer, frames * 2 * sizeof(int32_t),
-                       cudaMemcpyHostToDevice, e->stream));
+    int32_t *dst = e->d_bacc + ((size_t)bus * kMaxFrag + frame) * 2;
+    if (add) {
+        // stage in an extra bus row, then BUS_ADD in command order
+        int tmp = a2cu_block_bus(e);
+        if (tmp < 0) return tmp;
+        dst = e->d_bacc + ((size_t)tmp * kMaxFrag + frame) * 2;
+        CK(cudaMemcpyAsync(dst, e->h_xfer, frames * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        e->h2d_bytes += frames * 2 * sizeof(int32_t);
+        return a2cu_block_bus_add(e, tmp, bus, frame, frames);
+    }
+    CK(cudaMemcpyAsync(dst, e->h_xfer, frames * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->h2d_bytes += frames * 2 * sizeof(int32_t);
     return A2CU_OK;
+}
+
+int a2cu_block_upload(a2cu_engine *e, int bus, int nch, unsigned frame, unsigned frames, const int32_t *const *src) {
+    return block_upload(e, bus, nch, frame, frames, src, false);
+}
+
+int a2cu_block_upload_add(a2cu_engine *e, int bus, int nch, unsigned frame, unsigned frames,
+                          const int32_t *const *src) {
+    return block_upload(e, bus, nch, frame, frames, src, true);
 }
 
 int a2cu_block_download(a2cu_engine *e, int bus, int nch, unsigned frame, unsigned frames, int32_t *const *dst,

@@ -372,24 +372,141 @@ __global__ void __launch_bounds__(256) mix_root(const MixParams P) {
 
 // ---------------------------------------------------------------------------
 // Drop-in mode bus stage: the bus-level Process()/write calls the host made
-// during its tree walk, replayed in order by one CTA (panmix.c, all variants).
+// during its tree walk, replayed in order by one CTA.
+//
+//   BUS_PM_*   bus-level panmix (panmix.c, all variants): control part on
+//              thread 0, frames in closed form across the CTA
+//   BUS_U_*    any other replaced unit called outside a fused leaf voice
+//              ({inline; filter12}, {inline; wtosc; panmix}, {wtosc; panmix;
+//              fbdelay}, {inline; waveshaper; fbdelay; ...}): one Process()
+//              call of ONE unit, exactly as the reference runs it (unit by
+//              unit over the segment, core.c:1875-1876), with the voice's
+//              scratch channels held in a device bus row instead of
+//              st->scratch[nest]. The unit templates are the same code the
+//              fused kernels use, instantiated in replace mode; add / wire-out
+//              (A2_PROCADD, A2_IO_WIREOUT) are applied here. Recurrences run
+//              on thread 0.
+//   BUS_ADD    dst bus += src bus (an adding `inline` after device scratch)
 // ---------------------------------------------------------------------------
-enum BusOp { BUS_PM_PROC = 0, BUS_PM_WRITE = 1 };
+enum BusOp { BUS_PM_PROC = 0, BUS_PM_WRITE = 1, BUS_U_INIT = 2, BUS_U_WRITE = 3, BUS_U_SEED = 4, BUS_U_RUN = 5,
+             BUS_ADD = 6 };
 struct BusCmd {
-    int op, pm;             // pm: index of the panmix instance state
-    int nin, nout, add;
-    int in_bus, out_bus;    // device bus indices (stereo rows of acc)
+    int op, pm;             // pm: index of the panmix instance state / generic unit state
+    int nin, nout, add;     // add: bit 0 A2_PROCADD, bit 1 wire-out (BUS_U_RUN)
+    int in_bus, out_bus;    // device bus indices (stereo rows of acc); BUS_U_RUN: scratch bus, wire target
     int frame, frames;
     int reg, value, start, dur;
-    int pad[3];
+    int kind;               // BUS_U_*: unit kind (A2CU_*)
+    int pad[2];
 };
 
-__global__ void __launch_bounds__(kMaxFrag) bus_vm(const BusCmd *cmds, int ncmd, int *acc, int *pmstate) {
+constexpr int kUnitWords = 64;      // state words reserved per generic unit (fm4: 16 x 4)
+
+struct BusVmParams {
+    const BusCmd *cmds;
+    int ncmd;
+    int *acc;               // [bus][64][2]
+    int *pmstate;           // [pm][8]
+    int *ustate;            // [unit][kUnitWords]
+    Ctx ctx;                // fmsine points at the global table here
+};
+
+template <class U>
+__device__ __noinline__ void bus_unit_op(const Ctx &ctx, const BusCmd &c, int *st, int *acc, unsigned seed, bool seeded) {
+    U u;
+    const StatePtr sp{st, 1};
+    if (c.op == BUS_U_INIT) {
+        u.load(sp, 0);
+        u.init(ctx, c.value, (unsigned)c.start);
+        u.store(sp, 0);
+        return;
+    }
+    u.load(sp, 0);
+    if (c.op == BUS_U_WRITE) {
+        u.write(ctx, c.reg, c.value, c.start, c.dur);
+        u.store(sp, 0);
+        return;
+    }
+    const bool add = c.add & 1, wire = (c.add & 2) != 0;
+    u.prepare(ctx, c.frames);
+    if (seeded) u.seed(seed);       // after prepare: load()/prepare() do not touch it, but keep the order explicit
+    for (int i = 0; i < c.frames; ++i) {
+        int *s = acc + ((size_t)c.in_bus * kMaxFrag + c.frame + i) * 2;
+        const int in0 = s[0], in1 = s[1];
+        int s0 = in0, s1 = in1, o0 = 0, o1 = 0;
+        u.sample(ctx, s0, s1, o0, o1);
+        if (wire) {
+            int *o = acc + ((size_t)c.out_bus * kMaxFrag + c.frame + i) * 2;
+            o[0] = wadd(o[0], s0);
+            if (c.nout == 2) o[1] = wadd(o[1], s1);
+        } else if (add) {
+            s[0] = wadd(in0, s0);
+            if (c.nout == 2) s[1] = wadd(in1, s1);
+        } else {
+            s[0] = s0;
+            if (c.nout == 2) s[1] = s1;
+        }
+    }
+    u.finish();
+    u.store(sp, 0);
+}
+
+__device__ __noinline__ void bus_unit_dispatch(const Ctx &ctx, const BusCmd &c, int *st, int *acc, unsigned seed,
+                                               bool seeded) {
+    switch (c.kind) {
+    case 1: bus_unit_op<WtOsc<false, false>>(ctx, c, st, acc, seed, seeded); break;
+    case 2:     // panmix normally takes the BUS_PM path; kept for completeness
+        if (c.nin == 1 && c.nout == 1) bus_unit_op<PanMix<1, 1, false, false>>(ctx, c, st, acc, seed, seeded);
+        else if (c.nin == 1) bus_unit_op<PanMix<1, 2, false, false>>(ctx, c, st, acc, seed, seeded);
+        else if (c.nout == 1) bus_unit_op<PanMix<2, 1, false, false>>(ctx, c, st, acc, seed, seeded);
+        else bus_unit_op<PanMix<2, 2, false, false>>(ctx, c, st, acc, seed, seeded);
+        break;
+    case 3:
+        if (c.nin == 1) bus_unit_op<Filter12<1, false, false>>(ctx, c, st, acc, seed, seeded);
+        else bus_unit_op<Filter12<2, false, false>>(ctx, c, st, acc, seed, seeded);
+        break;
+    case 4:
+        if (c.nin == 1) bus_unit_op<WaveShaper<1, false, false>>(ctx, c, st, acc, seed, seeded);
+        else bus_unit_op<WaveShaper<2, false, false>>(ctx, c, st, acc, seed, seeded);
+        break;
+    case 16: bus_unit_op<Fm<1, 0, 0, false, false>>(ctx, c, st, acc, seed, seeded); break;
+    case 17: bus_unit_op<Fm<2, 1, 0, false, false>>(ctx, c, st, acc, seed, seeded); break;
+    case 18: bus_unit_op<Fm<3, 2, 0, false, false>>(ctx, c, st, acc, seed, seeded); break;
+    case 19: bus_unit_op<Fm<4, 2, 0, false, false>>(ctx, c, st, acc, seed, seeded); break;
+    case 20: bus_unit_op<Fm<3, 2, 1, false, false>>(ctx, c, st, acc, seed, seeded); break;
+    case 21: bus_unit_op<Fm<4, 2, 1, false, false>>(ctx, c, st, acc, seed, seeded); break;
+    case 22: bus_unit_op<Fm<2, 1, 2, false, false>>(ctx, c, st, acc, seed, seeded); break;
+    case 23: bus_unit_op<Fm<4, 2, 2, false, false>>(ctx, c, st, acc, seed, seeded); break;
+    default: break;
+    }
+}
+
+__global__ void __launch_bounds__(kMaxFrag) bus_vm(const BusVmParams P) {
     __shared__ MixSeg sg;
     const int tid = threadIdx.x;
-    for (int i = 0; i < ncmd; ++i) {
-        const BusCmd c = cmds[i];
-        int *st = pmstate + (size_t)c.pm * 8;
+    int *acc = P.acc;
+    unsigned seed = 0;
+    bool seeded = false;
+    for (int i = 0; i < P.ncmd; ++i) {
+        const BusCmd c = P.cmds[i];
+        if (c.op >= BUS_U_INIT && c.op <= BUS_U_RUN) {
+            if (c.op == BUS_U_SEED) { seed = (unsigned)c.value; seeded = true; continue; }
+            if (tid == 0) bus_unit_dispatch(P.ctx, c, P.ustate + (size_t)c.pm * kUnitWords, acc, seed, seeded);
+            if (c.op == BUS_U_RUN) seeded = false;
+            __syncthreads();
+            continue;
+        }
+        if (c.op == BUS_ADD) {
+            if (tid < c.frames) {
+                const int *in = acc + ((size_t)c.in_bus * kMaxFrag + c.frame + tid) * 2;
+                int *out = acc + ((size_t)c.out_bus * kMaxFrag + c.frame + tid) * 2;
+                out[0] = wadd(out[0], in[0]);
+                out[1] = wadd(out[1], in[1]);
+            }
+            __syncthreads();
+            continue;
+        }
+        int *st = P.pmstate + (size_t)c.pm * 8;
         if (c.op == BUS_PM_WRITE) {
             if (tid == 0) {
                 Ramp vol, pan;

@@ -276,8 +276,30 @@ int a2cu_block_pm_write(a2cu_engine *e, int pm, int reg, int32_t value,
 		unsigned start, uint32_t dur);
 int a2cu_block_pm_proc(a2cu_engine *e, int pm, int nin, int nout, int add,
 		int in_bus, int out_bus, unsigned frame, unsigned frames);
+/*
+ * Generic units: ONE replaced unit called on its own - bus-level filter12 /
+ * waveshaper / wtosc after an `inline`, or our units inside a chain that also
+ * holds host units ({wtosc; panmix 1 2; fbdelay 2 >}).  The voice's scratch
+ * channels (st->scratch[nest], src/core.c:364-395) live in a device bus row;
+ * a2cu_block_unit_proc is one Process(u, frame, frames) call (a2_units.h:176)
+ * in the host's order, 'add' = A2_PROCADD, 'wireout' = outputs are the voice's
+ * output bus 'out_bus' (A2_IO_WIREOUT, src/core.c:243-245).
+ */
+int a2cu_unit_alloc(a2cu_engine *e, int kind, int ninputs, int noutputs);
+int a2cu_unit_free(a2cu_engine *e, int unit);
+int a2cu_block_unit_init(a2cu_engine *e, int unit, int transpose, unsigned substart);
+int a2cu_block_unit_write(a2cu_engine *e, int unit, int reg, int32_t value,
+		int transpose, unsigned start, uint32_t dur);
+int a2cu_block_unit_proc(a2cu_engine *e, int unit, int add, int wireout,
+		int scratch_bus, int out_bus, unsigned frame, unsigned frames);
+/* dst bus += src bus over [frame, frame + frames) */
+int a2cu_block_bus_add(a2cu_engine *e, int src_bus, int dst_bus, unsigned frame,
+		unsigned frames);
 int a2cu_block_flush(a2cu_engine *e);
 int a2cu_block_upload(a2cu_engine *e, int bus, int nch, unsigned frame,
+		unsigned frames, const int32_t *const *src);
+/* bus += host data (what host units added to a bus our inline owns) */
+int a2cu_block_upload_add(a2cu_engine *e, int bus, int nch, unsigned frame,
 		unsigned frames, const int32_t *const *src);
 int a2cu_block_download(a2cu_engine *e, int bus, int nch, unsigned frame,
 		unsigned frames, int32_t *const *dst, int add);

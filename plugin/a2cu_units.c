@@ -25,12 +25,14 @@
  *
  * Classification of a voice (at its first Process call, when the unit chain
  * is complete; chains never change afterwards, src/core.c:155-161):
- *   LEAF  first unit is a generator of ours and every unit is ours:
- *         one device voice slot, the whole chain runs fused in one kernel
- *   BUS   first unit is our inline: sub-voices mix into a fresh device bus;
- *         our panmix units after it run on the device bus; host units in the
- *         chain (xinsert, fbdelay, ...) see materialised host buffers
- *   anything else involving our units is not supported yet (RT error).
+ *   LEAF  every audio unit is ours, no inline, and the structure has a fused
+ *         kernel: one device voice slot, the whole chain runs in one kernel
+ *         (host units without audio I/O, e.g. `env`, only write controls)
+ *   GEN   anything else: each of our units runs as its own device call on
+ *         the voice's scratch channels, which live in a device bus row
+ *         (`inline` = the bus its sub-voices mixed into); host units in the
+ *         chain (xinsert, fbdelay, dcblock, ...) see materialised host
+ *         buffers, and what they write is uploaded before our next unit.
  */
 #include <stdlib.h>
 #include <string.h>
@@ -57,7 +59,8 @@ typedef struct A2CU_unit
 	unsigned	substart;
 	int		init_transpose;
 	int		*transpose;
-	int		pm;		/* device panmix instance (BUS voices) */
+	int		pm;		/* device panmix instance (GEN voices) */
+	int		gu;		/* device generic unit (GEN voices) */
 	int		bus;		/* inline: device bus of this fragment */
 	unsigned	bus_serial;
 } A2CU_unit;
@@ -68,7 +71,7 @@ typedef struct A2CU_pending
 	unsigned	start, dur;
 } A2CU_pending;
 
-enum { VC_NEW = 0, VC_LEAF, VC_BUS, VC_BAD };
+enum { VC_NEW = 0, VC_LEAF, VC_GEN, VC_BAD };
 
 struct A2CU_voice
 {
@@ -80,9 +83,14 @@ struct A2CU_voice
 	int		pool, slot;
 	A2CU_pending	*pend;
 	int		npend, cpend;
-	/* BUS voices: where the scratch data currently lives */
-	int		cur_bus;
+	/* GEN voices: where the scratch channels of the current segment live */
+	int		scr_bus;	/* device bus row, or -1 */
+	unsigned	scr_serial;	/* fragment scr_bus belongs to */
+	int		scr_nch;
 	int		on_device;
+	/* Frame (fragment-relative) where the voice's next segment starts */
+	unsigned	cursor;
+	unsigned	cursor_serial;
 };
 
 typedef struct A2CU_wavemap { A2_wave *w; int id; } A2CU_wavemap;
@@ -240,6 +248,7 @@ static A2CU_voice *voice_for(A2CU_ctx *cx, A2_vmstate *vms, int first)
 		return NULL;
 	v->vms = vms;
 	v->pool = v->slot = -1;
+	v->scr_bus = -1;
 	cx->last_voice = v;
 	return v;
 }
@@ -266,8 +275,29 @@ static void emit_write(A2CU_ctx *cx, A2CU_voice *v, A2CU_unit *au, int reg,
 		a2cu_block_write(cx->eng, v->pool, v->slot, au->index, reg,
 				value, *au->transpose, frame, start, dur);
 	}
-	else if(v->cls == VC_BUS && au->kind == A2CU_PANMIX && au->pm >= 0)
+	else if(v->cls == VC_GEN && au->kind == A2CU_PANMIX && au->pm >= 0)
 		a2cu_block_pm_write(cx->eng, au->pm, reg, value, start, dur);
+	else if(v->cls == VC_GEN && au->gu >= 0)
+	{
+		if(au->kind == A2CU_WTOSC && reg == 0)
+			value = wave_id(cx, value >> 16) << 16;
+		a2cu_block_unit_write(cx->eng, au->gu, reg, value,
+				*au->transpose, start, dur);
+	}
+}
+
+static inline int has_audio_io(const A2_unit *u)
+{
+	return u->ninputs || u->noutputs;
+}
+
+/* Next unit of the chain that touches audio buffers (skips env & co) */
+static A2_unit *next_audio_unit(A2_unit *u)
+{
+	for(u = u->next; u; u = u->next)
+		if(is_ours(u->descriptor) || has_audio_io(u))
+			return u;
+	return NULL;
 }
 
 /* Decide what this voice is, now that its unit chain is complete. */
@@ -276,42 +306,24 @@ static void classify(A2CU_ctx *cx, A2CU_voice *v, unsigned frame)
 	A2_voice *hv = a2_voice_from_vms(v->vms);
 	A2_unit *u;
 	a2cu_unitspec chain[A2CU_MAXCHAIN];
-	int n = 0, all_ours = 1, i;
+	int n = 0, fused = 1, i;
 	for(u = hv->units; u; u = u->next)
-		if(!is_ours(u->descriptor))
-			all_ours = 0;
-	v->cls = VC_BAD;
-	if(hv->units && hv->units->descriptor == &a2_inline_unitdesc)
+		if(!is_ours(u->descriptor) && has_audio_io(u))
+			fused = 0;
+	for(i = 0; i < v->nunits && n < A2CU_MAXCHAIN; ++i, ++n)
 	{
-		/* BUS voice: our panmix units get device instances */
-		for(i = 0; i < v->nunits; ++i)
-		{
-			A2CU_unit *au = v->units[i];
-			if(au->kind == 0)
-				continue;
-			if(au->kind != A2CU_PANMIX)
-			{
-				a2r_Error(cx->st, A2_NOTIMPLEMENTED,
-						"a2cu: bus-level unit");
-				return;
-			}
-			au->pm = a2cu_pm_alloc(cx->eng);
-		}
-		v->cls = VC_BUS;
+		A2_unit *h = &v->units[i]->il.header;
+		if(!v->units[i]->kind)
+			fused = 0;		/* inline */
+		chain[n].kind = v->units[i]->kind;
+		chain[n].ninputs = h->ninputs;
+		chain[n].noutputs = h->noutputs;
+		chain[n].add = (v->units[i]->flags & A2_PROCADD) ? 1 : 0;
+		chain[n].wireout = h->outputs == hv->outputs;
 	}
-	else if(all_ours && v->nunits && v->units[0]->kind != A2CU_PANMIX &&
-			v->units[0]->kind != A2CU_FILTER12 &&
-			v->units[0]->kind != A2CU_WAVESHAPER)
+	v->cls = VC_BAD;
+	if(fused && n && a2cu_chain_supported(chain, n))
 	{
-		for(i = 0; i < v->nunits && n < A2CU_MAXCHAIN; ++i, ++n)
-		{
-			A2_unit *h = &v->units[i]->il.header;
-			chain[n].kind = v->units[i]->kind;
-			chain[n].ninputs = h->ninputs;
-			chain[n].noutputs = h->noutputs;
-			chain[n].add = (v->units[i]->flags & A2_PROCADD) ? 1 : 0;
-			chain[n].wireout = h->outputs == hv->outputs;
-		}
 		v->pool = a2cu_pool_open(cx->eng, chain, n);
 		if(v->pool < 0)
 		{
@@ -332,9 +344,35 @@ static void classify(A2CU_ctx *cx, A2CU_voice *v, unsigned frame)
 	}
 	else
 	{
-		a2r_Error(cx->st, A2_NOTIMPLEMENTED,
-				"a2cu: mixed host/device leaf voice");
-		return;
+		/* GEN voice: every DSP unit of ours gets its own device state */
+		for(i = 0; i < v->nunits; ++i)
+		{
+			A2CU_unit *au = v->units[i];
+			A2_unit *h = &au->il.header;
+			if(au->kind == 0)
+				continue;
+			if(au->kind == A2CU_PANMIX)
+			{
+				if((au->pm = a2cu_pm_alloc(cx->eng)) < 0)
+				{
+					a2r_Error(cx->st, A2_OOMEMORY,
+							a2cu_last_error());
+					return;
+				}
+				continue;
+			}
+			au->gu = a2cu_unit_alloc(cx->eng, au->kind, h->ninputs,
+					h->noutputs);
+			if(au->gu < 0)
+			{
+				a2r_Error(cx->st, A2_NOTIMPLEMENTED,
+						a2cu_last_error());
+				return;
+			}
+			a2cu_block_unit_init(cx->eng, au->gu,
+					au->init_transpose, au->substart);
+		}
+		v->cls = VC_GEN;
 	}
 	/* Control writes that arrived before the first Process() call */
 	for(i = 0; i < v->npend; ++i)
@@ -373,6 +411,7 @@ static A2_errors unit_init(A2_unit *u, A2_vmstate *vms, void *statedata,
 	au->transpose = vms->r + R_TRANSPOSE;
 	au->init_transpose = *au->transpose;
 	au->pm = -1;
+	au->gu = -1;
 	au->bus = -1;
 	au->bus_serial = 0;
 	v->units[v->nunits++] = au;
@@ -395,6 +434,8 @@ static void unit_deinit(A2_unit *u)
 	A2CU_unit *au = (A2CU_unit *)u;
 	if(au->pm >= 0)
 		a2cu_pm_free(au->cx->eng, au->pm);
+	if(au->gu >= 0)
+		a2cu_unit_free(au->cx->eng, au->gu);
 	if(au->voice)
 		voice_release(au->cx, au->voice);
 }
@@ -426,9 +467,14 @@ static void unit_write(A2_unit *u, int reg, int value, unsigned start,
 		return;
 	}
 	frag_check(cx);
-	/* The VM runs at "now": the frame of the next Process() segment */
+	/*
+	 * Writes take effect where the voice's next Process() segment starts:
+	 * the VM runs at "now" = the end of the previous segment
+	 * (core.c:1847-1880), and so do host units that write controls from
+	 * inside their own Process() (env.c:120-137) ahead of ours.
+	 */
 	emit_write(cx, v, au, reg, value,
-			(unsigned)(v->vms->waketime - cx->st->now_fragstart) >> 8,
+			v->cursor_serial == cx->serial ? v->cursor : 0,
 			start, dur);
 }
 
@@ -455,6 +501,45 @@ static void materialize(A2CU_ctx *cx, int bus, int nch, unsigned offset,
 	}
 }
 
+/* New segment of a GEN voice: nothing has written its scratch channels yet */
+static inline void seg_begin(A2CU_ctx *cx, A2CU_voice *v, A2CU_unit *au)
+{
+	if(v->scr_serial != cx->serial)
+	{
+		v->scr_serial = cx->serial;
+		v->scr_bus = -1;
+		v->on_device = 0;
+	}
+	if(au->index == 0)
+	{
+		v->on_device = 0;
+		v->scr_nch = 0;
+	}
+}
+
+static inline void seg_mark(A2CU_ctx *cx, A2CU_voice *v, unsigned offset,
+		unsigned frames)
+{
+	v->cursor = offset + frames;
+	v->cursor_serial = cx->serial;
+}
+
+/* A host unit follows and the scratch channels are on the device: hand over */
+static void handover(A2CU_ctx *cx, A2CU_voice *v, A2_unit *u, unsigned offset,
+		unsigned frames)
+{
+	A2_unit *n;
+	if(!v->on_device)
+		return;
+	n = next_audio_unit(u);
+	if(!n || is_ours(n->descriptor))
+		return;
+	if(v->scr_nch)
+		materialize(cx, v->scr_bus, v->scr_nch, offset, frames,
+				n->inputs, 0);
+	v->on_device = 0;
+}
+
 /* Process() of every replaced DSP unit (never inline) */
 static void unit_process(A2_unit *u, unsigned offset, unsigned frames)
 {
@@ -473,6 +558,7 @@ static void unit_process(A2_unit *u, unsigned offset, unsigned frames)
 		A2CU_unit *last, *owner;
 		if(au->index)
 			return;		/* one record per voice and segment */
+		seg_mark(cx, v, offset, frames);
 		last = v->units[v->nunits - 1];
 		owner = owner_find(cx, last->il.header.outputs);
 		TRACE("leaf proc slot %d [%u,+%u) owner %p\n", v->slot, offset,
@@ -518,56 +604,60 @@ static void unit_process(A2_unit *u, unsigned offset, unsigned frames)
 		}
 		return;
 	}
-	if(v->cls != VC_BUS || au->kind != A2CU_PANMIX || au->pm < 0)
+	if(v->cls != VC_GEN || (au->pm < 0 && au->gu < 0))
 		return;
-	/* Bus-level panmix */
-	TRACE("bus panmix pm %d [%u,+%u) on_device %d bus %d\n", au->pm, offset,
-			frames, v->on_device, v->cur_bus);
+	/* One unit on the voice's device scratch channels */
+	seg_begin(cx, v, au);
+	seg_mark(cx, v, offset, frames);
+	TRACE("gen unit kind %d pm %d gu %d [%u,+%u) on_device %d scr %d\n",
+			au->kind, au->pm, au->gu, offset, frames, v->on_device,
+			v->scr_bus);
 	{
-		int in_bus, out_bus, wireout, add;
+		int wire = u->outputs != u->inputs;
+		int add = (au->flags & A2_PROCADD) ? 1 : 0;
+		int out_bus = -1, host_out = 0;
 		A2CU_unit *owner;
-		wireout = u->outputs != u->inputs;
-		add = (au->flags & A2_PROCADD) ? 1 : 0;
-		if(v->on_device)
-			in_bus = v->cur_bus;
+		if(!v->on_device)
+		{
+			/* Input (if any) was written by a host unit: bring it over */
+			int nin = u->ninputs;
+			if(add && !wire && u->noutputs > nin)
+				nin = u->noutputs;
+			if(v->scr_bus < 0)
+				v->scr_bus = a2cu_block_bus(cx->eng);
+			if(nin)
+				a2cu_block_upload(cx->eng, v->scr_bus,
+						nin > 2 ? 2 : nin, offset, frames,
+						(const int32_t *const *)u->inputs);
+			if(nin > v->scr_nch)
+				v->scr_nch = nin;
+			v->on_device = 1;
+		}
+		if(wire)
+		{
+			if((owner = owner_find(cx, u->outputs)))
+				out_bus = owner->bus;
+			else
+			{
+				/* Output is a host-only bus (e.g. the master) */
+				out_bus = a2cu_block_bus(cx->eng);
+				host_out = 1;
+			}
+		}
+		if(au->pm >= 0)
+			a2cu_block_pm_proc(cx->eng, au->pm, u->ninputs,
+					u->noutputs, host_out ? 0 : add,
+					v->scr_bus, wire ? out_bus : v->scr_bus,
+					offset, frames);
 		else
-		{
-			/* A host unit wrote our input: bring it over */
-			in_bus = a2cu_block_bus(cx->eng);
-			a2cu_block_upload(cx->eng, in_bus,
-					u->ninputs > 2 ? 2 : u->ninputs,
-					offset, frames,
-					(const int32_t *const *)u->inputs);
-		}
-		if(wireout && (owner = owner_find(cx, u->outputs)))
-		{
-			a2cu_block_pm_proc(cx->eng, au->pm, u->ninputs,
-					u->noutputs, add, in_bus, owner->bus,
-					offset, frames);
-			return;
-		}
-		if(wireout)
-		{
-			/* Output is a host-only bus (e.g. the master) */
-			out_bus = a2cu_block_bus(cx->eng);
-			a2cu_block_pm_proc(cx->eng, au->pm, u->ninputs,
-					u->noutputs, 0, in_bus, out_bus,
-					offset, frames);
+			a2cu_block_unit_proc(cx->eng, au->gu, add, wire,
+					v->scr_bus, out_bus, offset, frames);
+		if(host_out)
 			materialize(cx, out_bus, u->noutputs, offset, frames,
 					u->outputs, 1);
-			return;
-		}
-		out_bus = in_bus;
-		a2cu_block_pm_proc(cx->eng, au->pm, u->ninputs, u->noutputs,
-				add, in_bus, out_bus, offset, frames);
-		v->cur_bus = out_bus;
-		v->on_device = 1;
-		if(!u->next || !is_ours(u->next->descriptor))
-		{
-			materialize(cx, out_bus, u->noutputs, offset, frames,
-					u->outputs, 0);
-			v->on_device = 0;
-		}
+		if(!wire && u->noutputs > v->scr_nch)
+			v->scr_nch = u->noutputs > 2 ? 2 : u->noutputs;
+		handover(cx, v, u, offset, frames);
 	}
 }
 
@@ -576,16 +666,31 @@ static void unit_process(A2_unit *u, unsigned offset, unsigned frames)
 	inline (src/units/inline.c, src/core.c:1763-1776)
 ---------------------------------------------------------*/
 
+static int any_nonzero(int32_t **bufs, int nch, unsigned offset, unsigned frames)
+{
+	int c;
+	unsigned i;
+	for(c = 0; c < nch; ++c)
+		for(i = 0; i < frames; ++i)
+			if(bufs[c][offset + i])
+				return 1;
+	return 0;
+}
+
 static void inline_process(A2_unit *u, unsigned offset, unsigned frames,
 		int add)
 {
 	A2CU_unit *au = (A2CU_unit *)u;
 	A2CU_voice *v = au->voice;
 	A2CU_ctx *cx = au->cx;
-	int i;
+	A2_unit *n;
+	int i, dev_pre, prev_bus;
+	int nch = u->noutputs > 2 ? 2 : u->noutputs;
 	frag_check(cx);
 	if(v->cls == VC_NEW)
 		classify(cx, v, offset);
+	seg_begin(cx, v, au);
+	seg_mark(cx, v, offset, frames);
 	if(au->bus_serial != cx->serial)
 	{
 		au->bus = a2cu_block_bus(cx->eng);
@@ -593,7 +698,14 @@ static void inline_process(A2_unit *u, unsigned offset, unsigned frames,
 	}
 	TRACE("inline %p [%u,+%u) add %d bus %d cls %d\n", (void *)au, offset,
 			frames, add, au->bus, v->cls);
-	if(!add)
+	/*
+	 * Adding inline after units of ours: what they wrote is on the device;
+	 * the host buffer then only collects what host units add below.
+	 */
+	dev_pre = add && v->on_device && (v->scr_bus >= 0) &&
+			(v->scr_bus != au->bus);
+	prev_bus = v->scr_bus;
+	if(!add || dev_pre)
 		for(i = 0; i < u->noutputs; ++i)
 			memset(u->outputs[i] + offset, 0, frames * sizeof(int));
 	/* Sub-voices that mix into u->outputs now mix into our device bus */
@@ -612,9 +724,26 @@ static void inline_process(A2_unit *u, unsigned offset, unsigned frames,
 			materialize(cx, cx->orphans[i].bus, cx->orphans[i].nch,
 					offset, frames, cx->orphans[i].outputs,
 					1);
-	v->cur_bus = au->bus;
-	v->on_device = 1;
-	if(v->cls != VC_BUS || !u->next || !is_ours(u->next->descriptor))
+	if(dev_pre)
+		a2cu_block_bus_add(cx->eng, prev_bus, au->bus, offset, frames);
+	n = next_audio_unit(u);
+	if(v->cls == VC_GEN && n && is_ours(n->descriptor) &&
+			(u->outputs == n->inputs))
+	{
+		/*
+		 * Stays on the device. Host units of sub-voices wired to this
+		 * bus (e.g. a song's `fbdelay * >`) added into the host
+		 * buffer: bring that over.
+		 */
+		if(any_nonzero(u->outputs, nch, offset, frames))
+			a2cu_block_upload_add(cx->eng, au->bus, nch, offset,
+					frames,
+					(const int32_t *const *)u->outputs);
+		v->scr_bus = au->bus;
+		v->scr_nch = nch;
+		v->on_device = 1;
+	}
+	else
 	{
 		/* A host unit (or nothing of ours) follows: hand the sum over */
 		materialize(cx, au->bus, u->noutputs, offset, frames,
