@@ -22,6 +22,7 @@
 #include <string.h>
 #include <time.h>
 #include "audiality2.h"
+#include "a2_waves.h"
 
 #ifdef A2CU_PLUGIN
 extern int a2cu_RegisterDriver(void);
@@ -48,6 +49,7 @@ int main(int argc, char **argv)
 	int noiseseed = -1;
 	const char *prog = "Song", *out = NULL, *file = NULL;
 	const char *driver = "buffer";
+	const char *dumpwave = NULL;
 	A2_config *cfg;
 	A2_driver *drv;
 	A2_interface *iface;
@@ -69,6 +71,7 @@ int main(int argc, char **argv)
 		else if(!strcmp(argv[i], "-o")) out = argv[++i];
 		else if(!strcmp(argv[i], "-d")) driver = argv[++i];
 		else if(!strcmp(argv[i], "-s")) noiseseed = atoi(argv[++i]);
+		else if(!strcmp(argv[i], "-W")) dumpwave = argv[++i];
 		else if(!strcmp(argv[i], "-a"))
 		{
 			/* 16:16 fixed point, same conversion as a2_Start() */
@@ -102,6 +105,34 @@ int main(int argc, char **argv)
 		die("a2_Open", a2_LastError());
 	if(noiseseed >= 0)
 		a2_SetStateProperty(iface, A2_PNOISESEED, noiseseed);
+	if(dumpwave)
+	{
+		/*
+		 * Checksum + the samples around the duty-cycle edge of a builtin
+		 * wave: a2_InitWaves() never writes buf[s1] of "pulse1"
+		 * (src/waves.c:639-646, `for(++s; ...)` skips one sample; later
+		 * pulses inherit -32767 from the previous one), so that sample is
+		 * whatever the stack held - it differs between processes.
+		 */
+		A2_handle wh = a2_Get(iface, A2_ROOTBANK, dumpwave);
+		A2_wave *w = wh >= 0 ? a2_GetWave(iface, wh) : NULL;
+		if(w && (w->type == A2_WWAVE || w->type == A2_WMIPWAVE))
+		{
+			unsigned k, sum = 0;
+			for(k = 0; k < w->d.wave.size[0]; ++k)
+				sum = sum * 31 + (unsigned short)
+						w->d.wave.data[0][A2_WAVEPRE + k];
+			fprintf(stderr, "wave %s size %u sum %u s[18..22] %d %d %d %d %d\n",
+					dumpwave, w->d.wave.size[0], sum,
+					w->d.wave.data[0][A2_WAVEPRE + 18],
+					w->d.wave.data[0][A2_WAVEPRE + 19],
+					w->d.wave.data[0][A2_WAVEPRE + 20],
+					w->d.wave.data[0][A2_WAVEPRE + 21],
+					w->d.wave.data[0][A2_WAVEPRE + 22]);
+		}
+		else
+			fprintf(stderr, "wave %s: not a table\n", dumpwave);
+	}
 	if((bank = a2_Load(iface, file, 0)) < 0)
 		die("a2_Load", -bank);
 	if((ph = a2_Get(iface, bank, prog)) < 0)

@@ -327,4 +327,7 @@ CASES = {
 SCRIPTS = {
     "hybrid_song": ("data/hybrid_song.a2s", "Song", 30000, 48000, 64),
     "hybrid_song_44k_b256": ("data/hybrid_song.a2s", "Song", 20000, 44100, 256),
+    # replaced units outside fused leaf voices (generic per-unit device ops)
+    "generic_chains": ("data/generic_chains.a2s", "Song", 40000, 48000, 64),
+    "generic_chains_44k_b200": ("data/generic_chains.a2s", "Song", 30000, 44100, 200),
 }

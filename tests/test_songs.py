@@ -48,6 +48,25 @@ TESTDATA = [
 ] + [("testdata", "octaves.a2s", "Octaves", 110250, 64)]
 
 
+def _wave_fingerprint(path, binary, wave):
+    import subprocess
+    res = subprocess.run([os.path.join(ao.REF_DIR, binary), "-W", wave, "-n", "64", "-p", "Song",
+                          os.path.basename(path)], cwd=os.path.dirname(path), capture_output=True, text=True)
+    for ln in res.stderr.splitlines():
+        if ln.startswith("wave " + wave):
+            return ln
+    return None
+
+
+# Songs that play builtin wave "pulse1". a2_InitWaves() leaves sample 20 of that
+# wave UNINITIALISED (src/waves.c:639-646: `for(++s; ...)` skips buf[s1]; for
+# pulse2.. the slot still holds the previous pulse's -32767, for pulse1 it is
+# whatever the stack held), so two reference processes with different call
+# histories disagree with each other. The plug-in uploads the host's own wave
+# data; the song is compared only when both processes got the same garbage.
+USES_PULSE1 = {"importtest.a2s"}
+
+
 def _render(path, program, frames, buffer, binary):
     # scripts import their neighbours by relative name: run from their directory
     cwd = os.getcwd()
@@ -65,6 +84,12 @@ def _render(path, program, frames, buffer, binary):
                          ids=[w + "/" + n for w, n, _, _, _ in BENCH + TESTDATA])
 def test_song_dropin_matches_reference(where, name, program, frames, buffer):
     path = os.path.join(SONGS, where, name)
+    if name in USES_PULSE1:
+        a = _wave_fingerprint(path, "a2render", "pulse1")
+        b = _wave_fingerprint(path, "a2render_cuda", "pulse1")
+        if a != b:
+            pytest.skip("reference UB: uninitialised sample in builtin wave pulse1 differs between "
+                        "processes (%s | %s)" % (a, b))
     ref, rinfo = _render(path, program, frames, buffer, "a2render")
     out, info = _render(path, program, frames, buffer, "a2render_cuda")
     assert np.abs(ref).max() > 0
