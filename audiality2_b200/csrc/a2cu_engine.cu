@@ -391,6 +391,17 @@ struct a2cu_engine {
     std::vector<BusCmd> buscmds;
     BusCmd *d_buscmds = nullptr;
     size_t buscmds_cap = 0;
+    // runs: the commands of one voice in this flush (one CTA of bus_level each)
+    struct HostRun { int level; unsigned count; };
+    std::vector<HostRun> runs;
+    int cur_run = -1;
+    uint32_t flush_serial = 1;
+    std::vector<BusCmd> sorted_cmds;
+    std::vector<BusRun> sorted_runs;
+    BusRun *d_runs = nullptr;
+    size_t runs_cap = 0;
+    // fbdelay delay lines (units/fbdelay.c:187-188): 2 x kFbdSize int32 each
+    std::vector<int *> fbd_free;
     int *d_bacc = nullptr;          // [bus][64][2]
     int bacc_cap = 0, nbbus = 0, prev_nbbus = 0;
     int *d_pmstate = nullptr;       // [pm][8]
@@ -398,7 +409,7 @@ struct a2cu_engine {
     std::vector<int> pm_free, pm_deferred;
     int32_t *h_xfer = nullptr;      // pinned, 64 x 2
     // generic units (any replaced unit outside a fused leaf voice, BUS_U_* ops)
-    struct GUnit { int kind = 0, nin = 0, nout = 0; bool live = false, has_osc = false; OscMirror osc; };
+    struct GUnit { int kind = 0, nin = 0, nout = 0; bool live = false, has_osc = false; OscMirror osc; int *fbd = nullptr; };
     std::vector<GUnit> gunits;
     std::vector<int> gunit_free, gunit_deferred;
     int *d_ustate = nullptr;        // [unit][kUnitWords]
@@ -504,6 +515,7 @@ static int unit_words(const a2cu_unitspec &u) {
     case A2CU_PANMIX: return 8;
     case A2CU_FILTER12: return 12 + 2 * u.ninputs;
     case A2CU_WAVESHAPER: return 4;
+    case A2CU_FBDELAY: return 10;
     default: {
         static const int nops[8] = {1, 2, 3, 4, 3, 4, 2, 4};
         return 16 * nops[u.kind - A2CU_FM1];
@@ -716,7 +728,9 @@ void a2cu_close(a2cu_engine *e) {
     cudaFree(e->d_waves); cudaFree(e->d_pool); cudaFree(e->d_cpool); cudaFree(e->d_ptab); cudaFree(e->d_fmsine);
     cudaFree(e->d_gstate); cudaFree(e->d_rstate); cudaFree(e->d_mixev);
     cudaFree(e->d_acc); cudaFree(e->d_master);
-    cudaFree(e->d_buscmds); cudaFree(e->d_bacc); cudaFree(e->d_pmstate); cudaFree(e->d_ustate);
+    cudaFree(e->d_buscmds); cudaFree(e->d_bacc); cudaFree(e->d_pmstate); cudaFree(e->d_ustate); cudaFree(e->d_runs);
+    for (auto &g : e->gunits) if (g.fbd) cudaFree(g.fbd);
+    for (int *p : e->fbd_free) cudaFree(p);
     if (e->h_xfer) cudaFreeHost(e->h_xfer);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->h_out) cudaFreeHost(e->h_out);
@@ -980,6 +994,10 @@ static int cook(a2cu_engine *e, int kind, int reg, int value, int start, uint32_
         break;
     case A2CU_WAVESHAPER:
         if (reg > 0) return fail(A2CU_EINVAL, "waveshaper has 1 register%s");
+        break;
+    case A2CU_FBDELAY:              // fbdelay.c:229-270: ms -> frames on the host, gains as they are
+        if (reg > 6) return fail(A2CU_EINVAL, "fbdelay has 7 registers%s");
+        if (reg < 3) value = (int)((int64_t)value * e->samplerate / 65536000);
         break;
     case A2CU_FILTER12:
         if (reg > 4) return fail(A2CU_EINVAL, "filter12 has 5 registers%s");
@@ -1589,6 +1607,8 @@ int a2cu_block_begin(a2cu_engine *e) {
     }
     e->pm_free.insert(e->pm_free.end(), e->pm_deferred.begin(), e->pm_deferred.end());
     e->pm_deferred.clear();
+    for (int id : e->gunit_deferred)
+        if (e->gunits[id].fbd) { e->fbd_free.push_back(e->gunits[id].fbd); e->gunits[id].fbd = nullptr; }
     e->gunit_free.insert(e->gunit_free.end(), e->gunit_deferred.begin(), e->gunit_deferred.end());
     e->gunit_deferred.clear();
     if (e->prev_nbbus < e->nbbus) e->prev_nbbus = e->nbbus;
@@ -1596,7 +1616,7 @@ int a2cu_block_begin(a2cu_engine *e) {
         CK(cudaMemsetAsync(e->d_bacc, 0, (size_t)e->prev_nbbus * kMaxFrag * 2 * sizeof(int), e->stream));
     e->prev_nbbus = 0;
     e->nbbus = 0;
-    e->buscmds.clear();
+    e->buscmds.clear(); e->runs.clear(); e->cur_run = -1; ++e->flush_serial;
     for (Bank *b : e->banks) { b->bev.clear(); b->bruns.clear(); b->cur_slot = -1; }
     int r = upload_waves(e);
     return r;
@@ -1687,7 +1707,7 @@ int a2cu_block_proc(a2cu_engine *e, int pool, int slot, unsigned frame, unsigned
     Bank *b = get_bank(e, pool);
     if (!b || !b->dynamic || frames < 1 || frame + frames > (unsigned)kMaxFrag || bus < 0 || bus >= e->nbbus)
         return fail(A2CU_EINVAL, "a2cu_block_proc: bad args%s");
-    auto mi = e->mirrors.find(((uint64_t)pool << 32) | (uint32_t)slot);
+    auto mi = e->mirrors.empty() ? e->mirrors.end() : e->mirrors.find(((uint64_t)pool << 32) | (uint32_t)slot);
     if (mi != e->mirrors.end())
         for (auto &om : mi->second.osc) {      // units run in chain order inside one segment
             bool is_noise;
@@ -1699,6 +1719,30 @@ int a2cu_block_proc(a2cu_engine *e, int pool, int slot, unsigned frame, unsigned
         }
     block_rec(b, slot, frame << 8, EV_PROC | (frames << 8), bus, 0);
     return A2CU_OK;
+}
+
+// Every bus command belongs to the run (voice) selected by a2cu_block_run().
+static void push_cmd(a2cu_engine *e, BusCmd &c) {
+    if (e->cur_run < 0) {       // caller did not name a voice: one run at the shallowest level
+        a2cu_engine::HostRun r = {0, 0};
+        e->runs.push_back(r);
+        e->cur_run = (int)e->runs.size() - 1;
+    }
+    c.run = e->cur_run;
+    ++e->runs[e->cur_run].count;
+    e->buscmds.push_back(c);
+}
+
+uint64_t a2cu_block_run(a2cu_engine *e, int level, uint64_t prev) {
+    if (!e) return 0;
+    if ((uint32_t)(prev >> 32) == e->flush_serial && (uint32_t)prev < e->runs.size()) {
+        e->cur_run = (int)(uint32_t)prev;
+        return prev;
+    }
+    a2cu_engine::HostRun r = {level < 0 ? 0 : level, 0};
+    e->runs.push_back(r);
+    e->cur_run = (int)e->runs.size() - 1;
+    return ((uint64_t)e->flush_serial << 32) | (uint32_t)e->cur_run;
 }
 
 int a2cu_pm_alloc(a2cu_engine *e) {
@@ -1736,7 +1780,7 @@ int a2cu_block_pm_write(a2cu_engine *e, int pm, int reg, int32_t value, unsigned
     BusCmd c;
     memset(&c, 0, sizeof(c));
     c.op = BUS_PM_WRITE; c.pm = pm; c.reg = reg; c.value = value; c.start = (int)(start & 0xff); c.dur = (int)dur;
-    e->buscmds.push_back(c);
+    push_cmd(e, c);
     return A2CU_OK;
 }
 
@@ -1749,7 +1793,7 @@ int a2cu_block_pm_proc(a2cu_engine *e, int pm, int nin, int nout, int add, int i
     memset(&c, 0, sizeof(c));
     c.op = BUS_PM_PROC; c.pm = pm; c.nin = nin; c.nout = nout; c.add = add ? 1 : 0;
     c.in_bus = in_bus; c.out_bus = out_bus; c.frame = (int)frame; c.frames = (int)frames;
-    e->buscmds.push_back(c);
+    push_cmd(e, c);
     return A2CU_OK;
 }
 
@@ -1758,12 +1802,21 @@ int a2cu_unit_alloc(a2cu_engine *e, int kind, int nin, int nout) {
     if (!e) return A2CU_EINVAL;
     a2cu_unitspec sp = {kind, nin, nout, 0, 0};
     bool known = kind == A2CU_WTOSC || kind == A2CU_PANMIX || kind == A2CU_FILTER12 || kind == A2CU_WAVESHAPER ||
-                 (kind >= A2CU_FM1 && kind <= A2CU_FM4R);
+                 kind == A2CU_FBDELAY || (kind >= A2CU_FM1 && kind <= A2CU_FM4R);
     if (!known || nin < 0 || nin > 2 || nout < 1 || nout > 2 || unit_words(sp) > kUnitWords)
         return fail(A2CU_ENOTIMPL, "a2cu_unit_alloc: unsupported unit / channel count%s");
     if ((kind == A2CU_FILTER12 || kind == A2CU_WAVESHAPER) && (nin != nout || nin < 1))
         return fail(A2CU_EINVAL, "a2cu_unit_alloc: unit needs matching i/o%s");
+    if (kind == A2CU_FBDELAY && nin < 1) return fail(A2CU_EINVAL, "a2cu_unit_alloc: fbdelay needs an input%s");
     cudaSetDevice(e->device);
+    int *fbd = nullptr;
+    if (kind == A2CU_FBDELAY) {
+        const size_t bytes = (size_t)2 * kFbdSize * sizeof(int);
+        if (!e->fbd_free.empty()) { fbd = e->fbd_free.back(); e->fbd_free.pop_back(); }
+        else if (cudaMalloc(&fbd, bytes) != cudaSuccess)
+            return fail(A2CU_ENOMEM, "cudaMalloc fbdelay lines: %s", cudaGetErrorString(cudaGetLastError()));
+        CK(cudaMemsetAsync(fbd, 0, bytes, e->stream));
+    }
     int id;
     if (!e->gunit_free.empty()) { id = e->gunit_free.back(); e->gunit_free.pop_back(); }
     else {
@@ -1784,7 +1837,7 @@ int a2cu_unit_alloc(a2cu_engine *e, int kind, int nin, int nout) {
         e->gunits.emplace_back();
     }
     a2cu_engine::GUnit &g = e->gunits[id];
-    g.kind = kind; g.nin = nin; g.nout = nout; g.live = true; g.has_osc = false;
+    g.kind = kind; g.nin = nin; g.nout = nout; g.live = true; g.has_osc = false; g.fbd = fbd;
     return id;
 }
 
@@ -1806,7 +1859,7 @@ static void gunit_cmd(a2cu_engine *e, int op, int unit, const a2cu_engine::GUnit
     memset(&c, 0, sizeof(c));
     c.op = op; c.pm = unit; c.kind = g.kind; c.nin = g.nin; c.nout = g.nout;
     c.reg = reg; c.value = value; c.start = start; c.dur = dur;
-    e->buscmds.push_back(c);
+    push_cmd(e, c);
 }
 
 int a2cu_block_unit_init(a2cu_engine *e, int unit, int transpose, unsigned substart) {
@@ -1815,6 +1868,17 @@ int a2cu_block_unit_init(a2cu_engine *e, int unit, int transpose, unsigned subst
     int arg = 0;
     if (g->kind == A2CU_WTOSC || g->kind >= A2CU_FM1) arg = transpose + e->basepitch;
     else if (g->kind == A2CU_FILTER12) arg = transpose;
+    if (g->kind == A2CU_FBDELAY) {
+        // fbdelay.c:176-208: cleared delay lines, default registers
+        const uint64_t ptr = (uint64_t)(uintptr_t)g->fbd;
+        gunit_cmd(e, BUS_U_INIT, unit, *g, 0, (int)(uint32_t)ptr, 0, (int)(uint32_t)(ptr >> 32));
+        static const int defaults[7] = {400 << 16, 280 << 16, 320 << 16, 65536, 16384, 32768, 32768};
+        for (int r = 0; r < 7; ++r) {
+            int r2 = a2cu_block_unit_write(e, unit, r, defaults[r], 0, 0, 0);
+            if (r2) return r2;
+        }
+        return A2CU_OK;
+    }
     gunit_cmd(e, BUS_U_INIT, unit, *g, 0, arg, (int)(substart & 0xff), 0);
     if (g->kind == A2CU_FILTER12)
         gunit_cmd(e, BUS_U_WRITE, unit, *g, 5, tables().f12_coeff((int)((unsigned)arg << 8), e->samplerate), 0, 0);
@@ -1859,7 +1923,7 @@ int a2cu_block_unit_proc(a2cu_engine *e, int unit, int add, int wireout, int scr
     c.add = (add ? 1 : 0) | (wireout ? 2 : 0);
     c.in_bus = scratch_bus; c.out_bus = wireout ? out_bus : scratch_bus;
     c.frame = (int)frame; c.frames = (int)frames;
-    e->buscmds.push_back(c);
+    push_cmd(e, c);
     return A2CU_OK;
 }
 
@@ -1870,7 +1934,7 @@ int a2cu_block_bus_add(a2cu_engine *e, int src_bus, int dst_bus, unsigned frame,
     BusCmd c;
     memset(&c, 0, sizeof(c));
     c.op = BUS_ADD; c.in_bus = src_bus; c.out_bus = dst_bus; c.frame = (int)frame; c.frames = (int)frames;
-    e->buscmds.push_back(c);
+    push_cmd(e, c);
     return A2CU_OK;
 }
 
@@ -1943,24 +2007,59 @@ static int block_flush_impl(a2cu_engine *e) {
         b->bev.clear(); b->bruns.clear(); b->cur_slot = -1;
     }
     if (!e->buscmds.empty()) {
-        size_t n = e->buscmds.size();
+        // Order runs by nest level, deepest first (stable), and lay their
+        // commands out contiguously; one bus_level launch per level.
+        const size_t n = e->buscmds.size(), nr = e->runs.size();
+        int maxlevel = 0;
+        for (const auto &r : e->runs) maxlevel = std::max(maxlevel, r.level);
+        std::vector<unsigned> level_runs(maxlevel + 2, 0);
+        for (const auto &r : e->runs) if (r.count) ++level_runs[r.level];
+        // run order: level maxlevel first
+        std::vector<unsigned> level_first(maxlevel + 2, 0);
+        unsigned pos = 0;
+        for (int l = maxlevel; l >= 0; --l) { level_first[l] = pos; pos += level_runs[l]; }
+        const unsigned nlive = pos;
+        e->sorted_runs.assign(nlive, BusRun{0, 0});
+        std::vector<unsigned> run_pos(nr, 0xffffffffu), fill(level_first);
+        for (size_t i = 0; i < nr; ++i)
+            if (e->runs[i].count) run_pos[i] = fill[e->runs[i].level]++;
+        for (size_t i = 0; i < nr; ++i)
+            if (e->runs[i].count) e->sorted_runs[run_pos[i]].count = e->runs[i].count;
+        unsigned cpos = 0;
+        for (unsigned i = 0; i < nlive; ++i) { e->sorted_runs[i].begin = cpos; cpos += e->sorted_runs[i].count; }
+        e->sorted_cmds.resize(n);
+        std::vector<unsigned> wr(nlive);
+        for (unsigned i = 0; i < nlive; ++i) wr[i] = e->sorted_runs[i].begin;
+        for (size_t i = 0; i < n; ++i) e->sorted_cmds[wr[run_pos[e->buscmds[i].run]]++] = e->buscmds[i];
         if (n > e->buscmds_cap) {
             CK(cudaStreamSynchronize(e->stream));
             if (e->d_buscmds) cudaFree(e->d_buscmds);
             e->buscmds_cap = n * 2;
             CK(cudaMalloc(&e->d_buscmds, e->buscmds_cap * sizeof(BusCmd)));
         }
-        CK(cudaMemcpyAsync(e->d_buscmds, e->buscmds.data(), n * sizeof(BusCmd), cudaMemcpyHostToDevice, e->stream));
-        e->h2d_bytes += n * sizeof(BusCmd);
+        if (nlive > e->runs_cap) {
+            CK(cudaStreamSynchronize(e->stream));
+            if (e->d_runs) cudaFree(e->d_runs);
+            e->runs_cap = (size_t)nlive * 2;
+            CK(cudaMalloc(&e->d_runs, e->runs_cap * sizeof(BusRun)));
+        }
+        CK(cudaMemcpyAsync(e->d_buscmds, e->sorted_cmds.data(), n * sizeof(BusCmd), cudaMemcpyHostToDevice, e->stream));
+        CK(cudaMemcpyAsync(e->d_runs, e->sorted_runs.data(), nlive * sizeof(BusRun), cudaMemcpyHostToDevice,
+                           e->stream));
+        e->h2d_bytes += n * sizeof(BusCmd) + nlive * sizeof(BusRun);
         BusVmParams BP;
         memset(&BP, 0, sizeof(BP));
-        BP.cmds = e->d_buscmds; BP.ncmd = (int)n; BP.acc = e->d_bacc; BP.pmstate = e->d_pmstate;
+        BP.cmds = e->d_buscmds; BP.acc = e->d_bacc; BP.pmstate = e->d_pmstate;
         BP.ustate = e->d_ustate;
         BP.ctx.waves = e->d_waves; BP.ctx.pool = e->d_pool; BP.ctx.cpool = e->d_cpool; BP.ctx.ptab = e->d_ptab;
         BP.ctx.fmsine = e->d_fmsine; BP.ctx.samplerate = e->samplerate;
-        bus_vm<<<1, kMaxFrag, 0, e->stream>>>(BP);
-        ++e->launches;
-        e->buscmds.clear();
+        for (int l = maxlevel; l >= 0; --l) {
+            if (!level_runs[l]) continue;
+            BP.runs = e->d_runs + level_first[l];
+            bus_level<<<level_runs[l], kMaxFrag, 0, e->stream>>>(BP);
+            ++e->launches;
+        }
+        e->buscmds.clear(); e->runs.clear(); e->cur_run = -1; ++e->flush_serial;
     }
     CK(cudaGetLastError());
     return A2CU_OK;

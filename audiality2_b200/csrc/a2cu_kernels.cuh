@@ -372,21 +372,32 @@ __global__ void __launch_bounds__(256) mix_root(const MixParams P) {
 
 // ---------------------------------------------------------------------------
 // Drop-in mode bus stage: the bus-level Process()/write calls the host made
-// during its tree walk, replayed in order by one CTA.
+// during its tree walk.
+//
+// Commands are grouped into RUNS: all commands one voice received in this
+// flush, in host order. Data only flows upwards in the voice tree (a voice's
+// output is `+=`-ed into its parent's bus, core.c:1763-1776), so runs of the
+// same nest level are independent of each other: the engine launches
+// bus_level once per nest level, deepest first, one CTA per run. Adds into a
+// bus another run of the level may also add to (wire-outs into the parent's
+// bus) are integer atomics - order-free, bit-exact.
 //
 //   BUS_PM_*   bus-level panmix (panmix.c, all variants): control part on
 //              thread 0, frames in closed form across the CTA
 //   BUS_U_*    any other replaced unit called outside a fused leaf voice
 //              ({inline; filter12}, {inline; wtosc; panmix}, {wtosc; panmix;
-//              fbdelay}, {inline; waveshaper; fbdelay; ...}): one Process()
-//              call of ONE unit, exactly as the reference runs it (unit by
-//              unit over the segment, core.c:1875-1876), with the voice's
-//              scratch channels held in a device bus row instead of
-//              st->scratch[nest]. The unit templates are the same code the
-//              fused kernels use, instantiated in replace mode; add / wire-out
-//              (A2_PROCADD, A2_IO_WIREOUT) are applied here. Recurrences run
-//              on thread 0.
-//   BUS_ADD    dst bus += src bus (an adding `inline` after device scratch)
+//              dcblock}, ...): one Process() call of ONE unit, exactly as the
+//              reference runs it (unit by unit over the segment,
+//              core.c:1875-1876), with the voice's scratch channels held in a
+//              device bus row instead of st->scratch[nest]. The unit templates
+//              are the code the fused kernels use, instantiated in replace
+//              mode; add / wire-out (A2_PROCADD, A2_IO_WIREOUT) are applied
+//              here. Recurrences run on thread 0.
+//              kind A2CU_FBDELAY: units/fbdelay.c:68-127; frames run in
+//              parallel when no tap of the call can see a sample written by
+//              the same call, else on thread 0.
+//   BUS_ADD    dst bus += src bus (an adding `inline` after device scratch,
+//              host contributions uploaded into a staging row)
 // ---------------------------------------------------------------------------
 enum BusOp { BUS_PM_PROC = 0, BUS_PM_WRITE = 1, BUS_U_INIT = 2, BUS_U_WRITE = 3, BUS_U_SEED = 4, BUS_U_RUN = 5,
              BUS_ADD = 6 };
@@ -397,14 +408,18 @@ struct BusCmd {
     int frame, frames;
     int reg, value, start, dur;
     int kind;               // BUS_U_*: unit kind (A2CU_*)
-    int pad[2];
+    int run;                // host side: run this command belongs to
+    int pad;
 };
+struct BusRun { unsigned begin, count; };
 
 constexpr int kUnitWords = 64;      // state words reserved per generic unit (fm4: 16 x 4)
+constexpr int kFbdKind = 5;         // A2CU_FBDELAY
+constexpr int kFbdSize = 131072;    // A2FBD_BUFSIZE, fbdelay.c:26
 
 struct BusVmParams {
     const BusCmd *cmds;
-    int ncmd;
+    const BusRun *runs;     // this level's runs; grid = number of runs
     int *acc;               // [bus][64][2]
     int *pmstate;           // [pm][8]
     int *ustate;            // [unit][kUnitWords]
@@ -429,7 +444,7 @@ __device__ __noinline__ void bus_unit_op(const Ctx &ctx, const BusCmd &c, int *s
     }
     const bool add = c.add & 1, wire = (c.add & 2) != 0;
     u.prepare(ctx, c.frames);
-    if (seeded) u.seed(seed);       // after prepare: load()/prepare() do not touch it, but keep the order explicit
+    if (seeded) u.seed(seed);
     for (int i = 0; i < c.frames; ++i) {
         int *s = acc + ((size_t)c.in_bus * kMaxFrag + c.frame + i) * 2;
         const int in0 = s[0], in1 = s[1];
@@ -437,8 +452,8 @@ __device__ __noinline__ void bus_unit_op(const Ctx &ctx, const BusCmd &c, int *s
         u.sample(ctx, s0, s1, o0, o1);
         if (wire) {
             int *o = acc + ((size_t)c.out_bus * kMaxFrag + c.frame + i) * 2;
-            o[0] = wadd(o[0], s0);
-            if (c.nout == 2) o[1] = wadd(o[1], s1);
+            atomicAdd(o, s0);
+            if (c.nout == 2) atomicAdd(o + 1, s1);
         } else if (add) {
             s[0] = wadd(in0, s0);
             if (c.nout == 2) s[1] = wadd(in1, s1);
@@ -481,17 +496,84 @@ __device__ __noinline__ void bus_unit_dispatch(const Ctx &ctx, const BusCmd &c, 
     }
 }
 
-__global__ void __launch_bounds__(kMaxFrag) bus_vm(const BusVmParams P) {
+// fbdelay (units/fbdelay.c). State words: 0 fbdelay, 1 ldelay, 2 rdelay (frames,
+// converted on the host, fbdelay.c:229-245), 3 drygain, 4 fbgain, 5 lgain,
+// 6 rgain (16:16), 7 bufpos, 8/9 device pointer of the two delay lines
+// [2][kFbdSize] (zeroed by the host at allocation, fbdelay.c:187-188).
+A2CU_DEV void fbd_frame(const BusCmd &c, const int *st, int *b0, int *b1, int *acc, int i, bool wire, bool add) {
+    const unsigned mask = kFbdSize - 1;
+    const unsigned pos = (unsigned)st[7] + (unsigned)i;
+    int *s = acc + ((size_t)c.in_bus * kMaxFrag + c.frame + i) * 2;
+    const int i0 = s[0];
+    const int i1 = c.nin == 2 ? s[1] : i0;
+    // fbdelay.c:86-101 (feedback taps are cross-fed: "reverse stereo")
+    int o0 = mulshr(b1[(pos - (unsigned)st[0]) & mask], st[4], 16);
+    int o1 = mulshr(b0[(pos - (unsigned)st[0]) & mask], st[4], 16);
+    b0[pos & mask] = wadd(i0, o0);
+    b1[pos & mask] = wadd(i1, o1);
+    o0 = wadd(o0, mulshr(b0[(pos - (unsigned)st[1]) & mask], st[5], 16));
+    o1 = wadd(o1, mulshr(b1[(pos - (unsigned)st[2]) & mask], st[6], 16));
+    o0 = wadd(o0, mulshr(i0, st[3], 16));
+    o1 = wadd(o1, mulshr(i1, st[3], 16));
+    if (c.nout == 1) { o0 = wadd(o0, o1) >> 1; o1 = 0; }        // fbdelay.c:110, 119
+    if (wire) {
+        int *o = acc + ((size_t)c.out_bus * kMaxFrag + c.frame + i) * 2;
+        atomicAdd(o, o0);
+        if (c.nout == 2) atomicAdd(o + 1, o1);
+    } else if (add) {
+        s[0] = wadd(s[0], o0);
+        if (c.nout == 2) s[1] = wadd(s[1], o1);
+    } else {
+        s[0] = o0;
+        if (c.nout == 2) s[1] = o1;
+    }
+}
+
+A2CU_DEV void fbd_op(const BusCmd &c, int *st, int *acc, int tid) {
+    if (c.op == BUS_U_INIT) {
+        if (tid == 0) {
+            for (int i = 0; i < 8; ++i) st[i] = 0;
+            st[8] = c.value; st[9] = c.dur;         // delay-line pointer, low / high word
+        }
+        return;
+    }
+    if (c.op == BUS_U_WRITE) {
+        if (tid == 0 && c.reg >= 0 && c.reg < 7) st[c.reg] = c.value;
+        return;
+    }
+    int *b0 = (int *)(((unsigned long long)(unsigned)st[9] << 32) | (unsigned)st[8]);
+    int *b1 = b0 + kFbdSize;
+    const bool add = c.add & 1, wire = (c.add & 2) != 0;
+    const unsigned mask = kFbdSize - 1;
+    bool par = true;        // no tap of this call reads a slot this call writes
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const unsigned d = (unsigned)st[k] & mask;
+        par = par && d >= (unsigned)c.frames && d <= (unsigned)(kFbdSize - c.frames);
+    }
+    if (par) {
+        if (tid < c.frames) fbd_frame(c, st, b0, b1, acc, tid, wire, add);
+    } else if (tid == 0) {
+        for (int i = 0; i < c.frames; ++i) fbd_frame(c, st, b0, b1, acc, i, wire, add);
+    }
+    __syncthreads();
+    if (tid == 0) st[7] = (int)((unsigned)st[7] + (unsigned)c.frames);
+}
+
+__global__ void __launch_bounds__(kMaxFrag) bus_level(const BusVmParams P) {
     __shared__ MixSeg sg;
     const int tid = threadIdx.x;
     int *acc = P.acc;
+    const BusRun run = P.runs[blockIdx.x];
     unsigned seed = 0;
     bool seeded = false;
-    for (int i = 0; i < P.ncmd; ++i) {
-        const BusCmd c = P.cmds[i];
+    for (unsigned ci = run.begin; ci < run.begin + run.count; ++ci) {
+        const BusCmd c = P.cmds[ci];
         if (c.op >= BUS_U_INIT && c.op <= BUS_U_RUN) {
             if (c.op == BUS_U_SEED) { seed = (unsigned)c.value; seeded = true; continue; }
-            if (tid == 0) bus_unit_dispatch(P.ctx, c, P.ustate + (size_t)c.pm * kUnitWords, acc, seed, seeded);
+            int *ust = P.ustate + (size_t)c.pm * kUnitWords;
+            if (c.kind == kFbdKind) fbd_op(c, ust, acc, tid);
+            else if (tid == 0) bus_unit_dispatch(P.ctx, c, ust, acc, seed, seeded);
             if (c.op == BUS_U_RUN) seeded = false;
             __syncthreads();
             continue;
@@ -500,8 +582,8 @@ __global__ void __launch_bounds__(kMaxFrag) bus_vm(const BusVmParams P) {
             if (tid < c.frames) {
                 const int *in = acc + ((size_t)c.in_bus * kMaxFrag + c.frame + tid) * 2;
                 int *out = acc + ((size_t)c.out_bus * kMaxFrag + c.frame + tid) * 2;
-                out[0] = wadd(out[0], in[0]);
-                out[1] = wadd(out[1], in[1]);
+                atomicAdd(out, in[0]);
+                atomicAdd(out + 1, in[1]);
             }
             __syncthreads();
             continue;
@@ -554,7 +636,11 @@ __global__ void __launch_bounds__(kMaxFrag) bus_vm(const BusVmParams P) {
                 else if (c.nout == 1) r0 = (int)(((long long)i0 * v0 + (long long)i1 * v1) >> 25);
                 else { r0 = mulshr(i0, v0, 24); r1 = mulshr(i1, v1, 24); }
             }
-            if (c.add) { out[0] = wadd(out[0], r0); if (c.nout == 2) out[1] = wadd(out[1], r1); }
+            if (c.out_bus != c.in_bus) {
+                // another voice's bus (wire-out) or a private row: atomics are safe in both cases
+                if (c.add) { atomicAdd(out, r0); if (c.nout == 2) atomicAdd(out + 1, r1); }
+                else { out[0] = r0; if (c.nout == 2) out[1] = r1; }
+            } else if (c.add) { out[0] = wadd(out[0], r0); if (c.nout == 2) out[1] = wadd(out[1], r1); }
             else { out[0] = r0; if (c.nout == 2) out[1] = r1; }
         }
         __syncthreads();

@@ -92,6 +92,15 @@ SYMBOLS = {
     "a2cu_block_flush": (_I, [_VP]),
     "a2cu_block_upload": (_I, [_VP, _I, _I, _U, _U, _VP]),
     "a2cu_block_download": (_I, [_VP, _I, _I, _U, _U, _VP, _I]),
+    "a2cu_block_upload_add": (_I, [_VP, _I, _I, _U, _U, _VP]),
+    # generic units (one replaced unit per call) and per-voice command runs
+    "a2cu_block_run": (_U64, [_VP, _I, _U64]),
+    "a2cu_unit_alloc": (_I, [_VP, _I, _I, _I]),
+    "a2cu_unit_free": (_I, [_VP, _I]),
+    "a2cu_block_unit_init": (_I, [_VP, _I, _I, _U]),
+    "a2cu_block_unit_write": (_I, [_VP, _I, _I, C.c_int32, _I, _U, C.c_uint32]),
+    "a2cu_block_unit_proc": (_I, [_VP, _I, _I, _I, _I, _I, _U, _U]),
+    "a2cu_block_bus_add": (_I, [_VP, _I, _I, _U, _U]),
 }
 
 

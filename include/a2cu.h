@@ -60,6 +60,7 @@ typedef enum a2cu_error {
 /* Unit kinds (a2_core_units[], src/audiality2.c:183-207) */
 enum {
 	A2CU_WTOSC = 1, A2CU_PANMIX = 2, A2CU_FILTER12 = 3, A2CU_WAVESHAPER = 4,
+	A2CU_FBDELAY = 5,	/* units/fbdelay.c; generic unit only */
 	A2CU_FM1 = 16, A2CU_FM2, A2CU_FM3, A2CU_FM4,
 	A2CU_FM3P, A2CU_FM4P, A2CU_FM2R, A2CU_FM4R
 };
@@ -285,6 +286,15 @@ int a2cu_block_pm_proc(a2cu_engine *e, int pm, int nin, int nout, int add,
  * in the host's order, 'add' = A2_PROCADD, 'wireout' = outputs are the voice's
  * output bus 'out_bus' (A2_IO_WIREOUT, src/core.c:243-245).
  */
+/*
+ * Bus commands (a2cu_block_pm_*, a2cu_block_unit_*, a2cu_block_bus_add,
+ * a2cu_block_upload_add) belong to the voice selected by the last
+ * a2cu_block_run(): 'level' is the voice's nest level (A2_voice.nestlevel,
+ * src/internals.h:571), 'prev' the handle this function returned for the same
+ * voice earlier (0 for none).  Voices of one level run concurrently on the
+ * device, levels deepest first; commands of one voice keep their order.
+ */
+uint64_t a2cu_block_run(a2cu_engine *e, int level, uint64_t prev);
 int a2cu_unit_alloc(a2cu_engine *e, int kind, int ninputs, int noutputs);
 int a2cu_unit_free(a2cu_engine *e, int unit);
 int a2cu_block_unit_init(a2cu_engine *e, int unit, int transpose, unsigned substart);

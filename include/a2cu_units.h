@@ -17,6 +17,10 @@
  *                              brackets each sub-tree's bus on the device and
  *                              calls the host's a2_inline_ProcessAdd,
  *                              src/core.c:1763-1767, for the recursion)
+ *   src/units/fbdelay.h:28     a2_fbdelay_unitdesc (the
+ *                              effect every song chains right after its
+ *                              mix-down; on the host it would force a device
+ *                              round trip per song and fragment)
  *
  * Each descriptor carries the reference's name, flags, register names in VM
  * register order, constants and I/O limits (include/a2_units.h:225-252), so
@@ -25,7 +29,7 @@
  * :176 (Process).
  *
  * Build the host as the reference minus src/units/{wtosc,panmix,filter12,fm,
- * waveshaper,inline}.c and link this library in their place.
+ * waveshaper,inline,fbdelay}.c and link this library in their place.
  *
  * a2cu_RegisterDriver() additionally registers a "cuda" audio driver
  * (a2_RegisterDriver, include/a2_drivers.h:193) that behaves like the
@@ -56,6 +60,7 @@ extern const struct A2_unitdesc a2_fm4p_unitdesc;
 extern const struct A2_unitdesc a2_fm2r_unitdesc;
 extern const struct A2_unitdesc a2_fm4r_unitdesc;
 extern const struct A2_unitdesc a2_inline_unitdesc;
+extern const struct A2_unitdesc a2_fbdelay_unitdesc;
 
 /* Returns an A2_errors code (0 = A2_OK). */
 int a2cu_RegisterDriver(void);

@@ -43,7 +43,7 @@ static void die(const char *what, int err)
 
 int main(int argc, char **argv)
 {
-	int rate = 48000, buffer = 64, channels = 2, nargs = 0, i;
+	int rate = 48000, buffer = 64, channels = 2, nargs = 0, i, copies = 1;
 	long frames = 48000, warmup = 0, done = 0;
 	int args[16];
 	int noiseseed = -1;
@@ -72,6 +72,7 @@ int main(int argc, char **argv)
 		else if(!strcmp(argv[i], "-d")) driver = argv[++i];
 		else if(!strcmp(argv[i], "-s")) noiseseed = atoi(argv[++i]);
 		else if(!strcmp(argv[i], "-W")) dumpwave = argv[++i];
+		else if(!strcmp(argv[i], "-x")) copies = atoi(argv[++i]);
 		else if(!strcmp(argv[i], "-a"))
 		{
 			/* 16:16 fixed point, same conversion as a2_Start() */
@@ -138,8 +139,28 @@ int main(int argc, char **argv)
 	if((ph = a2_Get(iface, bank, prog)) < 0)
 		die("a2_Get(program)", -ph);
 	a2_TimestampReset(iface);
-	if((vh = a2_Starta(iface, a2_RootVoice(iface), ph, nargs, args)) < 0)
-		die("a2_Starta", -vh);
+	/*
+	 * -x N: start the program N times under the root voice (BASELINE config
+	 * 5's "voice-spawn stress multiplier"); copy k gets its first argument
+	 * (P, transpose) offset by (k % 25 - 12) semitones.
+	 */
+	for(i = 0; i < copies; ++i)
+	{
+		int a[16];
+		int na = nargs;
+		memcpy(a, args, sizeof(a));
+		if(copies > 1)
+		{
+			if(!na)
+			{
+				a[0] = 0;
+				na = 1;
+			}
+			a[0] += ((i % 25) - 12) * 65536 / 12;
+		}
+		if((vh = a2_Starta(iface, a2_RootVoice(iface), ph, na, a)) < 0)
+			die("a2_Starta", -vh);
+	}
 
 	ad = (A2_audiodriver *)drv;
 	if(out && !(f = fopen(out, "wb")))

@@ -6,7 +6,9 @@
  *
  *     a2_wtosc_unitdesc  a2_panmix_unitdesc  a2_filter12_unitdesc
  *     a2_waveshaper_unitdesc  a2_fm1 .. a2_fm4, a2_fm3p, a2_fm4p, a2_fm2r,
- *     a2_fm4r _unitdesc,  and  a2_inline_unitdesc (bus bracketing)
+ *     a2_fm4r _unitdesc,  a2_inline_unitdesc (bus bracketing) and
+ *     a2_fbdelay_unitdesc (the song-level effect that follows the mix-down,
+ *     on the host it costs a device round trip per song)
  *
  * The host (A2S compiler, VM, event scheduler, voice tree, drivers) is the
  * reference's own code, unmodified; it calls Initialize / write / Process /
@@ -88,6 +90,7 @@ struct A2CU_voice
 	unsigned	scr_serial;	/* fragment scr_bus belongs to */
 	int		scr_nch;
 	int		on_device;
+	uint64_t	run;		/* a2cu_block_run handle (bus commands) */
 	/* Frame (fragment-relative) where the voice's next segment starts */
 	unsigned	cursor;
 	unsigned	cursor_serial;
@@ -265,6 +268,13 @@ static void voice_release(A2CU_ctx *cx, A2CU_voice *v)
 	free(v);
 }
 
+/* Bus commands recorded from here on belong to voice 'v' */
+static inline void select_run(A2CU_ctx *cx, A2CU_voice *v)
+{
+	v->run = a2cu_block_run(cx->eng, a2_voice_from_vms(v->vms)->nestlevel,
+			v->run);
+}
+
 static void emit_write(A2CU_ctx *cx, A2CU_voice *v, A2CU_unit *au, int reg,
 		int value, unsigned frame, unsigned start, unsigned dur)
 {
@@ -276,9 +286,13 @@ static void emit_write(A2CU_ctx *cx, A2CU_voice *v, A2CU_unit *au, int reg,
 				value, *au->transpose, frame, start, dur);
 	}
 	else if(v->cls == VC_GEN && au->kind == A2CU_PANMIX && au->pm >= 0)
+	{
+		select_run(cx, v);
 		a2cu_block_pm_write(cx->eng, au->pm, reg, value, start, dur);
+	}
 	else if(v->cls == VC_GEN && au->gu >= 0)
 	{
+		select_run(cx, v);
 		if(au->kind == A2CU_WTOSC && reg == 0)
 			value = wave_id(cx, value >> 16) << 16;
 		a2cu_block_unit_write(cx->eng, au->gu, reg, value,
@@ -345,6 +359,7 @@ static void classify(A2CU_ctx *cx, A2CU_voice *v, unsigned frame)
 	else
 	{
 		/* GEN voice: every DSP unit of ours gets its own device state */
+		select_run(cx, v);
 		for(i = 0; i < v->nunits; ++i)
 		{
 			A2CU_unit *au = v->units[i];
@@ -609,6 +624,7 @@ static void unit_process(A2_unit *u, unsigned offset, unsigned frames)
 	/* One unit on the voice's device scratch channels */
 	seg_begin(cx, v, au);
 	seg_mark(cx, v, offset, frames);
+	select_run(cx, v);
 	TRACE("gen unit kind %d pm %d gu %d [%u,+%u) on_device %d scr %d\n",
 			au->kind, au->pm, au->gu, offset, frames, v->on_device,
 			v->scr_bus);
@@ -724,6 +740,7 @@ static void inline_process(A2_unit *u, unsigned offset, unsigned frames,
 			materialize(cx, cx->orphans[i].bus, cx->orphans[i].nch,
 					offset, frames, cx->orphans[i].outputs,
 					1);
+	select_run(cx, v);	/* the recursion selected other voices */
 	if(dev_pre)
 		a2cu_block_bus_add(cx->eng, prev_bus, au->bus, offset, frames);
 	n = next_audio_unit(u);
@@ -805,6 +822,24 @@ INIT_CB(fm4p, A2CU_FM4P)
 INIT_CB(fm2r, A2CU_FM2R)
 INIT_CB(fm4r, A2CU_FM4R)
 
+/* units/fbdelay.c:176-225: default register values */
+static A2_errors fbdelay_Initialize(A2_unit *u, A2_vmstate *vms,
+		void *statedata, unsigned flags)
+{
+	A2_errors res = unit_init(u, vms, statedata, flags, A2CU_FBDELAY);
+	u->Process = unit_process;
+	if(res)
+		return res;
+	u->registers[0] = 400 << 16;
+	u->registers[1] = 280 << 16;
+	u->registers[2] = 320 << 16;
+	u->registers[3] = 65536;
+	u->registers[4] = 16384;
+	u->registers[5] = 32768;
+	u->registers[6] = 32768;
+	return A2_OK;
+}
+
 /* Register names and order: the reference's A2_crdesc tables */
 static const A2_crdesc wtosc_regs[] = {		/* wtosc.c:507-514 */
 	{ "w", unit_write0 }, { "p", unit_write1 }, { "a", unit_write2 },
@@ -820,6 +855,12 @@ static const A2_constdesc panmix_constants[] = {	/* panmix.c:305-311 */
 static const A2_crdesc filter12_regs[] = {	/* filter12.c:231-239 */
 	{ "cutoff", unit_write0 }, { "q", unit_write1 }, { "lp", unit_write2 },
 	{ "bp", unit_write3 }, { "hp", unit_write4 }, { NULL, NULL }
+};
+static const A2_crdesc fbdelay_regs[] = {	/* fbdelay.c:286-296 */
+	{ "fbdelay", unit_write0 }, { "ldelay", unit_write1 },
+	{ "rdelay", unit_write2 }, { "drygain", unit_write3 },
+	{ "fbgain", unit_write4 }, { "lgain", unit_write5 },
+	{ "rgain", unit_write6 }, { NULL, NULL }
 };
 static const A2_crdesc waveshaper_regs[] = {	/* waveshaper.c:166-170 */
 	{ "amount", unit_write0 }, { NULL, NULL }
@@ -881,6 +922,9 @@ UNITDESC(a2_fm2r_unitdesc, "fm2r", 0, fm2_regs, NULL, 0, 0, 1, 1,
 		fm2r_Initialize)
 UNITDESC(a2_fm4r_unitdesc, "fm4r", 0, fm_regs, NULL, 0, 0, 1, 1,
 		fm4r_Initialize)
+/* fbdelay.c:298-319 */
+UNITDESC(a2_fbdelay_unitdesc, "fbdelay", 0, fbdelay_regs, NULL, 1, 2, 1, 2,
+		fbdelay_Initialize)
 /* units/inline.c:49-69 */
 UNITDESC(a2_inline_unitdesc, "inline", 0, NULL, NULL, 0, 0, 1, A2_MAXCHANNELS,
 		inline_Initialize)
