@@ -309,11 +309,13 @@ struct Bank {
     std::vector<HostEvent> events;
     uint32_t seq = 0;
     // per-window device buffers (grown on demand)
-    unsigned *d_evoff = nullptr;
+    unsigned *d_evoff = nullptr;    // views into d_ev (bank mode): CSR offsets, then records
+    uint4 *d_evrecs = nullptr;
     uint4 *d_ev = nullptr;
     size_t ev_cap = 0;
     bool has_noise = false;
     bool exotic = false;    // selected a noise / non-mip / table-less wave: render_bank only
+    bool enabled = true;    // a2cu_bank_enable: a disabled bank is paused (not rendered, events kept)
     int stage_wave = -1;    // wave whose coefficient table render_split stages in shared memory
     uint32_t stamp = 0;
     // drop-in ("block") mode: dynamic slots + per-flush recording
@@ -328,6 +330,14 @@ struct Bank {
     bool dup_runs = false;              // some slot has more than one run in this flush
     VoiceRun *d_runs = nullptr;
     size_t runs_cap = 0;
+    // slot has an entry in a2cu_engine::mirrors (spares the map lookup on the
+    // per-call recording path)
+    std::vector<uint8_t> has_mirror;
+    bool mirrored(int slot) const { return (size_t)slot < has_mirror.size() && has_mirror[slot]; }
+    void set_mirrored(int slot, bool on) {
+        if ((size_t)slot >= has_mirror.size()) { if (!on) return; has_mirror.resize((size_t)slot + 256, 0); }
+        has_mirror[slot] = on ? 1 : 0;
+    }
 };
 
 struct MixHostEvent {
@@ -370,6 +380,23 @@ struct a2cu_engine {
     // pinned staging
     void *h_stage = nullptr;
     size_t stage_cap = 0;
+    // staging ring: run_window alternates between kStageRing pinned buffers so a
+    // window can be staged while the previous one's H2D copies are still queued
+    static const int kStageRing = 3;
+    void *stage_buf[kStageRing] = {nullptr, nullptr, nullptr};
+    size_t stage_bufcap[kStageRing] = {0, 0, 0};
+    cudaEvent_t stage_done[kStageRing] = {nullptr, nullptr, nullptr};
+    bool stage_used[kStageRing] = {false, false, false};
+    int stage_pos = 0;
+    // pipelined API (a2cu_submit / a2cu_collect): result slots
+    static const int kSlots = 4;
+    struct Slot {
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, done = nullptr;
+        int32_t *h_out = nullptr;
+        size_t cap = 0, n = 0;
+        bool busy = false;
+    } slots[kSlots];
+    int slot_pos = 0;
     int32_t *h_out = nullptr;
     size_t hout_cap = 0;
     uint64_t launches = 0, h2d_bytes = 0, d2h_bytes = 0;
@@ -548,14 +575,32 @@ static int mirror_create(a2cu_engine *e, int bank, int slot, VoiceMirror **out) 
     }
     e->mirrors[key] = vm;
     *out = &e->mirrors[key];
+    b->set_mirrored(slot, true);
     return A2CU_OK;
 }
 
+// Next pinned staging buffer of the ring, at least 'bytes' large. Blocks only if
+// the H2D copies issued from that buffer kStageRing windows ago are still
+// pending (they never are in steady state).
 static int ensure_stage(a2cu_engine *e, size_t bytes) {
-    if (bytes <= e->stage_cap) return 0;
-    if (e->h_stage) cudaFreeHost(e->h_stage);
-    e->stage_cap = std::max(bytes * 2, (size_t)1 << 20);
-    CK(cudaMallocHost(&e->h_stage, e->stage_cap));
+    const int k = e->stage_pos;
+    e->stage_pos = (k + 1) % a2cu_engine::kStageRing;
+    if (!e->stage_done[k]) CK(cudaEventCreateWithFlags(&e->stage_done[k], cudaEventDisableTiming));
+    if (e->stage_used[k]) CK(cudaEventSynchronize(e->stage_done[k]));
+    if (bytes > e->stage_bufcap[k]) {
+        if (e->stage_buf[k]) cudaFreeHost(e->stage_buf[k]);
+        e->stage_bufcap[k] = std::max(bytes * 2, (size_t)1 << 20);
+        CK(cudaMallocHost(&e->stage_buf[k], e->stage_bufcap[k]));
+    }
+    e->h_stage = e->stage_buf[k];
+    e->stage_cap = e->stage_bufcap[k];
+    e->stage_used[k] = true;
+    return 0;
+}
+// Call after the last H2D copy that reads the current staging buffer.
+static int stage_release(a2cu_engine *e) {
+    const int k = (e->stage_pos + a2cu_engine::kStageRing - 1) % a2cu_engine::kStageRing;
+    CK(cudaEventRecord(e->stage_done[k], e->stream));
     return 0;
 }
 
@@ -722,7 +767,7 @@ void a2cu_close(a2cu_engine *e) {
     cudaStreamSynchronize(e->stream);
     for (Bank *b : e->banks) {
         cudaFree(b->d_state); cudaFree(b->d_bus); cudaFree(b->d_noise);
-        cudaFree(b->d_evoff); cudaFree(b->d_ev); cudaFree(b->d_runs);
+        cudaFree(b->d_ev); cudaFree(b->d_runs);
         delete b;
     }
     cudaFree(e->d_waves); cudaFree(e->d_pool); cudaFree(e->d_cpool); cudaFree(e->d_ptab); cudaFree(e->d_fmsine);
@@ -732,7 +777,17 @@ void a2cu_close(a2cu_engine *e) {
     for (auto &g : e->gunits) if (g.fbd) cudaFree(g.fbd);
     for (int *p : e->fbd_free) cudaFree(p);
     if (e->h_xfer) cudaFreeHost(e->h_xfer);
-    if (e->h_stage) cudaFreeHost(e->h_stage);
+    for (int k = 0; k < a2cu_engine::kStageRing; ++k) {
+        if (e->stage_buf[k]) cudaFreeHost(e->stage_buf[k]);
+        if (e->stage_done[k]) cudaEventDestroy(e->stage_done[k]);
+    }
+    for (auto &sl : e->slots) {
+        if (sl.h_out) cudaFreeHost(sl.h_out);
+        if (sl.ev0) cudaEventDestroy(sl.ev0);
+        if (sl.ev1) cudaEventDestroy(sl.ev1);
+        if (sl.ev2) cudaEventDestroy(sl.ev2);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
     if (e->h_out) cudaFreeHost(e->h_out);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -923,8 +978,7 @@ int a2cu_bank_new(a2cu_engine *e, const a2cu_unitspec *chain, int nunits, int nv
         if (chain[u].kind == A2CU_WTOSC) b->has_noise = true;   // may select the noise wave later
     size_t sbytes = (size_t)b->k.words * b->stride * sizeof(int);
     if (cudaMalloc(&b->d_state, sbytes) != cudaSuccess || cudaMalloc(&b->d_bus, b->stride * sizeof(int)) != cudaSuccess ||
-        cudaMalloc(&b->d_noise, b->stride * sizeof(unsigned)) != cudaSuccess ||
-        cudaMalloc(&b->d_evoff, (b->stride + 1) * sizeof(unsigned)) != cudaSuccess) {
+        cudaMalloc(&b->d_noise, b->stride * sizeof(unsigned)) != cudaSuccess) {
         delete b;
         return fail(A2CU_ENOMEM, "cudaMalloc bank state: %s", cudaGetErrorString(cudaGetLastError()));
     }
@@ -1058,11 +1112,49 @@ int a2cu_bank_write_all(a2cu_engine *e, int bank, int unit, int reg, const int32
     Bank *b = get_bank(e, bank);
     if (!b || !values) return fail(A2CU_EINVAL, "bad bank%s");
     if (when < e->now) return fail(A2CU_ELATE, "event time already rendered%s");
-    b->events.reserve(b->events.size() + b->nvoices);
-    for (int i = 0; i < b->nvoices; ++i) {
-        int r = cook_write(e, b, i, unit, reg, values[(size_t)i * stride], when, dur);
-        if (r) return r;
+    if (unit < 0 || unit >= (int)b->chain.size()) return fail(A2CU_EINVAL, "bad unit%s");
+    b->events.reserve(b->events.size() + 2 * (size_t)b->nvoices);
+    const int kind = b->chain[unit].kind;
+    // registers whose cooked value depends on the voice (transpose) or needs the wave checks
+    const bool per_voice = (kind == A2CU_WTOSC && reg <= 1) || (kind == A2CU_FILTER12 && reg == 0) ||
+                           (kind >= A2CU_FM1 && reg == 1);
+    if (per_voice) {
+        for (int i = 0; i < b->nvoices; ++i) {
+            int r = cook_write(e, b, i, unit, reg, values[(size_t)i * stride], when, dur);
+            if (r) return r;
+        }
+        return A2CU_OK;
     }
+    // bulk path: the cooked record is a function of the value alone
+    Cooked c[2];
+    int n = cook(e, kind, reg, values[0], (int)(when & 0xff), dur, 0, c);
+    if (n < 0) return n;
+    const uint32_t y0 = (uint32_t)EV_WRITE | ((uint32_t)unit << 8);
+    HostEvent ev;
+    ev.time = when; ev.dur = dur;
+    for (int i = 0; i < b->nvoices; ++i) {
+        if (stride && i) {
+            n = cook(e, kind, reg, values[(size_t)i * stride], (int)(when & 0xff), dur, 0, c);
+            if (n < 0) return n;
+        }
+        ev.voice = i;
+        for (int k = 0; k < n; ++k) {
+            ev.seq = b->seq++;
+            ev.y = y0 | ((uint32_t)(c[k].reg & 0xff) << 16);
+            ev.value = c[k].value; ev.dur = c[k].dur;
+            b->events.push_back(ev);
+        }
+    }
+    return A2CU_OK;
+}
+
+// Pause / resume a bank: a disabled bank is not rendered (its voices keep their
+// state, its pending writes apply when it runs again). Lets one engine serve
+// many voice banks round-robin.
+int a2cu_bank_enable(a2cu_engine *e, int bank, int enabled) {
+    Bank *b = get_bank(e, bank);
+    if (!b || b->dynamic) return fail(A2CU_EINVAL, "bad bank%s");
+    b->enabled = enabled != 0;
     return A2CU_OK;
 }
 
@@ -1282,6 +1374,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     std::vector<std::vector<HostEvent>> due(e->banks.size());
     for (size_t bi = 0; bi < e->banks.size(); ++bi) {
         Bank *b = e->banks[bi];
+        if (!b->enabled || b->events.empty()) continue;
         bool all_due = true;
         for (auto &ev : b->events)
             if (ev.time >= t1) { all_due = false; break; }
@@ -1323,8 +1416,6 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         return a.seq < c.seq;
     });
     stage_bytes += mdue.size() * sizeof(MixEvent) + 64;
-    if (stage_bytes > 128)
-        CK(cudaStreamSynchronize(e->stream));  // the pinned staging buffer is reused
     r = ensure_stage(e, stage_bytes);
     if (r) return r;
     char *stage = (char *)e->h_stage;
@@ -1345,38 +1436,43 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         P.samplerate = e->samplerate;
         if (!due[bi].empty()) {
             size_t nev = due[bi].size();
+            // device layout: [CSR offsets (stride + 1, padded to 16 B) | records] - one H2D copy
+            const size_t off_bytes = (((b->stride + 1) * sizeof(unsigned)) + 15) & ~(size_t)15;
             if (nev > b->ev_cap) {
                 if (b->d_ev) cudaFree(b->d_ev);
                 b->ev_cap = nev * 2;
-                CK(cudaMalloc(&b->d_ev, b->ev_cap * sizeof(uint4)));
+                CK(cudaMalloc(&b->d_ev, off_bytes + b->ev_cap * sizeof(uint4)));
             }
-            unsigned *off = (unsigned *)(stage + spos);
-            spos += (b->stride + 1) * sizeof(unsigned);
             spos = (spos + 15) & ~(size_t)15;
-            uint4 *recs = (uint4 *)(stage + spos);
-            spos += nev * sizeof(uint4);
-            size_t k = 0;
-            for (size_t v = 0; v <= b->stride; ++v) {
-                while (k < nev && (size_t)due[bi][k].voice < v) ++k;
-                off[v] = (unsigned)k;
+            unsigned *off = (unsigned *)(stage + spos);
+            uint4 *recs = (uint4 *)(stage + spos + off_bytes);
+            spos += off_bytes + nev * sizeof(uint4);
+            {
+                // due[bi] is sorted by voice: CSR offsets in one pass
+                size_t k = 0;
+                const HostEvent *d = due[bi].data();
+                for (size_t v = 0; v <= b->stride; ++v) {
+                    while (k < nev && (size_t)d[k].voice < v) ++k;
+                    off[v] = (unsigned)k;
+                }
+                for (size_t i = 0; i < nev; ++i) {
+                    // events of a bank that was paused carry times before t0: they apply at the window start
+                    const unsigned rel = d[i].time >= t0 ? (unsigned)(d[i].time - t0) : (unsigned)(d[i].time & 0xff);
+                    recs[i] = make_uint4(rel, d[i].y, (unsigned)d[i].value, d[i].dur);
+                }
             }
-            for (size_t i = 0; i < nev; ++i) {
-                const HostEvent &ev = due[bi][i];
-                uint64_t rel = ev.time - t0;                // >= 0: late writes are refused
-                recs[i] = make_uint4((unsigned)rel, ev.y, (unsigned)ev.value, ev.dur);
-            }
-            CK(cudaMemcpyAsync(b->d_evoff, off, (b->stride + 1) * sizeof(unsigned), cudaMemcpyHostToDevice,
-                               e->stream));
-            CK(cudaMemcpyAsync(b->d_ev, recs, nev * sizeof(uint4), cudaMemcpyHostToDevice, e->stream));
+            CK(cudaMemcpyAsync(b->d_ev, off, off_bytes + nev * sizeof(uint4), cudaMemcpyHostToDevice, e->stream));
             e->h2d_bytes += (b->stride + 1) * sizeof(unsigned) + nev * sizeof(uint4);
-            P.ev_off = b->d_evoff; P.ev = b->d_ev;
+            b->d_evoff = (unsigned *)b->d_ev;
+            b->d_evrecs = (uint4 *)((char *)b->d_ev + off_bytes);
+            P.ev_off = b->d_evoff; P.ev = b->d_evrecs;
         }
     }
     // inputs are resident from here on: ev0 .. ev1 brackets the render kernels
     if (e->timing) CK(cudaEventRecord(e->ev0, e->stream));
     for (size_t bi = 0; bi < e->banks.size(); ++bi) {
         Bank *b = e->banks[bi];
-        if (b->dynamic || !b->nvoices) continue;
+        if (b->dynamic || !b->nvoices || !b->enabled) continue;
         bool split = e->use_split && b->k.split_fn && !b->exotic && nsplits <= 1;
         if (split && (!due[bi].empty() || nsplits)) {
             // at most kSplitSegs segments per voice and fragment
@@ -1389,7 +1485,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             for (const HostEvent &ev : due[bi]) {
                 if (ev.time != memo_time) {     // bulk writes share one time stamp
                     memo_time = ev.time;
-                    f = (int)((ev.time - t0) >> 8);
+                    f = ev.time >= t0 ? (int)((ev.time - t0) >> 8) : 0;
                     fs = frag_start(f);
                 }
                 if (ev.voice != cur_voice || fs != cur_frag) {
@@ -1448,6 +1544,8 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         e->h2d_bytes += mdue.size() * sizeof(MixEvent);
         M.ev = e->d_mixev;
     }
+    r = stage_release(e);
+    if (r) return r;
     M.master = dev_out ? dev_out : e->d_master;
     M.root_stage = e->post_root ? 1 : 0;
     if (e->ngroups) {
@@ -1508,6 +1606,65 @@ int a2cu_run(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *out) {
     r = a2cu_sync(e);
     if (r) return r;
     if (out) memcpy(out, e->h_out, n * sizeof(int32_t));
+    return A2CU_OK;
+}
+
+// ---- pipelined rendering ---------------------------------------------------
+// a2cu_submit queues one window (event staging, H2D, kernels, D2H of the
+// master block into a pinned result slot) and returns at once; a2cu_collect
+// waits for that window only. With two windows in flight the host stages
+// window i+1 while the device renders window i.
+int a2cu_submit(a2cu_engine *e, unsigned frames, unsigned buffer) {
+    if (!e) return A2CU_EINVAL;
+    cudaSetDevice(e->device);
+    const int k = e->slot_pos;
+    a2cu_engine::Slot &sl = e->slots[k];
+    if (sl.busy) return fail(A2CU_EINVAL, "a2cu_submit: %s", "all result slots in flight, a2cu_collect first");
+    if (!sl.done) {
+        CK(cudaEventCreate(&sl.ev0)); CK(cudaEventCreate(&sl.ev1)); CK(cudaEventCreate(&sl.ev2));
+        CK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    }
+    const int och = e->post_root ? e->channels : 2;
+    const size_t n = (size_t)frames * och;
+    if ((size_t)frames * 2 > e->master_cap) {
+        CK(cudaStreamSynchronize(e->stream));
+        if (e->d_master) cudaFree(e->d_master);
+        e->master_cap = (size_t)frames * 4;
+        CK(cudaMalloc(&e->d_master, e->master_cap * sizeof(int)));
+    }
+    if (n > sl.cap) {
+        if (sl.h_out) cudaFreeHost(sl.h_out);
+        sl.cap = n * 2;
+        CK(cudaMallocHost(&sl.h_out, sl.cap * sizeof(int32_t)));
+    }
+    // this window's spans go to the slot's own events
+    cudaEvent_t s0 = e->ev0, s1 = e->ev1, s2 = e->ev2;
+    e->ev0 = sl.ev0; e->ev1 = sl.ev1; e->ev2 = sl.ev2;
+    int r = run_window(e, frames, buffer, nullptr);
+    e->ev0 = s0; e->ev1 = s1; e->ev2 = s2;
+    if (r) return r;
+    CK(cudaMemcpyAsync(sl.h_out, e->d_master, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaEventRecord(sl.done, e->stream));
+    e->d2h_bytes += n * sizeof(int32_t);
+    sl.n = n;
+    sl.busy = true;
+    e->slot_pos = (k + 1) % a2cu_engine::kSlots;
+    return k;
+}
+
+int a2cu_collect(a2cu_engine *e, int ticket, int32_t *out) {
+    if (!e || ticket < 0 || ticket >= a2cu_engine::kSlots || !e->slots[ticket].busy)
+        return fail(A2CU_EINVAL, "a2cu_collect: bad ticket%s");
+    cudaSetDevice(e->device);
+    a2cu_engine::Slot &sl = e->slots[ticket];
+    CK(cudaEventSynchronize(sl.done));
+    if (out) memcpy(out, sl.h_out, sl.n * sizeof(int32_t));
+    if (e->timing) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sl.ev0, sl.ev1) == cudaSuccess) e->last_ms = ms;
+        if (cudaEventElapsedTime(&ms, sl.ev1, sl.ev2) == cudaSuccess) e->last_mix_ms = ms;
+    }
+    sl.busy = false;
     return A2CU_OK;
 }
 
@@ -1592,7 +1749,7 @@ int a2cu_pool_free(a2cu_engine *e, int pool, int slot) {
     Bank *b = get_bank(e, pool);
     if (!b || !b->dynamic || slot < 0 || slot >= b->used) return fail(A2CU_EINVAL, "bad pool/slot%s");
     b->deferred_free.push_back(slot);     // still referenced by records of this block
-    e->mirrors.erase(((uint64_t)pool << 32) | (uint32_t)slot);
+    if (b->mirrored(slot)) { e->mirrors.erase(((uint64_t)pool << 32) | (uint32_t)slot); b->set_mirrored(slot, false); }
     return A2CU_OK;
 }
 
@@ -1662,7 +1819,10 @@ int a2cu_block_init(a2cu_engine *e, int pool, int slot, int unit, int transpose,
     if (kind == A2CU_WTOSC || kind >= A2CU_FM1) arg = transpose + e->basepitch;
     else if (kind == A2CU_FILTER12) arg = transpose;
     unsigned x = (frame << 8) | (substart & 0xff);
-    if (unit == 0) e->mirrors.erase(((uint64_t)pool << 32) | (uint32_t)slot);   // slot reused by a new voice
+    if (unit == 0 && b->mirrored(slot)) {       // slot reused by a new voice
+        e->mirrors.erase(((uint64_t)pool << 32) | (uint32_t)slot);
+        b->set_mirrored(slot, false);
+    }
     block_rec(b, slot, x, EV_INIT | ((unsigned)unit << 8), arg, 0);
     if (kind == A2CU_FILTER12)
         block_rec(b, slot, x, EV_WRITE | ((unsigned)unit << 8) | (5u << 16),
@@ -1680,7 +1840,7 @@ int a2cu_block_write(a2cu_engine *e, int pool, int slot, int unit, int reg, int3
     unsigned x = (frame << 8) | (start & 0xff);
     if (b->chain[unit].kind == A2CU_WTOSC) {
         uint64_t key = ((uint64_t)pool << 32) | (uint32_t)slot;
-        auto mi = e->mirrors.find(key);
+        auto mi = b->mirrored(slot) ? e->mirrors.find(key) : e->mirrors.end();
         if (mi == e->mirrors.end() && c[0].reg == 0 && c[0].value >= 0 &&
             e->waves[c[0].value].type == A2CU_WNOISE) {
             // first noise selection of this voice: run what is recorded, then
@@ -1707,7 +1867,7 @@ int a2cu_block_proc(a2cu_engine *e, int pool, int slot, unsigned frame, unsigned
     Bank *b = get_bank(e, pool);
     if (!b || !b->dynamic || frames < 1 || frame + frames > (unsigned)kMaxFrag || bus < 0 || bus >= e->nbbus)
         return fail(A2CU_EINVAL, "a2cu_block_proc: bad args%s");
-    auto mi = e->mirrors.empty() ? e->mirrors.end() : e->mirrors.find(((uint64_t)pool << 32) | (uint32_t)slot);
+    auto mi = b->mirrored(slot) ? e->mirrors.find(((uint64_t)pool << 32) | (uint32_t)slot) : e->mirrors.end();
     if (mi != e->mirrors.end())
         for (auto &om : mi->second.osc) {      // units run in chain order inside one segment
             bool is_noise;

@@ -57,12 +57,15 @@ SYMBOLS = {
     "a2cu_bank_write": (_I, [_VP, _I, _I, _I, _I, C.c_int32, _U64, C.c_uint32]),
     "a2cu_bank_write_all": (_I, [_VP, _I, _I, _I, _VP, _I, _U64, C.c_uint32]),
     "a2cu_bank_wake": (_I, [_VP, _I, _I, _U64]),
+    "a2cu_bank_enable": (_I, [_VP, _I, _I]),
     "a2cu_group_write": (_I, [_VP, _I, _I, C.c_int32, _U64, C.c_uint32]),
     "a2cu_root_write": (_I, [_VP, _I, C.c_int32, _U64, C.c_uint32]),
     "a2cu_run": (_I, [_VP, _U, _U, _VP]),
     "a2cu_run_async": (_I, [_VP, _U, _U, _VP]),
     "a2cu_master_devptr": (_VP, [_VP]),
     "a2cu_sync": (_I, [_VP]),
+    "a2cu_submit": (_I, [_VP, _U, _U]),
+    "a2cu_collect": (_I, [_VP, _I, _VP]),
     "a2cu_set_post_root_stage": (_I, [_VP, _I]),
     "a2cu_apply_root_stage": (_I, [_VP, _VP, _VP, _U, _U, _U64]),
     "a2cu_launch_count": (_U64, [_VP]),
@@ -267,6 +270,9 @@ class Engine:
         self._ck(self.L.a2cu_bank_write_all(self.h, bank, unit, reg, a.ctypes.data,
                                             stride, when, dur))
 
+    def bank_enable(self, bank, on=True):
+        self._ck(self.L.a2cu_bank_enable(self.h, bank, int(on)))
+
     def wake(self, bank, voice, when):
         self._ck(self.L.a2cu_bank_wake(self.h, bank, voice, when))
 
@@ -287,6 +293,21 @@ class Engine:
         ch = self.channels if self.post_root else 2
         out = np.empty((frames, ch), dtype=np.int32)
         self._ck(self.L.a2cu_run(self.h, frames, buffer, out.ctypes.data))
+        return out
+
+    def submit(self, frames, buffer=64):
+        """Queue one window without waiting (a2cu_submit); returns a ticket."""
+        self._frames_of = getattr(self, "_frames_of", {})
+        t = self._ck(self.L.a2cu_submit(self.h, frames, buffer))
+        self._frames_of[t] = frames
+        return t
+
+    def collect(self, ticket, out=None):
+        """Wait for a submitted window and return its int32 8:24 output."""
+        if out is None:
+            ch = self.channels if self.post_root else 2
+            out = np.empty((self._frames_of[ticket], ch), dtype=np.int32)
+        self._ck(self.L.a2cu_collect(self.h, ticket, out.ctypes.data))
         return out
 
     def run_async(self, frames, buffer=64, dev_ptr=None):

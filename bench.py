@@ -13,11 +13,16 @@ frames (20 ms = 15 blocks of 64) = voices x 960 voice-samples.
 Numbers on the JSON line:
   value   voice-samples/s over the CUDA-event spans of the kernels (render +
           bus stage [+ NCCL reduce and root stage for N > 1]); the step's
-          events are already in HBM when the span starts.  L2 is flushed
-          between steps, outside the spans.
-  e2e     the same metric through a2cu_run() with HOST buffers: event staging,
-          H2D, kernels, D2H of the int32 master block, synchronise - host wall
-          time per call, max over ranks.
+          events are already in HBM when the span starts.  No L2 flush: every
+          step renders a DIFFERENT bank of 4096 voices, round-robin over enough
+          banks that their state exceeds the L2 by 1.5x (inputs larger than L2).
+  e2e     the same metric through the public API with HOST buffers: per step
+          a2cu_bank_write_all (host events), a2cu_submit (event staging, H2D,
+          kernels, D2H of the int32 master block into pinned memory) and
+          a2cu_collect (wait + copy to the caller's buffer), two windows in
+          flight so the host stages step i+1 while the device renders step i;
+          wall time of the whole timed region, max over ranks. (N > 1: one synchronous a2cu_run_async + NCCL reduce
+          + root stage + D2H per step, host wall time per step.)
   roofline  HBM roofline of the dominant kernel (render_bank<...>).
   cpu_baseline  the reference's own CPU render (oracle/_ref) on a bounded
           sample of the same workload, 1 core, rank 0, N = 1 only.
@@ -42,6 +47,7 @@ STEP_MS = 20
 RATE = 48000
 STEP_FRAMES = STEP_MS * RATE // 1000     # 960 = 15 blocks of 64
 BLOCK = 64
+L2_BYTES = 126 * 1024 * 1024    # B200 L2
 
 
 def ncu_traffic():
@@ -231,40 +237,74 @@ def bench_ours(args):
     stream = torch.cuda.current_stream()
     e.set_stream(stream.cuda_stream)
     e.set_timing(True)
+    # Round-robin over R independent banks of `voices` voices (one per step), so
+    # that the per-voice state a step reads was last touched R steps ago and the
+    # state of all banks together (R x voices x state bytes) exceeds the 126 MB
+    # L2 by 1.5x: "inputs larger than L2" instead of an L2 flush between steps.
     b = cfg2_bank(args.voices, seed=324357 + rank)
     w = e.builtin_wave(b["wave"])
     chain = autowire(list(b["kinds"]))
-    bank = e.new_bank(chain, args.voices)
-    e.write_all(bank, 0, 0, [w << 16], dur=STEP_FRAMES << 8)
-    e.write_all(bank, 0, 1, b["pitch"])
-    e.write_all(bank, 0, 2, [b["amp"]])
-    e.write_all(bank, 1, 0, b["cutoff"])
-    e.write_all(bank, 1, 1, [b["q"]])
-    e.write_all(bank, 2, 1, b["pan"])
+    banks = []
+    nbanks = args.banks
+    while True:
+        r = len(banks)
+        bb = b if r == 0 else cfg2_bank(args.voices, seed=324357 + rank + 1000 * r) if r < 8 else b
+        bank = e.new_bank(chain, args.voices)
+        e.write_all(bank, 0, 0, [w << 16], dur=STEP_FRAMES << 8)
+        e.write_all(bank, 0, 1, bb["pitch"])
+        e.write_all(bank, 0, 2, [bb["amp"]])
+        e.write_all(bank, 1, 0, bb["cutoff"])
+        e.write_all(bank, 1, 1, [bb["q"]])
+        e.write_all(bank, 2, 1, bb["pan"])
+        e.bank_enable(bank, False)
+        banks.append(bank)
+        if nbanks <= 0:
+            nbanks = int(1.5 * L2_BYTES / (e.bank_state_bytes(bank) * args.voices)) + 1
+        if len(banks) >= nbanks:
+            break
+    bank = banks[0]
+    state_mb = nbanks * e.bank_state_bytes(bank) * args.voices / 1e6
     multi = world > 1
     if multi:
         e.set_post_root_stage(False)
     rootbus = torch.zeros((STEP_FRAMES, 2), dtype=torch.int32, device=dev)
     master = torch.zeros((STEP_FRAMES, 2), dtype=torch.int32, device=dev)
     host_out = torch.zeros((STEP_FRAMES, 2), dtype=torch.int32).pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    amp = [b["amp"] // 2, b["amp"]]
-
+    amp = [np.array([b["amp"] // 2], dtype=np.int32), np.array([b["amp"]], dtype=np.int32)]
+    L = e.L
     ev_a = torch.cuda.Event(enable_timing=True)
     ev_b = torch.cuda.Event(enable_timing=True)
     dev_ms, host_s, render_ms = [], [], []
     state = {"step": 0}
 
+    out_host = np.empty((STEP_FRAMES, 2), dtype=np.int32)
+    pending = []            # tickets in flight (single GPU: pipelined a2cu_submit / a2cu_collect)
+
+    def collect_one(timed):
+        e.collect(pending.pop(0), out_host)        # waits for THAT window's D2H only
+        if timed:
+            dev_ms.append(e.last_render_ms() + e.last_mix_ms())
+            render_ms.append(e.last_render_ms())
+
     def one_step(timed):
-        flush.zero_()                       # L2 flush, outside every span
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        # --- the step, through the public API, host buffers in and out ---
-        e.write_all(bank, 0, 2, [amp[state["step"] & 1]], dur=STEP_FRAMES << 8)
+        i = state["step"]
+        cur = banks[i % nbanks]
+        # this step's bank: resume it, pause the one of the previous step
+        L.a2cu_bank_enable(e.h, banks[(i - 1) % nbanks], 0)
+        L.a2cu_bank_enable(e.h, cur, 1)
+        a = amp[(i // nbanks) & 1]
         if not multi:
-            out = e.run(STEP_FRAMES, BLOCK)            # H2D + kernels + D2H + sync
-            span = e.last_render_ms() + e.last_mix_ms()
+            # --- the step, through the public C ABI, host buffers in and out ---
+            L.a2cu_bank_write_all(e.h, cur, 0, 2, a.ctypes.data, 0, L.a2cu_now(e.h), STEP_FRAMES << 8)
+            # event staging + H2D + kernels + D2H queued; the host goes on to
+            # prepare the next step while the device renders this one
+            pending.append(e.submit(STEP_FRAMES, BLOCK))
+            if len(pending) > 2:
+                collect_one(timed)
         else:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            L.a2cu_bank_write_all(e.h, cur, 0, 2, a.ctypes.data, 0, L.a2cu_now(e.h), STEP_FRAMES << 8)
             e.run_async(STEP_FRAMES, BLOCK, rootbus.data_ptr())
             ev_a.record(stream)
             reduce_root_bus(rootbus)                   # NCCL int32 sum over NVLink
@@ -274,12 +314,16 @@ def bench_ours(args):
             e.sync()
             torch.cuda.synchronize()
             span = e.last_render_ms() + e.last_mix_ms() + ev_a.elapsed_time(ev_b)
-        t1 = time.perf_counter()
+            t1 = time.perf_counter()
+            if timed:
+                dev_ms.append(span)
+                host_s.append(t1 - t0)
+                render_ms.append(e.last_render_ms())
         state["step"] += 1
-        if timed:
-            dev_ms.append(span)
-            host_s.append(t1 - t0)
-            render_ms.append(e.last_render_ms())
+
+    def drain(timed):
+        while pending:
+            collect_one(timed)
 
     clocks = ClockSampler(local)
     if rank == 0:
@@ -288,10 +332,11 @@ def bench_ours(args):
     # under this load for ~1.5 s, so nvidia-smi (100 ms period) samples clocks
     # under load. Rank 0 decides and broadcasts (all ranks must run the same
     # number of collective steps).
-    nwarm = max(3, args.warmup)
+    nwarm = max(3, args.warmup, nbanks)     # every bank is rendered once before timing
     t_w = time.perf_counter()
     for _ in range(nwarm):
         one_step(False)
+    drain(False)
     while True:
         go = torch.tensor([1 if time.perf_counter() - t_w < 1.5 and nwarm < 100000 else 0], device=dev)
         if multi:
@@ -300,6 +345,7 @@ def bench_ours(args):
             break
         for _ in range(50):
             one_step(False)
+        drain(False)
         nwarm += 50
     if multi:
         dist.barrier()
@@ -308,10 +354,13 @@ def bench_ours(args):
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         one_step(True)
+    drain(True)
     torch.cuda.synchronize()
     if multi:
         dist.barrier()
     wall1 = time.perf_counter()
+    if not multi:
+        host_s.append(wall1 - wall0)        # pipelined: the whole timed region is the e2e time
     launches = e.launches - l0
     h2d = (e.h2d_bytes - h0) / args.steps
     d2h = (e.d2h_bytes - d0) / args.steps
@@ -346,13 +395,16 @@ def bench_ours(args):
                 "workload": "cfg2: %d voices/GPU wtosc->filter12->panmix, saw 2048-pt, 48 kHz, "
                             "64-frame blocks, 1 amplitude write/voice/20 ms" % args.voices,
                 "step": "%d frames (15 blocks of 64) per a2cu_run call" % STEP_FRAMES,
-                "l2": "flushed (256 MiB memset) between steps, outside the timed spans",
-                "timing": "value: CUDA-event spans of kernels summed over steps; "
-                          "e2e: host wall time of each a2cu_run incl. H2D/D2H; max over ranks",
+                "l2": "no flush: inputs larger than L2 - every step renders a different bank of %d voices, "
+                      "round-robin over %d banks whose per-voice state totals %.0f MB (1.5x the 126 MB L2)"
+                      % (args.voices, nbanks, state_mb),
+                "timing": "value: CUDA-event spans of kernels summed over steps; e2e: wall time of the "
+                          "timed region through write_all + a2cu_submit/a2cu_collect (2 windows in flight, "
+                          "H2D + D2H every step); max over ranks",
                 "multi_gpu": "voices sharded, one NCCL int32 all-reduce of the root bus per step"
                              if multi else "single GPU",
             },
-            "wall_ms_per_step_incl_flush": 1000.0 * (wall1 - wall0) / args.steps,
+            "wall_ms_per_step": 1000.0 * (wall1 - wall0) / args.steps,
             "e2e": {"value": e2e, "unit": "voice-samples/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": host_total_ms / args.steps},
@@ -391,6 +443,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--voices", type=int, default=4096)
+    ap.add_argument("--banks", type=int, default=0,
+                    help="banks served round-robin, one per step (0: enough for 1.5x L2 of voice state)")
     ap.add_argument("--cpu-frames", type=int, default=96000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -167,6 +167,14 @@ int a2cu_bank_write(a2cu_engine *e, int bank, int voice, int unit, int reg,
 int a2cu_bank_write_all(a2cu_engine *e, int bank, int unit, int reg,
 		const int32_t *values, int stride, uint64_t when, uint32_t dur);
 
+/*
+ * Pause (0) / resume (1) a bank. A paused bank is skipped by a2cu_run*: its
+ * voices keep their state and its pending writes apply at the start of the
+ * first window it runs in again. One engine can so serve many banks
+ * round-robin (bench.py uses this to keep per-step state colder than L2).
+ */
+int a2cu_bank_enable(a2cu_engine *e, int bank, int enabled);
+
 /* Bare wake-up (segment split) of one voice, or of all with voice < 0. */
 int a2cu_bank_wake(a2cu_engine *e, int bank, int voice, uint64_t when);
 
@@ -195,6 +203,18 @@ int a2cu_run_async(a2cu_engine *e, unsigned frames, unsigned buffer,
 		int32_t *dev_out);
 int32_t *a2cu_master_devptr(a2cu_engine *e);
 int a2cu_sync(a2cu_engine *e);
+
+/*
+ * Pipelined form of a2cu_run for offline rendering (a2_Render, src/render.c:
+ * 34-127, renders buffer after buffer without waiting for a consumer):
+ * a2cu_submit queues one window - event staging, H2D, kernels, D2H of the
+ * master block into a pinned result slot - and returns a ticket (>= 0) without
+ * waiting; a2cu_collect blocks until THAT window is done and copies its
+ * int32 8:24 output to 'out'.  Up to 4 windows may be in flight; the host
+ * prepares window i+1 (a2cu_bank_write*) while the device renders window i.
+ */
+int a2cu_submit(a2cu_engine *e, unsigned frames, unsigned buffer);
+int a2cu_collect(a2cu_engine *e, int ticket, int32_t *out);
 
 /*
  * Multi-GPU cut: with post_root_stage 0 the engine stops

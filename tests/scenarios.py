@@ -359,10 +359,11 @@ def run_oracle(scn):
     return out
 
 
-def run_cuda(scn, window=None, split=True, stats=None):
+def run_cuda(scn, window=None, split=True, stats=None, pipelined=False):
     """Render `scn` with the CUDA engine through its C ABI (ctypes).
     window: frames per a2cu_run call (multiple of scn.buffer), default all.
-    split=False forces the one-thread-per-voice kernel (render_bank)."""
+    split=False forces the one-thread-per-voice kernel (render_bank).
+    pipelined: windows go through a2cu_submit / a2cu_collect, up to 3 in flight."""
     from audiality2_b200 import engine as eng
     from oracle import a2oracle as ao
     e = eng.Engine(scn.samplerate, scn.channels)
@@ -402,6 +403,17 @@ def run_cuda(scn, window=None, split=True, stats=None):
             # root wake-ups (reg < 0) are the engine's own root_wake_period
         if window is None:
             out = e.run(scn.frames, scn.buffer)
+        elif pipelined:
+            parts, tickets, done = [], [], 0
+            while done < scn.frames:
+                n = min(window, scn.frames - done)
+                tickets.append(e.submit(n, scn.buffer))
+                done += n
+                if len(tickets) > 2:
+                    parts.append(e.collect(tickets.pop(0)))
+            while tickets:
+                parts.append(e.collect(tickets.pop(0)))
+            out = np.concatenate(parts, axis=0)
         else:
             parts, done = [], 0
             while done < scn.frames:

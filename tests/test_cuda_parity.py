@@ -42,6 +42,16 @@ def test_windowing_does_not_change_output(name):
     assert np.array_equal(one, many), _diff(one, many)
 
 
+@pytest.mark.parametrize("name", ["filter_sweep", "groups", "noise"])
+def test_pipelined_submit_collect_equals_run(name):
+    """a2cu_submit / a2cu_collect with three windows in flight (staging ring,
+    per-slot pinned results) equals one synchronous a2cu_run."""
+    scn = CASES[name]()
+    one = run_cuda(scn)
+    piped = run_cuda(scn, window=scn.buffer * 3, pipelined=True)
+    assert np.array_equal(one, piped), _diff(one, piped)
+
+
 def test_bank_4096_full_size():
     """BASELINE config 2 at full size (4096 voices) vs the oracle port."""
     scn = bank(4096, frames=640)
@@ -107,3 +117,48 @@ def test_empty_engine_renders_silence():
     out = e.run(200, 96)
     assert out.shape == (200, 2) and not out.any()
     e.close()
+
+
+def test_paused_bank_keeps_state_and_pending_writes():
+    """a2cu_bank_enable: a paused bank is not rendered, keeps its voices' state
+    and applies its pending writes when it runs again (bench.py serves many
+    banks round-robin this way)."""
+    from audiality2_b200 import engine as eng
+    from audiality2_b200.workloads import cfg2_bank
+    from scenarios import autowire
+    W = 640
+
+    def setup(e, seed):
+        b = cfg2_bank(64, seed=seed)
+        bank = e.new_bank(autowire(list(b["kinds"])), 64)
+        e.write_all(bank, 0, 0, [e.builtin_wave(b["wave"]) << 16])
+        e.write_all(bank, 0, 1, b["pitch"])
+        e.write_all(bank, 0, 2, [b["amp"] * 50], dur=W << 8)
+        e.write_all(bank, 1, 0, b["cutoff"])
+        e.write_all(bank, 1, 1, [b["q"]])
+        e.write_all(bank, 2, 1, b["pan"])
+        return bank
+
+    e1 = eng.Engine(48000, 2)
+    setup(e1, 1)
+    ref = [e1.run(W, 64) for _ in range(3)]
+    e1.close()
+
+    e2 = eng.Engine(48000, 2)
+    x = setup(e2, 1)
+    y = setup(e2, 2)
+    e2.bank_enable(y, False)
+    a = e2.run(W, 64)                   # x alone
+    e2.bank_enable(x, False)
+    e2.bank_enable(y, True)
+    other = e2.run(W, 64)               # y's first window: its writes from time 0 apply now
+    e2.bank_enable(y, False)
+    e2.bank_enable(x, True)
+    b2 = e2.run(W, 64)                  # x resumes where it stopped
+    c2 = e2.run(W, 64)
+    e2.close()
+    assert np.abs(ref[0]).max() > 1000 and np.abs(other).max() > 1000
+    assert np.array_equal(a, ref[0]), _diff(a, ref[0])
+    assert np.array_equal(b2, ref[1]), _diff(b2, ref[1])
+    assert np.array_equal(c2, ref[2]), _diff(c2, ref[2])
+    assert not np.array_equal(other, ref[0])
