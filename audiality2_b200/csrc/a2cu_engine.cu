@@ -37,6 +37,8 @@ static inline double now_us() {
 }
 struct BlockStats { double flush_us = 0, download_us = 0, sync_us = 0, begin_us = 0; long flushes = 0, downloads = 0, begins = 0, procs = 0; };
 static BlockStats g_bs;
+struct WindowStats { double prep_us = 0, stage_us = 0, api_us = 0, mix_us = 0; long windows = 0; };
+static WindowStats g_ws;
 static int fail(int code, const char *fmt, const char *detail = "") {
     snprintf(g_err, sizeof(g_err), fmt, detail);
     return code;
@@ -160,9 +162,10 @@ static void register_split() {
     reg_split<3, false, 10>({S_OSC0, S_OSCA, S_OSCA, S_PM12W});
     reg_split<4, false, 10>({S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_PM12W});
     reg_split<8, false, 6>({S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_PM12W});
-    reg_split<1, true, 14>({S_OSC0, S_F11, S_PM12W});
-    reg_split<2, true, 14>({S_OSC0, S_OSCA, S_F11, S_PM12W});
-    reg_split<3, true, 10>({S_OSC0, S_OSCA, S_OSCA, S_F11, S_PM12W});
+    // with filter12: 11 (8) helpers + control on sub-partitions 0-2, the recurrence alone on 3
+    reg_split<1, true, 11>({S_OSC0, S_F11, S_PM12W});
+    reg_split<2, true, 11>({S_OSC0, S_OSCA, S_F11, S_PM12W});
+    reg_split<3, true, 8>({S_OSC0, S_OSCA, S_OSCA, S_F11, S_PM12W});
 }
 
 // ---------------------------------------------------------------------------
@@ -759,6 +762,10 @@ a2cu_engine *a2cu_open(int device, int samplerate, int channels) {
 
 void a2cu_close(a2cu_engine *e) {
     if (!e) return;
+    if (getenv("A2CU_STATS") && g_ws.windows)
+        fprintf(stderr, "a2cu window stats: %ld windows, host us per window: collect/sort %.1f, stage+H2D %.1f, "
+                        "render launch %.1f, bus stage launch %.1f\n", g_ws.windows, g_ws.prep_us / g_ws.windows,
+                g_ws.stage_us / g_ws.windows, g_ws.api_us / g_ws.windows, g_ws.mix_us / g_ws.windows);
     if (getenv("A2CU_STATS"))
         fprintf(stderr, "a2cu stats: %ld flushes %.1f us avg (host side), %ld downloads, wait+copy %.1f us avg, "
                         "%ld launches\n", g_bs.flushes, g_bs.flushes ? g_bs.flush_us / g_bs.flushes : 0.0,
@@ -1370,6 +1377,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     }
 
     // ---- stage events (host -> pinned -> device) ----
+    const double ws_t0 = now_us();
     size_t stage_bytes = 0;
     std::vector<std::vector<HostEvent>> due(e->banks.size());
     for (size_t bi = 0; bi < e->banks.size(); ++bi) {
@@ -1416,6 +1424,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         return a.seq < c.seq;
     });
     stage_bytes += mdue.size() * sizeof(MixEvent) + 64;
+    const double ws_t1 = now_us();
     r = ensure_stage(e, stage_bytes);
     if (r) return r;
     char *stage = (char *)e->h_stage;
@@ -1468,6 +1477,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             P.ev_off = b->d_evoff; P.ev = b->d_evrecs;
         }
     }
+    const double ws_t2 = now_us();
     // inputs are resident from here on: ev0 .. ev1 brackets the render kernels
     if (e->timing) CK(cudaEventRecord(e->ev0, e->stream));
     for (size_t bi = 0; bi < e->banks.size(); ++bi) {
@@ -1519,6 +1529,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         ++e->launches;
     }
     if (e->timing) CK(cudaEventRecord(e->ev1, e->stream));
+    const double ws_t3 = now_us();
 
     MixParams M;
     memset(&M, 0, sizeof(M));
@@ -1558,6 +1569,8 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     if (e->timing) CK(cudaEventRecord(e->ev2, e->stream));
     e->last_mix = M;
     e->now = t1;
+    g_ws.prep_us += ws_t1 - ws_t0; g_ws.stage_us += ws_t2 - ws_t1; g_ws.api_us += ws_t3 - ws_t2;
+    g_ws.mix_us += now_us() - ws_t3; ++g_ws.windows;
     return A2CU_OK;
 }
 

@@ -15,10 +15,10 @@
 // filter recurrence. One CTA = 32 voices (lane = voice everywhere, so the SoA
 // state stays coalesced and the bus reduce stays a warp redux.sync):
 //
-//   warp 0      control: events, per-segment prologues (the same unit code as
+//   control     (warp NH) events, per-segment prologues (the same unit code as
 //               render_bank: WtOsc/Filter12/PanMix ::write/prepare/finish),
 //               publishes per-segment parameters, advances state in closed form
-//   warp 1      serial: filter12 recurrence (filter12.c:97-118), frame by frame
+//   serial      (warp NH+1) filter12 recurrence (filter12.c:97-118), frame by frame
 //   NH helpers  stage A: oscillator samples -> tile A; lane = voice, frames sliced
 //               stage C: panmix + bus sum <- tile A/B; lane = FRAME, each helper
 //               sums a few voices for 32 frames into a shared-memory bus
@@ -41,12 +41,18 @@ namespace a2cu {
 constexpr int kSplitSegs = 2;
 constexpr int kRing = 4;
 constexpr int kTileStride = 33;     // tile rows are voices; 33 keeps both access patterns conflict-free
-// Warp roles: 0 control, [1 serial if FILT], then NH helper warps. Every helper
-// runs a slice of stage A (lane = voice) and a part of stage C (lane = frame).
+// Warp roles: NH helper warps, one control warp, [one serial warp if FILT].
+// Every helper runs a slice of stage A (lane = voice) and a part of stage C
+// (lane = frame). Warp id % 4 is the SM sub-partition (one issue port each,
+// B300_MICROARCH.md "Instruction issue"): the filter12 recurrence is one long
+// dependent chain, and any other warp on its sub-partition takes issue slots
+// (and holds them while it has independent work), so with FILT the serial
+// warp gets sub-partition 3 to itself: it is the LAST warp (id % 4 == 3), the
+// other warps with id % 4 == 3 stay idle, helpers and the control warp use
+// ids with id % 4 != 3 in ascending order (logical index = id - id / 4).
 template <bool FILT, int NH> struct SplitWarps {
-    static constexpr int serial = FILT ? 1 : -1;
-    static constexpr int c0 = FILT ? 2 : 1;                     // first helper warp
-    static constexpr int total = c0 + NH;
+    static constexpr int rows = (NH + 1 + 2) / 3;               // FILT: groups of 4 warp ids
+    static constexpr int total = FILT ? rows * 4 : NH + 1;
     static constexpr int threads = total * 32;
     static constexpr int slice = (kMaxFrag + NH - 1) / NH;      // stage A: frames per helper
     static constexpr int groups = NH / 2;                       // stage C: voice groups (x 2 frame halves)
@@ -87,6 +93,11 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
     extern __shared__ __align__(128) int sm[];
     __shared__ __align__(8) unsigned long long s_mbar;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // logical role index (see SplitWarps): helpers 0..NA-1, control NA; -1 = idle
+    const int hq = FILT ? ((warp & 3) == 3 ? -1 : warp - (warp >> 2)) : warp;
+    const bool is_helper = hq >= 0 && hq < NA;
+    const bool is_ctl = hq == NA;
+    const bool is_ser = FILT && warp == WR::total - 1;
     const int v = blockIdx.x * 32 + lane;
     const bool valid = v < P.nvoices;
     const int W = P.W;
@@ -95,7 +106,7 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
     for (int f = 0; f < W; f = frag_end(f, P.buffer, W)) ++nfrag;
     const int mybus = valid ? P.bus_of[v] : -1;
     const int home = __shfl_sync(0xffffffffu, mybus, 0);
-    if (warp == 0) sm[L::bus + lane] = mybus;
+    if (is_ctl) sm[L::bus + lane] = mybus;
     for (int i = tid; i < kRing * kMaxFrag * 2; i += WR::threads) sm[L::sacc + i] = 0;
     // Stage the bank's wavetable (Hermite coefficient form, all mip levels) into
     // shared memory: one elected thread arms an mbarrier with the byte count and
@@ -133,7 +144,7 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
     // ---- serial warp state ----
     int d1 = 0, d2 = 0;
 
-    if (warp == 0 && valid) {
+    if (is_ctl && valid) {
         alive = sp.ld(0) & 1;
 #pragma unroll
         for (int i = 0; i < NOSC; ++i) osc[i].load(sp, 1 + 14 * i);
@@ -142,7 +153,7 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
         if (P.ev_off) { evp = P.ev_off[v]; eve = P.ev_off[v + 1]; }
         next_ev = evp < eve ? (int)(P.ev[evp].x >> 8) : 0x7fffffff;
     }
-    if (FILT && warp == WR::serial && valid) {
+    if (is_ser && valid) {
         d1 = sp.ld(L::filt_w + 12);
         d2 = sp.ld(L::filt_w + 13);
     }
@@ -152,7 +163,7 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
         long long t_begin = 0, t_mid = 0;
         if (P.prof) t_begin = clock64();
         // ================= control(it) =================
-        if (warp == 0 && it < nfrag) {
+        if (is_ctl && it < nfrag) {
             const int slot = it % kRing;
             const int f0 = cf0;
             const int fe = frag_end(f0, P.buffer, W);
@@ -250,7 +261,7 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
             cf0 = fe;
         }
         // ================= serial(it - 2): filter12 recurrence =================
-        if (FILT && warp == WR::serial && it >= 2 && it - 2 < nfrag) {
+        if (is_ser && it >= 2 && it - 2 < nfrag) {
             const int slot = (it - 2) % kRing;
             const int n = sm[L::meta + slot * 2 + 1];
             const int split = sm[L::split + slot * 32 + lane];
@@ -272,7 +283,9 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
                     const int in = ta[f * kTileStride];
                     const int d1s = d1 >> 4;
                     const int l = wadd(d2, wmul(fc, d1s) >> 8);
-                    const int h = wsub(wsub(in >> 5, l), wmul(qq, d1s) >> 8);
+                    // (in>>5) - l - (q*d1s>>8), re-associated (modular adds commute): the q term
+                    // is ready together with l, so h follows l by ONE add on the recurrence's chain
+                    const int h = wsub(wsub(in >> 5, wmul(qq, d1s) >> 8), l);
                     const int bb = wadd(wmul(fc, h >> 4) >> 8, d1);
                     tb[f * kTileStride] = wadd(wadd(wmul(l, lp), wmul(bb, bp)), wmul(h, hp)) >> 3;
                     d1 = bb; d2 = l;
@@ -282,8 +295,8 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
             }
         }
         // ================= stage A(it - 1): oscillators, lane = voice, frames sliced =================
-        if (warp >= WR::c0 && it >= 1 && it - 1 < nfrag) {
-            const int h = warp - WR::c0;
+        if (is_helper && it >= 1 && it - 1 < nfrag) {
+            const int h = hq;
             const int slot = (it - 1) % kRing;
             const int n = sm[L::meta + slot * 2 + 1];
             const int split = sm[L::split + slot * 32 + lane];
@@ -331,8 +344,8 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
         }
         if (P.prof) t_mid = clock64();
         // ================= stage C(it - lag_c): panmix + bus sum, lane = frame =================
-        if (warp >= WR::c0 && warp < WR::c0 + 2 * WR::groups && it >= lag_c && it - lag_c < nfrag) {
-            const int h = warp - WR::c0;
+        if (is_helper && hq < 2 * WR::groups && it >= lag_c && it - lag_c < nfrag) {
+            const int h = hq;
             const int slot = (it - lag_c) % kRing;
             const int f0 = sm[L::meta + slot * 2];
             const int n = sm[L::meta + slot * 2 + 1];
@@ -380,7 +393,7 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
             }
         }
         // ================= stage D(it - lag_c - 1): flush the fragment's bus sums =================
-        if (warp == WR::c0 && it >= lag_c + 1 && it - lag_c - 1 < nfrag && home >= 0) {
+        if (hq == 0 && it >= lag_c + 1 && it - lag_c - 1 < nfrag && home >= 0) {
             const int slot = (it - lag_c - 1) % kRing;
             const int f0 = sm[L::smeta + slot * 2];
             const int n = sm[L::smeta + slot * 2 + 1];
@@ -396,9 +409,9 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
         __syncthreads();
         if (P.prof && lane == 0) {
             // [0] control [1] serial [2] stage A [3] stage C [4] barrier wait, [5] iterations
-            if (warp == 0) atomicAdd(P.prof + 0, (unsigned long long)(t_done - t_begin));
-            else if (warp == WR::serial) atomicAdd(P.prof + 1, (unsigned long long)(t_done - t_begin));
-            else if (warp == WR::c0 + 1) {
+            if (is_ctl) atomicAdd(P.prof + 0, (unsigned long long)(t_done - t_begin));
+            else if (is_ser) atomicAdd(P.prof + 1, (unsigned long long)(t_done - t_begin));
+            else if (hq == 1) {
                 atomicAdd(P.prof + 2, (unsigned long long)(t_mid - t_begin));
                 atomicAdd(P.prof + 3, (unsigned long long)(t_done - t_mid));
                 atomicAdd(P.prof + 4, (unsigned long long)(clock64() - t_done));
@@ -407,7 +420,7 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
         }
     }
 
-    if (warp == 0 && valid) {
+    if (is_ctl && valid) {
         if (in_seg) {
 #pragma unroll
             for (int i = 0; i < NOSC; ++i) osc[i].finish();
@@ -421,7 +434,7 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
         pm.store(sp, L::pm_w);
     }
     __syncthreads();
-    if (FILT && warp == WR::serial && valid) {       // the recurrence state lives in the serial warp
+    if (is_ser && valid) {       // the recurrence state lives in the serial warp
         sp.st(L::filt_w + 12, d1);
         sp.st(L::filt_w + 13, d2);
     }
