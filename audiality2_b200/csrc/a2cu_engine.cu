@@ -1563,7 +1563,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         mix_groups<<<e->ngroups, 256, 0, e->stream>>>(M);
         ++e->launches;
     }
-    mix_root<<<1, 256, 0, e->stream>>>(M);
+    mix_root<<<std::max(1, std::min(8, ((int)M.W + 255) / 256)), 256, 0, e->stream>>>(M);
     ++e->launches;
     CK(cudaGetLastError());
     if (e->timing) CK(cudaEventRecord(e->ev2, e->stream));
@@ -1690,7 +1690,7 @@ int a2cu_apply_root_stage(a2cu_engine *e, const int32_t *dev_rootbus, int32_t *d
     (void)start_time;
     M.acc = (int *)dev_rootbus; M.W = (int)frames; M.buffer = (int)(buffer ? buffer : frames);
     M.ngroups = 0; M.master = dev_master; M.root_stage = 1;
-    mix_root<<<1, 256, 0, e->stream>>>(M);
+    mix_root<<<std::max(1, std::min(8, ((int)M.W + 255) / 256)), 256, 0, e->stream>>>(M);
     ++e->launches;
     CK(cudaGetLastError());
     return A2CU_OK;

@@ -359,11 +359,36 @@ __global__ void __launch_bounds__(256) mix_groups(const MixParams P) {
 __global__ void __launch_bounds__(256) mix_root(const MixParams P) {
     const int tid = threadIdx.x;
     const int *root = P.acc;
+    const int gtid = blockIdx.x * blockDim.x + tid, gsize = gridDim.x * blockDim.x;
     if (!P.root_stage) {
-        for (int i = tid; i < P.W * 2; i += blockDim.x) P.master[i] = root[i];
+        for (int i = gtid; i < P.W * 2; i += gsize) P.master[i] = root[i];
         return;
     }
     const bool mono = P.channels == 1;
+    // Steady state (no root events or splits in the window, both rampers at
+    // rest): a2_PrepareRamper leaves value = target, delta = 0 in every segment
+    // (a2_dsp.h:130-134), so every frame uses the same two gains and the whole
+    // grid evaluates frames independently. Otherwise CTA 0 replays the segments.
+    const bool steady = P.nev == 0 && P.nsplits == 0 && P.rstate[3] == 0 && P.rstate[7] == 0 &&
+                        P.rstate[0] == P.rstate[1] && P.rstate[4] == P.rstate[5];
+    if (steady) {
+        const int v = P.rstate[1], pn = P.rstate[5];            // targets
+        const int vp = mulshr(pn, v, 24);
+        int v0 = wsub(v, vp), v1 = wadd(v, vp);
+        if (pn > 0xffffff || pn < -0xffffff) {
+            const int lim = (int)((unsigned)v << 1);            // panmix.c:117-135 clamp variant
+            if (v0 > lim) v0 = lim;
+            if (v1 > lim) v1 = lim;
+        }
+        for (int f = gtid; f < P.W; f += gsize) {
+            const int i0 = root[f * 2], i1 = root[f * 2 + 1];
+            if (mono) P.master[f] = (int)(((long long)i0 * v0 + (long long)i1 * v1) >> 25);
+            else { P.master[f * 2] = mulshr(i0, v0, 24); P.master[f * 2 + 1] = mulshr(i1, v1, 24); }
+        }
+        if (gtid == 0 && P.W > 0) { P.rstate[2] = 0; P.rstate[6] = 0; }     // deltas as PrepareRamper leaves them
+        return;
+    }
+    if (blockIdx.x) return;
     pm_bus(P, -1, P.rstate, root, mono, [&](int f, int r0, int r1) {
         if (mono) P.master[f] = r0;
         else { P.master[f * 2] = r0; P.master[f * 2 + 1] = r1; }
