@@ -444,7 +444,6 @@ struct a2cu_engine {
     std::vector<int> gunit_free, gunit_deferred;
     int *d_ustate = nullptr;        // [unit][kUnitWords]
     int ustate_cap = 0;
-    int32_t *d_upload = nullptr;    // staging row for a2cu_block_upload_add
 };
 
 
@@ -1810,12 +1809,13 @@ int a2cu_block_bus(a2cu_engine *e) {
     return e->nbbus++;
 }
 
-static void block_rec(Bank *b, int slot, unsigned x, unsigned y, int z, unsigned w) {
+static inline void block_rec(Bank *b, int slot, unsigned x, unsigned y, int z, unsigned w) {
     if (b->cur_slot != slot || b->bruns.empty()) {
         VoiceRun r;
         r.slot = slot; r.ev_begin = (unsigned)b->bev.size(); r.ev_count = 0;
         b->bruns.push_back(r);
         b->cur_slot = slot;
+        // a slot with two runs in one flush (its parent was cut by a wake-up): merged before the launch
         if (b->slot_mark.size() < b->stride) b->slot_mark.resize(b->stride, 0);
         if (b->slot_mark[slot] == b->flush_id) b->dup_runs = true;
         b->slot_mark[slot] = b->flush_id;
@@ -2243,8 +2243,7 @@ static int ensure_xfer(a2cu_engine *e) {
     return A2CU_OK;
 }
 
-static int block_upload(a2cu_engine *e, int bus, int nch, unsigned frame, unsigned frames,
-                        const int32_t *const *src, bool add) {
+int a2cu_block_upload(a2cu_engine *e, int bus, int nch, unsigned frame, unsigned frames, const int32_t *const *src) {
     if (!e || bus < 0 || bus >= e->nbbus || frames < 1 || frame + frames > (unsigned)kMaxFrag || nch < 1 || nch > 2)
         return fail(A2CU_EINVAL, "a2cu_block_upload: bad args%s");
     cudaSetDevice(e->device);
@@ -2257,30 +2256,11 @@ static int block_upload(a2cu_engine *e, int bus, int nch, unsigned frame, unsign
         e->h_xfer[i * 2] = src[0][frame + i];
         e->h_xfer[i * 2 + 1] = nch > 1 ? src[1][frame + i] : 0;
     }
-    int32_t *dst = e->d_bacc + ((size_t)bus * kMaxFrag + frame) * 2;
-    if (add) {
-        // stage in an extra bus row, then BUS_ADD in command order
-        int tmp = a2cu_block_bus(e);
-        if (tmp < 0) return tmp;
-        dst = e->d_bacc + ((size_t)tmp * kMaxFrag + frame) * 2;
-        CK(cudaMemcpyAsync(dst, e->h_xfer, frames * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-        CK(cudaStreamSynchronize(e->stream));
-        e->h2d_bytes += frames * 2 * sizeof(int32_t);
-        return a2cu_block_bus_add(e, tmp, bus, frame, frames);
-    }
-    CK(cudaMemcpyAsync(dst, e->h_xfer, frames * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_bacc + ((size_t)bus * kMaxFrag + frame) * 2, e->h_xfer, frames * 2 * sizeof(int32_t),
+                       cudaMemcpyHostToDevice, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     e->h2d_bytes += frames * 2 * sizeof(int32_t);
     return A2CU_OK;
-}
-
-int a2cu_block_upload(a2cu_engine *e, int bus, int nch, unsigned frame, unsigned frames, const int32_t *const *src) {
-    return block_upload(e, bus, nch, frame, frames, src, false);
-}
-
-int a2cu_block_upload_add(a2cu_engine *e, int bus, int nch, unsigned frame, unsigned frames,
-                          const int32_t *const *src) {
-    return block_upload(e, bus, nch, frame, frames, src, true);
 }
 
 int a2cu_block_download(a2cu_engine *e, int bus, int nch, unsigned frame, unsigned frames, int32_t *const *dst,

@@ -95,7 +95,6 @@ SYMBOLS = {
     "a2cu_block_flush": (_I, [_VP]),
     "a2cu_block_upload": (_I, [_VP, _I, _I, _U, _U, _VP]),
     "a2cu_block_download": (_I, [_VP, _I, _I, _U, _U, _VP, _I]),
-    "a2cu_block_upload_add": (_I, [_VP, _I, _I, _U, _U, _VP]),
     # generic units (one replaced unit per call) and per-voice command runs
     "a2cu_block_run": (_U64, [_VP, _I, _U64]),
     "a2cu_unit_alloc": (_I, [_VP, _I, _I, _I]),

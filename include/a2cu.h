@@ -307,12 +307,13 @@ int a2cu_block_pm_proc(a2cu_engine *e, int pm, int nin, int nout, int add,
  * output bus 'out_bus' (A2_IO_WIREOUT, src/core.c:243-245).
  */
 /*
- * Bus commands (a2cu_block_pm_*, a2cu_block_unit_*, a2cu_block_bus_add,
- * a2cu_block_upload_add) belong to the voice selected by the last
- * a2cu_block_run(): 'level' is the voice's nest level (A2_voice.nestlevel,
- * src/internals.h:571), 'prev' the handle this function returned for the same
- * voice earlier (0 for none).  Voices of one level run concurrently on the
- * device, levels deepest first; commands of one voice keep their order.
+ * Bus commands (a2cu_block_pm_*, a2cu_block_unit_*, a2cu_block_bus_add) belong
+ * to the voice selected by the last a2cu_block_run(): 'level' is the voice's
+ * nest level (A2_voice.nestlevel, src/internals.h:571), 'prev' the handle this
+ * function returned for the same voice earlier (0 for none).  Voices of one
+ * level run concurrently on the device, levels deepest first; commands of one
+ * voice keep their order.  Every flush (a2cu_block_flush / _upload / _download /
+ * _begin) ends all runs: select the voice again before its next command.
  */
 uint64_t a2cu_block_run(a2cu_engine *e, int level, uint64_t prev);
 int a2cu_unit_alloc(a2cu_engine *e, int kind, int ninputs, int noutputs);
@@ -327,9 +328,6 @@ int a2cu_block_bus_add(a2cu_engine *e, int src_bus, int dst_bus, unsigned frame,
 		unsigned frames);
 int a2cu_block_flush(a2cu_engine *e);
 int a2cu_block_upload(a2cu_engine *e, int bus, int nch, unsigned frame,
-		unsigned frames, const int32_t *const *src);
-/* bus += host data (what host units added to a bus our inline owns) */
-int a2cu_block_upload_add(a2cu_engine *e, int bus, int nch, unsigned frame,
 		unsigned frames, const int32_t *const *src);
 int a2cu_block_download(a2cu_engine *e, int bus, int nch, unsigned frame,
 		unsigned frames, int32_t *const *dst, int add);

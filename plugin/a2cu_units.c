@@ -65,6 +65,17 @@ typedef struct A2CU_unit
 	int		gu;		/* device generic unit (GEN voices) */
 	int		bus;		/* inline: device bus of this fragment */
 	unsigned	bus_serial;
+	/*
+	 * First unit of a LEAF voice: everything its Process() needs, so the
+	 * per-segment path touches this block only (the host has just read
+	 * u->Process from it) and not the voice record or the last unit.
+	 */
+	int		leaf;		/* 1: fused leaf voice, fields below valid */
+	int		pool, slot;
+	int32_t		**leaf_outputs;	/* where the voice's last unit is wired */
+	int		leaf_nout;
+	unsigned	proc_serial;	/* fragment of the last recorded segment */
+	unsigned	cursor;		/* frame where the next segment starts */
 } A2CU_unit;
 
 typedef struct A2CU_pending
@@ -134,6 +145,34 @@ static int a2cu_trace = -1;
 
 static int is_ours(const A2_unitdesc *d);
 
+/*
+ * A2CU_STATS=1: time spent inside the plug-in's callbacks (TSC ticks), printed
+ * when the last engine state closes. Shows how much of a drop-in render is the
+ * host's own VM + tree walk and how much is our recording.
+ */
+static int a2cu_stats = -1;
+static unsigned long long st_proc_t, st_proc_n, st_write_t, st_write_n,
+		st_inline_t, st_inline_n, st_t0;
+static inline unsigned long long tsc(void)
+{
+#if defined(__x86_64__)
+	unsigned lo, hi;
+	__asm__ __volatile__("rdtsc" : "=a"(lo), "=d"(hi));
+	return ((unsigned long long)hi << 32) | lo;
+#else
+	return 0;
+#endif
+}
+static inline int stats_on(void)
+{
+	if(a2cu_stats < 0)
+	{
+		a2cu_stats = getenv("A2CU_STATS") ? 1 : 0;
+		st_t0 = tsc();
+	}
+	return a2cu_stats;
+}
+
 
 /*---------------------------------------------------------
 	Context (one per engine state), OpenState/CloseState
@@ -181,6 +220,19 @@ static void a2cu_CloseState(void *statedata)
 			*p = cx->next;
 			break;
 		}
+	if(stats_on())
+	{
+		unsigned long long total = tsc() - st_t0;
+		fprintf(stderr, "a2cu plug-in stats (TSC ticks, %% of the time since the first callback): "
+				"Process %llu calls %.1f%% (%.0f ticks/call), "
+				"write %llu calls %.1f%% (%.0f ticks/call), "
+				"inline (excl. recursion, incl. flush/sync) %llu calls %.1f%%\n",
+				st_proc_n, 100.0 * st_proc_t / total,
+				st_proc_n ? (double)st_proc_t / st_proc_n : 0.0,
+				st_write_n, 100.0 * st_write_t / total,
+				st_write_n ? (double)st_write_t / st_write_n : 0.0,
+				st_inline_n, 100.0 * (double)(long long)st_inline_t / total);
+	}
 	a2cu_close(cx->eng);
 	free(cx->waves);
 	free(cx);
@@ -314,6 +366,10 @@ static A2_unit *next_audio_unit(A2_unit *u)
 	return NULL;
 }
 
+static void leaf_follower_process(A2_unit *u, unsigned offset, unsigned frames)
+{
+}
+
 /* Decide what this voice is, now that its unit chain is complete. */
 static void classify(A2CU_ctx *cx, A2CU_voice *v, unsigned frame)
 {
@@ -355,6 +411,16 @@ static void classify(A2CU_ctx *cx, A2CU_voice *v, unsigned frame)
 			a2cu_block_init(cx->eng, v->pool, v->slot, i,
 					v->units[i]->init_transpose, frame,
 					v->units[i]->substart);
+		/* the first unit records the segment for the whole fused chain */
+		for(i = 1; i < v->nunits; ++i)
+			v->units[i]->il.header.Process = leaf_follower_process;
+		v->units[0]->leaf = 1;
+		v->units[0]->pool = v->pool;
+		v->units[0]->slot = v->slot;
+		v->units[0]->leaf_outputs =
+				v->units[v->nunits - 1]->il.header.outputs;
+		v->units[0]->leaf_nout =
+				v->units[v->nunits - 1]->il.header.noutputs;
 	}
 	else
 	{
@@ -428,6 +494,9 @@ static A2_errors unit_init(A2_unit *u, A2_vmstate *vms, void *statedata,
 	au->pm = -1;
 	au->gu = -1;
 	au->bus = -1;
+	au->leaf = 0;
+	au->proc_serial = 0;
+	au->cursor = 0;
 	au->bus_serial = 0;
 	v->units[v->nunits++] = au;
 	++v->refs;
@@ -455,7 +524,24 @@ static void unit_deinit(A2_unit *u)
 		voice_release(au->cx, au->voice);
 }
 
+static void unit_write_body(A2_unit *u, int reg, int value, unsigned start,
+		unsigned dur);
+
 static void unit_write(A2_unit *u, int reg, int value, unsigned start,
+		unsigned dur)
+{
+	if(stats_on())
+	{
+		unsigned long long t = tsc();
+		unit_write_body(u, reg, value, start, dur);
+		st_write_t += tsc() - t;
+		++st_write_n;
+	}
+	else
+		unit_write_body(u, reg, value, start, dur);
+}
+
+static void unit_write_body(A2_unit *u, int reg, int value, unsigned start,
 		unsigned dur)
 {
 	A2CU_unit *au = (A2CU_unit *)u;
@@ -488,9 +574,17 @@ static void unit_write(A2_unit *u, int reg, int value, unsigned start,
 	 * (core.c:1847-1880), and so do host units that write controls from
 	 * inside their own Process() (env.c:120-137) ahead of ours.
 	 */
-	emit_write(cx, v, au, reg, value,
-			v->cursor_serial == cx->serial ? v->cursor : 0,
-			start, dur);
+	{
+		unsigned frame;
+		if(v->cls == VC_LEAF)
+		{
+			A2CU_unit *u0 = v->units[0];
+			frame = u0->proc_serial == cx->serial ? u0->cursor : 0;
+		}
+		else
+			frame = v->cursor_serial == cx->serial ? v->cursor : 0;
+		emit_write(cx, v, au, reg, value, frame, start, dur);
+	}
 }
 
 #define	WRITE_CB(n)							\
@@ -555,13 +649,83 @@ static void handover(A2CU_ctx *cx, A2CU_voice *v, A2_unit *u, unsigned offset,
 	v->on_device = 0;
 }
 
+static void unit_process_body(A2_unit *u, unsigned offset, unsigned frames);
+
 /* Process() of every replaced DSP unit (never inline) */
 static void unit_process(A2_unit *u, unsigned offset, unsigned frames)
 {
+	if(stats_on())
+	{
+		unsigned long long t = tsc();
+		unit_process_body(u, offset, frames);
+		st_proc_t += tsc() - t;
+		++st_proc_n;
+	}
+	else
+		unit_process_body(u, offset, frames);
+}
+
+static void leaf_process(A2CU_ctx *cx, A2CU_unit *au, unsigned offset,
+		unsigned frames)
+{
+	A2CU_unit *owner;
+	au->proc_serial = cx->serial;
+	au->cursor = offset + frames;
+	owner = owner_find(cx, au->leaf_outputs);
+	TRACE("leaf proc slot %d [%u,+%u) owner %p\n", au->slot, offset, frames,
+			(void *)owner);
+	if(owner)
+		a2cu_block_proc(cx->eng, au->pool, au->slot, offset, frames,
+				owner->bus);
+	else
+	{
+		/*
+		 * The voice mixes into a bus no inline of ours owns (a voice
+		 * started before the root driver's INITV inherits the master
+		 * bus, core.c:479-480): give that host bus a device shadow,
+		 * added back when the outermost inline returns.
+		 */
+		int i, bus = -1;
+		int32_t **outs = au->leaf_outputs;
+		for(i = 0; i < cx->norphans; ++i)
+			if(cx->orphans[i].outputs == outs)
+				bus = cx->orphans[i].bus;
+		if(bus < 0)
+		{
+			if(cx->norphans >= A2CU_MAXORPHANS)
+			{
+				a2r_Error(cx->st, A2_NOTIMPLEMENTED,
+						"a2cu: too many host buses");
+				return;
+			}
+			bus = a2cu_block_bus(cx->eng);
+			cx->orphans[cx->norphans].outputs = outs;
+			cx->orphans[cx->norphans].bus = bus;
+			cx->orphans[cx->norphans].nch = 0;
+			i = cx->norphans++;
+		}
+		else
+			for(i = 0; cx->orphans[i].outputs != outs; ++i)
+				;
+		if(au->leaf_nout > cx->orphans[i].nch)
+			cx->orphans[i].nch = au->leaf_nout;
+		a2cu_block_proc(cx->eng, au->pool, au->slot, offset, frames,
+				bus);
+	}
+}
+
+static void unit_process_body(A2_unit *u, unsigned offset, unsigned frames)
+{
 	A2CU_unit *au = (A2CU_unit *)u;
-	A2CU_voice *v = au->voice;
+	A2CU_voice *v;
 	A2CU_ctx *cx = au->cx;
 	frag_check(cx);
+	if(au->leaf)
+	{
+		leaf_process(cx, au, offset, frames);
+		return;
+	}
+	v = au->voice;
 	if(v->cls == VC_NEW)
 	{
 		classify(cx, v, offset);
@@ -570,53 +734,8 @@ static void unit_process(A2_unit *u, unsigned offset, unsigned frames)
 	}
 	if(v->cls == VC_LEAF)
 	{
-		A2CU_unit *last, *owner;
-		if(au->index)
-			return;		/* one record per voice and segment */
-		seg_mark(cx, v, offset, frames);
-		last = v->units[v->nunits - 1];
-		owner = owner_find(cx, last->il.header.outputs);
-		TRACE("leaf proc slot %d [%u,+%u) owner %p\n", v->slot, offset,
-				frames, (void *)owner);
-		if(owner)
-			a2cu_block_proc(cx->eng, v->pool, v->slot, offset,
-					frames, owner->bus);
-		else
-		{
-			/*
-			 * The voice mixes into a bus no inline of ours owns
-			 * (a voice started before the root driver's INITV
-			 * inherits the master bus, core.c:479-480): give that
-			 * host bus a device shadow, added back when the
-			 * outermost inline returns.
-			 */
-			int i, bus = -1;
-			int32_t **outs = last->il.header.outputs;
-			for(i = 0; i < cx->norphans; ++i)
-				if(cx->orphans[i].outputs == outs)
-					bus = cx->orphans[i].bus;
-			if(bus < 0)
-			{
-				if(cx->norphans >= A2CU_MAXORPHANS)
-				{
-					a2r_Error(cx->st, A2_NOTIMPLEMENTED,
-							"a2cu: too many host buses");
-					return;
-				}
-				bus = a2cu_block_bus(cx->eng);
-				cx->orphans[cx->norphans].outputs = outs;
-				cx->orphans[cx->norphans].bus = bus;
-				cx->orphans[cx->norphans].nch = 0;
-				i = cx->norphans++;
-			}
-			else
-				for(i = 0; cx->orphans[i].outputs != outs; ++i)
-					;
-			if(last->il.header.noutputs > cx->orphans[i].nch)
-				cx->orphans[i].nch = last->il.header.noutputs;
-			a2cu_block_proc(cx->eng, v->pool, v->slot, offset,
-					frames, bus);
-		}
+		if(!au->index)
+			leaf_process(cx, v->units[0], offset, frames);
 		return;
 	}
 	if(v->cls != VC_GEN || (au->pm < 0 && au->gu < 0))
@@ -624,7 +743,6 @@ static void unit_process(A2_unit *u, unsigned offset, unsigned frames)
 	/* One unit on the voice's device scratch channels */
 	seg_begin(cx, v, au);
 	seg_mark(cx, v, offset, frames);
-	select_run(cx, v);
 	TRACE("gen unit kind %d pm %d gu %d [%u,+%u) on_device %d scr %d\n",
 			au->kind, au->pm, au->gu, offset, frames, v->on_device,
 			v->scr_bus);
@@ -660,6 +778,8 @@ static void unit_process(A2_unit *u, unsigned offset, unsigned frames)
 				host_out = 1;
 			}
 		}
+		/* after the upload above: a flush ends every command run */
+		select_run(cx, v);
 		if(au->pm >= 0)
 			a2cu_block_pm_proc(cx->eng, au->pm, u->ninputs,
 					u->noutputs, host_out ? 0 : add,
@@ -731,7 +851,14 @@ static void inline_process(A2_unit *u, unsigned offset, unsigned frames,
 		cx->owners[cx->nowners].il = au;
 		++cx->nowners;
 	}
-	a2_inline_ProcessAdd(u, offset, frames);	/* the host's recursion */
+	if(stats_on())
+	{
+		unsigned long long t = tsc();
+		a2_inline_ProcessAdd(u, offset, frames);
+		st_inline_t -= tsc() - t;	/* exclusive of the recursion */
+	}
+	else
+		a2_inline_ProcessAdd(u, offset, frames);	/* the host's recursion */
 	if(cx->nowners)
 		--cx->nowners;
 	frag_check(cx);
@@ -753,9 +880,14 @@ static void inline_process(A2_unit *u, unsigned offset, unsigned frames,
 		 * buffer: bring that over.
 		 */
 		if(any_nonzero(u->outputs, nch, offset, frames))
-			a2cu_block_upload_add(cx->eng, au->bus, nch, offset,
-					frames,
+		{
+			int tmp = a2cu_block_bus(cx->eng);
+			a2cu_block_upload(cx->eng, tmp, nch, offset, frames,
 					(const int32_t *const *)u->outputs);
+			select_run(cx, v);	/* the upload flushed */
+			a2cu_block_bus_add(cx->eng, tmp, au->bus, offset,
+					frames);
+		}
 		v->scr_bus = au->bus;
 		v->scr_nch = nch;
 		v->on_device = 1;
@@ -769,14 +901,27 @@ static void inline_process(A2_unit *u, unsigned offset, unsigned frames,
 	}
 }
 
+static void inline_timed(A2_unit *u, unsigned offset, unsigned frames, int add)
+{
+	if(stats_on())
+	{
+		unsigned long long t = tsc();
+		inline_process(u, offset, frames, add);
+		st_inline_t += tsc() - t;
+		++st_inline_n;
+	}
+	else
+		inline_process(u, offset, frames, add);
+}
+
 static void inline_Process(A2_unit *u, unsigned offset, unsigned frames)
 {
-	inline_process(u, offset, frames, 0);
+	inline_timed(u, offset, frames, 0);
 }
 
 static void inline_ProcessAdd(A2_unit *u, unsigned offset, unsigned frames)
 {
-	inline_process(u, offset, frames, 1);
+	inline_timed(u, offset, frames, 1);
 }
 
 static A2_errors inline_Initialize(A2_unit *u, A2_vmstate *vms,
