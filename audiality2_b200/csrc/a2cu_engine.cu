@@ -310,6 +310,12 @@ struct Bank {
     unsigned *d_noise = nullptr;
     std::vector<int> transpose, group;
     std::vector<HostEvent> events;
+    // a2cu_bank_write_all of a register whose cooked value does not depend on the voice's transpose:
+    // kept as ONE record (+ the value column) and expanded straight into the staging buffer
+    struct BulkEvent {
+        uint64_t time; uint32_t seq, y, dur; int32_t scalar; bool has_values; std::vector<int32_t> values;
+    };
+    std::vector<BulkEvent> bulk;
     uint32_t seq = 0;
     // per-window device buffers (grown on demand)
     unsigned *d_evoff = nullptr;    // views into d_ev (bank mode): CSR offsets, then records
@@ -368,6 +374,7 @@ struct a2cu_engine {
     unsigned *d_ptab = nullptr;
     int16_t *d_fmsine = nullptr;
     std::vector<Bank *> banks;
+    std::vector<RenderParams> params;
     int ngroups = 0;
     int *d_gstate = nullptr;
     int gstate_cap = 0;
@@ -378,6 +385,8 @@ struct a2cu_engine {
     size_t mixev_cap = 0;
     int *d_acc = nullptr;
     size_t acc_cap = 0;
+    size_t acc_clean_n = 0;     // d_acc is all-zero for this layout (see run_window)
+    int acc_clean_W = 0;
     int *d_master = nullptr;
     size_t master_cap = 0;
     // pinned staging
@@ -1119,7 +1128,7 @@ int a2cu_bank_write_all(a2cu_engine *e, int bank, int unit, int reg, const int32
     if (!b || !values) return fail(A2CU_EINVAL, "bad bank%s");
     if (when < e->now) return fail(A2CU_ELATE, "event time already rendered%s");
     if (unit < 0 || unit >= (int)b->chain.size()) return fail(A2CU_EINVAL, "bad unit%s");
-    b->events.reserve(b->events.size() + 2 * (size_t)b->nvoices);
+    b->events.reserve(b->events.size() + (size_t)b->nvoices);
     const int kind = b->chain[unit].kind;
     // registers whose cooked value depends on the voice (transpose) or needs the wave checks
     const bool per_voice = (kind == A2CU_WTOSC && reg <= 1) || (kind == A2CU_FILTER12 && reg == 0) ||
@@ -1135,22 +1144,20 @@ int a2cu_bank_write_all(a2cu_engine *e, int bank, int unit, int reg, const int32
     Cooked c[2];
     int n = cook(e, kind, reg, values[0], (int)(when & 0xff), dur, 0, c);
     if (n < 0) return n;
-    const uint32_t y0 = (uint32_t)EV_WRITE | ((uint32_t)unit << 8);
-    HostEvent ev;
-    ev.time = when; ev.dur = dur;
-    for (int i = 0; i < b->nvoices; ++i) {
-        if (stride && i) {
+    Bank::BulkEvent be;
+    be.time = when; be.seq = b->seq; b->seq += (uint32_t)b->nvoices;
+    be.y = (uint32_t)EV_WRITE | ((uint32_t)unit << 8) | ((uint32_t)(c[0].reg & 0xff) << 16);
+    be.dur = c[0].dur; be.scalar = c[0].value; be.has_values = stride != 0;
+    if (stride) {
+        be.values.resize((size_t)b->nvoices);
+        be.values[0] = c[0].value;
+        for (int i = 1; i < b->nvoices; ++i) {
             n = cook(e, kind, reg, values[(size_t)i * stride], (int)(when & 0xff), dur, 0, c);
             if (n < 0) return n;
-        }
-        ev.voice = i;
-        for (int k = 0; k < n; ++k) {
-            ev.seq = b->seq++;
-            ev.y = y0 | ((uint32_t)(c[k].reg & 0xff) << 16);
-            ev.value = c[k].value; ev.dur = c[k].dur;
-            b->events.push_back(ev);
+            be.values[i] = c[0].value;
         }
     }
+    b->bulk.push_back(std::move(be));
     return A2CU_OK;
 }
 
@@ -1366,6 +1373,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         if (e->d_acc) cudaFree(e->d_acc);
         e->acc_cap = acc_n * 2;
         CK(cudaMalloc(&e->d_acc, e->acc_cap * sizeof(int)));
+        e->acc_clean_n = 0;
     }
     size_t m_n = (size_t)W * 2;
     if (m_n > e->master_cap) {
@@ -1378,16 +1386,42 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     // ---- stage events (host -> pinned -> device) ----
     const double ws_t0 = now_us();
     size_t stage_bytes = 0;
+    // per-bank events of this window. The vectors are deliberately short-lived: with many banks served
+    // round-robin the allocator hands the same (cache-hot) block to every window, whereas per-bank
+    // persistent buffers would cycle through tens of MB of cold host memory
     std::vector<std::vector<HostEvent>> due(e->banks.size());
+    std::vector<uint8_t> fast(e->banks.size(), 0);     // bank's window consists of bulk writes only
+    const bool planner = e->noise_seen || !e->mirrors.empty();
     for (size_t bi = 0; bi < e->banks.size(); ++bi) {
         Bank *b = e->banks[bi];
-        if (!b->enabled || b->events.empty()) continue;
+        if (!b->enabled) continue;
+        if (!b->bulk.empty()) {
+            bool all_bulk_due = true;
+            for (auto &be : b->bulk) if (be.time >= t1) all_bulk_due = false;
+            if (b->events.empty() && all_bulk_due && !planner && !b->dynamic) {
+                fast[bi] = 1;
+                std::stable_sort(b->bulk.begin(), b->bulk.end(), [](const Bank::BulkEvent &a, const Bank::BulkEvent &c) {
+                    if ((a.time >> 8) != (c.time >> 8)) return a.time < c.time;
+                    return a.seq < c.seq;
+                });
+                continue;
+            }
+            // general path: bulk writes become ordinary per-voice events
+            for (auto &be : b->bulk)
+                for (int i = 0; i < b->nvoices; ++i) {
+                    HostEvent ev;
+                    ev.time = be.time; ev.seq = be.seq + (uint32_t)i; ev.voice = i; ev.y = be.y;
+                    ev.value = be.has_values ? be.values[i] : be.scalar; ev.dur = be.dur;
+                    b->events.push_back(ev);
+                }
+            b->bulk.clear();
+        }
+        if (b->events.empty()) continue;
         bool all_due = true;
         for (auto &ev : b->events)
             if (ev.time >= t1) { all_due = false; break; }
         if (all_due) {
-            due[bi].swap(b->events);
-            b->events.clear();
+            due[bi].swap(b->events);        // b->events is left empty and without storage
         } else {
             std::vector<HostEvent> keep;
             for (auto &ev : b->events)
@@ -1407,14 +1441,15 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         if (!due[bi].empty())
             stage_bytes += (b->stride + 1) * sizeof(unsigned) + due[bi].size() * sizeof(uint4) + 64;
     }
-    if (e->noise_seen || !e->mirrors.empty()) {
+    if (planner) {
         r = plan_noise(e, t0, W, (int)buffer, splits, nsplits, due);
         if (r) return r;
     }
     stage_bytes = 0;
-    for (size_t bi = 0; bi < e->banks.size(); ++bi)
-        if (!due[bi].empty())
-            stage_bytes += (e->banks[bi]->stride + 1) * sizeof(unsigned) + due[bi].size() * sizeof(uint4) + 64;
+    for (size_t bi = 0; bi < e->banks.size(); ++bi) {
+        const size_t nev = fast[bi] ? e->banks[bi]->bulk.size() * (size_t)e->banks[bi]->nvoices : due[bi].size();
+        if (nev) stage_bytes += (e->banks[bi]->stride + 1) * sizeof(unsigned) + nev * sizeof(uint4) + 64;
+    }
     std::vector<MixHostEvent> mdue, mkeep;
     for (auto &m : e->mixev) (m.time < t1 ? mdue : mkeep).push_back(m);
     e->mixev.swap(mkeep);
@@ -1429,11 +1464,18 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     char *stage = (char *)e->h_stage;
     size_t spos = 0;
 
-    CK(cudaMemsetAsync(e->d_acc, 0, acc_n * sizeof(int), e->stream));
+    // the bus stage of the previous window zeroed the rows it read (MixParams::clear); a memset is only
+    // needed when the layout [bus][W][2] changed or nothing has run yet
+    if (e->acc_clean_n != acc_n || e->acc_clean_W != W) {
+        CK(cudaMemsetAsync(e->d_acc, 0, acc_n * sizeof(int), e->stream));
+    }
+    e->acc_clean_n = acc_n; e->acc_clean_W = W;
 
-    std::vector<RenderParams> params(e->banks.size());
+    std::vector<RenderParams> &params = e->params;
+    if (params.size() < e->banks.size()) params.resize(e->banks.size());
     for (size_t bi = 0; bi < e->banks.size(); ++bi) {
         Bank *b = e->banks[bi];
+        if (b->dynamic || !b->nvoices || !b->enabled) continue;
         RenderParams &P = params[bi];
         memset(&P, 0, sizeof(P));
         P.state = b->d_state; P.stride = b->stride; P.nvoices = b->nvoices;
@@ -1442,8 +1484,9 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         for (int i = 0; i < nsplits; ++i) P.splits[i] = splits[i];
         P.waves = e->d_waves; P.pool = e->d_pool; P.cpool = e->d_cpool; P.ptab = e->d_ptab; P.fmsine = e->d_fmsine;
         P.samplerate = e->samplerate;
-        if (!due[bi].empty()) {
-            size_t nev = due[bi].size();
+        const size_t nbulk = fast[bi] ? b->bulk.size() : 0;
+        if (!due[bi].empty() || nbulk) {
+            size_t nev = nbulk ? nbulk * (size_t)b->nvoices : due[bi].size();
             // device layout: [CSR offsets (stride + 1, padded to 16 B) | records] - one H2D copy
             const size_t off_bytes = (((b->stride + 1) * sizeof(unsigned)) + 15) & ~(size_t)15;
             if (nev > b->ev_cap) {
@@ -1455,7 +1498,22 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             unsigned *off = (unsigned *)(stage + spos);
             uint4 *recs = (uint4 *)(stage + spos + off_bytes);
             spos += off_bytes + nev * sizeof(uint4);
-            {
+            if (nbulk) {
+                // every voice has the same nbulk records (already in time / sequence order)
+                const unsigned K = (unsigned)nbulk;
+                for (size_t v = 0; v <= b->stride; ++v) off[v] = (unsigned)std::min(v, (size_t)b->nvoices) * K;
+                for (unsigned k = 0; k < K; ++k) {
+                    const Bank::BulkEvent &be = b->bulk[k];
+                    const unsigned rel = be.time >= t0 ? (unsigned)(be.time - t0) : (unsigned)(be.time & 0xff);
+                    uint4 rec = make_uint4(rel, be.y, (unsigned)be.scalar, be.dur);
+                    uint4 *dst = recs + k;
+                    if (be.has_values) {
+                        const int32_t *val = be.values.data();
+                        for (int v = 0; v < b->nvoices; ++v, dst += K) { rec.z = (unsigned)val[v]; *dst = rec; }
+                    } else
+                        for (int v = 0; v < b->nvoices; ++v, dst += K) *dst = rec;
+                }
+            } else {
                 // due[bi] is sorted by voice: CSR offsets in one pass
                 size_t k = 0;
                 const HostEvent *d = due[bi].data();
@@ -1483,7 +1541,15 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         Bank *b = e->banks[bi];
         if (b->dynamic || !b->nvoices || !b->enabled) continue;
         bool split = e->use_split && b->k.split_fn && !b->exotic && nsplits <= 1;
-        if (split && (!due[bi].empty() || nsplits)) {
+        std::vector<HostEvent> bulk_probe;      // fast path: all voices share voice 0's event times
+        if (fast[bi])
+            for (auto &be : b->bulk) {
+                HostEvent ev;
+                ev.time = be.time; ev.seq = be.seq; ev.voice = 0; ev.y = be.y; ev.value = be.scalar; ev.dur = be.dur;
+                bulk_probe.push_back(ev);
+            }
+        const std::vector<HostEvent> &scan = fast[bi] ? bulk_probe : due[bi];
+        if (split && (!scan.empty() || nsplits)) {
             // at most kSplitSegs segments per voice and fragment
             auto frag_start = [&](int f) { int pos = f % (int)buffer; return f - pos + (pos / kMaxFrag) * kMaxFrag; };
             int split_frag = nsplits ? frag_start(splits[0]) : -1;
@@ -1491,7 +1557,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             int cur_voice = -1, cur_frag = -1, cnt = 0, last = -1;
             uint64_t memo_time = ~(uint64_t)0;
             int f = 0, fs = 0;
-            for (const HostEvent &ev : due[bi]) {
+            for (const HostEvent &ev : scan) {
                 if (ev.time != memo_time) {     // bulk writes share one time stamp
                     memo_time = ev.time;
                     f = ev.time >= t0 ? (int)((ev.time - t0) >> 8) : 0;
@@ -1526,6 +1592,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             b->k.fn<<<grid, kThreads, 0, e->stream>>>(params[bi]);
         }
         ++e->launches;
+        if (fast[bi]) b->bulk.clear();      // consumed (staged above)
     }
     if (e->timing) CK(cudaEventRecord(e->ev1, e->stream));
     const double ws_t3 = now_us();
@@ -1558,6 +1625,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     if (r) return r;
     M.master = dev_out ? dev_out : e->d_master;
     M.root_stage = e->post_root ? 1 : 0;
+    M.clear = 1;
     if (e->ngroups) {
         mix_groups<<<e->ngroups, 256, 0, e->stream>>>(M);
         ++e->launches;
@@ -1652,10 +1720,11 @@ int a2cu_submit(a2cu_engine *e, unsigned frames, unsigned buffer) {
     // this window's spans go to the slot's own events
     cudaEvent_t s0 = e->ev0, s1 = e->ev1, s2 = e->ev2;
     e->ev0 = sl.ev0; e->ev1 = sl.ev1; e->ev2 = sl.ev2;
-    int r = run_window(e, frames, buffer, nullptr);
+    // the bus stage writes the master block straight into the pinned result slot (mapped host memory,
+    // same address on the device under UVA): no separate D2H copy on the stream
+    int r = run_window(e, frames, buffer, sl.h_out);
     e->ev0 = s0; e->ev1 = s1; e->ev2 = s2;
     if (r) return r;
-    CK(cudaMemcpyAsync(sl.h_out, e->d_master, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     CK(cudaEventRecord(sl.done, e->stream));
     e->d2h_bytes += n * sizeof(int32_t);
     sl.n = n;
@@ -1688,7 +1757,7 @@ int a2cu_apply_root_stage(a2cu_engine *e, const int32_t *dev_rootbus, int32_t *d
     MixParams M = e->last_mix;
     (void)start_time;
     M.acc = (int *)dev_rootbus; M.W = (int)frames; M.buffer = (int)(buffer ? buffer : frames);
-    M.ngroups = 0; M.master = dev_master; M.root_stage = 1;
+    M.ngroups = 0; M.master = dev_master; M.root_stage = 1; M.clear = 0;
     mix_root<<<std::max(1, std::min(8, ((int)M.W + 255) / 256)), 256, 0, e->stream>>>(M);
     ++e->launches;
     CK(cudaGetLastError());

@@ -236,8 +236,9 @@ struct MixParams {
     int *rstate;            // [8]
     const MixEvent *ev;     // sorted by time
     int nev;
-    int *master;            // [W][channels], or raw root bus [W][2] if !root_stage
+    int *master;            // [W][channels], or raw root bus [W][2] if !root_stage (may be mapped host memory)
     int root_stage;
+    int clear;              // consumers zero the bus rows they read, so the next window needs no memset
 };
 
 A2CU_DEV void pm_load(const int *s, Ramp &vol, Ramp &pan) {
@@ -347,10 +348,12 @@ A2CU_DEV void pm_bus(const MixParams &P, int target, int *state, const int *in, 
 __global__ void __launch_bounds__(256) mix_groups(const MixParams P) {
     const int g = blockIdx.x;
     int *root = P.acc;
-    const int *in = P.acc + (size_t)(1 + g) * P.W * 2;
+    int *in = P.acc + (size_t)(1 + g) * P.W * 2;
+    const bool clear = P.clear != 0;
     pm_bus(P, g, P.gstate + g * 8, in, false, [&](int f, int r0, int r1) {
         atomicAdd(root + f * 2, r0);
         atomicAdd(root + f * 2 + 1, r1);
+        if (clear) { in[f * 2] = 0; in[f * 2 + 1] = 0; }
     });
 }
 
@@ -358,10 +361,11 @@ __global__ void __launch_bounds__(256) mix_groups(const MixParams P) {
 // with root_stage == 0 the raw root bus is copied out (multi-GPU cut).
 __global__ void __launch_bounds__(256) mix_root(const MixParams P) {
     const int tid = threadIdx.x;
-    const int *root = P.acc;
+    int *root = P.acc;
+    const bool clear = P.clear != 0;
     const int gtid = blockIdx.x * blockDim.x + tid, gsize = gridDim.x * blockDim.x;
     if (!P.root_stage) {
-        for (int i = gtid; i < P.W * 2; i += gsize) P.master[i] = root[i];
+        for (int i = gtid; i < P.W * 2; i += gsize) { P.master[i] = root[i]; if (clear) root[i] = 0; }
         return;
     }
     const bool mono = P.channels == 1;
@@ -382,6 +386,7 @@ __global__ void __launch_bounds__(256) mix_root(const MixParams P) {
         }
         for (int f = gtid; f < P.W; f += gsize) {
             const int i0 = root[f * 2], i1 = root[f * 2 + 1];
+            if (clear) { root[f * 2] = 0; root[f * 2 + 1] = 0; }
             if (mono) P.master[f] = (int)(((long long)i0 * v0 + (long long)i1 * v1) >> 25);
             else { P.master[f * 2] = mulshr(i0, v0, 24); P.master[f * 2 + 1] = mulshr(i1, v1, 24); }
         }
@@ -392,6 +397,7 @@ __global__ void __launch_bounds__(256) mix_root(const MixParams P) {
     pm_bus(P, -1, P.rstate, root, mono, [&](int f, int r0, int r1) {
         if (mono) P.master[f] = r0;
         else { P.master[f * 2] = r0; P.master[f * 2 + 1] = r1; }
+        if (clear) { root[f * 2] = 0; root[f * 2 + 1] = 0; }
     });
 }
 
