@@ -87,7 +87,7 @@ static void reg_chain(std::vector<a2cu_unitspec> specs, const char *name) {
     e.split_threads = 0;
     registry()[sig_of(specs.data(), (int)specs.size())] = e;
 }
-static const size_t kMaxSplitSmem = 226 * 1024;   // dynamic part; the kernel also has a few static bytes
+static const size_t kMaxSplitSmem = 222 * 1024;   // dynamic part; the kernel also has 4.7 KB static (fused root stage); 227 KB per CTA
 template <int NOSC, bool FILT, int NA>
 static void reg_split(std::vector<a2cu_unitspec> specs) {
     KernelEntry &e = registry()[sig_of(specs.data(), (int)specs.size())];
@@ -386,6 +386,8 @@ struct a2cu_engine {
     int *d_acc = nullptr;
     size_t acc_cap = 0;
     size_t acc_clean_n = 0;     // d_acc is all-zero for this layout (see run_window)
+    unsigned *d_fuse_counter = nullptr;     // render_split's fused root stage: CTA tickets
+    bool fused_root = false;                // last window ran the root stage inside render_split
     int acc_clean_W = 0;
     int *d_master = nullptr;
     size_t master_cap = 0;
@@ -788,7 +790,7 @@ void a2cu_close(a2cu_engine *e) {
     cudaFree(e->d_waves); cudaFree(e->d_pool); cudaFree(e->d_cpool); cudaFree(e->d_ptab); cudaFree(e->d_fmsine);
     cudaFree(e->d_gstate); cudaFree(e->d_rstate); cudaFree(e->d_mixev);
     cudaFree(e->d_acc); cudaFree(e->d_master);
-    cudaFree(e->d_buscmds); cudaFree(e->d_bacc); cudaFree(e->d_pmstate); cudaFree(e->d_ustate); cudaFree(e->d_runs);
+    cudaFree(e->d_buscmds); cudaFree(e->d_bacc); cudaFree(e->d_pmstate); cudaFree(e->d_ustate); cudaFree(e->d_runs); cudaFree(e->d_fuse_counter);
     for (auto &g : e->gunits) if (g.fbd) cudaFree(g.fbd);
     for (int *p : e->fbd_free) cudaFree(p);
     if (e->h_xfer) cudaFreeHost(e->h_xfer);
@@ -1534,6 +1536,25 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             P.ev_off = b->d_evoff; P.ev = b->d_evrecs;
         }
     }
+    // Fused root stage: when exactly one bank renders with render_split, there are no group buses, no
+    // root events in this window and the root panmix is wanted, the last CTA of
+    // that kernel runs the root stage itself (a2cu_split.cuh) and mix_root is not launched.
+    int fuse_bank = -1;
+    if (e->post_root && e->ngroups == 0 && mdue.empty() && e->use_split && !getenv("A2CU_NO_FUSE")) {
+        int live = 0;
+        for (size_t bi = 0; bi < e->banks.size(); ++bi) {
+            Bank *b = e->banks[bi];
+            if (b->dynamic || !b->nvoices || !b->enabled) continue;
+            ++live;
+            fuse_bank = (b->k.split_fn && !b->exotic) ? (int)bi : -1;
+        }
+        if (live != 1) fuse_bank = -1;
+        if (fuse_bank >= 0 && !e->d_fuse_counter) {
+            CK(cudaMalloc(&e->d_fuse_counter, sizeof(unsigned)));
+            CK(cudaMemsetAsync(e->d_fuse_counter, 0, sizeof(unsigned), e->stream));
+        }
+    }
+    e->fused_root = false;
     const double ws_t2 = now_us();
     // inputs are resident from here on: ev0 .. ev1 brackets the render kernels
     if (e->timing) CK(cudaEventRecord(e->ev0, e->stream));
@@ -1585,6 +1606,14 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
                 }
             }
             int grid = (b->nvoices + 31) / 32;
+            if ((int)bi == fuse_bank) {
+                params[bi].fuse_root = 1;
+                params[bi].fuse_counter = e->d_fuse_counter;
+                params[bi].fuse_rstate = e->d_rstate;
+                params[bi].fuse_master = dev_out ? dev_out : e->d_master;
+                params[bi].fuse_channels = e->channels;
+                e->fused_root = true;
+            }
             b->k.split_fn<<<grid, b->k.split_threads, smem, e->stream>>>(params[bi]);
             ++e->split_launches;
         } else {
@@ -1630,8 +1659,10 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         mix_groups<<<e->ngroups, 256, 0, e->stream>>>(M);
         ++e->launches;
     }
-    mix_root<<<std::max(1, std::min(8, ((int)M.W + 255) / 256)), 256, 0, e->stream>>>(M);
-    ++e->launches;
+    if (!e->fused_root) {
+        mix_root<<<std::max(1, std::min(8, ((int)M.W + 255) / 256)), 256, 0, e->stream>>>(M);
+        ++e->launches;
+    }
     CK(cudaGetLastError());
     if (e->timing) CK(cudaEventRecord(e->ev2, e->stream));
     e->last_mix = M;

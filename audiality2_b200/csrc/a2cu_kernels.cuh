@@ -57,6 +57,13 @@ struct RenderParams {
     // render_split: coefficient-pool range [stage_begin, stage_begin + stage_count)
     // of the bank's wave, staged into shared memory with one TMA bulk copy
     int stage_begin, stage_count;
+    // render_split: fused root stage. The last CTA to finish (ticket from fuse_counter) runs the root
+    // panmix over the whole window - same code as mix_root - so the step needs no second launch.
+    int fuse_root;
+    unsigned *fuse_counter;
+    int *fuse_rstate;
+    int *fuse_master;
+    int fuse_channels;
 };
 
 // End of the fragment that contains frame f: fragments restart at every driver
@@ -331,7 +338,7 @@ A2CU_DEV void pm_bus(const MixParams &P, int target, int *state, const int *in, 
                 if (v0 > lim) v0 = lim;
                 if (v1 > lim) v1 = lim;
             }
-            int i0 = in[f * 2], i1 = in[f * 2 + 1];
+            int i0 = __ldcg(in + f * 2), i1 = __ldcg(in + f * 2 + 1);
             if (mono)
                 emit(f, (int)(((long long)i0 * v0 + (long long)i1 * v1) >> 25), 0);
             else
@@ -359,11 +366,11 @@ __global__ void __launch_bounds__(256) mix_groups(const MixParams P) {
 
 // root: { inline 0 *|2; panmix * *|2 1; xinsert * > } into the cleared master;
 // with root_stage == 0 the raw root bus is copied out (multi-GPU cut).
-__global__ void __launch_bounds__(256) mix_root(const MixParams P) {
-    const int tid = threadIdx.x;
+// Root stage over the window for a group of threads (gtid of gsize); 'cta0' tells whether this CTA
+// runs the general (segment replay) path when the rampers are not at rest.
+A2CU_DEV void root_stage(const MixParams &P, int gtid, int gsize, bool cta0) {
     int *root = P.acc;
     const bool clear = P.clear != 0;
-    const int gtid = blockIdx.x * blockDim.x + tid, gsize = gridDim.x * blockDim.x;
     if (!P.root_stage) {
         for (int i = gtid; i < P.W * 2; i += gsize) { P.master[i] = root[i]; if (clear) root[i] = 0; }
         return;
@@ -385,7 +392,7 @@ __global__ void __launch_bounds__(256) mix_root(const MixParams P) {
             if (v1 > lim) v1 = lim;
         }
         for (int f = gtid; f < P.W; f += gsize) {
-            const int i0 = root[f * 2], i1 = root[f * 2 + 1];
+            const int i0 = __ldcg(root + f * 2), i1 = __ldcg(root + f * 2 + 1);
             if (clear) { root[f * 2] = 0; root[f * 2 + 1] = 0; }
             if (mono) P.master[f] = (int)(((long long)i0 * v0 + (long long)i1 * v1) >> 25);
             else { P.master[f * 2] = mulshr(i0, v0, 24); P.master[f * 2 + 1] = mulshr(i1, v1, 24); }
@@ -393,12 +400,18 @@ __global__ void __launch_bounds__(256) mix_root(const MixParams P) {
         if (gtid == 0 && P.W > 0) { P.rstate[2] = 0; P.rstate[6] = 0; }     // deltas as PrepareRamper leaves them
         return;
     }
-    if (blockIdx.x) return;
+    if (!cta0) return;
     pm_bus(P, -1, P.rstate, root, mono, [&](int f, int r0, int r1) {
         if (mono) P.master[f] = r0;
         else { P.master[f * 2] = r0; P.master[f * 2 + 1] = r1; }
         if (clear) { root[f * 2] = 0; root[f * 2 + 1] = 0; }
     });
+}
+
+// root: { inline 0 *|2; panmix * *|2 1; xinsert * > } into the cleared master;
+// with root_stage == 0 the raw root bus is copied out (multi-GPU cut).
+__global__ void __launch_bounds__(256) mix_root(const MixParams P) {
+    root_stage(P, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, blockIdx.x == 0);
 }
 
 // ---------------------------------------------------------------------------

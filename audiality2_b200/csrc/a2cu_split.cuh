@@ -438,6 +438,27 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
         sp.st(L::filt_w + 12, d1);
         sp.st(L::filt_w + 13, d2);
     }
+    // ---- fused root stage: the last CTA to get here owns the finished root bus ----
+    if (P.fuse_root) {
+        __shared__ int s_last;
+        __syncthreads();                    // every bus flush of this CTA has been issued
+        if (tid == 0) {
+            __threadfence();                // ... and is visible before the ticket is taken
+            s_last = atomicAdd(P.fuse_counter, 1u) == gridDim.x - 1 ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            MixParams M;
+            M.acc = P.acc; M.W = P.W; M.buffer = P.buffer; M.ngroups = 0; M.channels = P.fuse_channels;
+            M.nsplits = P.nsplits;          // root wake-ups cut the root panmix's segments too
+            for (int i = 0; i < kMaxSplits; ++i) M.splits[i] = P.splits[i];
+            M.gstate = nullptr; M.rstate = P.fuse_rstate; M.ev = nullptr; M.nev = 0;
+            M.master = P.fuse_master; M.root_stage = 1; M.clear = 1;
+            root_stage(M, tid, WR::threads, true);
+            if (tid == 0) *P.fuse_counter = 0u;     // ready for the next launch
+        }
+    }
 }
 
 }  // namespace a2cu
