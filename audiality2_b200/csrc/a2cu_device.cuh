@@ -129,9 +129,18 @@ A2CU_DEV int hermite4(int dm, int d0, int d1, int d2, unsigned ph) {
     a = wmul(a + b, x) >> 15;
     return d0 + (wmul(a + c, x) >> 15);
 }
+// The four taps d[i-1..i+2] are 8 consecutive bytes at a 2-byte aligned address: fetch the two
+// aligned 8-byte words that contain them and funnel-shift, instead of four 2-byte loads. For large
+// sampled waves (no coefficient table) every lane gathers somewhere else in HBM, so the kernel is
+// bound by sector requests through L1: this halves them (profiles/hbm_gather.py). The wave pool pads
+// each level with A2_WAVEPRE / A2_WAVEPOST samples, so the aligned words are always inside the pool.
 A2CU_DEV int hermite(const int16_t *d, unsigned ph) {
-    int i = (int)(ph >> 8);
-    return hermite4(d[i - 1], d[i], d[i + 1], d[i + 2], ph);
+    const unsigned long long a = (unsigned long long)(d + (int)(ph >> 8) - 1);
+    const unsigned long long *q = (const unsigned long long *)(a & ~7ull);
+    const unsigned long long lo = __ldg(q), hi = __ldg(q + 1);
+    const unsigned sh = (unsigned)(a & 7ull) * 8u;      // 0, 16, 32 or 48
+    const unsigned long long x = sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+    return hermite4((short)x, (short)(x >> 16), (short)(x >> 32), (short)(x >> 48), ph);
 }
 // a2_Hermite2 (a2_dsp.h:91-98) on precomputed a2_Hermite2c coefficients
 // (a2_dsp.h:83-89): term for term the same integers as a2_Hermite, but one
@@ -430,11 +439,15 @@ struct WtOsc {
     // The shared noise LCG (a2_dsp.h:37-42, wtosc.c:135-144) is advanced in
     // tree-walk order on the host; each noise segment gets its start state.
     A2CU_DEV void seed(unsigned s) { nstate = s; }
-    // True when the current segment is the common unchecked wavetable loop.
-    A2CU_DEV bool plain() const { return run == RUN_TABLE; }
-    // sample() specialised for plain(): no mode tests, so the compiler can
-    // overlap the two Hermite gathers of consecutive frames (wtosc.c:226-233).
+    // True when the current segment is a wavetable loop without a state change in the middle: the
+    // unchecked loop, or the per-sample wrapped loop of a looped non-mipmapped wave played faster
+    // than A2_MAXPHINC (wtosc.c:301-358) - the large-sampled-wave case whose gather goes to HBM.
+    A2CU_DEV bool plain() const { return run == RUN_TABLE || run == RUN_CHECK_LOOP; }
+    // sample() specialised for plain(): no liveness tests, so the compiler can overlap the Hermite
+    // gathers of consecutive frames (wtosc.c:226-233) - for sampled waves that means several HBM
+    // sectors in flight per voice instead of one frame's worth.
     A2CU_DEV void sample_fast(const Ctx &, int &s0, int &s1, int &o0, int &o1) {
+        if (run == RUN_CHECK_LOOP) ph = wrap_mod(ph, (unsigned long long)wsize << 24);
         unsigned p16 = (unsigned)(ph >> 16);
         int h = cf ? hermite_cf(cf, p16) + hermite_cf(cf, p16 + (dph >> 17))
                    : hermite(d, p16) + hermite(d, p16 + (dph >> 17));

@@ -53,7 +53,7 @@ L2_BYTES = 126 * 1024 * 1024    # B200 L2
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per
     launch, from the committed `ncu --set full` summary of this workload."""
-    path = os.path.join(ROOT, "profiles", "r01_v4_render_split_ncu.txt")
+    path = os.path.join(ROOT, "profiles", "r01_v5_render_split_ncu.txt")
     try:
         tot = 0.0
         for ln in open(path):
@@ -413,7 +413,7 @@ def bench_ours(args):
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
-                "traffic_source": "profiles/r01_v4_render_split_ncu.txt (ncu --set full, per launch)",
+                "traffic_source": "profiles/r01_v5_render_split_ncu.txt (ncu --set full, per launch)",
                 "kernel": "%s<%s>" % (kname, e.bank_kernel_name(bank)),
                 "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": alg_bytes,

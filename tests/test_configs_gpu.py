@@ -97,3 +97,44 @@ def test_cfg4_fm_shard_32768_voices():
     o.close()
     assert np.abs(ref).max() > 10000
     assert np.array_equal(out, ref), _diff(out, ref)
+
+
+@pytest.mark.parametrize("wtype,looped", [(2, True), (2, False), (3, True)])
+def test_uploaded_sampled_waves_all_gather_modes(wtype, looped):
+    """Uploaded (sampled) waves, CUDA vs the oracle port: non-mipmapped waves below and above
+    A2_MAXPHINC samples per frame (the per-sample wrapped loop / end check of wtosc.c:301-358, i.e.
+    the gather that goes to HBM for large waves, profiles/hbm_gather.py), non-looped waves that
+    run out mid-window, and an uploaded mipmapped wave. Raw int16 taps (no coefficient table)
+    and the table path are both hit: the second wave is longer than the table limit."""
+    from audiality2_b200 import engine as eng
+    V, frames = 96, 640
+    r = np.random.RandomState(5 + wtype + int(looped))
+    small = (r.randint(-30000, 30000, size=3001)).astype(np.int16)          # 3001: not a multiple of 256
+    big = (r.randint(-30000, 30000, size=(1 << 20) + 77)).astype(np.int16)   # > 2^20 samples: raw-tap path
+    flags = 0x100 if looped else 0
+    kinds = ["wtosc", "panmix"]
+    chain = autowire(kinds)
+    e = eng.Engine(48000, 2)
+    o = ao.Oracle(48000, 2)
+    waves_e = [e.upload_wave(wtype, 500, flags, small), e.upload_wave(wtype, 40000, flags, big)]
+    waves_o = [o.upload_wave(wtype, 500, flags, small), o.upload_wave(wtype, 40000, flags, big)]
+    bank = e.new_bank(chain, V)
+    for _ in range(V):
+        o.new_voice(chain)
+    # pitches from -3 to +6.5 octaves: period 500 -> up to ~250 samples per frame, period 40000 -> far
+    # beyond A2_MAXPHINC (muted / checked paths)
+    pitch = (np.linspace(-3, 6.5, V) * 65536).astype(np.int32)
+    phase = r.randint(0, 3 * 65536, size=V).astype(np.int32)
+    pan = r.randint(-65536, 65536, size=V).astype(np.int32)
+    we = np.array([waves_e[v % 2] << 16 for v in range(V)], dtype=np.int32)
+    wo = np.array([waves_o[v % 2] << 16 for v in range(V)], dtype=np.int32)
+    e.write_all(bank, 0, 0, we); o.write_all(0, V, 0, 0, wo)
+    for reg, vals in ((1, pitch), (2, [fx(0.01)]), (3, phase)):
+        e.write_all(bank, 0, reg, vals); o.write_all(0, V, 0, reg, vals)
+    e.write_all(bank, 1, 1, pan); o.write_all(0, V, 1, 1, pan)
+    out = e.run(frames, 64)
+    ref = o.render(np.zeros(0, dtype=ao.EVENT_DTYPE), frames, 64)
+    e.close()
+    o.close()
+    assert np.abs(ref).max() > 10000
+    assert np.array_equal(out, ref), _diff(out, ref)
