@@ -1537,10 +1537,10 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         }
     }
     // Fused root stage: when exactly one bank renders with render_split, there are no group buses, no
-    // root events in this window and the root panmix is wanted, the last CTA of
+    // root events in this window, the last CTA of
     // that kernel runs the root stage itself (a2cu_split.cuh) and mix_root is not launched.
     int fuse_bank = -1;
-    if (e->post_root && e->ngroups == 0 && mdue.empty() && e->use_split && !getenv("A2CU_NO_FUSE")) {
+    if (e->ngroups == 0 && mdue.empty() && e->use_split && !getenv("A2CU_NO_FUSE")) {
         int live = 0;
         for (size_t bi = 0; bi < e->banks.size(); ++bi) {
             Bank *b = e->banks[bi];
@@ -1612,6 +1612,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
                 params[bi].fuse_rstate = e->d_rstate;
                 params[bi].fuse_master = dev_out ? dev_out : e->d_master;
                 params[bi].fuse_channels = e->channels;
+                params[bi].fuse_root_stage = e->post_root ? 1 : 0;
                 e->fused_root = true;
             }
             b->k.split_fn<<<grid, b->k.split_threads, smem, e->stream>>>(params[bi]);
@@ -1725,7 +1726,16 @@ int a2cu_run(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *out) {
 // master block into a pinned result slot) and returns at once; a2cu_collect
 // waits for that window only. With two windows in flight the host stages
 // window i+1 while the device renders window i.
-int a2cu_submit(a2cu_engine *e, unsigned frames, unsigned buffer) {
+static int submit_impl(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *dev_out);
+int a2cu_submit(a2cu_engine *e, unsigned frames, unsigned buffer) { return submit_impl(e, frames, buffer, nullptr); }
+// Same, but the window's output (master block, or the raw root bus with post_root_stage 0) goes to
+// DEVICE memory 'dev_out' - for callers that go on with it on the stream (the multi-GPU reduce).
+// a2cu_collect(ticket, NULL) then only waits for the window's kernels and latches its timing spans.
+int a2cu_submit_dev(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *dev_out) {
+    if (!dev_out) return fail(A2CU_EINVAL, "a2cu_submit_dev: dev_out is NULL%s");
+    return submit_impl(e, frames, buffer, dev_out);
+}
+static int submit_impl(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *dev_out) {
     if (!e) return A2CU_EINVAL;
     cudaSetDevice(e->device);
     const int k = e->slot_pos;
@@ -1743,7 +1753,7 @@ int a2cu_submit(a2cu_engine *e, unsigned frames, unsigned buffer) {
         e->master_cap = (size_t)frames * 4;
         CK(cudaMalloc(&e->d_master, e->master_cap * sizeof(int)));
     }
-    if (n > sl.cap) {
+    if (!dev_out && n > sl.cap) {
         if (sl.h_out) cudaFreeHost(sl.h_out);
         sl.cap = n * 2;
         CK(cudaMallocHost(&sl.h_out, sl.cap * sizeof(int32_t)));
@@ -1753,12 +1763,12 @@ int a2cu_submit(a2cu_engine *e, unsigned frames, unsigned buffer) {
     e->ev0 = sl.ev0; e->ev1 = sl.ev1; e->ev2 = sl.ev2;
     // the bus stage writes the master block straight into the pinned result slot (mapped host memory,
     // same address on the device under UVA): no separate D2H copy on the stream
-    int r = run_window(e, frames, buffer, sl.h_out);
+    int r = run_window(e, frames, buffer, dev_out ? dev_out : sl.h_out);
     e->ev0 = s0; e->ev1 = s1; e->ev2 = s2;
     if (r) return r;
     CK(cudaEventRecord(sl.done, e->stream));
-    e->d2h_bytes += n * sizeof(int32_t);
-    sl.n = n;
+    if (!dev_out) e->d2h_bytes += n * sizeof(int32_t);
+    sl.n = dev_out ? 0 : n;
     sl.busy = true;
     e->slot_pos = (k + 1) % a2cu_engine::kSlots;
     return k;
@@ -1770,7 +1780,7 @@ int a2cu_collect(a2cu_engine *e, int ticket, int32_t *out) {
     cudaSetDevice(e->device);
     a2cu_engine::Slot &sl = e->slots[ticket];
     CK(cudaEventSynchronize(sl.done));
-    if (out) memcpy(out, sl.h_out, sl.n * sizeof(int32_t));
+    if (out && sl.n) memcpy(out, sl.h_out, sl.n * sizeof(int32_t));
     if (e->timing) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, sl.ev0, sl.ev1) == cudaSuccess) e->last_ms = ms;

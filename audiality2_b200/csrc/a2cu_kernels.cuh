@@ -64,6 +64,7 @@ struct RenderParams {
     int *fuse_rstate;
     int *fuse_master;
     int fuse_channels;
+    int fuse_root_stage;    // 0: copy the raw root bus out (multi-GPU cut) instead of the root panmix
 };
 
 // End of the fragment that contains frame f: fragments restart at every driver

@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
             M.nsplits = P.nsplits;          // root wake-ups cut the root panmix's segments too
             for (int i = 0; i < kMaxSplits; ++i) M.splits[i] = P.splits[i];
             M.gstate = nullptr; M.rstate = P.fuse_rstate; M.ev = nullptr; M.nev = 0;
-            M.master = P.fuse_master; M.root_stage = 1; M.clear = 1;
+            M.master = P.fuse_master; M.root_stage = P.fuse_root_stage; M.clear = 1;
             root_stage(M, tid, WR::threads, true);
             if (tid == 0) *P.fuse_counter = 0u;     // ready for the next launch
         }

@@ -65,6 +65,7 @@ SYMBOLS = {
     "a2cu_master_devptr": (_VP, [_VP]),
     "a2cu_sync": (_I, [_VP]),
     "a2cu_submit": (_I, [_VP, _U, _U]),
+    "a2cu_submit_dev": (_I, [_VP, _U, _U, _VP]),
     "a2cu_collect": (_I, [_VP, _I, _VP]),
     "a2cu_set_post_root_stage": (_I, [_VP, _I]),
     "a2cu_apply_root_stage": (_I, [_VP, _VP, _VP, _U, _U, _U64]),
@@ -300,6 +301,14 @@ class Engine:
         t = self._ck(self.L.a2cu_submit(self.h, frames, buffer))
         self._frames_of[t] = frames
         return t
+
+    def submit_dev(self, frames, buffer, dev_ptr):
+        """Queue one window whose output stays in device memory (a2cu_submit_dev)."""
+        return self._ck(self.L.a2cu_submit_dev(self.h, frames, buffer, dev_ptr))
+
+    def collect_spans(self, ticket):
+        """Wait for a submit_dev window's kernels; latches last_render_ms / last_mix_ms."""
+        self._ck(self.L.a2cu_collect(self.h, ticket, None))
 
     def collect(self, ticket, out=None):
         """Wait for a submitted window and return its int32 8:24 output."""

@@ -21,8 +21,9 @@ Numbers on the JSON line:
           kernels, D2H of the int32 master block into pinned memory) and
           a2cu_collect (wait + copy to the caller's buffer), two windows in
           flight so the host stages step i+1 while the device renders step i;
-          wall time of the whole timed region, max over ranks. (N > 1: one synchronous a2cu_run_async + NCCL reduce
-          + root stage + D2H per step, host wall time per step.)
+          wall time of the whole timed region, max over ranks. (N > 1: the same
+          pipeline with a2cu_submit_dev + NCCL all-reduce + root stage + D2H
+          queued per step, three windows in flight.)
   roofline  HBM roofline of the dominant kernel (render_bank<...>).
   cpu_baseline  the reference's own CPU render (oracle/_ref) on a bounded
           sample of the same workload, 1 core, rank 0, N = 1 only.
@@ -267,13 +268,15 @@ def bench_ours(args):
     multi = world > 1
     if multi:
         e.set_post_root_stage(False)
-    rootbus = torch.zeros((STEP_FRAMES, 2), dtype=torch.int32, device=dev)
-    master = torch.zeros((STEP_FRAMES, 2), dtype=torch.int32, device=dev)
-    host_out = torch.zeros((STEP_FRAMES, 2), dtype=torch.int32).pin_memory()
+    RING = 3                # multi-GPU: windows in flight (device buffers + events per slot)
+    rootbus = [torch.zeros((STEP_FRAMES, 2), dtype=torch.int32, device=dev) for _ in range(RING)]
+    master = [torch.zeros((STEP_FRAMES, 2), dtype=torch.int32, device=dev) for _ in range(RING)]
+    host_out = [torch.zeros((STEP_FRAMES, 2), dtype=torch.int32).pin_memory() for _ in range(RING)]
     amp = [np.array([b["amp"] // 2], dtype=np.int32), np.array([b["amp"]], dtype=np.int32)]
     L = e.L
-    ev_a = torch.cuda.Event(enable_timing=True)
-    ev_b = torch.cuda.Event(enable_timing=True)
+    ev_a = [torch.cuda.Event(enable_timing=True) for _ in range(RING)]
+    ev_b = [torch.cuda.Event(enable_timing=True) for _ in range(RING)]
+    fin = [torch.cuda.Event() for _ in range(RING)]
     dev_ms, host_s, render_ms = [], [], []
     state = {"step": 0}
 
@@ -302,28 +305,41 @@ def bench_ours(args):
             if len(pending) > 2:
                 collect_one(timed)
         else:
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
+            # N > 1: the same pipeline with the exchange step on the stream: raw stereo root bus of
+            # this rank's voices -> NCCL int32 all-reduce over NVLink -> truncating root stage -> D2H
+            k = i % RING
+            if inflight[k] is not None:
+                finish_slot(k)
             L.a2cu_bank_write_all(e.h, cur, 0, 2, a.ctypes.data, 0, L.a2cu_now(e.h), STEP_FRAMES << 8)
-            e.run_async(STEP_FRAMES, BLOCK, rootbus.data_ptr())
-            ev_a.record(stream)
-            reduce_root_bus(rootbus)                   # NCCL int32 sum over NVLink
-            e.apply_root_stage(rootbus.data_ptr(), master.data_ptr(), STEP_FRAMES, BLOCK)
-            ev_b.record(stream)
-            host_out.copy_(master, non_blocking=True)
-            e.sync()
-            torch.cuda.synchronize()
-            span = e.last_render_ms() + e.last_mix_ms() + ev_a.elapsed_time(ev_b)
-            t1 = time.perf_counter()
-            if timed:
-                dev_ms.append(span)
-                host_s.append(t1 - t0)
-                render_ms.append(e.last_render_ms())
+            t = e.submit_dev(STEP_FRAMES, BLOCK, rootbus[k].data_ptr())
+            ev_a[k].record(stream)
+            reduce_root_bus(rootbus[k])
+            e.apply_root_stage(rootbus[k].data_ptr(), master[k].data_ptr(), STEP_FRAMES, BLOCK)
+            ev_b[k].record(stream)
+            host_out[k].copy_(master[k], non_blocking=True)
+            fin[k].record(stream)
+            inflight[k] = (t, timed)
         state["step"] += 1
+
+    inflight = [None] * RING
+
+    def finish_slot(k):
+        t, timed = inflight[k]
+        inflight[k] = None
+        fin[k].synchronize()                        # this window's result is in host_out[k]
+        e.collect_spans(t)
+        if timed:
+            dev_ms.append(e.last_render_ms() + e.last_mix_ms() + ev_a[k].elapsed_time(ev_b[k]))
+            render_ms.append(e.last_render_ms())
 
     def drain(timed):
         while pending:
             collect_one(timed)
+        base = state["step"]
+        for j in range(RING):                       # oldest first
+            k = (base + j) % RING
+            if inflight[k] is not None:
+                finish_slot(k)
 
     clocks = ClockSampler(local)
     if rank == 0:
@@ -359,13 +375,12 @@ def bench_ours(args):
     if multi:
         dist.barrier()
     wall1 = time.perf_counter()
-    if not multi:
-        host_s.append(wall1 - wall0)        # pipelined: the whole timed region is the e2e time
+    host_s.append(wall1 - wall0)            # pipelined: the whole timed region is the e2e time
     launches = e.launches - l0
     h2d = (e.h2d_bytes - h0) / args.steps
     d2h = (e.d2h_bytes - d0) / args.steps
     if multi:
-        d2h = STEP_FRAMES * 2 * 4 if rank == 0 else 0
+        d2h = STEP_FRAMES * 2 * 4
     clk = clocks.stop() if rank == 0 else None
 
     tot = torch.tensor([sum(dev_ms), sum(host_s) * 1000.0], dtype=torch.float64, device=dev)

@@ -214,6 +214,10 @@ int a2cu_sync(a2cu_engine *e);
  * prepares window i+1 (a2cu_bank_write*) while the device renders window i.
  */
 int a2cu_submit(a2cu_engine *e, unsigned frames, unsigned buffer);
+/* Output stays in DEVICE memory 'dev_out' (multi-GPU: the raw root bus that is
+ * reduced next); a2cu_collect(e, ticket, NULL) waits for the window's kernels. */
+int a2cu_submit_dev(a2cu_engine *e, unsigned frames, unsigned buffer,
+		int32_t *dev_out);
 int a2cu_collect(a2cu_engine *e, int ticket, int32_t *out);
 
 /*
