@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
     extern __shared__ __align__(128) int sm[];
     __shared__ __align__(8) unsigned long long s_mbar;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long t_entry = P.prof ? clock64() : 0;
     // logical role index (see SplitWarps): helpers 0..NA-1, control NA; -1 = idle
     const int hq = FILT ? ((warp & 3) == 3 ? -1 : warp - (warp >> 2)) : warp;
     const bool is_helper = hq >= 0 && hq < NA;
@@ -159,6 +160,7 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
     }
 
     const int lag_c = FILT ? 3 : 2;     // stage C runs this many iterations behind control
+    const long long t_loop = P.prof ? clock64() : 0;
     for (int it = 0; it < nfrag + lag_c + 1; ++it) {
         long long t_begin = 0, t_mid = 0;
         if (P.prof) t_begin = clock64();
@@ -283,8 +285,9 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
                     const int in = ta[f * kTileStride];
                     const int d1s = d1 >> 4;
                     const int l = wadd(d2, wmul(fc, d1s) >> 8);
-                    // (in>>5) - l - (q*d1s>>8), re-associated (modular adds commute): the q term
-                    // is ready together with l, so h follows l by ONE add on the recurrence's chain
+                    // (in>>5) - l - (q*d1s>>8). ptxas turns this into two shift-adds after l
+                    // (LEA.HI.SX32); forcing "t = (in>>5) - q-term off the chain, h = t - l" with an
+                    // inline PTX sub puts an IMAD.IADD on the other pipe and measured 5 % SLOWER.
                     const int h = wsub(wsub(in >> 5, wmul(qq, d1s) >> 8), l);
                     const int bb = wadd(wmul(fc, h >> 4) >> 8, d1);
                     tb[f * kTileStride] = wadd(wadd(wmul(l, lp), wmul(bb, bp)), wmul(h, hp)) >> 3;
@@ -437,6 +440,10 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
     if (is_ser && valid) {       // the recurrence state lives in the serial warp
         sp.st(L::filt_w + 12, d1);
         sp.st(L::filt_w + 13, d2);
+    }
+    if (P.prof && tid == 0) {       // [6] prologue, [7] loop, per CTA (a2cu_split_profile)
+        atomicAdd(P.prof + 6, (unsigned long long)(t_loop - t_entry));
+        atomicAdd(P.prof + 7, (unsigned long long)(clock64() - t_loop));
     }
     // ---- fused root stage: the last CTA to get here owns the finished root bus ----
     if (P.fuse_root) {

@@ -244,7 +244,8 @@ uint64_t a2cu_split_launch_count(const a2cu_engine *e);
 /*
  * Profiling aid: per-role busy cycles of render_split summed over CTAs since
  * the last call: out[0] control, [1] filter recurrence, [2] oscillator stage,
- * [3] panmix/bus stage, [4] barrier wait of a helper warp, [5] iterations.
+ * [3] panmix/bus stage, [4] barrier wait of a helper warp, [5] iterations,
+ * [6] kernel entry -> pipeline start, [7] pipeline + state store, summed over CTAs.
  * enable != 0 (re)arms the counters, 0 turns them off. out may be NULL.
  */
 int a2cu_split_profile(a2cu_engine *e, int enable, uint64_t out[8]);

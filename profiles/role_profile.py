@@ -18,3 +18,5 @@ print('kernel ms', e.last_render_ms(), 'split launches', e.split_launches)
 names=['control','serial','stageA','stageC','barrier-wait(helper)','iters']
 it=p[5]
 for n,v in zip(names,p): print('%-22s %10.0f cycles per CTA-iteration'%(n, v/max(it,1)))
+nl = e.split_launches - 5
+print('per CTA and launch: prologue %.0f cycles, pipeline + state store %.0f cycles (%d launches x %d CTAs)' % (p[6]/(N*ncta), p[7]/(N*ncta), N, ncta))
