@@ -324,6 +324,7 @@ struct Bank {
     size_t ev_cap = 0;
     bool has_noise = false;
     bool exotic = false;    // selected a noise / non-mip / table-less wave: render_bank only
+    cudaEvent_t ev_consumed = nullptr;  // recorded after the last kernel that reads d_ev (bank mode)
     bool enabled = true;    // a2cu_bank_enable: a disabled bank is paused (not rendered, events kept)
     int stage_wave = -1;    // wave whose coefficient table render_split stages in shared memory
     uint32_t stamp = 0;
@@ -402,6 +403,10 @@ struct a2cu_engine {
     cudaEvent_t stage_done[kStageRing] = {nullptr, nullptr, nullptr};
     bool stage_used[kStageRing] = {false, false, false};
     int stage_pos = 0;
+    // event uploads go through their own stream so that the H2D copy of window i+1 overlaps the
+    // kernels of window i (it only waits for the last kernel that read the same bank's event buffer)
+    cudaStream_t copy_stream = nullptr;
+    bool copy_used = false;         // this window's uploads went through copy_stream
     // pipelined API (a2cu_submit / a2cu_collect): result slots
     static const int kSlots = 4;
     struct Slot {
@@ -785,6 +790,7 @@ void a2cu_close(a2cu_engine *e) {
     for (Bank *b : e->banks) {
         cudaFree(b->d_state); cudaFree(b->d_bus); cudaFree(b->d_noise);
         cudaFree(b->d_ev); cudaFree(b->d_runs);
+        if (b->ev_consumed) cudaEventDestroy(b->ev_consumed);
         delete b;
     }
     cudaFree(e->d_waves); cudaFree(e->d_pool); cudaFree(e->d_cpool); cudaFree(e->d_ptab); cudaFree(e->d_fmsine);
@@ -794,6 +800,7 @@ void a2cu_close(a2cu_engine *e) {
     for (auto &g : e->gunits) if (g.fbd) cudaFree(g.fbd);
     for (int *p : e->fbd_free) cudaFree(p);
     if (e->h_xfer) cudaFreeHost(e->h_xfer);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     for (int k = 0; k < a2cu_engine::kStageRing; ++k) {
         if (e->stage_buf[k]) cudaFreeHost(e->stage_buf[k]);
         if (e->stage_done[k]) cudaEventDestroy(e->stage_done[k]);
@@ -1464,6 +1471,10 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     r = ensure_stage(e, stage_bytes);
     if (r) return r;
     char *stage = (char *)e->h_stage;
+    // bank event uploads use the copy stream unless bus-stage events share this staging buffer
+    e->copy_used = mdue.empty() && !getenv("A2CU_NO_COPY_STREAM");
+    if (e->copy_used && !e->copy_stream) CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    cudaStream_t up = e->copy_used ? e->copy_stream : e->stream;
     size_t spos = 0;
 
     // the bus stage of the previous window zeroed the rows it read (MixParams::clear); a memset is only
@@ -1529,12 +1540,19 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
                     recs[i] = make_uint4(rel, d[i].y, (unsigned)d[i].value, d[i].dur);
                 }
             }
-            CK(cudaMemcpyAsync(b->d_ev, off, off_bytes + nev * sizeof(uint4), cudaMemcpyHostToDevice, e->stream));
+            if (e->copy_used && b->ev_consumed) CK(cudaStreamWaitEvent(e->copy_stream, b->ev_consumed, 0));
+            CK(cudaMemcpyAsync(b->d_ev, off, off_bytes + nev * sizeof(uint4), cudaMemcpyHostToDevice, up));
             e->h2d_bytes += (b->stride + 1) * sizeof(unsigned) + nev * sizeof(uint4);
             b->d_evoff = (unsigned *)b->d_ev;
             b->d_evrecs = (uint4 *)((char *)b->d_ev + off_bytes);
             P.ev_off = b->d_evoff; P.ev = b->d_evrecs;
         }
+    }
+    if (e->copy_used) {
+        // uploads done -> staging buffer reusable; the kernels wait for exactly this event
+        const int k = (e->stage_pos + a2cu_engine::kStageRing - 1) % a2cu_engine::kStageRing;
+        CK(cudaEventRecord(e->stage_done[k], e->copy_stream));
+        CK(cudaStreamWaitEvent(e->stream, e->stage_done[k], 0));
     }
     // Fused root stage: when exactly one bank renders with render_split, there are no group buses, no
     // root events in this window, the last CTA of
@@ -1622,6 +1640,8 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             b->k.fn<<<grid, kThreads, 0, e->stream>>>(params[bi]);
         }
         ++e->launches;
+        if (!b->ev_consumed) CK(cudaEventCreateWithFlags(&b->ev_consumed, cudaEventDisableTiming));
+        CK(cudaEventRecord(b->ev_consumed, e->stream));
         if (fast[bi]) b->bulk.clear();      // consumed (staged above)
     }
     if (e->timing) CK(cudaEventRecord(e->ev1, e->stream));
@@ -1651,8 +1671,10 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         e->h2d_bytes += mdue.size() * sizeof(MixEvent);
         M.ev = e->d_mixev;
     }
-    r = stage_release(e);
-    if (r) return r;
+    if (!e->copy_used) {
+        r = stage_release(e);
+        if (r) return r;
+    }
     M.master = dev_out ? dev_out : e->d_master;
     M.root_stage = e->post_root ? 1 : 0;
     M.clear = 1;
