@@ -4,7 +4,9 @@
   a2render_cuda  the UNMODIFIED reference host + our unit plug-in (drop-in mode)
 on the same box; outputs compared bit for bit, a2_Run loop wall time reported.
 
-    python profiles/cfg5_k2trance.py [copies] [frames]
+    python profiles/cfg5_k2trance.py [copies] [frames] [--stats]
+
+--stats sets A2CU_STATS=1: the plug-in times its own callbacks with rdtsc (adds ~15 % to the run).
 """
 import json
 import os
@@ -16,8 +18,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import a2oracle as ao  # noqa: E402
 
-copies = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
-frames = int(sys.argv[2]) if len(sys.argv) > 2 else 88200
+STATS = "--stats" in sys.argv
+argv = [a for a in sys.argv if a != "--stats"]
+copies = int(argv[1]) if len(argv) > 1 else 1000
+frames = int(argv[2]) if len(argv) > 2 else 88200
 song = os.path.join(ao.REF_DIR, "songs", "benchmark", "k2trance.a2s")
 
 
@@ -26,7 +30,8 @@ def render(binary):
     import tempfile
     with tempfile.NamedTemporaryFile(suffix=".raw") as tf:
         env = dict(os.environ)
-        env["A2CU_STATS"] = "1"
+        if STATS:
+            env["A2CU_STATS"] = "1"
         res = subprocess.run([os.path.join(ao.REF_DIR, binary), "-r", "44100", "-b", "500", "-n", str(frames),
                               "-x", str(copies), "-p", "Song", "-o", tf.name, os.path.basename(song)],
                              cwd=os.path.dirname(song), capture_output=True, text=True, env=env)
