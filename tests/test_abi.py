@@ -59,3 +59,37 @@ def test_chain_registry():
                   ["wtosc", "waveshaper", "panmix"]):
         assert engine.Engine.chain_supported(autowire(kinds)), kinds
     assert not engine.Engine.chain_supported([(99, 0, 1, 0, 1)])
+
+
+def test_dropin_fails_loudly_without_gpu(tmp_path):
+    """The unit plug-in never renders on the CPU: without a CUDA device the host's a2_Open fails
+    (our OpenState returns A2_DEVICEOPEN, src/units.c:43-76), it does not fall back."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    exe = os.path.join(ROOT, "oracle", "_ref", "a2render_cuda")
+    if not os.path.exists(exe):
+        pytest.skip("drop-in harness not built (needs the reference tree)")
+    out = tmp_path / "x.raw"
+    res = subprocess.run([exe, "-n", "640", "-p", "Song", "-o", str(out),
+                          os.path.join(ROOT, "tests", "golden", "osc_pan_ramps.a2s")],
+                         capture_output=True, text=True)
+    assert res.returncode != 0
+    assert "no CPU fallback" in res.stderr or "Error opening device" in res.stderr
+    assert not out.exists() or out.stat().st_size == 0
+
+
+def test_units_library_exports_every_descriptor():
+    """liba2cu_units.so exports each A2_unitdesc symbol include/a2cu_units.h declares."""
+    lib = os.path.join(ROOT, "audiality2_b200", "liba2cu_units.so")
+    if not os.path.exists(lib):
+        pytest.skip("plug-in not built (needs the reference headers)")
+    text = open(os.path.join(ROOT, "include", "a2cu_units.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"extern const struct A2_unitdesc (a2_[a-z0-9]+_unitdesc);", text)
+    assert len(names) == 14
+    import subprocess
+    syms = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True).stdout
+    for n in names + ["a2cu_RegisterDriver"]:
+        assert (" " + n + "\n") in syms, n
