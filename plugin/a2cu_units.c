@@ -76,6 +76,7 @@ typedef struct A2CU_unit
 	int		leaf_nout;
 	unsigned	proc_serial;	/* fragment of the last recorded segment */
 	unsigned	cursor;		/* frame where the next segment starts */
+	A2_voice	*hv;		/* the host voice this unit belongs to */
 } A2CU_unit;
 
 typedef struct A2CU_pending
@@ -129,6 +130,7 @@ struct A2CU_ctx
 	A2CU_orphan	orphans[A2CU_MAXORPHANS];
 	int		norphans;
 	A2CU_voice	*last_voice;	/* voice being populated */
+	A2_voice	*look;		/* walk_prefetch: sibling whose lines are in flight */
 	A2CU_ctx	*next;
 };
 
@@ -497,6 +499,7 @@ static A2_errors unit_init(A2_unit *u, A2_vmstate *vms, void *statedata,
 	au->leaf = 0;
 	au->proc_serial = 0;
 	au->cursor = 0;
+	au->hv = hv;
 	au->bus_serial = 0;
 	v->units[v->nunits++] = au;
 	++v->refs;
@@ -665,10 +668,53 @@ static void unit_process(A2_unit *u, unsigned offset, unsigned frames)
 		unit_process_body(u, offset, frames);
 }
 
+/*
+ * The host's tree walk (a2_ProcessVoices, core.c:1883-1896) is a pointer chase
+ * over voice structs (~1.5 KB each: `next` in the first line, `units` more
+ * than a KB further) and unit blocks: with tens of thousands of voices every
+ * one of those lines misses the CPU caches, for the host's own code and for
+ * ours. While voice k is being recorded we therefore prefetch the unit block
+ * of sibling k+1 (whose struct lines were requested one call earlier) and the
+ * struct lines of sibling k+2. Prefetches never fault; a stale pointer only
+ * wastes a line.
+ */
+static inline void prefetch_voice(const A2_voice *v)
+{
+	__builtin_prefetch(v);
+	__builtin_prefetch(&v->s.waketime);
+	__builtin_prefetch(&v->units);
+}
+
+static inline void walk_prefetch(A2CU_ctx *cx, const A2_voice *hv)
+{
+	A2_voice *n1 = hv->next;
+	if(n1 && (cx->look == n1))
+	{
+		A2_voice *n2 = n1->next;
+		const char *u1 = (const char *)n1->units;
+		if(u1)
+		{
+			__builtin_prefetch(u1);
+			__builtin_prefetch(u1 + 64);
+			__builtin_prefetch(u1 + 128);
+		}
+		if(n2)
+			prefetch_voice(n2);
+		cx->look = n2;
+	}
+	else
+	{
+		if(n1)
+			prefetch_voice(n1);
+		cx->look = n1;
+	}
+}
+
 static void leaf_process(A2CU_ctx *cx, A2CU_unit *au, unsigned offset,
 		unsigned frames)
 {
 	A2CU_unit *owner;
+	walk_prefetch(cx, au->hv);
 	au->proc_serial = cx->serial;
 	au->cursor = offset + frames;
 	owner = owner_find(cx, au->leaf_outputs);
@@ -844,6 +890,8 @@ static void inline_process(A2_unit *u, unsigned offset, unsigned frames,
 	if(!add || dev_pre)
 		for(i = 0; i < u->noutputs; ++i)
 			memset(u->outputs[i] + offset, 0, frames * sizeof(int));
+	if(au->il.voice->sub)
+		prefetch_voice(au->il.voice->sub);
 	/* Sub-voices that mix into u->outputs now mix into our device bus */
 	if(cx->nowners < A2_NESTLIMIT)
 	{
