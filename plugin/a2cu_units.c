@@ -77,6 +77,13 @@ typedef struct A2CU_unit
 	unsigned	proc_serial;	/* fragment of the last recorded segment */
 	unsigned	cursor;		/* frame where the next segment starts */
 	A2_voice	*hv;		/* the host voice this unit belongs to */
+	/*
+	 * History prefetcher: the first unit that was recorded right after this one in the
+	 * previous fragment (the walk order is stable from fragment to fragment), and this
+	 * voice's second unit. Only ever used as prefetch addresses.
+	 */
+	struct A2CU_unit *hint;
+	struct A2CU_unit *follower;
 } A2CU_unit;
 
 typedef struct A2CU_pending
@@ -131,6 +138,7 @@ struct A2CU_ctx
 	int		norphans;
 	A2CU_voice	*last_voice;	/* voice being populated */
 	A2_voice	*look;		/* walk_prefetch: sibling whose lines are in flight */
+	struct A2CU_unit *prev_first;	/* first unit recorded by the previous Process() */
 	A2CU_ctx	*next;
 };
 
@@ -417,6 +425,7 @@ static void classify(A2CU_ctx *cx, A2CU_voice *v, unsigned frame)
 		for(i = 1; i < v->nunits; ++i)
 			v->units[i]->il.header.Process = leaf_follower_process;
 		v->units[0]->leaf = 1;
+		v->units[0]->follower = v->nunits > 1 ? v->units[1] : NULL;
 		v->units[0]->pool = v->pool;
 		v->units[0]->slot = v->slot;
 		v->units[0]->leaf_outputs =
@@ -500,6 +509,8 @@ static A2_errors unit_init(A2_unit *u, A2_vmstate *vms, void *statedata,
 	au->proc_serial = 0;
 	au->cursor = 0;
 	au->hv = hv;
+	au->hint = NULL;
+	au->follower = NULL;
 	au->bus_serial = 0;
 	v->units[v->nunits++] = au;
 	++v->refs;
@@ -519,6 +530,8 @@ static A2_errors unit_init(A2_unit *u, A2_vmstate *vms, void *statedata,
 static void unit_deinit(A2_unit *u)
 {
 	A2CU_unit *au = (A2CU_unit *)u;
+	if(au->cx && (au->cx->prev_first == au))
+		au->cx->prev_first = NULL;	/* the block is about to be recycled */
 	if(au->pm >= 0)
 		a2cu_pm_free(au->cx->eng, au->pm);
 	if(au->gu >= 0)
@@ -685,6 +698,29 @@ static inline void prefetch_voice(const A2_voice *v)
 	__builtin_prefetch(&v->units);
 }
 
+/*
+ * Unit blocks two recordings ahead, through our own hints (the sibling pointers above
+ * reach the voice structs, but a voice's unit block address is only known once its
+ * struct has arrived). 'h1' was requested one call ago, so its hint can be read now.
+ */
+static inline void hint_prefetch(A2CU_ctx *cx, A2CU_unit *au)
+{
+	A2CU_unit *h1 = au->hint, *h2;
+	if(cx->prev_first)
+		cx->prev_first->hint = au;
+	cx->prev_first = au;
+	if(!h1)
+		return;
+	if(h1->follower)
+		__builtin_prefetch(h1->follower);
+	if((h2 = h1->hint))
+	{
+		__builtin_prefetch(h2);
+		__builtin_prefetch((const char *)h2 + 64);
+		__builtin_prefetch((const char *)h2 + 128);
+	}
+}
+
 static inline void walk_prefetch(A2CU_ctx *cx, const A2_voice *hv)
 {
 	A2_voice *n1 = hv->next;
@@ -715,6 +751,7 @@ static void leaf_process(A2CU_ctx *cx, A2CU_unit *au, unsigned offset,
 {
 	A2CU_unit *owner;
 	walk_prefetch(cx, au->hv);
+	hint_prefetch(cx, au);
 	au->proc_serial = cx->serial;
 	au->cursor = offset + frames;
 	owner = owner_find(cx, au->leaf_outputs);
