@@ -50,6 +50,7 @@ int main(int argc, char **argv)
 	const char *prog = "Song", *out = NULL, *file = NULL;
 	const char *driver = "buffer";
 	const char *dumpwave = NULL;
+	const char *upload = NULL;
 	A2_config *cfg;
 	A2_driver *drv;
 	A2_interface *iface;
@@ -73,6 +74,7 @@ int main(int argc, char **argv)
 		else if(!strcmp(argv[i], "-s")) noiseseed = atoi(argv[++i]);
 		else if(!strcmp(argv[i], "-W")) dumpwave = argv[++i];
 		else if(!strcmp(argv[i], "-x")) copies = atoi(argv[++i]);
+		else if(!strcmp(argv[i], "-U")) upload = argv[++i];
 		else if(!strcmp(argv[i], "-a"))
 		{
 			/* 16:16 fixed point, same conversion as a2_Start() */
@@ -138,6 +140,39 @@ int main(int argc, char **argv)
 		die("a2_Load", -bank);
 	if((ph = a2_Get(iface, bank, prog)) < 0)
 		die("a2_Get(program)", -ph);
+	if(upload)
+	{
+		/*
+		 * -U type:period:flags:length:seed  uploads a pseudo-random int16
+		 * wave through the public API (a2_UploadWave, a2_waves.h:148) and
+		 * passes its handle as the program's LAST argument, so scripts can
+		 * play sampled waves: `w W` with W the handle. The generator is the
+		 * LCG tests/test_sampled_waves.py repeats.
+		 */
+		int wt = 0, wperiod = 0, wflags = 0, wlen = 0, k;
+		unsigned wseed = 1;
+		int16_t *wd;
+		A2_handle wh;
+		if(sscanf(upload, "%d:%d:%d:%d:%u", &wt, &wperiod, &wflags, &wlen,
+				&wseed) != 5 || wlen < 1)
+		{
+			fprintf(stderr, "a2render: bad -U spec\n");
+			return 2;
+		}
+		wd = (int16_t *)malloc(sizeof(int16_t) * wlen);
+		for(k = 0; k < wlen; ++k)
+		{
+			wseed = wseed * 1664525u + 1013904223u;
+			wd[k] = (int16_t)((int)(wseed >> 16) % 50001 - 25000);
+		}
+		wh = a2_UploadWave(iface, (A2_wavetypes)wt, wperiod, wflags, A2_I16,
+				wd, sizeof(int16_t) * wlen);
+		free(wd);
+		if(wh < 0)
+			die("a2_UploadWave", -wh);
+		if(nargs < 16)
+			args[nargs++] = wh << 16;
+	}
 	a2_TimestampReset(iface);
 	/*
 	 * -x N: start the program N times under the root voice (BASELINE config

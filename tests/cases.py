@@ -305,6 +305,40 @@ def fm_bank(nvoices=64, frames=1280):
     return s
 
 
+
+def _sampled(wtype, period, flags, length, seed):
+    """An uploaded (sampled) wave played from -3 to +8.5 octaves: below and above A2_MAXPHINC
+    samples per frame (plain loop, per-sample wrapped loop / end check, muted range), with a pitch
+    ramp and a phase write. The reference's harness uploads the same data (a2render -U)."""
+    s = Scenario(48000, 2, 64, 2400)
+    w = s.upload(wtype, period, flags, length, seed)
+    for i in range(12):
+        p0 = -3.0 + 1.05 * i
+        s.add_voice(["wtosc", "panmix"], [
+            ("ramp", 0, W, w << 16), ("set", 0, P, fx(p0)),
+            ("set", 0, A, fx(0.15)), ("set", 1, PAN, fx(-0.9 + 0.15 * i)),
+            ("d", fx(9.25)),
+            ("ramp", 0, P, fx(p0 + 1.5)), ("ramp", 0, A, fx(0.05)), ("d", fx(21)),
+            ("set", 0, PH, fx(0.5)), ("d", fx(12)),
+        ])
+    return s
+
+
+def sampled_loop():
+    """Looped non-mipmapped wave (A2_WWAVE | A2_LOOPED), 3001 samples, period 500."""
+    return _sampled(2, 500, 0x100, 3001, 7)
+
+
+def sampled_oneshot():
+    """Non-looped non-mipmapped wave: voices run out of samples mid-window."""
+    return _sampled(2, 500, 0, 3001, 7)
+
+
+def sampled_mip():
+    """Uploaded mipmapped wave (A2_WMIPWAVE | A2_LOOPED): mip levels rendered by the host."""
+    return _sampled(3, 64, 0x100, 5000, 9)
+
+
 CASES = {
     "renderwave": renderwave,
     "osc_pan_ramps": osc_pan_ramps,
@@ -317,6 +351,9 @@ CASES = {
     "groups": groups,
     "rate44k_transposed": rate44k_transposed,
     "noise": noise,
+    "sampled_loop": sampled_loop,
+    "sampled_oneshot": sampled_oneshot,
+    "sampled_mip": sampled_mip,
     "bank256": bank,
     "fm_bank64": fm_bank,
     "bench_bank200": lambda: bench_bank(200, steps=3),

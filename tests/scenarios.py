@@ -131,6 +131,25 @@ class Scenario:
         self.ngroups = 0
         self.group_steps = {}     # group -> steps on its panmix (unit 0)
         self.waves = []           # names of builtin waves, index = wave id
+        self.uploaded = None      # (type, period, flags, length, seed) of the one sampled wave
+
+    def upload(self, wtype, period, flags, length, seed):
+        """One pseudo-random sampled wave, uploaded through a2_UploadWave by the reference
+        harness (`a2render -U`), a2cu_wave_upload / a2o_upload_wave here. Returns its wave id."""
+        assert self.uploaded is None
+        self.uploaded = (wtype, period, flags, length, seed)
+        self.waves.append(self.uploaded)
+        return len(self.waves) - 1
+
+    def uploaded_data(self):
+        """The harness's generator (oracle/a2render.c, -U): LCG, int16 in [-25000, 25000]."""
+        _, _, _, length, seed = self.uploaded
+        out = np.empty(length, dtype=np.int16)
+        x = seed & 0xffffffff
+        for k in range(length):
+            x = (x * 1664525 + 1013904223) & 0xffffffff
+            out[k] = (x >> 16) % 50001 - 25000
+        return out
 
     def wave(self, name):
         if name not in self.waves:
@@ -236,6 +255,12 @@ class Scenario:
     def to_a2s(self):
         """Script whose Song() spawns every group and voice at time 0."""
         L = ['def title "generated"', 'def a2sversion "1.9"', ""]
+        # an uploaded wave is known to the script only as a handle: program argument UW
+        arg = "UW" if self.uploaded is not None else ""
+
+        def wname(idx):
+            w = self.waves[idx]
+            return "UW" if isinstance(w, tuple) else w
 
         def body(kinds, steps, names, indent="\t", final=True):
             out = []
@@ -246,12 +271,12 @@ class Scenario:
                     out.append("%s}" % indent)
                 elif st[0] == "set":
                     rn = self._regname(kinds, names, st[1], st[2])
-                    val = self.waves[st[3] >> 16] if st[2] == 0 and \
+                    val = wname(st[3] >> 16) if st[2] == 0 and \
                         kinds[st[1]] == "wtosc" else lit(st[3])
                     out.append("%s@%s %s" % (indent, rn, val))
                 elif st[0] == "ramp":
                     rn = self._regname(kinds, names, st[1], st[2])
-                    val = self.waves[st[3] >> 16] if st[2] == 0 and \
+                    val = wname(st[3] >> 16) if st[2] == 0 and \
                         kinds[st[1]] == "wtosc" else lit(st[3])
                     out.append("%s%s %s" % (indent, rn, val))
                 elif st[0] == "d":
@@ -264,7 +289,7 @@ class Scenario:
             names = self._unit_names(v.kinds)
             units = "; ".join(k if nm is None else "%s %s" % (k, nm)
                               for k, nm in zip(v.kinds, names))
-            L.append("V%d()" % vi)
+            L.append("V%d(%s)" % (vi, arg))
             L.append("{")
             L.append("\tstruct { %s }" % units)
             L += body(v.kinds, v.steps, names)
@@ -273,17 +298,17 @@ class Scenario:
         # Groups: { inline 0 *; panmix * > } == a2_groupdriver numerically
         for g in range(self.ngroups):
             members = [vi for vi, v in enumerate(self.voices) if v.group == g]
-            L.append("G%d()" % g)
+            L.append("G%d(%s)" % (g, arg))
             L.append("{")
             L.append("\tstruct { inline 0 *; panmix * > }")
             for vi in members:
-                L.append("\tV%d" % vi)
+                L.append("\tV%d %s" % (vi, arg))
             L += body(["panmix"], self.group_steps[g], [None])
             L.append("}")
             L.append("")
         # Spawn order: my engines process newest-first at every level, like
         # a2_VoiceNew's head insertion; creation order here = index order.
-        L.append("export Song()")
+        L.append("export Song(%s)" % arg)
         L.append("{")
         if self.transpose:
             L.append("\ttr %s" % lit(self.transpose))
@@ -297,24 +322,24 @@ class Scenario:
                 items.append(("v", vi))
         if len(items) <= 100:
             for kind, idx in items:
-                L.append("\t%s%d" % ("G" if kind == "g" else "V", idx))
+                L.append("\t%s%d %s" % ("G" if kind == "g" else "V", idx, arg))
         else:
             # One program may run at most A2_INSLIMIT = 1000 VM instructions
             # between timing points (config.h:119): spawn through helper
             # voices without units (their children inherit the root bus).
             nsp = (len(items) + 63) // 64
             for k in range(nsp):
-                L.append("\tS%d" % k)
+                L.append("\tS%d %s" % (k, arg))
         L.append("\tfor { d 30000 }")
         L.append("}")
         if len(items) > 100:
             head = L[:3]
             sp = []
             for k in range(nsp):
-                sp.append("S%d()" % k)
+                sp.append("S%d(%s)" % (k, arg))
                 sp.append("{")
                 for kind, idx in items[k * 64:(k + 1) * 64]:
-                    sp.append("\t%s%d" % ("G" if kind == "g" else "V", idx))
+                    sp.append("\t%s%d %s" % ("G" if kind == "g" else "V", idx, arg))
                 sp.append("\tfor { d 30000 }")
                 sp.append("}")
                 sp.append("")
@@ -330,7 +355,8 @@ def run_ref(scn, path):
         f.write(scn.to_a2s())
     out, info = ao.ref_render(path, "Song", samplerate=scn.samplerate,
                               channels=scn.channels, buffer=scn.buffer,
-                              frames=scn.frames, noiseseed=scn.noiseseed)
+                              frames=scn.frames, noiseseed=scn.noiseseed,
+                              upload=scn.uploaded)
     if info["rt_error"]:
         raise RuntimeError("reference reported RT error %d" % info["rt_error"])
     return out
@@ -340,7 +366,10 @@ def build_engine(scn, eng, kindmod):
     """Create waves, groups and voices of `scn` in `eng` (oracle or cuda
     wrapper: both expose builtin_wave/new_group/new_voice)."""
     for w in scn.waves:
-        eng.builtin_wave(w)
+        if isinstance(w, tuple):
+            eng.upload_wave(w[0], w[1], w[2], scn.uploaded_data())
+        else:
+            eng.builtin_wave(w)
     for _ in range(scn.ngroups):
         eng.new_group()
     for v in scn.voices:
@@ -373,7 +402,10 @@ def run_cuda(scn, window=None, split=True, stats=None, pipelined=False):
         if scn.noiseseed is not None:
             e.set_noiseseed(scn.noiseseed)
         for w in scn.waves:
-            e.builtin_wave(w)
+            if isinstance(w, tuple):
+                e.upload_wave(w[0], w[1], w[2], scn.uploaded_data())
+            else:
+                e.builtin_wave(w)
         for _ in range(scn.ngroups):
             e.new_group()
         # one bank per distinct voice structure, slots in voice order

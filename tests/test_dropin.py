@@ -28,7 +28,7 @@ def test_dropin_matches_reference(name, driver):
                               samplerate=scn.samplerate, channels=scn.channels,
                               buffer=scn.buffer, frames=scn.frames,
                               noiseseed=scn.noiseseed,
-                              binary="a2render_cuda", driver=driver)
+                              binary="a2render_cuda", driver=driver, upload=scn.uploaded)
     assert info["rt_error"] == 0
     ref = np.load(GOLDEN)[name]
     assert out.shape == ref.shape
