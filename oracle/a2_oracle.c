@@ -264,9 +264,24 @@ typedef struct voice
 	int		nev, evpos;
 } voice;
 
+/* fbdelay (units/fbdelay.c): the effect every song chains after its mix-down */
+#define A2O_FBD_BUFSIZE	131072		/* A2FBD_BUFSIZE, fbdelay.c:26 */
+typedef struct st_fbdelay
+{
+	int		fbdelay, ldelay, rdelay;	/* frames */
+	int		drygain, fbgain, lgain, rgain;	/* 16:16 */
+	int32_t		*lbuf, *rbuf;
+	int		bufpos;
+} st_fbdelay;
+
+static int fbd_init(st_fbdelay *f, int samplerate);
+static void fbd_write(st_fbdelay *f, int reg, int v, int samplerate);
+
 typedef struct group
 {
 	st_panmix	pm;
+	int		has_fbd;	/* { inline 0 *; fbdelay * *; panmix * > } */
+	st_fbdelay	fbd;
 	int		*evi;
 	int		nev, evpos;
 } group;
@@ -1022,6 +1037,15 @@ void a2o_close(a2o_engine *e)
 			free(e->waves[i].data[j]);
 	free(e->waves);
 	free(e->voices);
+	{
+		int gi;
+		for(gi = 0; gi < e->ngroups; ++gi)
+			if(e->groups[gi].has_fbd)
+			{
+				free(e->groups[gi].fbd.lbuf);
+				free(e->groups[gi].fbd.rbuf);
+			}
+	}
 	free(e->groups);
 	free(e->order);
 	free(e);
@@ -1161,6 +1185,26 @@ int a2o_new_group(a2o_engine *e)
 	if(order_push(e, ~e->ngroups))
 		return -1;
 	return e->ngroups++;
+}
+
+/*
+ * Put a `fbdelay` between the group's inline and its panmix, i.e. the song-level chain
+ * { inline 0 *; fbdelay * *; panmix * > } (benchmark/k2trance.a2s:920-924), and write its seven
+ * registers (fbdelay, ldelay, rdelay in ms; drygain, fbgain, lgain, rgain; all 16:16).
+ */
+int a2o_group_fbdelay(a2o_engine *e, int group, const int32_t *regs)
+{
+	int r;
+	st_fbdelay *f;
+	if(!e || group < 0 || group >= e->ngroups || !regs)
+		return -1;
+	f = &e->groups[group].fbd;
+	if(!e->groups[group].has_fbd && fbd_init(f, e->samplerate))
+		return -1;
+	e->groups[group].has_fbd = 1;
+	for(r = 0; r < 7; ++r)
+		fbd_write(f, r, regs[r], e->samplerate);
+	return 0;
 }
 
 int a2o_new_voice(a2o_engine *e, const a2o_unitspec *chain, int nunits,
@@ -1350,7 +1394,66 @@ static void voice_process(a2o_engine *e, int vi, int32_t **bus,
 	}
 }
 
-/* group = { inline 0 *; panmix * *; xinsert * > } (audiality2.c:294-304) */
+/* fbdelay.c:176-208: zeroed delay lines, default registers */
+static int fbd_init(st_fbdelay *f, int samplerate)
+{
+	memset(f, 0, sizeof(*f));
+	f->lbuf = (int32_t *)calloc(A2O_FBD_BUFSIZE, sizeof(int32_t));
+	f->rbuf = (int32_t *)calloc(A2O_FBD_BUFSIZE, sizeof(int32_t));
+	if(!f->lbuf || !f->rbuf)
+		return -1;
+	f->fbdelay = (int)((int64_t)(400 << 16) * samplerate / 65536000);
+	f->ldelay = (int)((int64_t)(280 << 16) * samplerate / 65536000);
+	f->rdelay = (int)((int64_t)(320 << 16) * samplerate / 65536000);
+	f->drygain = 65536;
+	f->fbgain = 16384;
+	f->lgain = 32768;
+	f->rgain = 32768;
+	return 0;
+}
+
+/* fbdelay.c:229-270: register write callbacks (start / duration are ignored there) */
+static void fbd_write(st_fbdelay *f, int reg, int v, int samplerate)
+{
+	switch(reg)
+	{
+	  case 0: f->fbdelay = (int)((int64_t)v * samplerate / 65536000); break;
+	  case 1: f->ldelay = (int)((int64_t)v * samplerate / 65536000); break;
+	  case 2: f->rdelay = (int)((int64_t)v * samplerate / 65536000); break;
+	  case 3: f->drygain = v; break;
+	  case 4: f->fbgain = v; break;
+	  case 5: f->lgain = v; break;
+	  case 6: f->rgain = v; break;
+	}
+}
+
+/* fbdelay.c:68-127, the 2 -> 2 replacing variant (fbdelay_Process22), in place */
+static void fbd_process22(st_fbdelay *f, int32_t **buf, unsigned offset,
+		unsigned frames)
+{
+	unsigned s, end = offset + frames;
+#define	WI(x)	((f->bufpos - (x)) & (A2O_FBD_BUFSIZE - 1))
+	for(s = offset; s < end; ++s)
+	{
+		int i0 = buf[0][s];
+		int i1 = buf[1][s];
+		/* feedback taps, cross-fed ("reverse stereo") */
+		int o0 = (int)((int64_t)f->rbuf[WI(f->fbdelay)] * f->fbgain >> 16);
+		int o1 = (int)((int64_t)f->lbuf[WI(f->fbdelay)] * f->fbgain >> 16);
+		f->lbuf[WI(0)] = i0 + o0;
+		f->rbuf[WI(0)] = i1 + o1;
+		o0 += (int)((int64_t)f->lbuf[WI(f->ldelay)] * f->lgain >> 16);
+		o1 += (int)((int64_t)f->rbuf[WI(f->rdelay)] * f->rgain >> 16);
+		o0 += (int)((int64_t)i0 * f->drygain >> 16);
+		o1 += (int)((int64_t)i1 * f->drygain >> 16);
+		buf[0][s] = o0;
+		buf[1][s] = o1;
+		++f->bufpos;
+	}
+#undef	WI
+}
+
+/* group = { inline 0 *; [fbdelay * *;] panmix * *; xinsert * > } (audiality2.c:294-304) */
 static void group_process(a2o_engine *e, int gi, unsigned offset,
 		unsigned frames)
 {
@@ -1372,6 +1475,8 @@ static void group_process(a2o_engine *e, int gi, unsigned offset,
 		for(vi = e->nvoices - 1; vi >= 0; --vi)
 			if(e->voices[vi].group == gi)
 				voice_process(e, vi, gb, s, res);
+		if(g->has_fbd)
+			fbd_process22(&g->fbd, gb, s, res);
 		pm_process(&g->pm, 2, 2, gb, gb, s, res, 0);
 		/* xinsert without clients: bypass-add, xinsert.c:149-156 */
 		for(c = 0; c < 2; ++c)

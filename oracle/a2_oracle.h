@@ -109,6 +109,8 @@ const int16_t *a2o_wave_data(a2o_engine *e, int wave, int level,
 
 /* Groups (a2_groupdriver-like: inline; panmix; add to root bus). */
 int a2o_new_group(a2o_engine *e);
+/* song-level chain { inline 0 *; fbdelay * *; panmix * > } (units/fbdelay.c): 7 registers, 16:16 */
+int a2o_group_fbdelay(a2o_engine *e, int group, const int32_t *regs);
 
 /*
  * Voices. 'transpose' is the voice's R_TRANSPOSE (16:16), 'substart' the

@@ -134,6 +134,15 @@ class Oracle:
     def new_group(self):
         return self.L.a2o_new_group(self.h)
 
+    def group_fbdelay(self, group, regs):
+        """{ inline 0 *; fbdelay * *; panmix * > }: the 7 fbdelay registers, 16:16."""
+        a = np.ascontiguousarray(regs, dtype=np.int32)
+        assert a.size == 7
+        self.L.a2o_group_fbdelay.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        self.L.a2o_group_fbdelay.restype = C.c_int
+        if self.L.a2o_group_fbdelay(self.h, group, a.ctypes.data) != 0:
+            raise MemoryError("a2o_group_fbdelay")
+
     def new_voice(self, chain, transpose=0, substart=0, group=-1):
         arr = (UnitSpec * len(chain))(*[UnitSpec(*u) for u in chain])
         v = self.L.a2o_new_voice(self.h, arr, len(chain), transpose, substart,

@@ -203,6 +203,34 @@ def groups():
     return s
 
 
+def song_fbdelay():
+    """Two song-level chains { inline 0 *; fbdelay * *; panmix * > } (the structure of every song of
+    the reference, benchmark/k2trance.a2s:920-924) fed by plucked voices, with short delays (taps
+    inside the current fragment: the serial path of the device fbdelay) and long ones (parallel
+    path), a volume ramp on the song panmix and a voice outside the songs. Drop-in mode and the
+    oracle port only: bank mode has no group-level fbdelay."""
+    s = Scenario(48000, 2, 64, 9600)
+    saw = s.wave("saw")
+    sq = s.wave("square")
+    # fbdelay, ldelay, rdelay in ms; drygain, fbgain, lgain, rgain
+    g0 = s.add_group([("set", 0, VOL, fx(0.9)), ("d", fx(60)), ("ramp", 0, VOL, fx(0.4)),
+                      ("ramp", 0, PAN, fx(0.5)), ("d", fx(80))],
+                     fbdelay=[fx(31.7), fx(23.1), fx(41.9), fx(1.0), fx(0.35), fx(0.3), fx(0.3)])
+    g1 = s.add_group([("set", 0, VOL, fx(0.7)), ("set", 0, PAN, fx(-0.3))],
+                     fbdelay=[fx(0.9), fx(0.4), fx(1.1), fx(0.8), fx(0.5), fx(0.4), fx(0.45)])
+    r = _rng(21)
+    for i in range(10):
+        s.add_voice(["wtosc", "panmix"], [
+            ("ramp", 0, W, (saw if i & 1 else sq) << 16),
+            ("set", 0, P, fx(float(r.randint(-128, 128)) / 64)),
+            ("set", 0, A, fx(0.12)),
+            ("set", 1, PAN, fx(float(r.randint(-64, 64)) / 64)),
+            ("d", fx(3 + 2 * i)), ("ramp", 0, A, fx(0.0)), ("d", fx(25)),
+            ("set", 0, A, fx(0.1)), ("ramp", 0, A, fx(0.0)), ("d", fx(40)),
+        ], group=[g0, g1, g0, g1, -1][i % 5])
+    return s
+
+
 def rate44k_transposed():
     """44.1 kHz: ms delays land on fractional frames -> sub-sample starts."""
     s = Scenario(44100, 2, 100, 5000)
@@ -349,6 +377,7 @@ CASES = {
     "waveshaper": waveshaper,
     "mono_voice_and_chains": mono_voice_and_chains,
     "groups": groups,
+    "song_fbdelay": song_fbdelay,
     "rate44k_transposed": rate44k_transposed,
     "noise": noise,
     "sampled_loop": sampled_loop,

@@ -130,6 +130,7 @@ class Scenario:
         self.voices = []
         self.ngroups = 0
         self.group_steps = {}     # group -> steps on its panmix (unit 0)
+        self.group_fbd = {}       # group -> 7 fbdelay registers (16:16) of a song-level chain
         self.waves = []           # names of builtin waves, index = wave id
         self.uploaded = None      # (type, period, flags, length, seed) of the one sampled wave
 
@@ -156,8 +157,12 @@ class Scenario:
             self.waves.append(name)
         return self.waves.index(name)
 
-    def add_group(self, steps=()):
+    def add_group(self, steps=(), fbdelay=None):
+        """fbdelay: (fbdelay, ldelay, rdelay [ms], drygain, fbgain, lgain, rgain), 16:16 - makes the
+        group the song-level chain { inline 0 *; fbdelay * *; panmix * > } (k2trance.a2s:920-924)."""
         self.group_steps[self.ngroups] = list(steps)
+        if fbdelay is not None:
+            self.group_fbd[self.ngroups] = [int(x) for x in fbdelay]
         self.ngroups += 1
         return self.ngroups - 1
 
@@ -300,7 +305,14 @@ class Scenario:
             members = [vi for vi, v in enumerate(self.voices) if v.group == g]
             L.append("G%d(%s)" % (g, arg))
             L.append("{")
-            L.append("\tstruct { inline 0 *; panmix * > }")
+            if g in self.group_fbd:
+                L.append("\tstruct { inline 0 *; fbdelay D * *; panmix * > }")
+                for rn, val in zip(("fbdelay", "ldelay", "rdelay", "drygain", "fbgain", "lgain",
+                                    "rgain"), self.group_fbd[g]):
+                    L.append("\tD.%s %s" % (rn, lit(val)))
+                L.append("\tset")
+            else:
+                L.append("\tstruct { inline 0 *; panmix * > }")
             for vi in members:
                 L.append("\tV%d %s" % (vi, arg))
             L += body(["panmix"], self.group_steps[g], [None])
@@ -370,8 +382,10 @@ def build_engine(scn, eng, kindmod):
             eng.upload_wave(w[0], w[1], w[2], scn.uploaded_data())
         else:
             eng.builtin_wave(w)
-    for _ in range(scn.ngroups):
+    for g in range(scn.ngroups):
         eng.new_group()
+        if g in scn.group_fbd:
+            eng.group_fbdelay(g, scn.group_fbd[g])
     for v in scn.voices:
         eng.new_voice(autowire(v.kinds), transpose=v.transpose, substart=0,
                       group=v.group)
@@ -406,6 +420,8 @@ def run_cuda(scn, window=None, split=True, stats=None, pipelined=False):
                 e.upload_wave(w[0], w[1], w[2], scn.uploaded_data())
             else:
                 e.builtin_wave(w)
+        if scn.group_fbd:
+            raise NotImplementedError("bank mode has no group-level fbdelay (drop-in mode only)")
         for _ in range(scn.ngroups):
             e.new_group()
         # one bank per distinct voice structure, slots in voice order
