@@ -7,8 +7,8 @@
 Workload (config.workload "cfg2"): 4 096 voices wtosc -> filter12 -> panmix on
 the shared 2 048-point saw, 48 kHz, 64-frame blocks, plus ONE control write
 per voice per step (amplitude re-targeted and ramped across the step) so that
-every step has real host->device input.  One step = one a2cu_run call of 960
-frames (20 ms = 15 blocks of 64) = voices x 960 voice-samples.
+every step has real host->device input.  One step = one 960-frame window
+(20 ms = 15 blocks of 64; one a2cu_submit) = voices x 960 voice-samples.
 
 Numbers on the JSON line:
   value   voice-samples/s over the CUDA-event spans of the kernels (render +
@@ -24,7 +24,8 @@ Numbers on the JSON line:
           wall time of the whole timed region, max over ranks. (N > 1: the same
           pipeline with a2cu_submit_dev + NCCL all-reduce + root stage + D2H
           queued per step, three windows in flight.)
-  roofline  HBM roofline of the dominant kernel (render_bank<...>).
+  roofline  HBM roofline of the dominant kernel (render_split<...>, one launch per step: the
+          root stage is fused into its last CTA).
   cpu_baseline  the reference's own CPU render (oracle/_ref) on a bounded
           sample of the same workload, 1 core, rank 0, N = 1 only.
 Multi-GPU (weak scaling): every rank renders its own bank; the raw stereo root
@@ -409,7 +410,7 @@ def bench_ours(args):
             "config": {
                 "workload": "cfg2: %d voices/GPU wtosc->filter12->panmix, saw 2048-pt, 48 kHz, "
                             "64-frame blocks, 1 amplitude write/voice/20 ms" % args.voices,
-                "step": "%d frames (15 blocks of 64) per a2cu_run call" % STEP_FRAMES,
+                "step": "%d frames (15 blocks of 64) per window (one a2cu_submit)" % STEP_FRAMES,
                 "l2": "no flush: inputs larger than L2 - every step renders a different bank of %d voices, "
                       "round-robin over %d banks whose per-voice state totals %.0f MB (1.5x the 126 MB L2)"
                       % (args.voices, nbanks, state_mb),
@@ -424,7 +425,8 @@ def bench_ours(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": host_total_ms / args.steps},
             "gpu_launches": int(launches),
-            "kernel": "%s<%s> + mix_root" % (kname, e.bank_kernel_name(bank)),
+            "kernel": "%s<%s>%s" % (kname, e.bank_kernel_name(bank),
+                                     " (root stage fused)" if not multi and kname == "render_split" else " + mix_root"),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
