@@ -16,8 +16,11 @@ LIB = os.path.join(HERE, "liba2cu.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--expt-extended-lambda", "-Xcompiler", "-fPIC", "-shared", "-cudart", "shared",
+    "--expt-extended-lambda", "-Xcompiler", "-fPIC", "-cudart", "shared", "-Xfatbin", "-compress-all",
 ]
+# translation units of liba2cu.so: host + bus kernels, and one per kernel family
+UNITS = ["a2cu_engine.cu", "a2cu_reg_bank_wt.cu", "a2cu_reg_bank_fm.cu", "a2cu_reg_split.cu"]
+OBJDIR = os.path.join(HERE, "build")
 
 
 def _stale(target, sources):
@@ -28,15 +31,25 @@ def _stale(target, sources):
 
 
 def build_engine(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)
-            if f.endswith((".cu", ".cuh", ".h"))]
-    srcs.append(os.path.join(ROOT, "include", "a2cu.h"))
-    if not force and not _stale(LIB, srcs):
-        return LIB
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-        "-I", os.path.join(ROOT, "include"), "-o", LIB,
-        os.path.join(CSRC, "a2cu_engine.cu")]
-    subprocess.check_call(cmd)
+    """nvcc -c every unit (in parallel, only the stale ones), then link."""
+    hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hdrs.append(os.path.join(ROOT, "include", "a2cu.h"))
+    os.makedirs(OBJDIR, exist_ok=True)
+    procs, objs = [], []
+    for u in UNITS:
+        src = os.path.join(CSRC, u)
+        obj = os.path.join(OBJDIR, u[:-3] + ".o")
+        objs.append(obj)
+        if force or _stale(obj, hdrs + [src]):
+            cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
+                "-I", os.path.join(ROOT, "include"), "-c", "-o", obj, src]
+            procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, p in procs:
+        if p.wait():
+            raise subprocess.CalledProcessError(p.returncode, cmd)
+    if procs or not os.path.exists(LIB):
+        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared",
+                               "-o", LIB] + objs)
     return LIB
 
 

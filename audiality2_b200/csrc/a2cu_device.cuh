@@ -49,6 +49,7 @@ struct Ctx {
     const int4 *cpool;              // two-stage Hermite coefficients {d0, a, b, c} per sample
     const unsigned *ptab;           // 64 x {base, coeff}, pitch.c:70-96
     const int16_t *fmsine;          // 2049-entry sine LUT (shared memory)
+    const int *f12tab;              // filter12 coefficient of every 21-bit (shift, fraction) pitch code
     int samplerate;
 };
 
@@ -165,16 +166,15 @@ A2CU_DEV unsigned p2i(const unsigned *ptab, int pitch) {
     return dph >> ((7 - oct) & 31);
 }
 
-// filter12.c:65-72: float multiply, double sin. The float/double operations
-// are IEEE-exact (no contraction); sin() is CUDA's (<= 2 ulp), glibc's on the
-// host is <= 1 ulp: after the truncation to int the two differ with
-// probability ~1e-8 per evaluation (DESIGN.md "filter12 coefficient").
-A2CU_DEV int f12_coeff(const unsigned *ptab, int cutoff_value, int samplerate) {
-    float f = __fmul_rn(__uint2float_rn(p2i(ptab, cutoff_value >> 8)), 261.626f / 16777216.0f);
-    if (f > (float)(samplerate >> 2))
-        return 362 << 16;
-    double x = __ddiv_rn(__dmul_rn(3.14159265358979323846, (double)f), (double)samplerate);
-    return (int)__dmul_rn(33554432.0, sin(x));
+// filter12.c:65-72, f12_pitch2coeff(): `float f = a2_P2I(cutoff >> 8) * (261.626f / 16777216.0f)`, then
+// the double `sin` of the host libm. a2_P2I (pitch.c:57-67) only looks at the 16 fraction bits of
+// the pitch and at (7 - octave) & 31, so for one sample rate the function has 32 x 65536 distinct
+// arguments: the host evaluates all of them once with ITS libm (the reference's own expression,
+// a2cu_engine.cu f12_table) and the device looks the result up. Bit-exact by construction: no
+// device libm is involved.
+A2CU_DEV int f12_coeff(const Ctx &c, int cutoff_value) {
+    const int pitch = cutoff_value >> 8;
+    return __ldg(c.f12tab + ((((7 - (pitch >> 16)) & 31) << 16) | (pitch & 0xffff)));
 }
 
 // Same interpolation through a generic pointer: the table staged in shared
@@ -572,7 +572,7 @@ struct Filter12 {
         switch (reg) {
         case 0:
             ramp_set(cutoff, v, start, dur);
-            if ((unsigned)dur < 256u) f1 = f12_coeff(c.ptab, cutoff.value, c.samplerate);
+            if ((unsigned)dur < 256u) f1 = f12_coeff(c, cutoff.value);
             break;
         case 1: ramp_set(q, v, start, dur); break;
         case 2: lp = v; break;
@@ -588,7 +588,7 @@ struct Filter12 {
         ramp_prepare(cutoff, frames);
         if (cutoff.delta) {
             ramp_run(cutoff, frames);
-            f1 = f12_coeff(c.ptab, cutoff.value, c.samplerate);
+            f1 = f12_coeff(c, cutoff.value);
             df = (wsub(f1, f0) + (frames >> 1)) / frames;
         } else
             df = 0;

@@ -22,7 +22,8 @@
 
 #include "../../include/a2cu.h"
 #include "a2cu_kernels.cuh"
-#include "a2cu_split.cuh"
+#include "a2cu_bus.cuh"
+#include "a2cu_registry.h"
 
 using namespace a2cu;
 
@@ -36,9 +37,7 @@ static inline double now_us() {
     return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3;
 }
 struct BlockStats { double flush_us = 0, download_us = 0, sync_us = 0, begin_us = 0; long flushes = 0, downloads = 0, begins = 0, procs = 0; };
-static BlockStats g_bs;
 struct WindowStats { double prep_us = 0, stage_us = 0, api_us = 0, mix_us = 0; long windows = 0; };
-static WindowStats g_ws;
 static int fail(int code, const char *fmt, const char *detail = "") {
     snprintf(g_err, sizeof(g_err), fmt, detail);
     return code;
@@ -51,122 +50,22 @@ static int fail(int code, const char *fmt, const char *detail = "") {
     } while (0)
 
 // ---------------------------------------------------------------------------
-// Chain registry: signature string -> kernel
+// Chain registry: signature string -> kernel. The kernels are instantiated in
+// their own translation units (a2cu_reg_*.cu, compiled in parallel by build.py).
 // ---------------------------------------------------------------------------
-typedef void (*render_fn)(const RenderParams);
-struct KernelEntry {
-    render_fn fn;
-    int words;      // incl. the flags word
-    const char *name;
-    render_fn split_fn;     // warp-specialised variant (a2cu_split.cuh) or nullptr
-    size_t split_smem;
-    int split_threads;
-};
-static std::map<std::string, KernelEntry> &registry() {
+std::map<std::string, KernelEntry> &a2cu_registry() {
     static std::map<std::string, KernelEntry> r;
     return r;
 }
-static std::string sig_of(const a2cu_unitspec *c, int n) {
-    std::string s;
-    char b[32];
-    for (int i = 0; i < n; ++i) {
-        snprintf(b, sizeof(b), "%d:%d%d%d%d;", c[i].kind, c[i].ninputs, c[i].noutputs,
-                 c[i].add ? 1 : 0, c[i].wireout ? 1 : 0);
-        s += b;
-    }
-    return s;
-}
-template <class CH>
-static void reg_chain(std::vector<a2cu_unitspec> specs, const char *name) {
-    KernelEntry e;
-    e.fn = render_bank<CH>;
-    e.words = CH::kWords + 1;
-    e.name = name;
-    e.split_fn = nullptr;
-    e.split_smem = 0;
-    e.split_threads = 0;
-    registry()[sig_of(specs.data(), (int)specs.size())] = e;
-}
-static const size_t kMaxSplitSmem = 222 * 1024;   // dynamic part; the kernel also has 4.7 KB static (fused root stage); 227 KB per CTA
-template <int NOSC, bool FILT, int NA>
-static void reg_split(std::vector<a2cu_unitspec> specs) {
-    KernelEntry &e = registry()[sig_of(specs.data(), (int)specs.size())];
-    e.split_fn = render_split<NOSC, FILT, NA>;
-    e.split_smem = SplitLayout<NOSC, FILT>::bytes;
-    e.split_threads = SplitWarps<FILT, NA>::threads;
-    cudaFuncSetAttribute(render_split<NOSC, FILT, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)kMaxSplitSmem);
-}
-
-// spec helpers: {kind, nin, nout, add, wireout}
-#define S_OSC0 {A2CU_WTOSC, 0, 1, 0, 0}       /* first generator: replaces scratch */
-#define S_OSCA {A2CU_WTOSC, 0, 1, 1, 0}       /* further generators: add */
-#define S_OSCW {A2CU_WTOSC, 0, 1, 1, 1}       /* lone wtosc, straight to the bus */
-#define S_PM12W {A2CU_PANMIX, 1, 2, 1, 1}
-#define S_F11 {A2CU_FILTER12, 1, 1, 0, 0}
-#define S_F11W {A2CU_FILTER12, 1, 1, 1, 1}
-#define S_WS11 {A2CU_WAVESHAPER, 1, 1, 0, 0}
-#define S_FM(k) {k, 0, 1, 0, 0}
-
-typedef WtOsc<false, false> Osc0;
-typedef WtOsc<true, false> OscA;
-typedef WtOsc<true, true> OscW;
-typedef PanMix<1, 2, true, true> Pm12W;
-typedef Filter12<1, false, false> F11;
-typedef Filter12<1, true, true> F11W;
-typedef WaveShaper<1, false, false> Ws11;
-typedef Fm<1, 0, 0, false, false> Fm1;
-typedef Fm<2, 1, 0, false, false> Fm2;
-typedef Fm<3, 2, 0, false, false> Fm3;
-typedef Fm<4, 2, 0, false, false> Fm4;
-typedef Fm<3, 2, 1, false, false> Fm3p;
-typedef Fm<4, 2, 1, false, false> Fm4p;
-typedef Fm<2, 1, 2, false, false> Fm2r;
-typedef Fm<4, 2, 2, false, false> Fm4r;
-
+static std::map<std::string, KernelEntry> &registry() { return a2cu_registry(); }
 static void register_all() {
     static bool done = false;
     if (done) return;
     done = true;
-    reg_chain<Chain<OscW>>({S_OSCW}, "wtosc");
-    reg_chain<Chain<Osc0, Pm12W>>({S_OSC0, S_PM12W}, "wtosc_panmix");
-    reg_chain<Chain<Osc0, F11, Pm12W>>({S_OSC0, S_F11, S_PM12W}, "wtosc_filter12_panmix");
-    reg_chain<Chain<Osc0, F11W>>({S_OSC0, S_F11W}, "wtosc_filter12");
-    reg_chain<Chain<Osc0, OscA, Pm12W>>({S_OSC0, S_OSCA, S_PM12W}, "wtosc2_panmix");
-    reg_chain<Chain<Osc0, OscA, OscA, Pm12W>>({S_OSC0, S_OSCA, S_OSCA, S_PM12W}, "wtosc3_panmix");
-    reg_chain<Chain<Osc0, OscA, OscA, OscA, Pm12W>>({S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_PM12W}, "wtosc4_panmix");
-    reg_chain<Chain<Osc0, OscA, OscA, OscA, OscA, OscA, OscA, OscA, Pm12W>>(
-        {S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_PM12W}, "wtosc8_panmix");
-    reg_chain<Chain<Osc0, OscA, F11W>>({S_OSC0, S_OSCA, S_F11W}, "wtosc2_filter12");
-    reg_chain<Chain<Osc0, OscA, F11, Pm12W>>({S_OSC0, S_OSCA, S_F11, S_PM12W}, "wtosc2_filter12_panmix");
-    reg_chain<Chain<Osc0, OscA, OscA, F11, Pm12W>>({S_OSC0, S_OSCA, S_OSCA, S_F11, S_PM12W},
-                                                  "wtosc3_filter12_panmix");
-    reg_chain<Chain<Osc0, Ws11, Pm12W>>({S_OSC0, S_WS11, S_PM12W}, "wtosc_waveshaper_panmix");
-    reg_chain<Chain<Fm1, Pm12W>>({S_FM(A2CU_FM1), S_PM12W}, "fm1_panmix");
-    reg_chain<Chain<Fm2, Pm12W>>({S_FM(A2CU_FM2), S_PM12W}, "fm2_panmix");
-    reg_chain<Chain<Fm3, Pm12W>>({S_FM(A2CU_FM3), S_PM12W}, "fm3_panmix");
-    reg_chain<Chain<Fm4, Pm12W>>({S_FM(A2CU_FM4), S_PM12W}, "fm4_panmix");
-    reg_chain<Chain<Fm3p, Pm12W>>({S_FM(A2CU_FM3P), S_PM12W}, "fm3p_panmix");
-    reg_chain<Chain<Fm4p, Pm12W>>({S_FM(A2CU_FM4P), S_PM12W}, "fm4p_panmix");
-    reg_chain<Chain<Fm2r, Pm12W>>({S_FM(A2CU_FM2R), S_PM12W}, "fm2r_panmix");
-    reg_chain<Chain<Fm4r, Pm12W>>({S_FM(A2CU_FM4R), S_PM12W}, "fm4r_panmix");
-    reg_chain<Chain<Fm2, Ws11, Pm12W>>({S_FM(A2CU_FM2), S_WS11, S_PM12W}, "fm2_waveshaper_panmix");
+    a2cu_register_bank_wt();
+    a2cu_register_bank_fm();
 }
-
-// Warp-specialised variants; needs a current device (function attributes).
-static void register_split() {
-    // <oscillators, filter12, helper warps>: the control warp keeps the whole
-    // voice in registers, so wider voices get fewer warps per CTA
-    reg_split<1, false, 14>({S_OSC0, S_PM12W});
-    reg_split<2, false, 14>({S_OSC0, S_OSCA, S_PM12W});
-    reg_split<3, false, 10>({S_OSC0, S_OSCA, S_OSCA, S_PM12W});
-    reg_split<4, false, 10>({S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_PM12W});
-    reg_split<8, false, 6>({S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_PM12W});
-    // with filter12: 11 (8) helpers + control on sub-partitions 0-2, the recurrence alone on 3
-    reg_split<1, true, 11>({S_OSC0, S_F11, S_PM12W});
-    reg_split<2, true, 11>({S_OSC0, S_OSCA, S_F11, S_PM12W});
-    reg_split<3, true, 8>({S_OSC0, S_OSCA, S_OSCA, S_F11, S_PM12W});
-}
+static void register_split() { a2cu_register_split(); }
 
 // ---------------------------------------------------------------------------
 // Host-side tables (same libm calls as the reference, uploaded as integers)
@@ -200,6 +99,30 @@ struct HostTables {
 };
 static const HostTables &tables() {
     static HostTables t;
+    return t;
+}
+
+// f12_pitch2coeff (filter12.c:65-72) for every argument it can see at one sample rate: the 16
+// fraction bits of the pitch x the 32 values of (7 - octave) & 31 (a2_P2I, pitch.c:57-67).
+// Evaluated with the HOST libm, the same expression as the reference, once per sample rate and
+// process (~2 M sin calls); the device only looks results up (a2cu_device.cuh f12_coeff), so
+// a ramping cutoff is bit-exact by construction.
+#include <mutex>
+static const std::vector<int> &f12_table(int samplerate) {
+    static std::mutex mu;
+    static std::map<int, std::vector<int>> memo;
+    std::lock_guard<std::mutex> lock(mu);
+    std::vector<int> &t = memo[samplerate];
+    if (t.empty()) {
+        t.resize((size_t)32 << 16);
+        const HostTables &h = tables();
+        for (int shift = 0; shift < 32; ++shift)
+            for (int n = 0; n < 65536; ++n) {
+                // a pitch whose a2_P2I shift count is `shift`: octave 7 - shift
+                const int pitch = ((7 - shift) << 16) | n;
+                t[((size_t)shift << 16) | n] = h.f12_coeff((int)((unsigned)pitch << 8), samplerate);
+            }
+    }
     return t;
 }
 
@@ -358,6 +281,12 @@ struct MixHostEvent {
 };
 
 struct a2cu_engine {
+    // host-side statistics (printed at close with A2CU_STATS=1); per engine: different states may
+    // run on different threads (audiality2.h.cmake:163-166)
+    BlockStats bs;
+    WindowStats ws;
+    // environment toggles, read once in a2cu_open (A/B switches for profiles/)
+    bool env_stats = false, env_no_copy_stream = false, env_no_fuse = false, env_no_stage = false;
     int device = 0, samplerate = 48000, channels = 2;
     int basepitch = 0;
     uint32_t msdur = 0;
@@ -374,6 +303,7 @@ struct a2cu_engine {
     size_t pool_cap = 0, waves_cap = 0, cpool_cap = 0;
     unsigned *d_ptab = nullptr;
     int16_t *d_fmsine = nullptr;
+    int *d_f12tab = nullptr;        // f12_table(samplerate)
     std::vector<Bank *> banks;
     std::vector<RenderParams> params;
     int ngroups = 0;
@@ -382,6 +312,11 @@ struct a2cu_engine {
     int *d_rstate = nullptr;
     std::vector<MixHostEvent> mixev;
     uint32_t mixseq = 0;
+    // root panmix: a write / ramp is (or may still be) in flight until this time; the windows it
+    // touches, and one more (the ramper snaps value = target one segment later, a2_dsp.h:130-134),
+    // take mix_root's single-CTA general path
+    uint64_t root_until = 0;
+    bool root_written = false, root_extra = false;
     MixEvent *d_mixev = nullptr;
     size_t mixev_cap = 0;
     int *d_acc = nullptr;
@@ -460,7 +395,69 @@ struct a2cu_engine {
     std::vector<int> gunit_free, gunit_deferred;
     int *d_ustate = nullptr;        // [unit][kUnitWords]
     int ustate_cap = 0;
+    // multi-GPU root-bus exchange over peer memory (a2cu_xchg_*, kernels: xchg_root_bus)
+    struct Xchg {
+        bool enabled = false;
+        int world = 1, rank = 0, max_frames = 0;
+        unsigned epoch = 0;
+        void *base = nullptr;               // own symmetric buffer: 256 B of flags, then data
+        void *peer[kMaxPeers] = {nullptr};  // every rank's buffer as mapped here
+        bool ipc_opened[kMaxPeers] = {false};
+        unsigned *h_status = nullptr;       // mapped pinned word, written by the kernel on timeout
+        unsigned long long timeout_cycles = 4000000000ull;
+    } xchg;
 };
+// Grow a device buffer, keeping the old one if the allocation fails.
+template <class T>
+static int grow_device(a2cu_engine *e, T **buf, size_t *cap, size_t need_elems, bool sync_first) {
+    if (need_elems <= *cap) return A2CU_OK;
+    if (sync_first) CK(cudaStreamSynchronize(e->stream));
+    T *n = nullptr;
+    const size_t ncap = need_elems * 2;
+    if (cudaMalloc(&n, ncap * sizeof(T)) != cudaSuccess)
+        return fail(A2CU_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(cudaGetLastError()));
+    if (*buf) cudaFree(*buf);
+    *buf = n;
+    *cap = ncap;
+    return A2CU_OK;
+}
+
+static const size_t kXchgFlagBytes = 256;
+static void xchg_release(a2cu_engine *e) {
+    a2cu_engine::Xchg &x = e->xchg;
+    for (int r = 0; r < kMaxPeers; ++r) {
+        if (x.ipc_opened[r] && x.peer[r]) cudaIpcCloseMemHandle(x.peer[r]);
+        x.peer[r] = nullptr; x.ipc_opened[r] = false;
+    }
+    if (x.base) cudaFree(x.base);
+    if (x.h_status) cudaFreeHost(x.h_status);
+    x = a2cu_engine::Xchg();
+}
+
+static XchgParams xchg_params(a2cu_engine *e) {
+    XchgParams X;
+    memset(&X, 0, sizeof(X));
+    a2cu_engine::Xchg &x = e->xchg;
+    if (!x.enabled || x.world < 2) return X;
+    X.world = x.world; X.rank = x.rank; X.max_frames = x.max_frames;
+    X.epoch = ++x.epoch;
+    for (int r = 0; r < x.world; ++r) {
+        X.flags[r] = (unsigned *)x.peer[r];
+        X.data[r] = (int *)((char *)x.peer[r] + kXchgFlagBytes);
+    }
+    X.status = x.h_status;
+    X.timeout_cycles = x.timeout_cycles;
+    return X;
+}
+static int xchg_check(a2cu_engine *e) {
+    if (e->xchg.h_status && *(volatile unsigned *)e->xchg.h_status) {
+        char b[64];
+        snprintf(b, sizeof(b), "window %u", *(volatile unsigned *)e->xchg.h_status);
+        *(volatile unsigned *)e->xchg.h_status = 0;
+        return fail(A2CU_ECUDA, "root-bus exchange timed out waiting for a peer (%s)", b);
+    }
+    return A2CU_OK;
+}
 
 
 void OscMirror::set_phase(const a2cu_engine *e, int phv, unsigned sst) {   // wtosc.c:378-387
@@ -749,6 +746,10 @@ a2cu_engine *a2cu_open(int device, int samplerate, int channels) {
     register_split();
     a2cu_engine *e = new a2cu_engine();
     e->use_split = getenv("A2CU_NO_SPLIT") == nullptr;
+    e->env_stats = getenv("A2CU_STATS") != nullptr;
+    e->env_no_copy_stream = getenv("A2CU_NO_COPY_STREAM") != nullptr;
+    e->env_no_fuse = getenv("A2CU_NO_FUSE") != nullptr;
+    e->env_no_stage = getenv("A2CU_NO_STAGE") != nullptr;
     e->noise_ptr = &e->noiseseed;
     e->device = device;
     e->samplerate = samplerate;
@@ -757,7 +758,10 @@ a2cu_engine *a2cu_open(int device, int samplerate, int channels) {
     e->basepitch = (int)((float)log2(261.626f / (float)samplerate) * 65536.0f + 0.5f);
     e->msdur = (uint32_t)(samplerate * 65.536f + .5f);
     const HostTables &t = tables();
+    const std::vector<int> &f12 = f12_table(samplerate);
     bool ok = cudaMalloc(&e->d_ptab, sizeof(t.ptab)) == cudaSuccess &&
+              cudaMalloc(&e->d_f12tab, f12.size() * sizeof(int)) == cudaSuccess &&
+              cudaMemcpy(e->d_f12tab, f12.data(), f12.size() * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMalloc(&e->d_fmsine, sizeof(t.fmsine)) == cudaSuccess &&
               cudaMalloc(&e->d_rstate, 8 * sizeof(int)) == cudaSuccess &&
               cudaMemcpy(e->d_ptab, t.ptab, sizeof(t.ptab), cudaMemcpyHostToDevice) == cudaSuccess &&
@@ -777,23 +781,24 @@ a2cu_engine *a2cu_open(int device, int samplerate, int channels) {
 
 void a2cu_close(a2cu_engine *e) {
     if (!e) return;
-    if (getenv("A2CU_STATS") && g_ws.windows)
+    if (e->env_stats && e->ws.windows)
         fprintf(stderr, "a2cu window stats: %ld windows, host us per window: collect/sort %.1f, stage+H2D %.1f, "
-                        "render launch %.1f, bus stage launch %.1f\n", g_ws.windows, g_ws.prep_us / g_ws.windows,
-                g_ws.stage_us / g_ws.windows, g_ws.api_us / g_ws.windows, g_ws.mix_us / g_ws.windows);
-    if (getenv("A2CU_STATS"))
+                        "render launch %.1f, bus stage launch %.1f\n", e->ws.windows, e->ws.prep_us / e->ws.windows,
+                e->ws.stage_us / e->ws.windows, e->ws.api_us / e->ws.windows, e->ws.mix_us / e->ws.windows);
+    if (e->env_stats)
         fprintf(stderr, "a2cu stats: %ld flushes %.1f us avg (host side), %ld downloads, wait+copy %.1f us avg, "
-                        "%ld launches\n", g_bs.flushes, g_bs.flushes ? g_bs.flush_us / g_bs.flushes : 0.0,
-                g_bs.downloads, g_bs.downloads ? g_bs.sync_us / g_bs.downloads : 0.0, (long)e->launches);
+                        "%ld launches\n", e->bs.flushes, e->bs.flushes ? e->bs.flush_us / e->bs.flushes : 0.0,
+                e->bs.downloads, e->bs.downloads ? e->bs.sync_us / e->bs.downloads : 0.0, (long)e->launches);
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
+    xchg_release(e);
     for (Bank *b : e->banks) {
         cudaFree(b->d_state); cudaFree(b->d_bus); cudaFree(b->d_noise);
         cudaFree(b->d_ev); cudaFree(b->d_runs);
         if (b->ev_consumed) cudaEventDestroy(b->ev_consumed);
         delete b;
     }
-    cudaFree(e->d_waves); cudaFree(e->d_pool); cudaFree(e->d_cpool); cudaFree(e->d_ptab); cudaFree(e->d_fmsine);
+    cudaFree(e->d_waves); cudaFree(e->d_pool); cudaFree(e->d_cpool); cudaFree(e->d_ptab); cudaFree(e->d_fmsine); cudaFree(e->d_f12tab);
     cudaFree(e->d_gstate); cudaFree(e->d_rstate); cudaFree(e->d_mixev);
     cudaFree(e->d_acc); cudaFree(e->d_master);
     cudaFree(e->d_buscmds); cudaFree(e->d_bacc); cudaFree(e->d_pmstate); cudaFree(e->d_ustate); cudaFree(e->d_runs); cudaFree(e->d_fuse_counter);
@@ -1205,6 +1210,10 @@ static int mix_write(a2cu_engine *e, int target, int reg, int value, uint64_t wh
     m.time = when; m.seq = e->mixseq++; m.target = target; m.reg = reg < 0 ? -1 : reg;
     m.value = value; m.dur = dur;
     e->mixev.push_back(m);
+    if (target < 0 && reg >= 0) {
+        e->root_written = true;
+        e->root_until = std::max(e->root_until, when + dur + 512 + ((uint64_t)kMaxFrag << 8));
+    }
     if (target >= 0) {
         // the group's wake-up cuts its children's segments (core.c:1769-1776)
         for (Bank *b : e->banks)
@@ -1361,15 +1370,31 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     if (!frames) return A2CU_OK;
     if (!buffer) buffer = frames;
     const uint64_t t0 = e->now, t1 = e->now + ((uint64_t)frames << 8);
+    // the engine-owned master block must hold the WHOLE window before it may be split below
+    if (!dev_out) {
+        int gr = grow_device(e, &e->d_master, &e->master_cap, (size_t)frames * 2, true);
+        if (gr) return gr;
+    }
     int splits[kMaxSplits], nsplits = 0;
     if (collect_splits(e, t0, t1, splits, &nsplits)) {
-        // too many root-level cuts for one launch: render in two halves
-        if (frames <= buffer) return fail(A2CU_EINVAL, "too many root events in one buffer%s");
-        unsigned nb = (frames + buffer - 1) / buffer;
-        unsigned h = (nb / 2) * buffer;
-        int r = run_window(e, h, buffer, dev_out);
+        // Too many root-level cuts for one launch: render the window as two sub-windows, each
+        // writing its own part of the output block. Cut at a driver-buffer boundary, or - inside
+        // one buffer - at a fragment boundary (fragments restart every 64 frames from the buffer
+        // start, core.c:1964-1973, so both parts keep the original fragment grid).
+        const int och = e->post_root ? e->channels : 2;
+        int32_t *base = dev_out ? dev_out : e->d_master;
+        unsigned h, b0, b1;
+        if (frames > buffer) {
+            h = ((frames + buffer - 1) / buffer / 2) * buffer;
+            b0 = b1 = buffer;
+        } else if (frames > (unsigned)kMaxFrag) {
+            h = ((frames + kMaxFrag - 1) / kMaxFrag / 2) * kMaxFrag;
+            b0 = h; b1 = frames - h;
+        } else
+            return fail(A2CU_EINVAL, "too many root events in one fragment%s");
+        int r = run_window(e, h, b0, base);
         if (r) return r;
-        return run_window(e, frames - h, buffer, dev_out ? dev_out + (size_t)h * e->channels : nullptr);
+        return run_window(e, frames - h, b1, base + (size_t)h * och);
     }
     int r = upload_waves(e);
     if (r) return r;
@@ -1378,18 +1403,9 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     const int nbus = 1 + e->ngroups;
     size_t acc_n = (size_t)nbus * W * 2;
     if (acc_n > e->acc_cap) {
-        CK(cudaStreamSynchronize(e->stream));
-        if (e->d_acc) cudaFree(e->d_acc);
-        e->acc_cap = acc_n * 2;
-        CK(cudaMalloc(&e->d_acc, e->acc_cap * sizeof(int)));
+        r = grow_device(e, &e->d_acc, &e->acc_cap, acc_n, true);
+        if (r) return r;
         e->acc_clean_n = 0;
-    }
-    size_t m_n = (size_t)W * 2;
-    if (m_n > e->master_cap) {
-        CK(cudaStreamSynchronize(e->stream));
-        if (e->d_master) cudaFree(e->d_master);
-        e->master_cap = m_n * 2;
-        CK(cudaMalloc(&e->d_master, e->master_cap * sizeof(int)));
     }
 
     // ---- stage events (host -> pinned -> device) ----
@@ -1472,7 +1488,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     if (r) return r;
     char *stage = (char *)e->h_stage;
     // bank event uploads use the copy stream unless bus-stage events share this staging buffer
-    e->copy_used = mdue.empty() && !getenv("A2CU_NO_COPY_STREAM");
+    e->copy_used = mdue.empty() && !e->env_no_copy_stream;
     if (e->copy_used && !e->copy_stream) CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     cudaStream_t up = e->copy_used ? e->copy_stream : e->stream;
     size_t spos = 0;
@@ -1496,6 +1512,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         P.nsplits = nsplits;
         for (int i = 0; i < nsplits; ++i) P.splits[i] = splits[i];
         P.waves = e->d_waves; P.pool = e->d_pool; P.cpool = e->d_cpool; P.ptab = e->d_ptab; P.fmsine = e->d_fmsine;
+        P.f12tab = e->d_f12tab;
         P.samplerate = e->samplerate;
         const size_t nbulk = fast[bi] ? b->bulk.size() : 0;
         if (!due[bi].empty() || nbulk) {
@@ -1558,7 +1575,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     // root events in this window, the last CTA of
     // that kernel runs the root stage itself (a2cu_split.cuh) and mix_root is not launched.
     int fuse_bank = -1;
-    if (e->ngroups == 0 && mdue.empty() && e->use_split && !getenv("A2CU_NO_FUSE")) {
+    if (e->ngroups == 0 && mdue.empty() && e->use_split && !e->env_no_fuse) {
         int live = 0;
         for (size_t bi = 0; bi < e->banks.size(); ++bi) {
             Bank *b = e->banks[bi];
@@ -1573,6 +1590,9 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         }
     }
     e->fused_root = false;
+    if (e->xchg.enabled && e->xchg.world > 1 && W > e->xchg.max_frames)
+        return fail(A2CU_EINVAL, "window longer than the exchange buffer (a2cu_xchg_create max_frames)%s");
+    const XchgParams X = xchg_params(e);
     const double ws_t2 = now_us();
     // inputs are resident from here on: ev0 .. ev1 brackets the render kernels
     if (e->timing) CK(cudaEventRecord(e->ev0, e->stream));
@@ -1613,7 +1633,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         if (split) {
             params[bi].prof = e->d_prof;
             size_t smem = b->k.split_smem;
-            if (b->stage_wave >= 0 && e->waves[b->stage_wave].cbegin >= 0 && !getenv("A2CU_NO_STAGE")) {
+            if (b->stage_wave >= 0 && e->waves[b->stage_wave].cbegin >= 0 && !e->env_no_stage) {
                 // whole wave (all mip levels) + read-ahead slack, if it fits beside the pipeline buffers
                 const HostWave &hw = e->waves[b->stage_wave];
                 size_t tb = ((size_t)hw.ccount + 64) * sizeof(int4);
@@ -1631,6 +1651,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
                 params[bi].fuse_master = dev_out ? dev_out : e->d_master;
                 params[bi].fuse_channels = e->channels;
                 params[bi].fuse_root_stage = e->post_root ? 1 : 0;
+                params[bi].xchg = X;
                 e->fused_root = true;
             }
             b->k.split_fn<<<grid, b->k.split_threads, smem, e->stream>>>(params[bi]);
@@ -1678,20 +1699,23 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     M.master = dev_out ? dev_out : e->d_master;
     M.root_stage = e->post_root ? 1 : 0;
     M.clear = 1;
+    if (e->root_written && t0 < e->root_until) { M.general = 1; e->root_extra = true; }
+    else if (e->root_extra) { M.general = 1; e->root_extra = false; }
     if (e->ngroups) {
         mix_groups<<<e->ngroups, 256, 0, e->stream>>>(M);
         ++e->launches;
     }
     if (!e->fused_root) {
-        mix_root<<<std::max(1, std::min(8, ((int)M.W + 255) / 256)), 256, 0, e->stream>>>(M);
+        if (X.world > 1) mix_root_xchg<<<1, 512, 0, e->stream>>>(M, X);
+        else mix_root<<<M.general ? 1 : std::max(1, std::min(8, ((int)M.W + 255) / 256)), 256, 0, e->stream>>>(M);
         ++e->launches;
     }
     CK(cudaGetLastError());
     if (e->timing) CK(cudaEventRecord(e->ev2, e->stream));
     e->last_mix = M;
     e->now = t1;
-    g_ws.prep_us += ws_t1 - ws_t0; g_ws.stage_us += ws_t2 - ws_t1; g_ws.api_us += ws_t3 - ws_t2;
-    g_ws.mix_us += now_us() - ws_t3; ++g_ws.windows;
+    e->ws.prep_us += ws_t1 - ws_t0; e->ws.stage_us += ws_t2 - ws_t1; e->ws.api_us += ws_t3 - ws_t2;
+    e->ws.mix_us += now_us() - ws_t3; ++e->ws.windows;
     return A2CU_OK;
 }
 
@@ -1711,7 +1735,7 @@ int a2cu_sync(a2cu_engine *e) {
         if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) e->last_ms = ms;
         if (cudaEventElapsedTime(&ms, e->ev1, e->ev2) == cudaSuccess) e->last_mix_ms = ms;
     }
-    return A2CU_OK;
+    return xchg_check(e);
 }
 
 int a2cu_run(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *out) {
@@ -1719,13 +1743,6 @@ int a2cu_run(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *out) {
     cudaSetDevice(e->device);
     const int och = e->post_root ? e->channels : 2;
     size_t n = (size_t)frames * och;
-    // make sure the engine-owned master buffer is large enough before launching
-    if ((size_t)frames * 2 > e->master_cap) {
-        CK(cudaStreamSynchronize(e->stream));
-        if (e->d_master) cudaFree(e->d_master);
-        e->master_cap = (size_t)frames * 4;
-        CK(cudaMalloc(&e->d_master, e->master_cap * sizeof(int)));
-    }
     int r = run_window(e, frames, buffer, nullptr);
     if (r) return r;
     if (out) {
@@ -1769,12 +1786,6 @@ static int submit_impl(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t
     }
     const int och = e->post_root ? e->channels : 2;
     const size_t n = (size_t)frames * och;
-    if ((size_t)frames * 2 > e->master_cap) {
-        CK(cudaStreamSynchronize(e->stream));
-        if (e->d_master) cudaFree(e->d_master);
-        e->master_cap = (size_t)frames * 4;
-        CK(cudaMalloc(&e->d_master, e->master_cap * sizeof(int)));
-    }
     if (!dev_out && n > sl.cap) {
         if (sl.h_out) cudaFreeHost(sl.h_out);
         sl.cap = n * 2;
@@ -1809,7 +1820,7 @@ int a2cu_collect(a2cu_engine *e, int ticket, int32_t *out) {
         if (cudaEventElapsedTime(&ms, sl.ev1, sl.ev2) == cudaSuccess) e->last_mix_ms = ms;
     }
     sl.busy = false;
-    return A2CU_OK;
+    return xchg_check(e);
 }
 
 int a2cu_apply_root_stage(a2cu_engine *e, const int32_t *dev_rootbus, int32_t *dev_master, unsigned frames,
@@ -1821,9 +1832,118 @@ int a2cu_apply_root_stage(a2cu_engine *e, const int32_t *dev_rootbus, int32_t *d
     (void)start_time;
     M.acc = (int *)dev_rootbus; M.W = (int)frames; M.buffer = (int)(buffer ? buffer : frames);
     M.ngroups = 0; M.master = dev_master; M.root_stage = 1; M.clear = 0;
-    mix_root<<<std::max(1, std::min(8, ((int)M.W + 255) / 256)), 256, 0, e->stream>>>(M);
+    mix_root<<<M.general ? 1 : std::max(1, std::min(8, ((int)M.W + 255) / 256)), 256, 0, e->stream>>>(M);
     ++e->launches;
     CK(cudaGetLastError());
+    return A2CU_OK;
+}
+
+// Device-side f12_pitch2coeff for an array of cutoff ramper values (8:24), for the parity tests.
+int a2cu_debug_f12_coeff(a2cu_engine *e, const int32_t *cutoff_values, int n, int32_t *out) {
+    if (!e || !cutoff_values || !out || n < 1) return A2CU_EINVAL;
+    cudaSetDevice(e->device);
+    int *d = nullptr;
+    CK(cudaMalloc(&d, (size_t)n * 2 * sizeof(int)));
+    cudaError_t err = cudaMemcpy(d, cutoff_values, (size_t)n * sizeof(int), cudaMemcpyHostToDevice);
+    Ctx c;
+    memset(&c, 0, sizeof(c));
+    c.ptab = e->d_ptab; c.f12tab = e->d_f12tab; c.samplerate = e->samplerate;
+    if (err == cudaSuccess) {
+        f12_coeff_probe<<<(n + 255) / 256, 256, 0, e->stream>>>(c, d, n, d + n);
+        err = cudaStreamSynchronize(e->stream);
+    }
+    if (err == cudaSuccess) err = cudaMemcpy(out, d + n, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (err != cudaSuccess) return fail(A2CU_ECUDA, "a2cu_debug_f12_coeff: %s", cudaGetErrorString(err));
+    return A2CU_OK;
+}
+
+// ===========================================================================
+// Multi-GPU: root-bus exchange over NVLink peer memory (include/a2cu.h)
+// ===========================================================================
+int a2cu_xchg_create(a2cu_engine *e, int rank, int world, unsigned max_frames, unsigned timeout_ms,
+                     void *handle_out) {
+    if (!e || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || !max_frames)
+        return fail(A2CU_EINVAL, "a2cu_xchg_create: bad args%s");
+    cudaSetDevice(e->device);
+    CK(cudaStreamSynchronize(e->stream));
+    xchg_release(e);
+    a2cu_engine::Xchg &x = e->xchg;
+    x.world = world; x.rank = rank; x.max_frames = (int)max_frames;
+    const size_t bytes = kXchgFlagBytes + (size_t)2 * world * max_frames * 2 * sizeof(int);
+    if (cudaMalloc(&x.base, bytes) != cudaSuccess)
+        return fail(A2CU_ENOMEM, "cudaMalloc exchange buffer: %s", cudaGetErrorString(cudaGetLastError()));
+    CK(cudaMemset(x.base, 0, bytes));
+    CK(cudaHostAlloc((void **)&x.h_status, sizeof(unsigned), cudaHostAllocMapped));
+    *x.h_status = 0;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->device);
+    if (khz <= 0) khz = 1900000;
+    x.timeout_cycles = (unsigned long long)(timeout_ms ? timeout_ms : 2000) * (unsigned long long)khz;
+    x.peer[rank] = x.base;
+    if (handle_out) {
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, x.base));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(handle_out, &h, sizeof(h));
+    }
+    return A2CU_OK;
+}
+
+int a2cu_xchg_connect_ipc(a2cu_engine *e, const void *handles) {
+    if (!e || !handles || !e->xchg.base) return fail(A2CU_EINVAL, "a2cu_xchg_connect_ipc: create first%s");
+    cudaSetDevice(e->device);
+    a2cu_engine::Xchg &x = e->xchg;
+    for (int r = 0; r < x.world; ++r) {
+        if (r == x.rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const char *)handles + (size_t)r * sizeof(h), sizeof(h));
+        void *p = nullptr;
+        cudaError_t err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (err != cudaSuccess) return fail(A2CU_ECUDA, "cudaIpcOpenMemHandle: %s", cudaGetErrorString(err));
+        x.peer[r] = p; x.ipc_opened[r] = true;
+    }
+    x.enabled = true;
+    return A2CU_OK;
+}
+
+int a2cu_xchg_connect_local(a2cu_engine *e, a2cu_engine *const *peers) {
+    if (!e || !peers || !e->xchg.base) return fail(A2CU_EINVAL, "a2cu_xchg_connect_local: create first%s");
+    cudaSetDevice(e->device);
+    a2cu_engine::Xchg &x = e->xchg;
+    for (int r = 0; r < x.world; ++r) {
+        if (r == x.rank) continue;
+        const a2cu_engine *p = peers[r];
+        if (!p || !p->xchg.base || p->xchg.world != x.world || p->xchg.rank != r ||
+            p->xchg.max_frames != x.max_frames)
+            return fail(A2CU_EINVAL, "a2cu_xchg_connect_local: peer %s", "not created with the same geometry");
+        if (p->device != e->device) {
+            cudaError_t err = cudaDeviceEnablePeerAccess(p->device, 0);
+            if (err != cudaSuccess && err != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(A2CU_ECUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(err));
+            cudaGetLastError();
+        }
+        x.peer[r] = p->xchg.base;
+    }
+    x.enabled = true;
+    return A2CU_OK;
+}
+
+int a2cu_xchg_enable(a2cu_engine *e, int enabled) {
+    if (!e) return A2CU_EINVAL;
+    if (enabled && !e->xchg.base) return fail(A2CU_EINVAL, "a2cu_xchg_enable: no exchange buffer%s");
+    if (enabled)
+        for (int r = 0; r < e->xchg.world; ++r)
+            if (!e->xchg.peer[r]) return fail(A2CU_EINVAL, "a2cu_xchg_enable: peers not connected%s");
+    e->xchg.enabled = enabled != 0;
+    return A2CU_OK;
+}
+
+int a2cu_xchg_close(a2cu_engine *e) {
+    if (!e) return A2CU_EINVAL;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    xchg_release(e);
     return A2CU_OK;
 }
 
@@ -2247,8 +2367,7 @@ static int block_flush_impl(a2cu_engine *e);
 int a2cu_block_flush(a2cu_engine *e) {
     double t0 = now_us();
     int r = block_flush_impl(e);
-    g_bs.flush_us += now_us() - t0;
-    ++g_bs.flushes;
+    if (e) { e->bs.flush_us += now_us() - t0; ++e->bs.flushes; }
     return r;
 }
 static int block_flush_impl(a2cu_engine *e) {
@@ -2304,6 +2423,7 @@ static int block_flush_impl(a2cu_engine *e) {
         P.state = b->d_state; P.stride = b->stride; P.nvoices = (int)nr;
         P.acc = e->d_bacc; P.W = kMaxFrag; P.buffer = kMaxFrag;
         P.waves = e->d_waves; P.pool = e->d_pool; P.cpool = e->d_cpool; P.ptab = e->d_ptab; P.fmsine = e->d_fmsine;
+        P.f12tab = e->d_f12tab;
         P.samplerate = e->samplerate;
         P.ev = b->d_ev; P.runs = b->d_runs; P.explicit_ = 1;
         int grid = ((int)nr + kThreads - 1) / kThreads;
@@ -2357,7 +2477,7 @@ static int block_flush_impl(a2cu_engine *e) {
         BP.cmds = e->d_buscmds; BP.acc = e->d_bacc; BP.pmstate = e->d_pmstate;
         BP.ustate = e->d_ustate;
         BP.ctx.waves = e->d_waves; BP.ctx.pool = e->d_pool; BP.ctx.cpool = e->d_cpool; BP.ctx.ptab = e->d_ptab;
-        BP.ctx.fmsine = e->d_fmsine; BP.ctx.samplerate = e->samplerate;
+        BP.ctx.fmsine = e->d_fmsine; BP.ctx.f12tab = e->d_f12tab; BP.ctx.samplerate = e->samplerate;
         for (int l = maxlevel; l >= 0; --l) {
             if (!level_runs[l]) continue;
             BP.runs = e->d_runs + level_first[l];
@@ -2408,8 +2528,8 @@ int a2cu_block_download(a2cu_engine *e, int bus, int nch, unsigned frame, unsign
     CK(cudaMemcpyAsync(e->h_xfer, e->d_bacc + ((size_t)bus * kMaxFrag + frame) * 2, frames * 2 * sizeof(int32_t),
                        cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
-    g_bs.sync_us += now_us() - t0;
-    ++g_bs.downloads;
+    e->bs.sync_us += now_us() - t0;
+    ++e->bs.downloads;
     e->d2h_bytes += frames * 2 * sizeof(int32_t);
     for (int c = 0; c < nch; ++c)
         for (unsigned i = 0; i < frames; ++i) {

@@ -18,6 +18,7 @@ namespace a2cu {
 
 constexpr int kThreads = 128;
 constexpr int kMaxSplits = 8;
+constexpr int kSplitSegs = 2;      // render_split: segments per voice and fragment (host eligibility check)
 
 // Event record, 16 bytes. x = (frame_in_window << 8) | substart
 // y = kind | unit << 8 | reg << 16 ; z = value ; w = duration (24:8)
@@ -29,6 +30,80 @@ enum EvKind { EV_WRITE = 0, EV_WAKE = 1, EV_INIT = 2, EV_START = 3, EV_STOP = 4,
 
 // One active voice of a drop-in block: slot and its run of event records.
 struct VoiceRun { int slot; unsigned ev_begin, ev_count; };
+
+// ---------------------------------------------------------------------------
+// Multi-GPU exchange of the root bus over NVLink peer memory.
+//
+// Voices shard across GPUs; the only coupling is the integer sum of the stereo root
+// scratch bus BEFORE the truncating root panmix (audiality2.c:271-280). Every rank owns
+// a "symmetric" buffer  flags[2][world] | data[2][world][max_frames][2]  that all peers
+// have mapped (CUDA IPC / peer access). At the end of a window the CTA that holds the
+// finished root bus
+//   1. stores its raw bus into row [epoch & 1][rank] of EVERY rank's buffer (plain
+//      stores through the peer mapping: NVLink writes), fences system-wide and
+//      releases flag [epoch & 1][rank] = epoch on every rank,
+//   2. waits until all `world` flags of its OWN buffer show this epoch,
+//   3. sums the rows (integer add: any order is bit-exact) back into its root bus,
+// and goes on with the ordinary root stage. No launch, no NCCL call and no host
+// round trip is involved; two buffer halves alternate so that a rank that is one
+// window ahead never overwrites rows a slower rank still reads (a rank cannot get two
+// windows ahead: finishing window k+1 needs every peer's push of k+1, which peers
+// issue only after they finished reading window k).
+// The wait is bounded (timeout -> status word), so a missing peer cannot hang the GPU.
+// ---------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+struct XchgParams {
+    int world, rank;                    // world <= 1: no exchange
+    unsigned epoch;                     // sequence number of this window (> 0, same on all ranks)
+    int max_frames;                     // row pitch of the data area, frames
+    int *data[kMaxPeers];               // every rank's buffer: data area
+    unsigned *flags[kMaxPeers];         // every rank's buffer: flag area
+    unsigned *status;                   // mapped host word: set to the epoch that timed out
+    unsigned long long timeout_cycles;
+};
+
+A2CU_DEV void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+A2CU_DEV unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All threads of ONE CTA (nthreads of them) call this with the finished local root bus.
+A2CU_DEV void xchg_root_bus(const XchgParams &X, int *root, int W, int tid, int nthreads) {
+    const int par = (int)(X.epoch & 1u);
+    const size_t pitch = (size_t)X.max_frames * 2;
+    const size_t myrow = ((size_t)par * X.world + X.rank) * pitch;
+    for (int i = tid; i < W * 2; i += nthreads) {
+        const int v = __ldcg(root + i);
+        for (int r = 0; r < X.world; ++r) X.data[r][myrow + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < X.world) st_release_sys(X.flags[tid] + par * X.world + X.rank, X.epoch);
+    if (tid < X.world) {
+        const unsigned *f = X.flags[X.rank] + par * X.world + tid;
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(f) - X.epoch) < 0) {
+            if ((unsigned long long)(clock64() - t0) > X.timeout_cycles) {
+                *X.status = X.epoch;        // reported by a2cu_collect / a2cu_sync
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    const int *mine = X.data[X.rank] + (size_t)par * X.world * pitch;
+    for (int i = tid; i < W * 2; i += nthreads) {
+        int s = 0;
+        for (int r = 0; r < X.world; ++r) s = wadd(s, __ldcg(mine + (size_t)r * pitch + i));
+        root[i] = s;
+    }
+    __threadfence_block();
+    __syncthreads();
+}
 
 struct RenderParams {
     int *state;               // [words][stride]
@@ -47,6 +122,7 @@ struct RenderParams {
     const int4 *cpool;
     const unsigned *ptab;
     const int16_t *fmsine;
+    const int *f12tab;
     int samplerate;
     // drop-in ("block") mode: thread i renders runs[i]; segments are the
     // host's explicit EV_PROC records and carry their own target bus
@@ -65,6 +141,7 @@ struct RenderParams {
     int *fuse_master;
     int fuse_channels;
     int fuse_root_stage;    // 0: copy the raw root bus out (multi-GPU cut) instead of the root panmix
+    XchgParams xchg;        // world > 1: sum the root bus over all ranks before the root stage
 };
 
 // End of the fragment that contains frame f: fragments restart at every driver
@@ -96,7 +173,7 @@ __global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
     const int home = s_home;
 
     Ctx c;
-    c.waves = P.waves; c.pool = P.pool; c.cpool = P.cpool; c.ptab = P.ptab; c.fmsine = s_sine;
+    c.waves = P.waves; c.pool = P.pool; c.cpool = P.cpool; c.ptab = P.ptab; c.fmsine = s_sine; c.f12tab = P.f12tab;
     c.samplerate = P.samplerate;
 
     CH ch;
@@ -218,6 +295,19 @@ __global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
     }
     if (valid) {
         if (in_seg) ch.finish();
+        // Drop-in mode: control writes the host made AFTER the voice's last segment of this
+        // fragment (stamped with the frame where its next segment would start, i.e. up to 64) have
+        // no boundary left to be applied at - the reference applies a write immediately
+        // (a2_units.h:115), so they take effect here, before the state goes back to HBM.
+        if (expl)
+            while (evp < eve) {
+                const uint4 e = P.ev[evp++];
+                const int kind = e.y & 0xff, unit = (e.y >> 8) & 0xff, reg = (e.y >> 16) & 0xff;
+                if (kind == EV_WRITE) ch.write(c, unit, reg, (int)e.z, (int)(e.x & 0xff), (int)e.w);
+                else if (kind == EV_INIT) ch.init_unit(c, unit, (int)e.z, e.x & 0xff);
+                else if (kind == EV_START) alive = 1;
+                else if (kind == EV_STOP) alive = 0;
+            }
         sp.st(0, alive);
         ch.store(sp, 1);
     }
@@ -247,6 +337,7 @@ struct MixParams {
     int *master;            // [W][channels], or raw root bus [W][2] if !root_stage (may be mapped host memory)
     int root_stage;
     int clear;              // consumers zero the bus rows they read, so the next window needs no memset
+    int general;            // host: a root ramp may be in flight - one CTA replays segments, no steady path
 };
 
 A2CU_DEV void pm_load(const int *s, Ramp &vol, Ramp &pan) {
@@ -351,20 +442,6 @@ A2CU_DEV void pm_bus(const MixParams &P, int target, int *state, const int *in, 
         for (int i = 0; i < 8; ++i) state[i] = s_state[i];
 }
 
-// groups: { inline 0 *; panmix * *; xinsert * > } -> add into the root bus.
-// grid = ngroups
-__global__ void __launch_bounds__(256) mix_groups(const MixParams P) {
-    const int g = blockIdx.x;
-    int *root = P.acc;
-    int *in = P.acc + (size_t)(1 + g) * P.W * 2;
-    const bool clear = P.clear != 0;
-    pm_bus(P, g, P.gstate + g * 8, in, false, [&](int f, int r0, int r1) {
-        atomicAdd(root + f * 2, r0);
-        atomicAdd(root + f * 2 + 1, r1);
-        if (clear) { in[f * 2] = 0; in[f * 2 + 1] = 0; }
-    });
-}
-
 // root: { inline 0 *|2; panmix * *|2 1; xinsert * > } into the cleared master;
 // with root_stage == 0 the raw root bus is copied out (multi-GPU cut).
 // Root stage over the window for a group of threads (gtid of gsize); 'cta0' tells whether this CTA
@@ -381,7 +458,9 @@ A2CU_DEV void root_stage(const MixParams &P, int gtid, int gsize, bool cta0) {
     // rest): a2_PrepareRamper leaves value = target, delta = 0 in every segment
     // (a2_dsp.h:130-134), so every frame uses the same two gains and the whole
     // grid evaluates frames independently. Otherwise CTA 0 replays the segments.
-    const bool steady = P.nev == 0 && P.nsplits == 0 && P.rstate[3] == 0 && P.rstate[7] == 0 &&
+    // The host sets P.general (and launches ONE CTA) for every window a root write or ramp can
+    // reach, so CTAs of one launch never disagree about `steady` while CTA 0 rewrites rstate.
+    const bool steady = !P.general && P.nev == 0 && P.nsplits == 0 && P.rstate[3] == 0 && P.rstate[7] == 0 &&
                         P.rstate[0] == P.rstate[1] && P.rstate[4] == P.rstate[5];
     if (steady) {
         const int v = P.rstate[1], pn = P.rstate[5];            // targets
@@ -407,289 +486,6 @@ A2CU_DEV void root_stage(const MixParams &P, int gtid, int gsize, bool cta0) {
         else { P.master[f * 2] = r0; P.master[f * 2 + 1] = r1; }
         if (clear) { root[f * 2] = 0; root[f * 2 + 1] = 0; }
     });
-}
-
-// root: { inline 0 *|2; panmix * *|2 1; xinsert * > } into the cleared master;
-// with root_stage == 0 the raw root bus is copied out (multi-GPU cut).
-__global__ void __launch_bounds__(256) mix_root(const MixParams P) {
-    root_stage(P, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x, blockIdx.x == 0);
-}
-
-// ---------------------------------------------------------------------------
-// Drop-in mode bus stage: the bus-level Process()/write calls the host made
-// during its tree walk.
-//
-// Commands are grouped into RUNS: all commands one voice received in this
-// flush, in host order. Data only flows upwards in the voice tree (a voice's
-// output is `+=`-ed into its parent's bus, core.c:1763-1776), so runs of the
-// same nest level are independent of each other: the engine launches
-// bus_level once per nest level, deepest first, one CTA per run. Adds into a
-// bus another run of the level may also add to (wire-outs into the parent's
-// bus) are integer atomics - order-free, bit-exact.
-//
-//   BUS_PM_*   bus-level panmix (panmix.c, all variants): control part on
-//              thread 0, frames in closed form across the CTA
-//   BUS_U_*    any other replaced unit called outside a fused leaf voice
-//              ({inline; filter12}, {inline; wtosc; panmix}, {wtosc; panmix;
-//              dcblock}, ...): one Process() call of ONE unit, exactly as the
-//              reference runs it (unit by unit over the segment,
-//              core.c:1875-1876), with the voice's scratch channels held in a
-//              device bus row instead of st->scratch[nest]. The unit templates
-//              are the code the fused kernels use, instantiated in replace
-//              mode; add / wire-out (A2_PROCADD, A2_IO_WIREOUT) are applied
-//              here. Recurrences run on thread 0.
-//              kind A2CU_FBDELAY: units/fbdelay.c:68-127; frames run in
-//              parallel when no tap of the call can see a sample written by
-//              the same call, else on thread 0.
-//   BUS_ADD    dst bus += src bus (an adding `inline` after device scratch,
-//              host contributions uploaded into a staging row)
-// ---------------------------------------------------------------------------
-enum BusOp { BUS_PM_PROC = 0, BUS_PM_WRITE = 1, BUS_U_INIT = 2, BUS_U_WRITE = 3, BUS_U_SEED = 4, BUS_U_RUN = 5,
-             BUS_ADD = 6 };
-struct BusCmd {
-    int op, pm;             // pm: index of the panmix instance state / generic unit state
-    int nin, nout, add;     // add: bit 0 A2_PROCADD, bit 1 wire-out (BUS_U_RUN)
-    int in_bus, out_bus;    // device bus indices (stereo rows of acc); BUS_U_RUN: scratch bus, wire target
-    int frame, frames;
-    int reg, value, start, dur;
-    int kind;               // BUS_U_*: unit kind (A2CU_*)
-    int run;                // host side: run this command belongs to
-    int pad;
-};
-struct BusRun { unsigned begin, count; };
-
-constexpr int kUnitWords = 64;      // state words reserved per generic unit (fm4: 16 x 4)
-constexpr int kFbdKind = 5;         // A2CU_FBDELAY
-constexpr int kFbdSize = 131072;    // A2FBD_BUFSIZE, fbdelay.c:26
-
-struct BusVmParams {
-    const BusCmd *cmds;
-    const BusRun *runs;     // this level's runs; grid = number of runs
-    int *acc;               // [bus][64][2]
-    int *pmstate;           // [pm][8]
-    int *ustate;            // [unit][kUnitWords]
-    Ctx ctx;                // fmsine points at the global table here
-};
-
-template <class U>
-__device__ __noinline__ void bus_unit_op(const Ctx &ctx, const BusCmd &c, int *st, int *acc, unsigned seed, bool seeded) {
-    U u;
-    const StatePtr sp{st, 1};
-    if (c.op == BUS_U_INIT) {
-        u.load(sp, 0);
-        u.init(ctx, c.value, (unsigned)c.start);
-        u.store(sp, 0);
-        return;
-    }
-    u.load(sp, 0);
-    if (c.op == BUS_U_WRITE) {
-        u.write(ctx, c.reg, c.value, c.start, c.dur);
-        u.store(sp, 0);
-        return;
-    }
-    const bool add = c.add & 1, wire = (c.add & 2) != 0;
-    u.prepare(ctx, c.frames);
-    if (seeded) u.seed(seed);
-    for (int i = 0; i < c.frames; ++i) {
-        int *s = acc + ((size_t)c.in_bus * kMaxFrag + c.frame + i) * 2;
-        const int in0 = s[0], in1 = s[1];
-        int s0 = in0, s1 = in1, o0 = 0, o1 = 0;
-        u.sample(ctx, s0, s1, o0, o1);
-        if (wire) {
-            int *o = acc + ((size_t)c.out_bus * kMaxFrag + c.frame + i) * 2;
-            atomicAdd(o, s0);
-            if (c.nout == 2) atomicAdd(o + 1, s1);
-        } else if (add) {
-            s[0] = wadd(in0, s0);
-            if (c.nout == 2) s[1] = wadd(in1, s1);
-        } else {
-            s[0] = s0;
-            if (c.nout == 2) s[1] = s1;
-        }
-    }
-    u.finish();
-    u.store(sp, 0);
-}
-
-__device__ __noinline__ void bus_unit_dispatch(const Ctx &ctx, const BusCmd &c, int *st, int *acc, unsigned seed,
-                                               bool seeded) {
-    switch (c.kind) {
-    case 1: bus_unit_op<WtOsc<false, false>>(ctx, c, st, acc, seed, seeded); break;
-    case 2:     // panmix normally takes the BUS_PM path; kept for completeness
-        if (c.nin == 1 && c.nout == 1) bus_unit_op<PanMix<1, 1, false, false>>(ctx, c, st, acc, seed, seeded);
-        else if (c.nin == 1) bus_unit_op<PanMix<1, 2, false, false>>(ctx, c, st, acc, seed, seeded);
-        else if (c.nout == 1) bus_unit_op<PanMix<2, 1, false, false>>(ctx, c, st, acc, seed, seeded);
-        else bus_unit_op<PanMix<2, 2, false, false>>(ctx, c, st, acc, seed, seeded);
-        break;
-    case 3:
-        if (c.nin == 1) bus_unit_op<Filter12<1, false, false>>(ctx, c, st, acc, seed, seeded);
-        else bus_unit_op<Filter12<2, false, false>>(ctx, c, st, acc, seed, seeded);
-        break;
-    case 4:
-        if (c.nin == 1) bus_unit_op<WaveShaper<1, false, false>>(ctx, c, st, acc, seed, seeded);
-        else bus_unit_op<WaveShaper<2, false, false>>(ctx, c, st, acc, seed, seeded);
-        break;
-    case 16: bus_unit_op<Fm<1, 0, 0, false, false>>(ctx, c, st, acc, seed, seeded); break;
-    case 17: bus_unit_op<Fm<2, 1, 0, false, false>>(ctx, c, st, acc, seed, seeded); break;
-    case 18: bus_unit_op<Fm<3, 2, 0, false, false>>(ctx, c, st, acc, seed, seeded); break;
-    case 19: bus_unit_op<Fm<4, 2, 0, false, false>>(ctx, c, st, acc, seed, seeded); break;
-    case 20: bus_unit_op<Fm<3, 2, 1, false, false>>(ctx, c, st, acc, seed, seeded); break;
-    case 21: bus_unit_op<Fm<4, 2, 1, false, false>>(ctx, c, st, acc, seed, seeded); break;
-    case 22: bus_unit_op<Fm<2, 1, 2, false, false>>(ctx, c, st, acc, seed, seeded); break;
-    case 23: bus_unit_op<Fm<4, 2, 2, false, false>>(ctx, c, st, acc, seed, seeded); break;
-    default: break;
-    }
-}
-
-// fbdelay (units/fbdelay.c). State words: 0 fbdelay, 1 ldelay, 2 rdelay (frames,
-// converted on the host, fbdelay.c:229-245), 3 drygain, 4 fbgain, 5 lgain,
-// 6 rgain (16:16), 7 bufpos, 8/9 device pointer of the two delay lines
-// [2][kFbdSize] (zeroed by the host at allocation, fbdelay.c:187-188).
-A2CU_DEV void fbd_frame(const BusCmd &c, const int *st, int *b0, int *b1, int *acc, int i, bool wire, bool add) {
-    const unsigned mask = kFbdSize - 1;
-    const unsigned pos = (unsigned)st[7] + (unsigned)i;
-    int *s = acc + ((size_t)c.in_bus * kMaxFrag + c.frame + i) * 2;
-    const int i0 = s[0];
-    const int i1 = c.nin == 2 ? s[1] : i0;
-    // fbdelay.c:86-101 (feedback taps are cross-fed: "reverse stereo")
-    int o0 = mulshr(b1[(pos - (unsigned)st[0]) & mask], st[4], 16);
-    int o1 = mulshr(b0[(pos - (unsigned)st[0]) & mask], st[4], 16);
-    b0[pos & mask] = wadd(i0, o0);
-    b1[pos & mask] = wadd(i1, o1);
-    o0 = wadd(o0, mulshr(b0[(pos - (unsigned)st[1]) & mask], st[5], 16));
-    o1 = wadd(o1, mulshr(b1[(pos - (unsigned)st[2]) & mask], st[6], 16));
-    o0 = wadd(o0, mulshr(i0, st[3], 16));
-    o1 = wadd(o1, mulshr(i1, st[3], 16));
-    if (c.nout == 1) { o0 = wadd(o0, o1) >> 1; o1 = 0; }        // fbdelay.c:110, 119
-    if (wire) {
-        int *o = acc + ((size_t)c.out_bus * kMaxFrag + c.frame + i) * 2;
-        atomicAdd(o, o0);
-        if (c.nout == 2) atomicAdd(o + 1, o1);
-    } else if (add) {
-        s[0] = wadd(s[0], o0);
-        if (c.nout == 2) s[1] = wadd(s[1], o1);
-    } else {
-        s[0] = o0;
-        if (c.nout == 2) s[1] = o1;
-    }
-}
-
-A2CU_DEV void fbd_op(const BusCmd &c, int *st, int *acc, int tid) {
-    if (c.op == BUS_U_INIT) {
-        if (tid == 0) {
-            for (int i = 0; i < 8; ++i) st[i] = 0;
-            st[8] = c.value; st[9] = c.dur;         // delay-line pointer, low / high word
-        }
-        return;
-    }
-    if (c.op == BUS_U_WRITE) {
-        if (tid == 0 && c.reg >= 0 && c.reg < 7) st[c.reg] = c.value;
-        return;
-    }
-    int *b0 = (int *)(((unsigned long long)(unsigned)st[9] << 32) | (unsigned)st[8]);
-    int *b1 = b0 + kFbdSize;
-    const bool add = c.add & 1, wire = (c.add & 2) != 0;
-    const unsigned mask = kFbdSize - 1;
-    bool par = true;        // no tap of this call reads a slot this call writes
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const unsigned d = (unsigned)st[k] & mask;
-        par = par && d >= (unsigned)c.frames && d <= (unsigned)(kFbdSize - c.frames);
-    }
-    if (par) {
-        if (tid < c.frames) fbd_frame(c, st, b0, b1, acc, tid, wire, add);
-    } else if (tid == 0) {
-        for (int i = 0; i < c.frames; ++i) fbd_frame(c, st, b0, b1, acc, i, wire, add);
-    }
-    __syncthreads();
-    if (tid == 0) st[7] = (int)((unsigned)st[7] + (unsigned)c.frames);
-}
-
-__global__ void __launch_bounds__(kMaxFrag) bus_level(const BusVmParams P) {
-    __shared__ MixSeg sg;
-    const int tid = threadIdx.x;
-    int *acc = P.acc;
-    const BusRun run = P.runs[blockIdx.x];
-    unsigned seed = 0;
-    bool seeded = false;
-    for (unsigned ci = run.begin; ci < run.begin + run.count; ++ci) {
-        const BusCmd c = P.cmds[ci];
-        if (c.op >= BUS_U_INIT && c.op <= BUS_U_RUN) {
-            if (c.op == BUS_U_SEED) { seed = (unsigned)c.value; seeded = true; continue; }
-            int *ust = P.ustate + (size_t)c.pm * kUnitWords;
-            if (c.kind == kFbdKind) fbd_op(c, ust, acc, tid);
-            else if (tid == 0) bus_unit_dispatch(P.ctx, c, ust, acc, seed, seeded);
-            if (c.op == BUS_U_RUN) seeded = false;
-            __syncthreads();
-            continue;
-        }
-        if (c.op == BUS_ADD) {
-            if (tid < c.frames) {
-                const int *in = acc + ((size_t)c.in_bus * kMaxFrag + c.frame + tid) * 2;
-                int *out = acc + ((size_t)c.out_bus * kMaxFrag + c.frame + tid) * 2;
-                atomicAdd(out, in[0]);
-                atomicAdd(out + 1, in[1]);
-            }
-            __syncthreads();
-            continue;
-        }
-        int *st = P.pmstate + (size_t)c.pm * 8;
-        if (c.op == BUS_PM_WRITE) {
-            if (tid == 0) {
-                Ramp vol, pan;
-                pm_load(st, vol, pan);
-                ramp_set(c.reg == 0 ? vol : pan, c.value, c.start, c.dur);
-                pm_store(st, vol, pan);
-            }
-            __syncthreads();
-            continue;
-        }
-        if (tid == 0) {
-            Ramp vol, pan;
-            pm_load(st, vol, pan);
-            const bool one = c.nin == 1 && c.nout == 1;     // panmix.c:49-64
-            sg.clamp = !one && (pan.target > 0xffffff || pan.target < -0xffffff ||
-                                pan.value > 0xffffff || pan.value < -0xffffff);
-            ramp_prepare(vol, c.frames);
-            if (!one) ramp_prepare(pan, c.frames);
-            sg.vol = vol.value; sg.dvol = vol.delta;
-            sg.pan = pan.value; sg.dpan = one ? 0 : pan.delta;
-            ramp_run(vol, c.frames);
-            if (!one) ramp_run(pan, c.frames);
-            pm_store(st, vol, pan);
-        }
-        __syncthreads();
-        if (tid < c.frames) {
-            const int f = c.frame + tid;
-            const int *in = acc + ((size_t)c.in_bus * kMaxFrag + f) * 2;
-            int *out = acc + ((size_t)c.out_bus * kMaxFrag + f) * 2;
-            const int i0 = in[0], i1 = in[1];
-            const int v = wadd(sg.vol, wmul(sg.dvol, tid));
-            int r0, r1 = 0;
-            if (c.nin == 1 && c.nout == 1) {
-                r0 = mulshr(i0, v, 24);
-            } else {
-                const int pn = wadd(sg.pan, wmul(sg.dpan, tid));
-                const int vp = mulshr(pn, v, 24);
-                int v0 = wsub(v, vp), v1 = wadd(v, vp);
-                if (sg.clamp) {
-                    const int lim = (int)((unsigned)v << 1);
-                    if (v0 > lim) v0 = lim;
-                    if (v1 > lim) v1 = lim;
-                }
-                if (c.nin == 1) { r0 = mulshr(i0, v0, 24); r1 = mulshr(i0, v1, 24); }
-                else if (c.nout == 1) r0 = (int)(((long long)i0 * v0 + (long long)i1 * v1) >> 25);
-                else { r0 = mulshr(i0, v0, 24); r1 = mulshr(i1, v1, 24); }
-            }
-            if (c.out_bus != c.in_bus) {
-                // another voice's bus (wire-out) or a private row: atomics are safe in both cases
-                if (c.add) { atomicAdd(out, r0); if (c.nout == 2) atomicAdd(out + 1, r1); }
-                else { out[0] = r0; if (c.nout == 2) out[1] = r1; }
-            } else if (c.add) { out[0] = wadd(out[0], r0); if (c.nout == 2) out[1] = wadd(out[1], r1); }
-            else { out[0] = r0; if (c.nout == 2) out[1] = r1; }
-        }
-        __syncthreads();
-    }
 }
 
 }  // namespace a2cu

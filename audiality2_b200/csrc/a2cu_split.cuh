@@ -38,7 +38,6 @@
 
 namespace a2cu {
 
-constexpr int kSplitSegs = 2;
 constexpr int kRing = 4;
 constexpr int kTileStride = 33;     // tile rows are voices; 33 keeps both access patterns conflict-free
 // Warp roles: NH helper warps, one control warp, [one serial warp if FILT].
@@ -129,7 +128,7 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
     bool tab_ready = stage_n == 0;
 
     Ctx c;
-    c.waves = P.waves; c.pool = P.pool; c.cpool = P.cpool; c.ptab = P.ptab; c.fmsine = nullptr;
+    c.waves = P.waves; c.pool = P.pool; c.cpool = P.cpool; c.ptab = P.ptab; c.fmsine = nullptr; c.f12tab = P.f12tab;
     c.samplerate = P.samplerate;
     StatePtr sp{P.state + (valid ? v : 0), P.stride};
 
@@ -461,7 +460,9 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
             M.nsplits = P.nsplits;          // root wake-ups cut the root panmix's segments too
             for (int i = 0; i < kMaxSplits; ++i) M.splits[i] = P.splits[i];
             M.gstate = nullptr; M.rstate = P.fuse_rstate; M.ev = nullptr; M.nev = 0;
-            M.master = P.fuse_master; M.root_stage = P.fuse_root_stage; M.clear = 1;
+            M.master = P.fuse_master; M.root_stage = P.fuse_root_stage; M.clear = 1; M.general = 0;
+            // sharded render: the root bus of all ranks is summed here, through NVLink peer memory
+            if (P.xchg.world > 1) xchg_root_bus(P.xchg, P.acc, P.W, tid, WR::threads);
             root_stage(M, tid, WR::threads, true);
             if (tid == 0) *P.fuse_counter = 0u;     // ready for the next launch
         }

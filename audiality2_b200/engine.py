@@ -69,6 +69,11 @@ SYMBOLS = {
     "a2cu_collect": (_I, [_VP, _I, _VP]),
     "a2cu_set_post_root_stage": (_I, [_VP, _I]),
     "a2cu_apply_root_stage": (_I, [_VP, _VP, _VP, _U, _U, _U64]),
+    "a2cu_xchg_create": (_I, [_VP, _I, _I, _U, _U, _VP]),
+    "a2cu_xchg_connect_ipc": (_I, [_VP, _VP]),
+    "a2cu_xchg_connect_local": (_I, [_VP, C.POINTER(_VP)]),
+    "a2cu_xchg_enable": (_I, [_VP, _I]),
+    "a2cu_xchg_close": (_I, [_VP]),
     "a2cu_launch_count": (_U64, [_VP]),
     "a2cu_split_launch_count": (_U64, [_VP]),
     "a2cu_set_split": (_I, [_VP, _I]),
@@ -80,6 +85,7 @@ SYMBOLS = {
     "a2cu_h2d_bytes": (_U64, [_VP]),
     "a2cu_d2h_bytes": (_U64, [_VP]),
     "a2cu_set_timing": (_I, [_VP, _I]),
+    "a2cu_debug_f12_coeff": (_I, [_VP, _VP, _I, _VP]),
     # drop-in ("block") mode, used by the unit plug-in
     "a2cu_pool_open": (_I, [_VP, C.POINTER(UnitSpec), _I]),
     "a2cu_pool_alloc": (_I, [_VP, _I]),
@@ -211,6 +217,12 @@ class Engine:
     def d2h_bytes(self):
         return self.L.a2cu_d2h_bytes(self.h)
 
+    def debug_f12_coeff(self, cutoff_values):
+        a = np.ascontiguousarray(cutoff_values, dtype=np.int32)
+        out = np.empty_like(a)
+        self._ck(self.L.a2cu_debug_f12_coeff(self.h, a.ctypes.data, a.size, out.ctypes.data))
+        return out
+
     def set_post_root_stage(self, on):
         self.post_root = bool(on)
         self._ck(self.L.a2cu_set_post_root_stage(self.h, int(on)))
@@ -326,6 +338,29 @@ class Engine:
 
     def sync(self):
         self._ck(self.L.a2cu_sync(self.h))
+
+    # -- multi-GPU: root-bus exchange inside the render kernel (a2cu_xchg_*)
+    def xchg_create(self, rank, world, max_frames, timeout_ms=0):
+        """Allocate this rank's symmetric buffer; returns its 64-byte IPC handle."""
+        h = (C.c_ubyte * 64)()
+        self._ck(self.L.a2cu_xchg_create(self.h, rank, world, max_frames, timeout_ms, h))
+        return bytes(h)
+
+    def xchg_connect_ipc(self, handles):
+        """handles: world x 64 bytes in rank order (other processes' buffers)."""
+        buf = b"".join(handles)
+        self._ck(self.L.a2cu_xchg_connect_ipc(self.h, buf))
+
+    def xchg_connect_local(self, engines):
+        """engines[r] = the Engine of rank r, all living in this process."""
+        arr = (_VP * len(engines))(*[e.h for e in engines])
+        self._ck(self.L.a2cu_xchg_connect_local(self.h, arr))
+
+    def xchg_enable(self, on=True):
+        self._ck(self.L.a2cu_xchg_enable(self.h, int(on)))
+
+    def xchg_close(self):
+        self._ck(self.L.a2cu_xchg_close(self.h))
 
     def apply_root_stage(self, dev_rootbus, dev_master, frames, buffer=64):
         self._ck(self.L.a2cu_apply_root_stage(self.h, dev_rootbus, dev_master,

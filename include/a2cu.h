@@ -231,6 +231,33 @@ int a2cu_apply_root_stage(a2cu_engine *e, const int32_t *dev_rootbus,
 		int32_t *dev_master, unsigned frames, unsigned buffer,
 		uint64_t start_time);
 
+/*
+ * Sharded render with the exchange INSIDE the render kernel (no NCCL call, no
+ * extra launch): every rank creates a "symmetric" buffer, the ranks swap its
+ * handle (64 bytes; over torch.distributed, MPI, a pipe ... - plumbing the
+ * caller owns) and map each other's buffers (CUDA IPC between processes, peer
+ * access inside one process). From then on each a2cu_run / a2cu_submit window
+ * ends like this on every rank: the CTA holding the finished root bus stores
+ * it into all peers' buffers over NVLink, releases a flag, waits for the
+ * world's flags, sums the rows and runs the root stage - all ranks obtain the
+ * identical master block (integer sum: bit-identical to one engine rendering
+ * all voices). All ranks must render the same sequence of windows.
+ *   rank, world   0 <= rank < world <= 8
+ *   max_frames    longest window that will be rendered
+ *   timeout_ms    bound of the in-kernel wait for peers (0: 2000); on expiry
+ *                 the window's a2cu_collect / a2cu_sync returns A2CU_ECUDA
+ *   handle_out    64 bytes (cudaIpcMemHandle_t) or NULL
+ */
+int a2cu_xchg_create(a2cu_engine *e, int rank, int world, unsigned max_frames,
+		unsigned timeout_ms, void *handle_out);
+/* handles: world x 64 bytes in rank order (the own entry is ignored). */
+int a2cu_xchg_connect_ipc(a2cu_engine *e, const void *handles);
+/* Engines of ONE process (any devices): peers[r] = the engine of rank r. */
+int a2cu_xchg_connect_local(a2cu_engine *e, a2cu_engine *const *peers);
+/* Turn the exchange off / on again without unmapping (A/B measurements). */
+int a2cu_xchg_enable(a2cu_engine *e, int enabled);
+int a2cu_xchg_close(a2cu_engine *e);
+
 /* Kernel launches issued by this engine so far (bench's gpu_launches). */
 uint64_t a2cu_launch_count(const a2cu_engine *e);
 /*
@@ -262,6 +289,15 @@ uint64_t a2cu_h2d_bytes(const a2cu_engine *e);
 uint64_t a2cu_d2h_bytes(const a2cu_engine *e);
 /* Turn the event timing above on/off (adds three event records per run). */
 int a2cu_set_timing(a2cu_engine *e, int enabled);
+/*
+ * Self-test hook: f12_pitch2coeff (src/units/filter12.c:65-72) as the kernels
+ * evaluate it, for n cutoff ramper values (8:24 fixed point, i.e. what
+ * A2_filter12.cutoff.value holds). The device looks the coefficient up in a
+ * table the host built with its own libm for every possible argument, so the
+ * result must equal the reference's for ALL inputs (tests sweep the domain).
+ */
+int a2cu_debug_f12_coeff(a2cu_engine *e, const int32_t *cutoff_values, int n,
+		int32_t *out);
 
 /* ---- drop-in ("block") mode ------------------------------------------------
  *

@@ -706,6 +706,14 @@ int a2o_f12_coeff(int cutoff_value, int samplerate)
 	return (int)(512.0f * 65536.0f * sin(M_PI * f / samplerate));
 }
 
+/* The same for an array (test sweeps over the whole argument domain) */
+void a2o_f12_coeff_array(const int *cutoff_values, int n, int samplerate, int *out)
+{
+	int i;
+	for(i = 0; i < n; ++i)
+		out[i] = a2o_f12_coeff(cutoff_values[i], samplerate);
+}
+
 /* filter12.c:141-177 */
 static void f12_write(a2o_engine *e, voice *v, st_f12 *f, int reg, int val,
 		unsigned start, unsigned dur)

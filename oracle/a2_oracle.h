@@ -142,6 +142,7 @@ int a2o_hermite(const int16_t *d, unsigned ph);
 int a2o_lerp(const int16_t *d, unsigned ph);
 int a2o_noise(uint32_t *state);
 int a2o_f12_coeff(int cutoff_value_8_24, int samplerate);
+void a2o_f12_coeff_array(const int *cutoff_values, int n, int samplerate, int *out);
 
 #ifdef __cplusplus
 }

@@ -75,8 +75,18 @@ def lib():
         L.a2o_lerp.argtypes = [C.c_void_p, C.c_uint]
         L.a2o_noise.argtypes = [C.POINTER(C.c_uint32)]
         L.a2o_f12_coeff.argtypes = [C.c_int, C.c_int]
+        L.a2o_f12_coeff_array.restype = None
+        L.a2o_f12_coeff_array.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         _lib = L
     return _lib
+
+
+def f12_coeff_array(cutoff_values, samplerate):
+    """f12_pitch2coeff (filter12.c:65-72) of the port, host libm, for an int32 array."""
+    a = np.ascontiguousarray(cutoff_values, dtype=np.int32)
+    out = np.empty_like(a)
+    lib().a2o_f12_coeff_array(a.ctypes.data, a.size, samplerate, out.ctypes.data)
+    return out
 
 
 class Oracle:

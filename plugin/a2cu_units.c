@@ -115,7 +115,7 @@ struct A2CU_voice
 	unsigned	cursor_serial;
 };
 
-typedef struct A2CU_wavemap { A2_wave *w; int id; } A2CU_wavemap;
+typedef struct A2CU_wavemap { A2_wave *w; int id; const void *d0; unsigned s0; } A2CU_wavemap;
 typedef struct A2CU_owner { int32_t **outputs; A2CU_unit *il; } A2CU_owner;
 /* Host-only bus (no inline of ours owns it, e.g. the master) fed by voices */
 typedef struct A2CU_orphan { int32_t **outputs; int bus, nch; } A2CU_orphan;
@@ -270,15 +270,40 @@ static A2CU_unit *owner_find(A2CU_ctx *cx, int32_t **outputs)
 	return NULL;
 }
 
+/*
+ * Device copy of a host wave. The cache is keyed on what the oscillator would
+ * see through a2_GetWave at this moment - the A2_wave object, its level 0 data
+ * pointer and length - so a wave that was released and re-created at the same
+ * address, or re-rendered into new buffers, gets a fresh upload instead of
+ * the stale copy, and a wave unloaded while in use (size[0] == 0,
+ * waves.c:718-724, wtosc_check_unloaded wtosc.c:168-183) is unloaded on the
+ * device too. Called on every `w` register write.
+ */
 static int wave_id(A2CU_ctx *cx, int handle)
 {
 	int i;
 	A2_wave *w = a2_GetWave(cx->cfg->interface, handle);
+	const void *d0 = NULL;
+	unsigned s0 = 0;
 	if(!w)
 		return -1;
+	if(w->type == A2_WWAVE || w->type == A2_WMIPWAVE)
+	{
+		d0 = w->d.wave.data[0];
+		s0 = w->d.wave.size[0];
+	}
 	for(i = 0; i < cx->nwaves; ++i)
 		if(cx->waves[i].w == w)
-			return cx->waves[i].id;
+		{
+			if(cx->waves[i].d0 == d0 && cx->waves[i].s0 == s0)
+				return cx->waves[i].id;
+			/* same object, other contents: retire the device copy */
+			a2cu_wave_unload(cx->eng, cx->waves[i].id);
+			cx->waves[i] = cx->waves[--cx->nwaves];
+			break;
+		}
+	if((w->type == A2_WWAVE || w->type == A2_WMIPWAVE) && !s0)
+		return -1;		/* unloaded: the oscillator turns off */
 	{
 		A2CU_wavemap *nw = (A2CU_wavemap *)realloc(cx->waves,
 				sizeof(A2CU_wavemap) * (cx->nwaves + 1));
@@ -294,6 +319,8 @@ static int wave_id(A2CU_ctx *cx, int handle)
 			return -1;
 		cx->waves[cx->nwaves].w = w;
 		cx->waves[cx->nwaves].id = id;
+		cx->waves[cx->nwaves].d0 = d0;
+		cx->waves[cx->nwaves].s0 = s0;
 		++cx->nwaves;
 		return id;
 	}
@@ -387,9 +414,23 @@ static void classify(A2CU_ctx *cx, A2CU_voice *v, unsigned frame)
 	A2_unit *u;
 	a2cu_unitspec chain[A2CU_MAXCHAIN];
 	int n = 0, fused = 1, i;
-	for(u = hv->units; u; u = u->next)
-		if(!is_ours(u->descriptor) && has_audio_io(u))
-			fused = 0;
+	{
+		/*
+		 * A fused (LEAF) voice records its whole chain at its first unit's
+		 * Process(): that is only the reference's order of effects while
+		 * no host unit sits BEHIND one of ours. A host unit with audio I/O
+		 * needs the buffers; a control-only host unit (env) in mid-chain
+		 * writes our registers between two of our Process() calls
+		 * (core.c:1875-1876, env.c:120-137), which only the unit-by-unit
+		 * (GEN) path reproduces.
+		 */
+		int seen_ours = 0;
+		for(u = hv->units; u; u = u->next)
+			if(is_ours(u->descriptor))
+				seen_ours = 1;
+			else if(has_audio_io(u) || seen_ours)
+				fused = 0;
+	}
 	for(i = 0; i < v->nunits && n < A2CU_MAXCHAIN; ++i, ++n)
 	{
 		A2_unit *h = &v->units[i]->il.header;

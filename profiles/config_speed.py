@@ -4,7 +4,8 @@ import sys, time
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import numpy as np
 from audiality2_b200 import engine as eng
-from scenarios import autowire, fx
+from audiality2_b200.chains import autowire
+from audiality2_b200.workloads import fx
 from cases import _FM_SETTINGS
 
 

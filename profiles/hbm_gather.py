@@ -16,7 +16,7 @@ import time
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import numpy as np
 from audiality2_b200 import engine as eng
-from scenarios import autowire
+from audiality2_b200.chains import autowire
 
 V = int(sys.argv[1]) if len(sys.argv) > 1 else 131072
 NW = int(sys.argv[2]) if len(sys.argv) > 2 else 12

@@ -7,7 +7,7 @@ sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import numpy as np
 from audiality2_b200 import engine as eng
 from audiality2_b200.workloads import cfg2_bank
-from scenarios import autowire
+from audiality2_b200.chains import autowire
 e = eng.Engine(48000, 2); b = cfg2_bank(4096); w = e.builtin_wave('saw')
 bank = e.new_bank(autowire(list(b['kinds'])), 4096)
 e.write_all(bank, 0, 0, [w << 16]); e.write_all(bank, 0, 1, b['pitch']); e.write_all(bank, 0, 2, [b['amp']])

@@ -1,7 +1,7 @@
 import sys; sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
 from audiality2_b200 import engine as eng
 from audiality2_b200.workloads import cfg2_bank
-from scenarios import autowire
+from audiality2_b200.chains import autowire
 import numpy as np
 e=eng.Engine(48000,2); b=cfg2_bank(4096); w=e.builtin_wave('saw')
 bank=e.new_bank(autowire(list(b['kinds'])),4096)

@@ -105,18 +105,7 @@ def additive8():
     return s
 
 
-_FM_SETTINGS = {
-    # (a, fb), then (p, a, fb) per further operator - the shapes used by the
-    # reference's fmtest4 instruments, held for a few ms and then decayed
-    "fm1": [(1.0, 0.5)],
-    "fm2": [(1.0, 0.4), (1.0, 0.8, 0.3)],
-    "fm3": [(1.0, 0.7), (0.99, 0.5, 0.2), (1.01, 1.0, 0.2)],
-    "fm4": [(1.0, 0.3), (1.0, 0.6, 0.2), (2.0, 0.5, 0.1), (3.01, 0.4, 0.3)],
-    "fm3p": [(1.0, 0.7), (0.99, 0.5, 0.2), (1.01, 1.0, 0.2)],
-    "fm4p": [(1.0, 0.5), (1.0, 0.5, 0.2), (1.98, 0.7, 0.5), (3.02, 0.5, 0.3)],
-    "fm2r": [(1.0, 0.9), (1.01, 1.0, 0.8)],
-    "fm4r": [(1.0, 0.6), (1.0, 1.0, 0.7), (1.98, 0.7, 0.5), (3.02, 0.5, 0.3)],
-}
+from audiality2_b200.workloads import FM_SETTINGS as _FM_SETTINGS  # noqa: E402
 
 
 def fm_steps(kind, pitch, vel, pan):

@@ -22,30 +22,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-GENERATORS = {"wtosc", "fm1", "fm2", "fm3", "fm4", "fm3p", "fm4p", "fm2r", "fm4r"}
-FM_OPS = {"fm1": 1, "fm2": 2, "fm3": 3, "fm4": 4, "fm3p": 3, "fm4p": 4,
-          "fm2r": 2, "fm4r": 4}
-# (mininputs, maxinputs, minoutputs, maxoutputs, matchio)
-UNIT_IO = {"panmix": (1, 2, 1, 2, False), "filter12": (1, 2, 1, 2, True),
-           "waveshaper": (1, 2, 1, 2, True)}
-for _g in GENERATORS:
-    UNIT_IO[_g] = (0, 0, 1, 1, False)
-
-REGS = {
-    "wtosc": ["w", "p", "a", "phase"],
-    "panmix": ["vol", "pan"],
-    "filter12": ["cutoff", "q", "lp", "bp", "hp"],
-    "waveshaper": ["amount"],
-}
-for _k, _n in FM_OPS.items():
-    r = ["phase", "p", "a", "fb"]
-    for _o in range(1, _n):
-        r += ["p%d" % _o, "a%d" % _o, "fb%d" % _o]
-    REGS[_k] = r
-
-KIND_CODE = {"wtosc": 1, "panmix": 2, "filter12": 3, "waveshaper": 4,
-             "fm1": 16, "fm2": 17, "fm3": 18, "fm4": 19, "fm3p": 20,
-             "fm4p": 21, "fm2r": 22, "fm4r": 23}
+from audiality2_b200.chains import (GENERATORS, FM_OPS, UNIT_IO, REGS, KIND_CODE,  # noqa: E402,F401
+                                     autowire)
 
 
 ROOT_WAKE_PERIOD = 1000000     # core.c:1195
@@ -61,46 +39,6 @@ def lit(v):
     s = "%.9f" % (v / 65536.0)   # a2_GetNum overflows at 10 decimals (compiler.c:876,889)
     s = s.rstrip("0").rstrip(".")
     return s if s not in ("", "-0") else "0"
-
-
-def autowire(kinds, voice_channels=2):
-    """Default-I/O autowiring of a struct: compiler.c:3036-3138 followed by the
-    instantiation rules of core.c:163-243. Returns a list of
-    (kind, ninputs, noutputs, add, wireout)."""
-    out = []
-    chain = 0
-    n = len(kinds)
-    for i, k in enumerate(kinds):
-        mini, maxi, mino, maxo, matchio = UNIT_IO[k]
-        add = 0
-        if maxi == 0:
-            nin = 0
-            if chain:
-                add = 1
-        else:
-            nin = mini
-            if not chain:
-                raise ValueError("A2_NOINPUT: %s has inputs but no chain" % k)
-            if nin != chain:
-                # default mininputs == 1; a 2-channel chain needs explicit I/O
-                nin = chain
-        dsi = any(UNIT_IO[kk][1] > 0 for kk in kinds[i + 1:])
-        if i == n - 1 or not dsi:
-            wireout = 1
-            add = 1
-            lo, hi = (nin, nin) if matchio else (mino, maxo)
-            nout = min(max(voice_channels, lo), hi)
-            chain = 0
-        else:
-            wireout = 0
-            nout = chain if chain else mino
-            if matchio:
-                nout = nin
-            if chain and not nin:
-                add = 1
-            chain = nout
-        out.append((KIND_CODE[k], nin, nout, add, wireout))
-    return out
 
 
 class Voice:
@@ -133,6 +71,9 @@ class Scenario:
         self.group_fbd = {}       # group -> 7 fbdelay registers (16:16) of a song-level chain
         self.waves = []           # names of builtin waves, index = wave id
         self.uploaded = None      # (type, period, flags, length, seed) of the one sampled wave
+        # writes to the ROOT driver's panmix, (time 24:8, reg, value, dur): only an API client can
+        # do that (a2_Send to the root voice), so these exist for the port and the CUDA engine only
+        self.root_writes = []
 
     def upload(self, wtype, period, flags, length, seed):
         """One pseudo-random sampled wave, uploaded through a2_UploadWave by the reference
@@ -246,6 +187,8 @@ class Scenario:
         # The root voice runs a2_rootdriver, whose program falls into OP_END
         # while attached: it re-arms its wake-up every 1000000 (24:8) time
         # units (core.c:1191-1216), splitting every voice's segments there.
+        for (tw, reg, value, dur) in self.root_writes:
+            ev.append((tw, ao.EV_ROOTWRITE, 0, 0, reg, value, dur))
         t = ROOT_WAKE_PERIOD
         while t < (self.frames << 8):
             ev.append((t, ao.EV_ROOTWRITE, 0, 0, -1, 0, 0))
@@ -475,3 +418,99 @@ def run_cuda(scn, window=None, split=True, stats=None, pipelined=False):
         return out
     finally:
         e.close()
+
+
+def _build_cuda_shard(scn, e, voice_ids):
+    """Create the waves and the voices `voice_ids` of `scn` (root-level voices only) in engine
+    `e` and queue their events. Returns nothing; mirrors run_cuda's setup."""
+    from oracle import a2oracle as ao
+    for w in scn.waves:
+        if isinstance(w, tuple):
+            e.upload_wave(w[0], w[1], w[2], scn.uploaded_data())
+        else:
+            e.builtin_wave(w)
+    assert scn.ngroups == 0, "sharding cuts at the root bus: root-level voices only"
+    chains, where = {}, {}
+    for vi in voice_ids:
+        v = scn.voices[vi]
+        key = tuple(v.kinds)
+        chains.setdefault(key, []).append(v)
+        where[vi] = (key, len(chains[key]) - 1)
+    bank_of = {}
+    for key, vs in chains.items():
+        bank_of[key] = e.new_bank(autowire(list(key)), len(vs),
+                                  transpose=[v.transpose for v in vs])
+    for ev in scn.events():
+        t, kind, tgt = int(ev["time"]), int(ev["kind"]), int(ev["voice"])
+        if kind == ao.EV_WRITE and tgt in where:
+            key, slot = where[tgt]
+            e.write(bank_of[key], slot, int(ev["unit"]), int(ev["reg"]), int(ev["value"]), t,
+                    int(ev["dur"]))
+        elif kind == ao.EV_WAKE and tgt in where:
+            key, slot = where[tgt]
+            e.wake(bank_of[key], slot, t)
+        elif kind == ao.EV_ROOTWRITE and int(ev["reg"]) >= 0:
+            # every shard sees the root's writes: they cut all voices' segments, and the
+            # root panmix runs (identically) on every rank after the exchange
+            e.root_write(int(ev["reg"]), int(ev["value"]), t, int(ev["dur"]))
+
+
+def run_cuda_sharded(scn, nshards=2, window=None, split=True, mode="fused", stats=None):
+    """Render `scn` on `nshards` engines of ONE process (all on cuda:0, one CUDA stream each),
+    voices dealt round-robin, and return every shard's master output.
+      mode "fused": in-kernel exchange over peer memory (a2cu_xchg_*): each window is submitted on
+                    all engines before any is collected - the kernels wait for each other.
+      mode "cut":   set_post_root_stage(0) per shard, host-side integer sum of the raw root buses,
+                    a2cu_apply_root_stage on shard 0 (the library-collective baseline's data path)."""
+    import torch
+    from audiality2_b200 import engine as eng
+    window = window or scn.frames
+    engines, streams = [], []
+    try:
+        for s in range(nshards):
+            e = eng.Engine(scn.samplerate, scn.channels)
+            st = torch.cuda.Stream()
+            e.set_stream(st.cuda_stream)
+            if not split:
+                e.set_split(False)
+            _build_cuda_shard(scn, e, range(s, len(scn.voices), nshards))
+            engines.append(e)
+            streams.append(st)
+        if mode == "fused":
+            for s, e in enumerate(engines):
+                e.xchg_create(s, nshards, window, timeout_ms=5000)
+            for e in engines:
+                e.xchg_connect_local(engines)
+            outs = [[] for _ in engines]
+            done = 0
+            while done < scn.frames:
+                n = min(window, scn.frames - done)
+                tickets = [e.submit(n, scn.buffer) for e in engines]
+                for s, e in enumerate(engines):
+                    outs[s].append(e.collect(tickets[s]))
+                done += n
+            if stats is not None:
+                stats["launches"] = [e.launches for e in engines]
+                stats["split_launches"] = [e.split_launches for e in engines]
+            return [np.concatenate(o, axis=0) for o in outs]
+        assert mode == "cut"
+        for e in engines:
+            e.set_post_root_stage(False)
+        parts, done = [], 0
+        dev = torch.device("cuda", 0)
+        while done < scn.frames:
+            n = min(window, scn.frames - done)
+            raw = [e.run(n, scn.buffer).astype(np.int64) for e in engines]
+            total = sum(raw)
+            total = ((total + 2 ** 31) % 2 ** 32 - 2 ** 31).astype(np.int32)   # int32 wrap-around sum
+            bus = torch.from_numpy(total).to(dev)
+            master = torch.zeros((n, scn.channels), dtype=torch.int32, device=dev)
+            with torch.cuda.stream(streams[0]):
+                engines[0].apply_root_stage(bus.data_ptr(), master.data_ptr(), n, scn.buffer)
+            streams[0].synchronize()
+            parts.append(master.cpu().numpy())
+            done += n
+        return [np.concatenate(parts, axis=0)]
+    finally:
+        for e in engines:
+            e.close()

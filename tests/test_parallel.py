@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from audiality2_b200.parallel import reduce_root_bus, shard_range
+from audiality2_b200.parallel import exchange_handles, reduce_root_bus, shard_range
 
 
 def test_shard_range_partitions():
@@ -35,6 +35,11 @@ def _worker(rank, world, port, q):
     scn.voices = scn.voices[lo:hi]
     part = torch.from_numpy(run_oracle(scn))
     reduce_root_bus(part)
+    # the plumbing of the in-kernel exchange: 64-byte buffer handles, all-gathered in rank order
+    handles = exchange_handles(bytes([rank * 16 + (i % 16) for i in range(64)]))
+    assert len(handles) == world
+    for r, h in enumerate(handles):
+        assert h == bytes([r * 16 + (i % 16) for i in range(64)])
     if rank == 0:
         q.put(part.numpy())
     dist.destroy_process_group()
