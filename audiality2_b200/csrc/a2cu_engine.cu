@@ -286,7 +286,8 @@ struct a2cu_engine {
     BlockStats bs;
     WindowStats ws;
     // environment toggles, read once in a2cu_open (A/B switches for profiles/)
-    bool env_stats = false, env_no_copy_stream = false, env_no_fuse = false, env_no_stage = false;
+    bool env_stats = false, env_no_copy_stream = false, env_no_fuse = false, env_no_stage = false, env_one_set = false;
+    int sm_count = 148;
     int device = 0, samplerate = 48000, channels = 2;
     int basepitch = 0;
     uint32_t msdur = 0;
@@ -750,6 +751,9 @@ a2cu_engine *a2cu_open(int device, int samplerate, int channels) {
     e->env_no_copy_stream = getenv("A2CU_NO_COPY_STREAM") != nullptr;
     e->env_no_fuse = getenv("A2CU_NO_FUSE") != nullptr;
     e->env_no_stage = getenv("A2CU_NO_STAGE") != nullptr;
+    e->env_one_set = getenv("A2CU_ONE_SET") != nullptr;
+    cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e->sm_count <= 0) e->sm_count = 148;
     e->noise_ptr = &e->noiseseed;
     e->device = device;
     e->samplerate = samplerate;
@@ -842,6 +846,7 @@ int a2cu_set_noise_state_ptr(a2cu_engine *e, uint32_t *p) {
 uint64_t a2cu_launch_count(const a2cu_engine *e) { return e->launches; }
 uint64_t a2cu_split_launch_count(const a2cu_engine *e) { return e->split_launches; }
 int a2cu_set_split(a2cu_engine *e, int on) { e->use_split = on != 0; return A2CU_OK; }
+static const size_t kProfWords = 8 + 6 * 64 * 2;    // role counters + timeline of CTA 0 (a2cu_split.cuh)
 int a2cu_split_profile(a2cu_engine *e, int enable, uint64_t out[8]) {
     if (!e) return A2CU_EINVAL;
     cudaSetDevice(e->device);
@@ -850,10 +855,20 @@ int a2cu_split_profile(a2cu_engine *e, int enable, uint64_t out[8]) {
         CK(cudaMemcpy(out, e->d_prof, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     }
     if (enable && !e->d_prof) {
-        CK(cudaMalloc(&e->d_prof, 8 * sizeof(uint64_t)));
+        CK(cudaMalloc(&e->d_prof, kProfWords * sizeof(uint64_t)));
     }
     if (e->d_prof) CK(cudaMemset(e->d_prof, 0, 8 * sizeof(uint64_t)));
     if (!enable && e->d_prof) { cudaFree(e->d_prof); e->d_prof = nullptr; }
+    return A2CU_OK;
+}
+// Timeline of CTA 0 / voice set 0 of the LAST render_split launch while profiling is armed:
+// out[((role * 64 + fragment) * 2 + end)] cycles since the pipeline start; roles 0 control,
+// 1 filter recurrence, 2 / 3 stage A / C of helper 0, 4 / 5 of the last helper. 768 words.
+int a2cu_split_trace(a2cu_engine *e, uint64_t *out) {
+    if (!e || !out || !e->d_prof) return A2CU_EINVAL;
+    cudaSetDevice(e->device);
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(out, e->d_prof + 8, (kProfWords - 8) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return A2CU_OK;
 }
 uint64_t a2cu_h2d_bytes(const a2cu_engine *e) { return e->h2d_bytes; }
@@ -1120,9 +1135,13 @@ static int cook_write(a2cu_engine *e, Bank *b, int voice, int unit, int reg, int
         const HostWave &hw = e->waves[c[0].value];
         size_t total = 0;
         for (int l = 0; l < kMipLevels; ++l) total += hw.data[l].size();
-        if (hw.type != A2CU_WMIPWAVE || total > ((size_t)1 << 20)) b->exotic = true;
+        // render_split evaluates oscillators in closed form: fine for every looped or mip-mapped
+        // wave (coefficient table, or raw taps from the pool for large sampled waves); the shared
+        // noise LCG and the per-sample end check of a one-shot wave above A2_MAXPHINC
+        // (wtosc.c:301-358) need the frame-serial kernel
+        if (hw.type == A2CU_WNOISE || (hw.type == A2CU_WWAVE && !(hw.flags & A2CU_LOOPED))) b->exotic = true;
         if (hw.type == A2CU_WNOISE) e->noise_seen = true;
-        if (hw.type == A2CU_WMIPWAVE) b->stage_wave = c[0].value;
+        if (hw.type == A2CU_WMIPWAVE && total <= ((size_t)1 << 20)) b->stage_wave = c[0].value;
     }
     for (int i = 0; i < n; ++i) push_event(b, when, voice, EV_WRITE, unit, c[i].reg, c[i].value, c[i].dur);
     return A2CU_OK;
@@ -1376,7 +1395,10 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         if (gr) return gr;
     }
     int splits[kMaxSplits], nsplits = 0;
-    if (collect_splits(e, t0, t1, splits, &nsplits)) {
+    // one launch renders at most kSplitMaxWin frames (render_split keeps the CTA's bus sums of the
+    // whole window in shared memory); longer windows are rendered as sub-windows, like windows with
+    // too many root-level cuts for one launch
+    if (frames > (unsigned)kSplitMaxWin || collect_splits(e, t0, t1, splits, &nsplits)) {
         // Too many root-level cuts for one launch: render the window as two sub-windows, each
         // writing its own part of the output block. Cut at a driver-buffer boundary, or - inside
         // one buffer - at a fragment boundary (fragments restart every 64 frames from the buffer
@@ -1581,7 +1603,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             Bank *b = e->banks[bi];
             if (b->dynamic || !b->nvoices || !b->enabled) continue;
             ++live;
-            fuse_bank = (b->k.split_fn && !b->exotic) ? (int)bi : -1;
+            fuse_bank = (b->k.split[0].fn && !b->exotic) ? (int)bi : -1;
         }
         if (live != 1) fuse_bank = -1;
         if (fuse_bank >= 0 && !e->d_fuse_counter) {
@@ -1599,7 +1621,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     for (size_t bi = 0; bi < e->banks.size(); ++bi) {
         Bank *b = e->banks[bi];
         if (b->dynamic || !b->nvoices || !b->enabled) continue;
-        bool split = e->use_split && b->k.split_fn && !b->exotic && nsplits <= 1;
+        bool split = e->use_split && b->k.split[0].fn && !b->exotic && nsplits <= 1;
         std::vector<HostEvent> bulk_probe;      // fast path: all voices share voice 0's event times
         if (fast[bi])
             for (auto &be : b->bulk) {
@@ -1632,18 +1654,22 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         }
         if (split) {
             params[bi].prof = e->d_prof;
-            size_t smem = b->k.split_smem;
+            // two voice sets per CTA once the bank has more 32-voice sets than the chip has SMs
+            int var = (b->k.split[1].fn && b->nvoices > e->sm_count * 32 && !e->env_one_set) ? 1 : 0;
+            size_t smem = b->k.split[var].smem;
             if (b->stage_wave >= 0 && e->waves[b->stage_wave].cbegin >= 0 && !e->env_no_stage) {
                 // whole wave (all mip levels) + read-ahead slack, if it fits beside the pipeline buffers
                 const HostWave &hw = e->waves[b->stage_wave];
                 size_t tb = ((size_t)hw.ccount + 64) * sizeof(int4);
+                if (smem + tb > kMaxSplitSmem && var == 1) { var = 0; smem = b->k.split[0].smem; }
                 if (smem + tb <= kMaxSplitSmem) {
                     params[bi].stage_begin = hw.cbegin;
                     params[bi].stage_count = hw.ccount + 64;
                     smem += tb;
                 }
             }
-            int grid = (b->nvoices + 31) / 32;
+            const SplitVariant &sv = b->k.split[var];
+            int grid = (b->nvoices + sv.voices - 1) / sv.voices;
             if ((int)bi == fuse_bank) {
                 params[bi].fuse_root = 1;
                 params[bi].fuse_counter = e->d_fuse_counter;
@@ -1654,7 +1680,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
                 params[bi].xchg = X;
                 e->fused_root = true;
             }
-            b->k.split_fn<<<grid, b->k.split_threads, smem, e->stream>>>(params[bi]);
+            sv.fn<<<grid, sv.threads, smem, e->stream>>>(params[bi]);
             ++e->split_launches;
         } else {
             int grid = (b->nvoices + kThreads - 1) / kThreads;

@@ -19,6 +19,7 @@ namespace a2cu {
 constexpr int kThreads = 128;
 constexpr int kMaxSplits = 8;
 constexpr int kSplitSegs = 2;      // render_split: segments per voice and fragment (host eligibility check)
+constexpr int kSplitMaxWin = 1024;  // render_split: frames per launch (per-CTA bus accumulator in shared memory)
 
 // Event record, 16 bytes. x = (frame_in_window << 8) | substart
 // y = kind | unit << 8 | reg << 16 ; z = value ; w = duration (24:8)

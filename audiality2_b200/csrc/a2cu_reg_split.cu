@@ -3,26 +3,42 @@
 #include "a2cu_split.cuh"
 using namespace a2cu;
 
-template <int NOSC, bool FILT, int NA>
-static void reg_split(std::vector<a2cu_unitspec> specs) {
-    KernelEntry &e = a2cu_registry()[sig_of(specs.data(), (int)specs.size())];
-    e.split_fn = render_split<NOSC, FILT, NA>;
-    e.split_smem = SplitLayout<NOSC, FILT>::bytes;
-    e.split_threads = SplitWarps<FILT, NA>::threads;
-    cudaFuncSetAttribute(render_split<NOSC, FILT, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+// room the staged Hermite-coefficient table of a builtin 2048-point wave needs (all mip levels)
+static constexpr size_t kTableRoom = 90 * 1024;
+
+template <int NOSC, bool FILT, int NH, int VS, int R>
+static void reg_variant(KernelEntry &e, int slot) {
+    e.split[slot].fn = render_split<NOSC, FILT, NH, VS, R>;
+    e.split[slot].smem = split_smem_bytes<NOSC, FILT, R, VS>();
+    e.split[slot].threads = SplitWarps<FILT, NH, VS>::threads;
+    e.split[slot].voices = 32 * VS;
+    cudaFuncSetAttribute(render_split<NOSC, FILT, NH, VS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)kMaxSplitSmem);
 }
 
+// <oscillators, filter12, helper warps for one set per CTA, helper warps per set for two sets per CTA>
+template <int NOSC, bool FILT, int NH1, int NH2>
+static void reg_split(std::vector<a2cu_unitspec> specs) {
+    KernelEntry &e = a2cu_registry()[sig_of(specs.data(), (int)specs.size())];
+    reg_variant<NOSC, FILT, NH1, 1, 4>(e, 0);
+    // two voice sets: pays where the recurrence warp is the critical path (helpers have slack) and
+    // both sets and the table fit the 227 KB of one CTA
+    if constexpr (!FILT) return;
+    else if constexpr (split_smem_bytes<NOSC, FILT, 4, 2>() + kTableRoom <= kMaxSplitSmem)
+        reg_variant<NOSC, FILT, NH2, 2, 4>(e, 1);
+    else if constexpr (split_smem_bytes<NOSC, FILT, 3, 2>() + kTableRoom <= kMaxSplitSmem)
+        reg_variant<NOSC, FILT, NH2, 2, 3>(e, 1);
+}
+
 void a2cu_register_split() {
-    // <oscillators, filter12, helper warps>: the control warp keeps the whole
-    // voice in registers, so wider voices get fewer warps per CTA
-    reg_split<1, false, 14>({S_OSC0, S_PM12W});
-    reg_split<2, false, 14>({S_OSC0, S_OSCA, S_PM12W});
-    reg_split<3, false, 10>({S_OSC0, S_OSCA, S_OSCA, S_PM12W});
-    reg_split<4, false, 10>({S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_PM12W});
-    reg_split<8, false, 6>({S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_PM12W});
-    // with filter12: 11 (8) helpers + control on sub-partitions 0-2, the recurrence alone on 3
-    reg_split<1, true, 11>({S_OSC0, S_F11, S_PM12W});
-    reg_split<2, true, 11>({S_OSC0, S_OSCA, S_F11, S_PM12W});
-    reg_split<3, true, 8>({S_OSC0, S_OSCA, S_OSCA, S_F11, S_PM12W});
+    // the control warp keeps the whole voice in registers, so wider voices get fewer warps per CTA
+    reg_split<1, false, 14, 7>({S_OSC0, S_PM12W});
+    reg_split<2, false, 14, 7>({S_OSC0, S_OSCA, S_PM12W});
+    reg_split<3, false, 10, 5>({S_OSC0, S_OSCA, S_OSCA, S_PM12W});
+    reg_split<4, false, 10, 5>({S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_PM12W});
+    reg_split<8, false, 6, 3>({S_OSC0, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_OSCA, S_PM12W});
+    // with filter12: helpers + control on sub-partitions 0-2, the recurrence warps alone on 3
+    reg_split<1, true, 11, 5>({S_OSC0, S_F11, S_PM12W});
+    reg_split<2, true, 11, 5>({S_OSC0, S_OSCA, S_F11, S_PM12W});
+    reg_split<3, true, 8, 5>({S_OSC0, S_OSCA, S_OSCA, S_F11, S_PM12W});
 }

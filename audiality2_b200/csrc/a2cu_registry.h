@@ -14,13 +14,20 @@
 #include "a2cu_kernels.cuh"
 
 typedef void (*render_fn)(const a2cu::RenderParams);
+// One instantiation of the warp-specialised kernel (a2cu_split.cuh)
+struct SplitVariant {
+    render_fn fn;           // nullptr: none
+    size_t smem;            // dynamic shared memory without the staged wavetable
+    int threads;
+    int voices;             // voices per CTA (32 x voice sets)
+};
 struct KernelEntry {
     render_fn fn;
     int words;      // incl. the flags word
     const char *name;
-    render_fn split_fn;     // warp-specialised variant (a2cu_split.cuh) or nullptr
-    size_t split_smem;
-    int split_threads;
+    // [0]: one voice set per CTA (small banks: most CTAs, shortest critical path);
+    // [1]: two voice sets per CTA sharing one staged wavetable (large banks: more voices per SM)
+    SplitVariant split[2];
 };
 std::map<std::string, KernelEntry> &a2cu_registry();
 void a2cu_register_bank_wt();      // render_bank<...>: wavetable chains
@@ -43,13 +50,12 @@ static void reg_chain(std::vector<a2cu_unitspec> specs, const char *name) {
     e.fn = a2cu::render_bank<CH>;
     e.words = CH::kWords + 1;
     e.name = name;
-    e.split_fn = nullptr;
-    e.split_smem = 0;
-    e.split_threads = 0;
+    e.split[0] = SplitVariant{nullptr, 0, 0, 0};
+    e.split[1] = SplitVariant{nullptr, 0, 0, 0};
     a2cu_registry()[sig_of(specs.data(), (int)specs.size())] = e;
 }
 // dynamic part; the kernel also has ~4.7 KB static (fused root stage); 227 KB per CTA
-static const size_t kMaxSplitSmem = 222 * 1024;
+static constexpr size_t kMaxSplitSmem = 222 * 1024;
 
 // spec helpers: {kind, nin, nout, add, wireout}
 #define S_OSC0 {A2CU_WTOSC, 0, 1, 0, 0}       /* first generator: replaces scratch */

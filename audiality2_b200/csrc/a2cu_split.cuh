@@ -12,46 +12,59 @@
 // (a2_RunRamper and "ph += dph" are exact modular recurrences, wtosc.c:231-232,
 // a2_dsp.h:152-155), so those two stages are evaluated per FRAME by helper
 // warps while one warp per 32 voices runs the control-rate code and another the
-// filter recurrence. One CTA = 32 voices (lane = voice everywhere, so the SoA
-// state stays coalesced and the bus reduce stays a warp redux.sync):
+// filter recurrence. A CTA renders VS "voice sets" of 32 voices; lane = voice in
+// the control, recurrence and oscillator roles (the SoA state stays coalesced),
+// lane = frame in the panmix / bus role. Roles of one set:
 //
-//   control     (warp NH) events, per-segment prologues (the same unit code as
-//               render_bank: WtOsc/Filter12/PanMix ::write/prepare/finish),
-//               publishes per-segment parameters, advances state in closed form
-//   serial      (warp NH+1) filter12 recurrence (filter12.c:97-118), frame by frame
-//   NH helpers  stage A: oscillator samples -> tile A; lane = voice, frames sliced
-//               stage C: panmix + bus sum <- tile A/B; lane = FRAME, each helper
-//               sums a few voices for 32 frames into a shared-memory bus
-//               (no cross-lane traffic); flushed with one coalesced atomic per
-//               frame and channel one iteration later (stage D)
+//   control     events, per-segment prologues (the same unit code as render_bank:
+//               WtOsc/Filter12/PanMix ::write/prepare/finish), publishes the
+//               per-segment parameters, advances state in closed form
+//   serial      filter12 recurrence (filter12.c:97-118), frame by frame, in place
+//               on the fragment's tile
+//   NH helpers  stage A: oscillator samples -> tile (lane = voice, frames sliced);
+//               taps come from the Hermite-coefficient table staged in shared
+//               memory by TMA, or - large sampled waves - straight from the int16
+//               pool in HBM (closed-form phase: every helper has 2 x slice
+//               independent sector requests in flight per lane)
+//               stage C: panmix + bus sum <- tile (lane = FRAME; each helper sums
+//               a few voices for 32 frames and adds them to the device bus with
+//               one coalesced reduction per channel)
 //
-// The stages form a software pipeline over the window's fragments (ring of 4
-// fragment slots in shared memory, one __syncthreads per fragment):
-//   iteration i:  control(i)  stageA(i-1)  serial(i-2)  stageC(i-3)  flush(i-4)
+// The roles form a pipeline over the window's fragments through a ring of R
+// fragment slots in shared memory. Every edge is an mbarrier per slot
+// (producer arrives, consumer waits on the slot's phase parity):
+//
+//   control --P--> helpers(A) --A--> serial --B--> helpers(C) --C--> control (slot free)
+//
+// so the recurrence warp - the critical path of a filtered voice - runs back to
+// back, one fragment after the other, and nothing ever waits for the slowest
+// warp of the CTA (round 1 used one __syncthreads per fragment: 4 of 19
+// iterations were pipeline fill/drain and every role ran at the pace of the
+// slowest).
 //
 // Eligibility is decided by the host per launch (a2cu_engine.cu): at most
-// kSplitSegs segments per voice and fragment, only waves with a coefficient
-// table, no noise / non-mipmapped waves in the bank. Otherwise render_bank runs
-// on the same state layout. Results are bit-identical (tests).
+// kSplitSegs segments per voice and fragment, no noise / one-shot sampled waves
+// in the bank. Otherwise render_bank runs on the same state layout. Results are
+// bit-identical (tests).
 #pragma once
 #include "a2cu_kernels.cuh"
 
 namespace a2cu {
 
-constexpr int kRing = 4;
-constexpr int kTileStride = 33;     // tile rows are voices; 33 keeps both access patterns conflict-free
-// Warp roles: NH helper warps, one control warp, [one serial warp if FILT].
-// Every helper runs a slice of stage A (lane = voice) and a part of stage C
-// (lane = frame). Warp id % 4 is the SM sub-partition (one issue port each,
-// B300_MICROARCH.md "Instruction issue"): the filter12 recurrence is one long
-// dependent chain, and any other warp on its sub-partition takes issue slots
-// (and holds them while it has independent work), so with FILT the serial
-// warp gets sub-partition 3 to itself: it is the LAST warp (id % 4 == 3), the
-// other warps with id % 4 == 3 stay idle, helpers and the control warp use
-// ids with id % 4 != 3 in ascending order (logical index = id - id / 4).
-template <bool FILT, int NH> struct SplitWarps {
-    static constexpr int rows = (NH + 1 + 2) / 3;               // FILT: groups of 4 warp ids
-    static constexpr int total = FILT ? rows * 4 : NH + 1;
+constexpr int kTileStride = 33;     // tile rows are frames, columns voices; 33 keeps both access patterns conflict-free
+constexpr int kOscWords = 8;        // published per oscillator and segment
+
+// Warp roles. Warp id % 4 is the SM sub-partition (one issue port each,
+// B300_MICROARCH.md "Instruction issue"). The filter12 recurrence is one long
+// dependent chain: any other warp on its sub-partition takes issue slots, so
+// with FILT the serial warps own sub-partition 3 (warp ids 3, 7, ...): the
+// other warps with id % 4 == 3 stay idle, helpers and control warps use the ids
+// with id % 4 != 3 in ascending order (logical index q = id - id / 4).
+// q < VS * NH: helper (set q / NH, index q % NH); then VS control warps.
+template <bool FILT, int NH, int VS> struct SplitWarps {
+    static constexpr int workers = VS * (NH + 1);
+    static constexpr int rows = (workers + 2) / 3 > VS ? (workers + 2) / 3 : VS;     // FILT: groups of 4 warp ids
+    static constexpr int total = FILT ? rows * 4 : workers;
     static constexpr int threads = total * 32;
     static constexpr int slice = (kMaxFrag + NH - 1) / NH;      // stage A: frames per helper
     static constexpr int groups = NH / 2;                       // stage C: voice groups (x 2 frame halves)
@@ -62,68 +75,135 @@ typedef WtOsc<true, false> SOsc;
 typedef Filter12<1, false, false> SFilt;
 typedef PanMix<1, 2, true, true> SPan;
 
-template <int NOSC, bool FILT>
+template <int NOSC, bool FILT, int R>
 struct SplitLayout {
-    // int offsets into dynamic shared memory
-    static constexpr int oscp = 0;                                           // [ring][seg][osc][6][32]
-    static constexpr int fp = oscp + kRing * kSplitSegs * NOSC * 6 * 32;     // [ring][seg][7][32]
-    static constexpr int pmp = fp + (FILT ? kRing * kSplitSegs * 7 * 32 : 0);  // [ring][seg][5][32]
-    static constexpr int split = pmp + kRing * kSplitSegs * 5 * 32;          // [ring][32]
-    static constexpr int flags = split + kRing * 32;                         // [ring][32]
-    static constexpr int meta = flags + kRing * 32;                          // [ring][2]: f0, n
-    static constexpr int bus = meta + kRing * 2;                             // [32] bus of each voice
-    static constexpr int sacc = bus + 32;                                    // [ring][64][2] home-bus sums
-    static constexpr int smeta = sacc + kRing * kMaxFrag * 2;                // [ring][2]: f0, n for the flush
-    static constexpr int tileA = smeta + kRing * 2;                          // [ring][64][33]
-    static constexpr int tileB = tileA + kRing * kMaxFrag * kTileStride;     // [ring][64][33] (FILT)
-    static constexpr int total = tileB + (FILT ? kRing * kMaxFrag * kTileStride : 0);
-    static constexpr int table = (total + 31) & ~31;                         // staged coefficient table (int4)
-    static constexpr size_t bytes = (size_t)table * sizeof(int);            // + 16 B per staged entry
-    static constexpr int words = 1 + 14 * NOSC + (FILT ? 14 : 0) + 8;       // state words per voice
-    static constexpr int filt_w = 1 + 14 * NOSC;                             // first word of filter12
+    // int offsets into one voice set's part of dynamic shared memory
+    static constexpr int oscp = 0;                                               // [R][seg][osc][8][32]
+    static constexpr int fp = oscp + R * kSplitSegs * NOSC * kOscWords * 32;     // [R][seg][7][32]
+    static constexpr int pmp = fp + (FILT ? R * kSplitSegs * 7 * 32 : 0);        // [R][seg][8][32]
+    static constexpr int split = pmp + R * kSplitSegs * 8 * 32;                  // [R][32]
+    static constexpr int flags = split + R * 32;                                 // [R][32]
+    static constexpr int meta = flags + R * 32;                                  // [R][2]: f0, n
+    static constexpr int bus = meta + R * 2;                                     // [32] bus of each voice
+    static constexpr int tile = ((bus + 32) + 31) & ~31;                         // [R][64][33]
+    static constexpr int set_ints = ((tile + R * kMaxFrag * kTileStride) + 31) & ~31;
+    static constexpr int words = 1 + 14 * NOSC + (FILT ? 14 : 0) + 8;           // state words per voice
+    static constexpr int filt_w = 1 + 14 * NOSC;                                 // first word of filter12
     static constexpr int pm_w = filt_w + (FILT ? 14 : 0);
 };
+// Each voice set's contribution to its home bus is accumulated in shared memory over the WHOLE
+// window ([kSplitMaxWin][2] ints per set) and goes to the device bus once, at the end of the launch. The root bus
+// is a handful of cache lines that every CTA of the grid adds into and L2 serialises same-line
+// atomics (~20 cycles per 128-byte request): flushing per fragment made every CTA wait ~2.8 k
+// cycles per fragment for the other 127 (profiles/r02_split_timeline_*.txt).
+template <int NOSC, bool FILT, int R, int VS>
+constexpr size_t split_smem_bytes() {     // + 16 B per staged table entry
+    return (size_t)VS * (SplitLayout<NOSC, FILT, R>::set_ints + kSplitMaxWin * 2) * sizeof(int);
+}
 
-template <int NOSC, bool FILT, int NA>
-__global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(const RenderParams P) {
-    typedef SplitLayout<NOSC, FILT> L;
-    typedef SplitWarps<FILT, NA> WR;
+A2CU_DEV void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// filter12.c:97-118 over frames [a, b) of one voice, in place on its tile column. Inputs are
+// fetched eight frames ahead of the dependent chain. (Tried and measured slower on the B200:
+// volatile loads/stores to pin the prefetch before the chain, 4.6 k instead of 3.7 k cycles per
+// fragment; taking (in>>5) - (q*d1s>>8) off the chain - ptxas already schedules the two shift-adds
+// behind l well, the explicit form only adds an instruction.)
+template <bool RAMP>
+A2CU_DEV void filter_run(int *t, int a, int b, int &d1, int &d2, int f0v, int df, int qv, int qstep,
+                         int lp, int bp, int hp) {
+    int fc = f0v >> 12, qq = qv >> 12;
+    auto step = [&](int in) -> int {
+        const int d1s = d1 >> 4;
+        const int l = wadd(d2, wmul(fc, d1s) >> 8);
+        const int h = wsub(wsub(in >> 5, wmul(qq, d1s) >> 8), l);
+        const int bb = wadd(wmul(fc, h >> 4) >> 8, d1);
+        const int out = wadd(wadd(wmul(l, lp), wmul(bb, bp)), wmul(h, hp)) >> 3;
+        d1 = bb; d2 = l;
+        if (RAMP) {
+            f0v = wadd(f0v, df); qv = wadd(qv, qstep);
+            fc = f0v >> 12; qq = qv >> 12;
+        }
+        return out;
+    };
+    int f = a;
+    if (f + 8 <= b) {
+        int cur[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cur[k] = t[(f + k) * kTileStride];
+        while (true) {
+            const bool more = f + 16 <= b;
+            int nxt[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) nxt[k] = more ? t[(f + 8 + k) * kTileStride] : 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t[(f + k) * kTileStride] = step(cur[k]);
+            f += 8;
+            if (!more) break;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
+        }
+    }
+    for (; f < b; ++f) t[f * kTileStride] = step(t[f * kTileStride]);
+}
+
+template <int NOSC, bool FILT, int NH, int VS, int R>
+__global__ void __launch_bounds__(SplitWarps<FILT, NH, VS>::threads) render_split(const RenderParams P) {
+    typedef SplitLayout<NOSC, FILT, R> L;
+    typedef SplitWarps<FILT, NH, VS> WR;
     constexpr int kSlice = WR::slice;
-    extern __shared__ __align__(128) int sm[];
-    __shared__ __align__(8) unsigned long long s_mbar;
+    extern __shared__ __align__(128) int sm_all[];
+    __shared__ __align__(8) unsigned long long s_mbar;               // table staging (TMA)
+    __shared__ __align__(8) unsigned long long s_bar[VS][4][R];     // P, A, B, C per slot
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long t_entry = P.prof ? clock64() : 0;
-    // logical role index (see SplitWarps): helpers 0..NA-1, control NA; -1 = idle
-    const int hq = FILT ? ((warp & 3) == 3 ? -1 : warp - (warp >> 2)) : warp;
-    const bool is_helper = hq >= 0 && hq < NA;
-    const bool is_ctl = hq == NA;
-    const bool is_ser = FILT && warp == WR::total - 1;
-    const int v = blockIdx.x * 32 + lane;
+    // ---- role of this warp ----
+    const int q = FILT ? ((warp & 3) == 3 ? -1 : warp - (warp >> 2)) : warp;
+    const bool is_helper = q >= 0 && q < VS * NH;
+    const bool is_ctl = q >= VS * NH && q < VS * (NH + 1);
+    const bool is_ser = FILT && (warp & 3) == 3 && (warp >> 2) < VS;
+    const int set = is_helper ? q / NH : is_ctl ? q - VS * NH : is_ser ? (warp >> 2) : 0;
+    const int hq = is_helper ? q % NH : -1;
+    int *sm = sm_all + set * L::set_ints;
+    unsigned long long *barP = s_bar[set][0], *barA = s_bar[set][1], *barB = s_bar[set][2], *barC = s_bar[set][3];
+    const int v = (blockIdx.x * VS + set) * 32 + lane;
     const bool valid = v < P.nvoices;
     const int W = P.W;
 
     int nfrag = 0;
     for (int f = 0; f < W; f = frag_end(f, P.buffer, W)) ++nfrag;
     const int mybus = valid ? P.bus_of[v] : -1;
-    const int home = __shfl_sync(0xffffffffu, mybus, 0);
+    // home bus of a voice set: the bus of its first voice
+    const int home = (blockIdx.x * VS + set) * 32 < P.nvoices ? P.bus_of[(blockIdx.x * VS + set) * 32] : -1;
     if (is_ctl) sm[L::bus + lane] = mybus;
-    for (int i = tid; i < kRing * kMaxFrag * 2; i += WR::threads) sm[L::sacc + i] = 0;
-    // Stage the bank's wavetable (Hermite coefficient form, all mip levels) into
-    // shared memory: one elected thread arms an mbarrier with the byte count and
-    // issues TMA bulk copies; the helper warps wait on it before their first gather.
-    const int4 *s_tab = reinterpret_cast<const int4 *>(sm + L::table);
+    int *wacc_all = sm_all + VS * L::set_ints;              // [VS][kSplitMaxWin][2] home-bus sums
+    for (int i = tid; i < VS * kSplitMaxWin * 2; i += WR::threads) wacc_all[i] = 0;
+    int *wacc = wacc_all + set * kSplitMaxWin * 2;
+    // Stage the bank's wavetable (Hermite coefficient form, all mip levels) into shared memory:
+    // one elected thread arms an mbarrier with the byte count and issues TMA bulk copies; the
+    // helper warps wait on it before their first gather.
+    int *sm_table = wacc_all + VS * kSplitMaxWin * 2;
+    const int4 *s_tab = reinterpret_cast<const int4 *>(sm_table);
     const int stage_n = P.stage_count;
-    if (stage_n) {
-        if (tid == 0) mbar_init(&s_mbar, 1);
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned total_b = (unsigned)stage_n * 16u;
-            mbar_expect_tx(&s_mbar, total_b);
-            const char *src = reinterpret_cast<const char *>(P.cpool + P.stage_begin);
-            char *dst = reinterpret_cast<char *>(sm + L::table);
-            for (unsigned off = 0; off < total_b; off += 32768u)
-                tma_bulk_g2s(dst + off, src + off, min(32768u, total_b - off), &s_mbar);
-        }
+    if (tid == 0) {
+        if (stage_n) mbar_init(&s_mbar, 1);
+        for (int s = 0; s < VS; ++s)
+            for (int k = 0; k < R; ++k) {
+                mbar_init(&s_bar[s][0][k], 1);          // P: control
+                mbar_init(&s_bar[s][1][k], NH);         // A: every helper
+                mbar_init(&s_bar[s][2][k], 1);          // B: serial
+                mbar_init(&s_bar[s][3][k], NH);         // C: every helper
+            }
+    }
+    __syncthreads();
+    if (stage_n && tid == 0) {
+        const unsigned total_b = (unsigned)stage_n * 16u;
+        mbar_expect_tx(&s_mbar, total_b);
+        const char *src = reinterpret_cast<const char *>(P.cpool + P.stage_begin);
+        char *dst = reinterpret_cast<char *>(sm_table);
+        for (unsigned off = 0; off < total_b; off += 32768u)
+            tma_bulk_g2s(dst + off, src + off, min(32768u, total_b - off), &s_mbar);
     }
     bool tab_ready = stage_n == 0;
 
@@ -131,42 +211,41 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
     c.waves = P.waves; c.pool = P.pool; c.cpool = P.cpool; c.ptab = P.ptab; c.fmsine = nullptr; c.f12tab = P.f12tab;
     c.samplerate = P.samplerate;
     StatePtr sp{P.state + (valid ? v : 0), P.stride};
-
-    // ---- control warp state ----
-    SOsc osc[NOSC];
-    SFilt filt;
-    SPan pm;
-    int alive = 0;
-    unsigned evp = 0, eve = 0;
-    int next_ev = 0x7fffffff, seg_end = 0;
-    bool in_seg = false;
-    int cf0 = 0;
-    // ---- serial warp state ----
-    int d1 = 0, d2 = 0;
-
-    if (is_ctl && valid) {
-        alive = sp.ld(0) & 1;
-#pragma unroll
-        for (int i = 0; i < NOSC; ++i) osc[i].load(sp, 1 + 14 * i);
-        if (FILT) filt.load(sp, L::filt_w);
-        pm.load(sp, L::pm_w);
-        if (P.ev_off) { evp = P.ev_off[v]; eve = P.ev_off[v + 1]; }
-        next_ev = evp < eve ? (int)(P.ev[evp].x >> 8) : 0x7fffffff;
-    }
-    if (is_ser && valid) {
-        d1 = sp.ld(L::filt_w + 12);
-        d2 = sp.ld(L::filt_w + 13);
-    }
-
-    const int lag_c = FILT ? 3 : 2;     // stage C runs this many iterations behind control
     const long long t_loop = P.prof ? clock64() : 0;
-    for (int it = 0; it < nfrag + lag_c + 1; ++it) {
-        long long t_begin = 0, t_mid = 0;
-        if (P.prof) t_begin = clock64();
-        // ================= control(it) =================
-        if (is_ctl && it < nfrag) {
-            const int slot = it % kRing;
-            const int f0 = cf0;
+    long long busy = 0, busy2 = 0;
+    // timeline of CTA 0 / set 0 (a2cu_split_trace): prof[8 + ((role * 64 + fragment) * 2 + end)]
+    // roles: 0 control, 1 serial, 2 / 3 stage A / C of helper 0, 4 / 5 of the last helper
+    auto trace = [&](int role, int frag, int end) {
+        if (P.prof && blockIdx.x == 0 && set == 0 && lane == 0 && frag < 64)
+            P.prof[8 + ((role * 64 + frag) * 2 + end)] = (unsigned long long)(clock64() - t_loop);
+    };
+
+    // =====================================================================================
+    // control: events, prologues, publish
+    // =====================================================================================
+    if (is_ctl) {
+        SOsc osc[NOSC];
+        SFilt filt;
+        SPan pm;
+        int alive = 0;
+        unsigned evp = 0, eve = 0;
+        int next_ev = 0x7fffffff;
+        bool in_seg = false;
+        if (valid) {
+            alive = sp.ld(0) & 1;
+#pragma unroll
+            for (int i = 0; i < NOSC; ++i) osc[i].load(sp, 1 + 14 * i);
+            if (FILT) filt.load(sp, L::filt_w);
+            pm.load(sp, L::pm_w);
+            if (P.ev_off) { evp = P.ev_off[v]; eve = P.ev_off[v + 1]; }
+            next_ev = evp < eve ? (int)(P.ev[evp].x >> 8) : 0x7fffffff;
+        }
+        int f0 = 0;
+        for (int it = 0; it < nfrag; ++it) {
+            const int slot = it % R;
+            if (it >= R) mbar_wait(&barC[slot], ((it / R) - 1) & 1);       // slot free again
+            const long long tb = P.prof ? clock64() : 0;
+            trace(0, it, 0);
             const int fe = frag_end(f0, P.buffer, W);
             int split = fe - f0, flags = 0;
             if (valid) {
@@ -207,7 +286,6 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
                     int nxt = min(fe, next_ev);
                     for (int k = 0; k < P.nsplits; ++k)
                         if (P.splits[k] > f) nxt = min(nxt, P.splits[k]);
-                    seg_end = nxt;
                     in_seg = alive != 0;
                     const int n = nxt - f;
                     if (in_seg) {
@@ -222,29 +300,52 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
                         const int sb = (slot * kSplitSegs + seg);
 #pragma unroll
                         for (int i = 0; i < NOSC; ++i) {
-                            int *q = sm + L::oscp + ((sb * NOSC + i) * 6) * 32 + lane;
-                            const bool live = in_seg && osc[i].run == RUN_TABLE && osc[i].cf;
-                            q[0] = live ? (int)(osc[i].cf - c.cpool) : -1;
-                            q[32] = (int)(unsigned)osc[i].ph;
-                            q[64] = (int)(unsigned)(osc[i].ph >> 32);
-                            q[96] = (int)osc[i].dph;
-                            q[128] = osc[i].a.value;
-                            q[160] = osc[i].astep;
-                            if (live) {     // wtosc.c:231-232 over n frames
+                            int *o = sm + L::oscp + ((sb * NOSC + i) * kOscWords) * 32 + lane;
+                            // mode 0: silent; 1: coefficient table; 2: raw int16 taps; 3: raw taps, wrapped per sample
+                            int mode = 0;
+                            if (in_seg && osc[i].plain())
+                                mode = osc[i].run == RUN_CHECK_LOOP ? 3 : (osc[i].cf ? 1 : 2);
+                            o[0] = mode == 1 ? (int)(osc[i].cf - c.cpool) : mode ? (int)(osc[i].d - c.pool) : 0;
+                            o[32] = (int)(unsigned)osc[i].ph;
+                            o[64] = (int)(unsigned)(osc[i].ph >> 32);
+                            o[96] = (int)osc[i].dph;
+                            o[128] = osc[i].a.value;
+                            o[160] = osc[i].astep;
+                            o[192] = mode;
+                            o[224] = (int)osc[i].wsize;
+                            if (mode == 3) {
+                                // wtosc.c:301-358, wrapped loop: sample k reads at (ph + k dph) mod M and the
+                                // accumulator is left one increment past the last (reduced) read position
+                                const unsigned long long M = (unsigned long long)osc[i].wsize << 24;
+                                osc[i].ph = (osc[i].ph + (unsigned long long)osc[i].dph * (unsigned)(n - 1)) % M + osc[i].dph;
+                                osc[i].a.value = wadd(osc[i].a.value, wmul(osc[i].astep, n));
+                            } else if (mode) {          // wtosc.c:231-232 over n frames
                                 osc[i].ph += (unsigned long long)osc[i].dph * (unsigned)n;
                                 osc[i].a.value = wadd(osc[i].a.value, wmul(osc[i].astep, n));
                             }
                         }
                         if (FILT) {
-                            int *q = sm + L::fp + (sb * 7) * 32 + lane;
-                            q[0] = filt.f0; q[32] = filt.df; q[64] = filt.q.value; q[96] = filt.qstep;
-                            q[128] = filt.lp; q[160] = filt.bp; q[192] = filt.hp;
+                            int *o = sm + L::fp + (sb * 7) * 32 + lane;
+                            o[0] = filt.f0; o[32] = filt.df; o[64] = filt.q.value; o[96] = filt.qstep;
+                            o[128] = filt.lp; o[160] = filt.bp; o[192] = filt.hp;
                             if (in_seg) filt.q.value = wadd(filt.q.value, wmul(filt.qstep, n));
                         }
                         {
-                            int *q = sm + L::pmp + (sb * 5) * 32 + lane;
-                            q[0] = pm.vol.value; q[32] = pm.vstep; q[64] = pm.pan.value; q[96] = pm.pstep;
-                            q[128] = pm.clamp ? 1 : 0;
+                            int *o = sm + L::pmp + (sb * 8) * 32 + lane;
+                            o[0] = pm.vol.value; o[32] = pm.vstep; o[64] = pm.pan.value; o[96] = pm.pstep;
+                            o[128] = pm.clamp ? 1 : 0;
+                            // gains at rest (the usual case): the two channel gains of panmix.c:78-115
+                            // are the same for every frame of the segment - computed here once per
+                            // voice (lane = voice) instead of per frame and voice in stage C
+                            const bool rest = pm.vstep == 0 && pm.pstep == 0;
+                            const int vp = mulshr(pm.pan.value, pm.vol.value, 24);
+                            int g0 = wsub(pm.vol.value, vp), g1 = wadd(pm.vol.value, vp);
+                            if (pm.clamp) {
+                                const int lim = (int)((unsigned)pm.vol.value << 1);
+                                if (g0 > lim) g0 = lim;
+                                if (g1 > lim) g1 = lim;
+                            }
+                            o[160] = g0; o[192] = g1; o[224] = rest ? 1 : 0;
                             if (in_seg) {
                                 pm.vol.value = wadd(pm.vol.value, wmul(pm.vstep, n));
                                 pm.pan.value = wadd(pm.pan.value, wmul(pm.pstep, n));
@@ -257,197 +358,273 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NA>::threads) render_split(co
                 }
             }
             sm[L::split + slot * 32 + lane] = split;
-            sm[L::flags + slot * 32 + lane] = flags;
+            // stage C reads one word per voice: split | flags << 8 | (mixes into the CTA's home bus) << 16
+            sm[L::flags + slot * 32 + lane] = flags | (split << 8) | ((valid && mybus == home) ? 1 << 16 : 0);
             if (lane == 0) { sm[L::meta + slot * 2] = f0; sm[L::meta + slot * 2 + 1] = fe - f0; }
-            cf0 = fe;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&barP[slot]);
+            trace(0, it, 1);
+            f0 = fe;
+            if (P.prof) busy += clock64() - tb;
         }
-        // ================= serial(it - 2): filter12 recurrence =================
-        if (is_ser && it >= 2 && it - 2 < nfrag) {
-            const int slot = (it - 2) % kRing;
+        if (valid) {
+            if (in_seg) {
+#pragma unroll
+                for (int i = 0; i < NOSC; ++i) osc[i].finish();
+                if (FILT) filt.finish();
+                pm.finish();
+            }
+            sp.st(0, alive);
+#pragma unroll
+            for (int i = 0; i < NOSC; ++i) osc[i].store(sp, 1 + 14 * i);
+            if (FILT) {
+                // d1 / d2 belong to the serial warp: store everything but them
+                sp.st_ramp(L::filt_w, filt.cutoff); sp.st_ramp(L::filt_w + 4, filt.q);
+                sp.st(L::filt_w + 8, filt.lp); sp.st(L::filt_w + 9, filt.bp); sp.st(L::filt_w + 10, filt.hp);
+                sp.st(L::filt_w + 11, filt.f1);
+            }
+            pm.store(sp, L::pm_w);
+        }
+        // a staged copy still in flight may not outlive the CTA
+        if (stage_n && set == 0 && lane == 0) mbar_wait(&s_mbar, 0);
+    }
+
+    // =====================================================================================
+    // serial: filter12 recurrence, in place on the tile
+    // =====================================================================================
+    if (is_ser) {
+        int d1 = 0, d2 = 0;
+        if (valid) { d1 = sp.ld(L::filt_w + 12); d2 = sp.ld(L::filt_w + 13); }
+        for (int it = 0; it < nfrag; ++it) {
+            const int slot = it % R, par = (it / R) & 1;
+            const long long tw = P.prof ? clock64() : 0;
+            // A implies P: every helper acquired P before it wrote its part of the tile and released A
+            mbar_wait(&barA[slot], par);
+            const long long tb = P.prof ? clock64() : 0;
+            trace(1, it, 0);
             const int n = sm[L::meta + slot * 2 + 1];
             const int split = sm[L::split + slot * 32 + lane];
-            const int flags = sm[L::flags + slot * 32 + lane];
-            const int *ta = sm + L::tileA + slot * kMaxFrag * kTileStride + lane;
-            int *tb = sm + L::tileB + slot * kMaxFrag * kTileStride + lane;
+            const int flags = sm[L::flags + slot * 32 + lane] & 0xff;
+            int *t = sm + L::tile + slot * kMaxFrag * kTileStride + lane;
             for (int seg = 0; seg < kSplitSegs; ++seg) {
                 const int a = seg ? split : 0, b = seg ? n : min(split, n);
-                if (a >= b) continue;
-                if (!((flags >> seg) & 1)) continue;    // inactive: state frozen, output unused
-                const int *q = sm + L::fp + ((slot * kSplitSegs + seg) * 7) * 32 + lane;
-                int f0v = q[0];
-                const int df = q[32];
-                int qv = q[64];
-                const int qstep = q[96], lp = q[128], bp = q[160], hp = q[192];
-#pragma unroll 4
-                for (int f = a; f < b; ++f) {           // filter12.c:97-118
-                    const int fc = f0v >> 12, qq = qv >> 12;
-                    const int in = ta[f * kTileStride];
-                    const int d1s = d1 >> 4;
-                    const int l = wadd(d2, wmul(fc, d1s) >> 8);
-                    // (in>>5) - l - (q*d1s>>8). ptxas turns this into two shift-adds after l
-                    // (LEA.HI.SX32); forcing "t = (in>>5) - q-term off the chain, h = t - l" with an
-                    // inline PTX sub puts an IMAD.IADD on the other pipe and measured 5 % SLOWER.
-                    const int h = wsub(wsub(in >> 5, wmul(qq, d1s) >> 8), l);
-                    const int bb = wadd(wmul(fc, h >> 4) >> 8, d1);
-                    tb[f * kTileStride] = wadd(wadd(wmul(l, lp), wmul(bb, bp)), wmul(h, hp)) >> 3;
-                    d1 = bb; d2 = l;
-                    f0v = wadd(f0v, df);
-                    qv = wadd(qv, qstep);
-                }
+                const bool live = a < b && ((flags >> seg) & 1);     // inactive: state frozen, output unused
+                const int *o = sm + L::fp + ((slot * kSplitSegs + seg) * 7) * 32 + lane;
+                const int df = o[32], qstep = o[96];
+                const bool ramp = live && (df != 0 || qstep != 0);
+                // warp-uniform choice: the constant-coefficient loop is the common case
+                if (__any_sync(0xffffffffu, ramp)) {
+                    if (live) filter_run<true>(t, a, b, d1, d2, o[0], df, o[64], qstep, o[128], o[160], o[192]);
+                } else if (live)
+                    filter_run<false>(t, a, b, d1, d2, o[0], 0, o[64], 0, o[128], o[160], o[192]);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&barB[slot]);
+            trace(1, it, 1);
+            if (P.prof) { busy += clock64() - tb; busy2 += tb - tw; }
         }
-        // ================= stage A(it - 1): oscillators, lane = voice, frames sliced =================
-        if (is_helper && it >= 1 && it - 1 < nfrag) {
-            const int h = hq;
-            const int slot = (it - 1) % kRing;
-            const int n = sm[L::meta + slot * 2 + 1];
-            const int split = sm[L::split + slot * 32 + lane];
-            const int flags = sm[L::flags + slot * 32 + lane];
-            int *ta = sm + L::tileA + slot * kMaxFrag * kTileStride + lane;
-            const int s0 = h * kSlice, s1 = min(n, s0 + kSlice);
-            for (int seg = 0; seg < kSplitSegs; ++seg) {
-                const int sa = seg ? split : 0;
-                const int a = max(s0, sa), b = min(s1, seg ? n : split);
-                if (a >= b) continue;
-                int acc[kSlice];
+        if (valid) {       // the recurrence state lives here
+            sp.st(L::filt_w + 12, d1);
+            sp.st(L::filt_w + 13, d2);
+        }
+    }
+
+    // =====================================================================================
+    // helpers: stage A (oscillators) of fragment it, stage C (panmix + bus) of fragment it - 1
+    // =====================================================================================
+    if (is_helper) {
+        for (int it = 0; it <= nfrag; ++it) {
+            // ---------------- stage A(it): lane = voice, frames sliced ----------------
+            if (it < nfrag) {
+                const int slot = it % R, par = (it / R) & 1;
+                mbar_wait(&barP[slot], par);
+                const long long tb = P.prof ? clock64() : 0;
+                if (hq == 0) trace(2, it, 0);
+                if (hq == NH - 1) trace(4, it, 0);
+                const int n = sm[L::meta + slot * 2 + 1];
+                const int split = sm[L::split + slot * 32 + lane];
+                const int flags = sm[L::flags + slot * 32 + lane] & 0xff;
+                int *ta = sm + L::tile + slot * kMaxFrag * kTileStride + lane;
+                const int s0 = hq * kSlice, s1 = min(n, s0 + kSlice);
+                for (int seg = 0; seg < kSplitSegs; ++seg) {
+                    const int sa = seg ? split : 0;
+                    const int a = max(s0, sa), b = min(s1, seg ? n : split);
+                    if (a >= b) continue;
+                    int acc[kSlice];
 #pragma unroll
-                for (int k = 0; k < kSlice; ++k) acc[k] = 0;
-                if ((flags >> seg) & 1) {
+                    for (int k = 0; k < kSlice; ++k) acc[k] = 0;
+                    if ((flags >> seg) & 1) {
 #pragma unroll 1
-                    for (int i = 0; i < NOSC; ++i) {    // not unrolled: keeps the hot loop in the I-cache
-                        const int *q = sm + L::oscp + (((slot * kSplitSegs + seg) * NOSC + i) * 6) * 32 + lane;
-                        const int cfo = q[0];
-                        if (cfo < 0) continue;          // silent segment of this oscillator
-                        if (!tab_ready) { mbar_wait(&s_mbar, 0); tab_ready = true; }
-                        const int srel = cfo - P.stage_begin;
-                        // generic pointer: the staged copy in shared memory or the pool in global memory
-                        const int4 *cf = (srel >= 0 && srel < stage_n - 64) ? s_tab + srel : c.cpool + cfo;
-                        const unsigned dph = (unsigned)q[96];
-                        unsigned long long ph = ((unsigned long long)(unsigned)q[64] << 32) | (unsigned)q[32];
-                        ph += (unsigned long long)dph * (unsigned)(a - sa);
-                        const int astep = q[160];
-                        const int av0 = wadd(q[128], wmul(astep, a - sa));
-                        const unsigned half = dph >> 17;
-                        // all kSlice frames are evaluated (independent chains the
-                        // scheduler can overlap); frames past the segment end read
-                        // table slack and are dropped at the store (wtosc.c:226-233)
+                        for (int i = 0; i < NOSC; ++i) {    // not unrolled: keeps the hot loop in the I-cache
+                            const int *o = sm + L::oscp + (((slot * kSplitSegs + seg) * NOSC + i) * kOscWords) * 32 + lane;
+                            const int mode = o[192];
+                            if (!mode) continue;            // silent segment of this oscillator
+                            const unsigned dph = (unsigned)o[96];
+                            unsigned long long ph = ((unsigned long long)(unsigned)o[64] << 32) | (unsigned)o[32];
+                            const int astep = o[160];
+                            const int av0 = wadd(o[128], wmul(astep, a - sa));
+                            const unsigned half = dph >> 17;
+                            if (mode == 1) {
+                                if (!tab_ready) { mbar_wait(&s_mbar, 0); tab_ready = true; }
+                                const int cfo = o[0];
+                                const int srel = cfo - P.stage_begin;
+                                // generic pointer: the staged copy in shared memory or the pool in global memory
+                                const int4 *cf = (srel >= 0 && srel < stage_n - 64) ? s_tab + srel : c.cpool + cfo;
+                                ph += (unsigned long long)dph * (unsigned)(a - sa);
+                                // all kSlice frames are evaluated (independent chains the scheduler can
+                                // overlap); frames past the segment end read table slack and are dropped
+                                // at the store (wtosc.c:226-233)
 #pragma unroll
-                        for (int k = 0; k < kSlice; ++k) {
-                            const unsigned p16 = (unsigned)((ph + (unsigned long long)dph * (unsigned)k) >> 16);
-                            const int hv = hermite_cf_smem(cf, p16) + hermite_cf_smem(cf, p16 + half);
-                            acc[k] = wadd(acc[k], mulshr(hv, wadd(av0, wmul(astep, k)), 17));
+                                for (int k = 0; k < kSlice; ++k) {
+                                    const unsigned p16 = (unsigned)((ph + (unsigned long long)dph * (unsigned)k) >> 16);
+                                    const int hv = hermite_cf_smem(cf, p16) + hermite_cf_smem(cf, p16 + half);
+                                    acc[k] = wadd(acc[k], mulshr(hv, wadd(av0, wmul(astep, k)), 17));
+                                }
+                            } else {
+                                // Raw int16 taps from the pool (sampled waves too large for a table): the
+                                // gather that goes to HBM. The phase is closed-form, so the taps of all
+                                // frames of the slice are requested before the first is used.
+                                const int16_t *d = c.pool + o[0];
+                                unsigned p16s[kSlice];
+                                if (mode == 3) {
+                                    const unsigned long long M = (unsigned long long)(unsigned)o[224] << 24;
+                                    unsigned long long x = (ph + (unsigned long long)dph * (unsigned)(a - sa)) % M;
+#pragma unroll
+                                    for (int k = 0; k < kSlice; ++k) {
+                                        p16s[k] = (unsigned)(x >> 16);
+                                        x = wrap_mod(x + dph, M);
+                                    }
+                                } else {
+                                    ph += (unsigned long long)dph * (unsigned)(a - sa);
+#pragma unroll
+                                    for (int k = 0; k < kSlice; ++k)
+                                        p16s[k] = (unsigned)((ph + (unsigned long long)dph * (unsigned)k) >> 16);
+                                }
+#pragma unroll
+                                for (int k = 0; k < kSlice; ++k) {
+                                    // frames past the segment end are not fetched (no table slack in the pool)
+                                    const bool in_range = a + k < b;
+                                    const int hv = in_range ? hermite(d, p16s[k]) + hermite(d, p16s[k] + half) : 0;
+                                    acc[k] = wadd(acc[k], mulshr(hv, wadd(av0, wmul(astep, k)), 17));
+                                }
+                            }
                         }
                     }
-                }
 #pragma unroll
-                for (int k = 0; k < kSlice; ++k)
-                    if (a + k < b) ta[(a + k) * kTileStride] = acc[k];
+                    for (int k = 0; k < kSlice; ++k)
+                        if (a + k < b) ta[(a + k) * kTileStride] = acc[k];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&barA[slot]);
+                if (hq == 0) trace(2, it, 1);
+                if (hq == NH - 1) trace(4, it, 1);
+                if (P.prof) busy += clock64() - tb;
             }
-        }
-        if (P.prof) t_mid = clock64();
-        // ================= stage C(it - lag_c): panmix + bus sum, lane = frame =================
-        if (is_helper && hq < 2 * WR::groups && it >= lag_c && it - lag_c < nfrag) {
-            const int h = hq;
-            const int slot = (it - lag_c) % kRing;
-            const int f0 = sm[L::meta + slot * 2];
-            const int n = sm[L::meta + slot * 2 + 1];
-            const int f = (h & 1) * 32 + lane;              // my frame of the fragment
-            const int vlo = (h >> 1) * WR::vpg;
-            if (h == 0 && lane == 0) {                      // the params slot is recycled before the flush
-                sm[L::smeta + slot * 2] = f0;
-                sm[L::smeta + slot * 2 + 1] = n;
-            }
-            const int *tin = sm + (FILT ? L::tileB : L::tileA) + slot * kMaxFrag * kTileStride + f * kTileStride;
-            int sum0 = 0, sum1 = 0;
-            if (f < n) {
+            // ---------------- stage C(it - 1): panmix + bus sum, lane = frame ----------------
+            if (it >= 1) {
+                const int jt = it - 1;
+                const int slot = jt % R, par = (jt / R) & 1;
+                mbar_wait(FILT ? &barB[slot] : &barA[slot], par);
+                const long long tb = P.prof ? clock64() : 0;
+                if (hq == 0) trace(3, jt, 0);
+                if (hq == NH - 1) trace(5, jt, 0);
+                {
+                    // lane = voice, my slice of the fragment's frames (the same slice as stage A).
+                    // The voice's gains live in registers, a frame costs one conflict-free tile read,
+                    // two 64-bit multiplies and two warp reductions (redux.sync: PROCADD "+=" over
+                    // the 32 voices, panmix.c:104-105), and the slice's sums are added to the set's
+                    // window accumulator by their one owner - no atomics, no per-voice parameter
+                    // fetches per frame.
+                    const int f0 = sm[L::meta + slot * 2];
+                    const int n = sm[L::meta + slot * 2 + 1];
+                    const int info = sm[L::flags + slot * 32 + lane];
+                    const int split = (info >> 8) & 0xff;
+                    const bool athome = (info >> 16) != 0;
+                    const int *pm0 = sm + L::pmp + ((slot * kSplitSegs + 0) * 8) * 32 + lane;
+                    const int *pm1 = sm + L::pmp + ((slot * kSplitSegs + 1) * 8) * 32 + lane;
+                    const int ga0 = pm0[160], gb0 = pm0[192], ga1 = pm1[160], gb1 = pm1[192];
+                    const bool rest0 = pm0[224] != 0, rest1 = pm1[224] != 0;
+                    const int *tin = sm + L::tile + slot * kMaxFrag * kTileStride + lane;
+                    const int s0 = hq * kSlice, s1 = min(n, s0 + kSlice);
+                    int keep0 = 0, keep1 = 0;
 #pragma unroll
-                for (int j = 0; j < WR::vpg; ++j) {
-                    const int vv = vlo + j;
-                    if (vv >= 32) break;
-                    const int split = sm[L::split + slot * 32 + vv];
-                    const int flags = sm[L::flags + slot * 32 + vv];
-                    const int seg = f >= split ? 1 : 0;
-                    if (!((flags >> seg) & 1)) continue;
-                    const int *q = sm + L::pmp + ((slot * kSplitSegs + seg) * 5) * 32 + vv;
-                    const int k = f - (seg ? split : 0);    // panmix.c:78-115
-                    const int vol = wadd(q[0], wmul(q[32], k));
-                    const int pan = wadd(q[64], wmul(q[96], k));
-                    const int vp = mulshr(pan, vol, 24);
-                    int v0 = wsub(vol, vp), v1 = wadd(vol, vp);
-                    if (q[128]) {
-                        const int lim = (int)((unsigned)vol << 1);
-                        if (v0 > lim) v0 = lim;
-                        if (v1 > lim) v1 = lim;
+                    for (int k = 0; k < kSlice; ++k) {
+                        const int f = s0 + k;
+                        if (f >= s1) break;                 // warp-uniform
+                        const int seg = f >= split ? 1 : 0;
+                        const bool active = ((info >> seg) & 1) != 0;
+                        int v0 = seg ? ga1 : ga0, v1 = seg ? gb1 : gb0;
+                        if (active && !(seg ? rest1 : rest0)) {     // ramping gains: panmix.c:78-115 per frame
+                            const int *o = seg ? pm1 : pm0;
+                            const int kk = f - (seg ? split : 0);
+                            const int vol = wadd(o[0], wmul(o[32], kk));
+                            const int pan = wadd(o[64], wmul(o[96], kk));
+                            const int vp = mulshr(pan, vol, 24);
+                            v0 = wsub(vol, vp); v1 = wadd(vol, vp);
+                            if (o[128]) {
+                                const int lim = (int)((unsigned)vol << 1);
+                                if (v0 > lim) v0 = lim;
+                                if (v1 > lim) v1 = lim;
+                            }
+                        }
+                        const int in = tin[f * kTileStride];
+                        int o0 = active ? mulshr(in, v0, 24) : 0;
+                        int o1 = active ? mulshr(in, v1, 24) : 0;
+                        if (active && !athome) {            // a voice of another bus (group): straight to it
+                            int *gp = P.acc + ((size_t)sm[L::bus + lane] * W + f0 + f) * 2;
+                            atomicAdd(gp, o0);
+                            atomicAdd(gp + 1, o1);
+                            o0 = o1 = 0;
+                        }
+                        const int r0 = __reduce_add_sync(0xffffffffu, o0);
+                        const int r1 = __reduce_add_sync(0xffffffffu, o1);
+                        if (lane == k) { keep0 = r0; keep1 = r1; }
                     }
-                    const int in = tin[vv];
-                    const int o0 = mulshr(in, v0, 24), o1 = mulshr(in, v1, 24);
-                    const int vb = sm[L::bus + vv];
-                    if (vb == home) { sum0 = wadd(sum0, o0); sum1 = wadd(sum1, o1); }
-                    else {
-                        int *a = P.acc + ((size_t)vb * W + f0 + f) * 2;
-                        atomicAdd(a, o0);
-                        atomicAdd(a + 1, o1);
+                    if (lane < s1 - s0) {
+                        int2 *sa = reinterpret_cast<int2 *>(wacc + (f0 + s0 + lane) * 2);
+                        int2 cur = *sa;
+                        cur.x = wadd(cur.x, keep0); cur.y = wadd(cur.y, keep1);
+                        *sa = cur;
                     }
                 }
-                int *sa = sm + L::sacc + (slot * kMaxFrag + f) * 2;
-                if (sum0) atomicAdd(sa, sum0);
-                if (sum1) atomicAdd(sa + 1, sum1);
-            }
-        }
-        // ================= stage D(it - lag_c - 1): flush the fragment's bus sums =================
-        if (hq == 0 && it >= lag_c + 1 && it - lag_c - 1 < nfrag && home >= 0) {
-            const int slot = (it - lag_c - 1) % kRing;
-            const int f0 = sm[L::smeta + slot * 2];
-            const int n = sm[L::smeta + slot * 2 + 1];
-            int *sa = sm + L::sacc + slot * kMaxFrag * 2;
-            int *ga = P.acc + ((size_t)home * W + f0) * 2;
-            for (int i = lane; i < n * 2; i += 32) {
-                const int val = sa[i];
-                if (val) { atomicAdd(ga + i, val); sa[i] = 0; }
-            }
-        }
-        long long t_done = 0;
-        if (P.prof) t_done = clock64();
-        __syncthreads();
-        if (P.prof && lane == 0) {
-            // [0] control [1] serial [2] stage A [3] stage C [4] barrier wait, [5] iterations
-            if (is_ctl) atomicAdd(P.prof + 0, (unsigned long long)(t_done - t_begin));
-            else if (is_ser) atomicAdd(P.prof + 1, (unsigned long long)(t_done - t_begin));
-            else if (hq == 1) {
-                atomicAdd(P.prof + 2, (unsigned long long)(t_mid - t_begin));
-                atomicAdd(P.prof + 3, (unsigned long long)(t_done - t_mid));
-                atomicAdd(P.prof + 4, (unsigned long long)(clock64() - t_done));
-                atomicAdd(P.prof + 5, 1ull);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&barC[slot]);
+                if (hq == 0) trace(3, jt, 1);
+                if (hq == NH - 1) trace(5, jt, 1);
+                if (P.prof) busy2 += clock64() - tb;
             }
         }
     }
 
-    if (is_ctl && valid) {
-        if (in_seg) {
-#pragma unroll
-            for (int i = 0; i < NOSC; ++i) osc[i].finish();
-            if (FILT) filt.finish();
-            pm.finish();
+    if (P.prof && lane == 0) {
+        // [0] control [1] serial compute [2] stage A [3] stage C [4] serial wait, [5] fragments, summed over CTAs
+        if (is_ctl) atomicAdd(P.prof + 0, (unsigned long long)busy);
+        else if (is_ser) { atomicAdd(P.prof + 1, (unsigned long long)busy); atomicAdd(P.prof + 4, (unsigned long long)busy2); }
+        else if (is_helper && hq == 1) {
+            atomicAdd(P.prof + 2, (unsigned long long)busy);
+            atomicAdd(P.prof + 3, (unsigned long long)busy2);
+            if (set == 0) atomicAdd(P.prof + 5, (unsigned long long)nfrag);
         }
-        sp.st(0, alive);
-#pragma unroll
-        for (int i = 0; i < NOSC; ++i) osc[i].store(sp, 1 + 14 * i);
-        if (FILT) filt.store(sp, L::filt_w);
-        pm.store(sp, L::pm_w);
     }
-    __syncthreads();
-    if (is_ser && valid) {       // the recurrence state lives in the serial warp
-        sp.st(L::filt_w + 12, d1);
-        sp.st(L::filt_w + 13, d2);
+    __syncthreads();                        // all stage C work of this CTA is done
+    for (int s2 = 0; s2 < VS; ++s2) {
+        const int first = (blockIdx.x * VS + s2) * 32;
+        if (first >= P.nvoices) break;
+        int *ga = P.acc + (size_t)P.bus_of[first] * W * 2;
+        const int *wa = wacc_all + s2 * kSplitMaxWin * 2;
+        for (int i = tid; i < W * 2; i += WR::threads) {
+            const int val = wa[i];
+            if (val) atomicAdd(ga + i, val);
+        }
     }
-    if (P.prof && tid == 0) {       // [6] prologue, [7] loop, per CTA (a2cu_split_profile)
+    __syncthreads();                        // every bus reduction of this CTA has been issued
+    if (P.prof && tid == 0) {               // [6] prologue, [7] pipeline + state store, per CTA (a2cu_split_profile)
         atomicAdd(P.prof + 6, (unsigned long long)(t_loop - t_entry));
         atomicAdd(P.prof + 7, (unsigned long long)(clock64() - t_loop));
     }
     // ---- fused root stage: the last CTA to get here owns the finished root bus ----
     if (P.fuse_root) {
         __shared__ int s_last;
-        __syncthreads();                    // every bus flush of this CTA has been issued
         if (tid == 0) {
             __threadfence();                // ... and is visible before the ticket is taken
             s_last = atomicAdd(P.fuse_counter, 1u) == gridDim.x - 1 ? 1 : 0;

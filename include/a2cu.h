@@ -270,12 +270,20 @@ int a2cu_set_split(a2cu_engine *e, int enabled);
 uint64_t a2cu_split_launch_count(const a2cu_engine *e);
 /*
  * Profiling aid: per-role busy cycles of render_split summed over CTAs since
- * the last call: out[0] control, [1] filter recurrence, [2] oscillator stage,
- * [3] panmix/bus stage, [4] barrier wait of a helper warp, [5] iterations,
- * [6] kernel entry -> pipeline start, [7] pipeline + state store, summed over CTAs.
+ * the last call: out[0] control, [1] filter recurrence (computing), [2]
+ * oscillator stage and [3] panmix/bus stage of one helper warp per voice set,
+ * [4] filter recurrence warp waiting for its input, [5] fragments rendered,
+ * [6] kernel entry -> pipeline start, [7] pipeline + state store (per CTA).
  * enable != 0 (re)arms the counters, 0 turns them off. out may be NULL.
  */
 int a2cu_split_profile(a2cu_engine *e, int enable, uint64_t out[8]);
+/*
+ * Timeline of CTA 0 / voice set 0 of the last render_split launch while the
+ * profile is armed: out[(role * 64 + fragment) * 2 + end] = cycles since the
+ * pipeline start; roles 0 control, 1 filter recurrence, 2 / 3 oscillator /
+ * panmix stage of helper 0, 4 / 5 of the last helper. out holds 768 words.
+ */
+int a2cu_split_trace(a2cu_engine *e, uint64_t *out);
 /* Name of the render kernel a bank uses (for profiles/). */
 const char *a2cu_bank_kernel_name(a2cu_engine *e, int bank);
 /* Bytes of per-voice state a bank keeps in HBM (roofline arithmetic). */

@@ -1,22 +1,39 @@
-import sys; sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+"""Per-role busy cycles inside render_split (a2cu_split_profile) for the cfg2 bank.
+
+    python profiles/role_profile.py [voices]
+"""
+import sys
+sys.path.insert(0, '.')
 from audiality2_b200 import engine as eng
-from audiality2_b200.workloads import cfg2_bank
-from audiality2_b200.chains import autowire
-import numpy as np
-e=eng.Engine(48000,2); b=cfg2_bank(4096); w=e.builtin_wave('saw')
-bank=e.new_bank(autowire(list(b['kinds'])),4096)
-e.write_all(bank,0,0,[w<<16]); e.write_all(bank,0,1,b['pitch']); e.write_all(bank,0,2,[b['amp']])
-e.write_all(bank,1,0,b['cutoff']); e.write_all(bank,1,1,[b['q']]); e.write_all(bank,2,1,b['pan'])
+from audiality2_b200.workloads import setup_cfg2
+
+V = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+e = eng.Engine(48000, 2)
+bank, b = setup_cfg2(e, V)
 e.set_timing(True)
-for i in range(5): e.write_all(bank,0,2,[b['amp']//(1+i%2)],dur=960<<8); e.run(960,64)
+for i in range(5):
+    e.write_all(bank, 0, 2, [b['amp'] // (1 + i % 2)], dur=960 << 8)
+    e.run(960, 64)
 e.split_profile(True, False)
-N=20
-for i in range(N): e.write_all(bank,0,2,[b['amp']//(1+i%2)],dur=960<<8); e.run(960,64)
-p=e.split_profile(False, True)
-ncta=128
-print('kernel ms', e.last_render_ms(), 'split launches', e.split_launches)
-names=['control','serial','stageA','stageC','barrier-wait(helper)','iters']
-it=p[5]
-for n,v in zip(names,p): print('%-22s %10.0f cycles per CTA-iteration'%(n, v/max(it,1)))
-nl = e.split_launches - 5
-print('per CTA and launch: prologue %.0f cycles, pipeline + state store %.0f cycles (%d launches x %d CTAs)' % (p[6]/(N*ncta), p[7]/(N*ncta), N, ncta))
+N = 20
+ms = []
+for i in range(N):
+    e.write_all(bank, 0, 2, [b['amp'] // (1 + i % 2)], dur=960 << 8)
+    e.run(960, 64)
+    ms.append(e.last_render_ms())
+tr = e.split_trace()
+p = e.split_profile(False, True)
+sets = (V + 31) // 32
+frag = 15
+print('voices %d: kernel %.1f us (min %.1f), split launches %d' % (V, 1e3 * sum(ms) / N, 1e3 * min(ms), e.split_launches))
+names = ['control', 'serial compute', 'stage A (one helper)', 'stage C (one helper)', 'serial wait']
+for n, v in zip(names, p[:5]):
+    print('%-24s %8.0f cycles per fragment and voice set' % (n, v / (N * sets * frag)))
+print('fragments counted %d' % p[5])
+ncta = max(1, p[5] // (N * frag)) if p[5] else sets
+print('per CTA and launch: prologue %.0f cycles, pipeline + state store %.0f cycles' % (
+    p[6] / (N * ncta), p[7] / (N * ncta)))
+
+print('timeline of CTA 0, set 0 (cycles since pipeline start): begin-end per fragment')
+for r, nm in enumerate(['control', 'serial', 'A helper0', 'C helper0', 'A helperN', 'C helperN']):
+    print('%-10s' % nm, ' '.join('%d-%d' % (tr[r, f, 0], tr[r, f, 1]) for f in range(frag)))
