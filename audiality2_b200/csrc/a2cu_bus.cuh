@@ -38,6 +38,11 @@ __global__ void __launch_bounds__(512) mix_root_xchg(const MixParams P, const Xc
     root_stage(P, threadIdx.x, blockDim.x, true);
 }
 
+// The last window of a lagged sequence (nothing follows that could finish it).
+__global__ void __launch_bounds__(512) xchg_drain(const XchgParams X, int *rstate, int channels, int root_stage_on) {
+    xchg_finish_previous(X, rstate, channels, root_stage_on, threadIdx.x, blockDim.x);
+}
+
 // ---------------------------------------------------------------------------
 // Drop-in mode bus stage: the bus-level Process()/write calls the host made
 // during its tree walk.

@@ -406,6 +406,17 @@ struct a2cu_engine {
         bool ipc_opened[kMaxPeers] = {false};
         unsigned *h_status = nullptr;       // mapped pinned word, written by the kernel on timeout
         unsigned long long timeout_cycles = 4000000000ull;
+        // lagged mode (a2cu_submit): the window whose root bus is published but whose root stage
+        // has not run yet - the next launch (or a2cu_collect) finishes it
+        int *d_sum = nullptr;               // [max_frames][2]
+        struct Pending {
+            bool valid = false;
+            unsigned epoch = 0;
+            int W = 0, buffer = 0, nsplits = 0;
+            int splits[kMaxSplits] = {0};
+            int32_t *master = nullptr;
+        } pending;
+        int deferred_slot = -1;             // result slot (ticket) that waits for `pending`
     } xchg;
 };
 // Grow a device buffer, keeping the old one if the allocation fails.
@@ -431,6 +442,7 @@ static void xchg_release(a2cu_engine *e) {
         x.peer[r] = nullptr; x.ipc_opened[r] = false;
     }
     if (x.base) cudaFree(x.base);
+    if (x.d_sum) cudaFree(x.d_sum);
     if (x.h_status) cudaFreeHost(x.h_status);
     x = a2cu_engine::Xchg();
 }
@@ -449,6 +461,20 @@ static XchgParams xchg_params(a2cu_engine *e) {
     X.status = x.h_status;
     X.timeout_cycles = x.timeout_cycles;
     return X;
+}
+// Fill the "previous window" half of X from the pending record.
+static void xchg_fill_prev(a2cu_engine *e, XchgParams &X) {
+    const a2cu_engine::Xchg::Pending &p = e->xchg.pending;
+    X.prev_valid = p.valid ? 1 : 0;
+    X.prev_epoch = p.epoch; X.prev_W = p.W; X.prev_buffer = p.buffer; X.prev_nsplits = p.nsplits;
+    for (int i = 0; i < kMaxSplits; ++i) X.prev_splits[i] = p.splits[i];
+    X.prev_master = p.master; X.sum = e->xchg.d_sum;
+}
+// The pending window's result slot is complete once the work queued so far has run.
+extern "C" {
+static int xchg_pending_done(a2cu_engine *e);
+// Finish the pending window with its own small launch (nothing follows, or what follows cannot).
+static int xchg_drain_pending(a2cu_engine *e);
 }
 static int xchg_check(a2cu_engine *e) {
     if (e->xchg.h_status && *(volatile unsigned *)e->xchg.h_status) {
@@ -1385,7 +1411,7 @@ static int plan_noise(a2cu_engine *e, uint64_t t0, int W, int buffer, const int 
     return A2CU_OK;
 }
 
-static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *dev_out) {
+static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *dev_out, bool allow_lag = false) {
     if (!frames) return A2CU_OK;
     if (!buffer) buffer = frames;
     const uint64_t t0 = e->now, t1 = e->now + ((uint64_t)frames << 8);
@@ -1414,9 +1440,9 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             b0 = h; b1 = frames - h;
         } else
             return fail(A2CU_EINVAL, "too many root events in one fragment%s");
-        int r = run_window(e, h, b0, base);
+        int r = run_window(e, h, b0, base, allow_lag);
         if (r) return r;
-        return run_window(e, frames - h, b1, base + (size_t)h * och);
+        return run_window(e, frames - h, b1, base + (size_t)h * och, allow_lag);
     }
     int r = upload_waves(e);
     if (r) return r;
@@ -1612,6 +1638,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         }
     }
     e->fused_root = false;
+    bool lag_consumed = false, lag_created = false;
     if (e->xchg.enabled && e->xchg.world > 1 && W > e->xchg.max_frames)
         return fail(A2CU_EINVAL, "window longer than the exchange buffer (a2cu_xchg_create max_frames)%s");
     const XchgParams X = xchg_params(e);
@@ -1678,10 +1705,28 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
                 params[bi].fuse_channels = e->channels;
                 params[bi].fuse_root_stage = e->post_root ? 1 : 0;
                 params[bi].xchg = X;
+                if (X.world > 1 && allow_lag) {
+                    // pipelined + sharded: this launch publishes its bus and finishes the pending window
+                    params[bi].xchg.lag = 1;
+                    xchg_fill_prev(e, params[bi].xchg);
+                    lag_consumed = e->xchg.pending.valid;
+                    a2cu_engine::Xchg::Pending &pn = e->xchg.pending;
+                    pn.valid = true; pn.epoch = X.epoch; pn.W = W; pn.buffer = (int)buffer; pn.nsplits = nsplits;
+                    for (int i = 0; i < nsplits; ++i) pn.splits[i] = splits[i];
+                    pn.master = params[bi].fuse_master;
+                    lag_created = true;
+                } else if (e->xchg.pending.valid) {
+                    r = xchg_drain_pending(e);
+                    if (r) return r;
+                }
                 e->fused_root = true;
             }
             sv.fn<<<grid, sv.threads, smem, e->stream>>>(params[bi]);
             ++e->split_launches;
+            if ((int)bi == fuse_bank && lag_consumed) {
+                r = xchg_pending_done(e);       // the previous window's output is complete after this launch
+                if (r) return r;
+            }
         } else {
             int grid = (b->nvoices + kThreads - 1) / kThreads;
             b->k.fn<<<grid, kThreads, 0, e->stream>>>(params[bi]);
@@ -1731,6 +1776,11 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
         mix_groups<<<e->ngroups, 256, 0, e->stream>>>(M);
         ++e->launches;
     }
+    if (!e->fused_root && e->xchg.pending.valid) {
+        r = xchg_drain_pending(e);      // root stages run in window order (the rampers carry over)
+        if (r) return r;
+    }
+    (void)lag_created;
     if (!e->fused_root) {
         if (X.world > 1) mix_root_xchg<<<1, 512, 0, e->stream>>>(M, X);
         else mix_root<<<M.general ? 1 : std::max(1, std::min(8, ((int)M.W + 255) / 256)), 256, 0, e->stream>>>(M);
@@ -1745,6 +1795,33 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     return A2CU_OK;
 }
 
+static int xchg_pending_done(a2cu_engine *e) {
+    const int k = e->xchg.deferred_slot;
+    if (k >= 0) {
+        CK(cudaEventRecord(e->slots[k].done, e->stream));
+        e->xchg.deferred_slot = -1;
+    }
+    return A2CU_OK;
+}
+static int xchg_drain_pending(a2cu_engine *e) {
+    if (!e->xchg.pending.valid) return A2CU_OK;
+    XchgParams X;
+    memset(&X, 0, sizeof(X));
+    a2cu_engine::Xchg &x = e->xchg;
+    X.world = x.world; X.rank = x.rank; X.max_frames = x.max_frames;
+    for (int r = 0; r < x.world; ++r) {
+        X.flags[r] = (unsigned *)x.peer[r];
+        X.data[r] = (int *)((char *)x.peer[r] + kXchgFlagBytes);
+    }
+    X.status = x.h_status; X.timeout_cycles = x.timeout_cycles;
+    xchg_fill_prev(e, X);
+    xchg_drain<<<1, 512, 0, e->stream>>>(X, e->d_rstate, e->channels, e->post_root ? 1 : 0);
+    ++e->launches;
+    CK(cudaGetLastError());
+    x.pending.valid = false;
+    return xchg_pending_done(e);
+}
+
 int a2cu_run_async(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *dev_out) {
     if (!e) return A2CU_EINVAL;
     cudaSetDevice(e->device);
@@ -1755,6 +1832,11 @@ int32_t *a2cu_master_devptr(a2cu_engine *e) { return e ? e->d_master : nullptr; 
 
 int a2cu_sync(a2cu_engine *e) {
     if (!e) return A2CU_EINVAL;
+    if (e->xchg.pending.valid) {
+        cudaSetDevice(e->device);
+        int r = xchg_drain_pending(e);
+        if (r) return r;
+    }
     CK(cudaStreamSynchronize(e->stream));
     if (e->timing) {
         float ms = 0.f;
@@ -1822,10 +1904,12 @@ static int submit_impl(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t
     e->ev0 = sl.ev0; e->ev1 = sl.ev1; e->ev2 = sl.ev2;
     // the bus stage writes the master block straight into the pinned result slot (mapped host memory,
     // same address on the device under UVA): no separate D2H copy on the stream
-    int r = run_window(e, frames, buffer, dev_out ? dev_out : sl.h_out);
+    int r = run_window(e, frames, buffer, dev_out ? dev_out : sl.h_out, /*allow_lag=*/true);
     e->ev0 = s0; e->ev1 = s1; e->ev2 = s2;
     if (r) return r;
-    CK(cudaEventRecord(sl.done, e->stream));
+    // sharded + lagged: this window's output is finished by the next launch (or by a2cu_collect)
+    if (e->xchg.pending.valid) e->xchg.deferred_slot = k;
+    else CK(cudaEventRecord(sl.done, e->stream));
     if (!dev_out) e->d2h_bytes += n * sizeof(int32_t);
     sl.n = dev_out ? 0 : n;
     sl.busy = true;
@@ -1838,6 +1922,10 @@ int a2cu_collect(a2cu_engine *e, int ticket, int32_t *out) {
         return fail(A2CU_EINVAL, "a2cu_collect: bad ticket%s");
     cudaSetDevice(e->device);
     a2cu_engine::Slot &sl = e->slots[ticket];
+    if (e->xchg.deferred_slot == ticket) {      // nothing was submitted after it: finish it now
+        int r = xchg_drain_pending(e);
+        if (r) return r;
+    }
     CK(cudaEventSynchronize(sl.done));
     if (out && sl.n) memcpy(out, sl.h_out, sl.n * sizeof(int32_t));
     if (e->timing) {
@@ -1900,6 +1988,7 @@ int a2cu_xchg_create(a2cu_engine *e, int rank, int world, unsigned max_frames, u
     if (cudaMalloc(&x.base, bytes) != cudaSuccess)
         return fail(A2CU_ENOMEM, "cudaMalloc exchange buffer: %s", cudaGetErrorString(cudaGetLastError()));
     CK(cudaMemset(x.base, 0, bytes));
+    CK(cudaMalloc(&x.d_sum, (size_t)max_frames * 2 * sizeof(int)));
     CK(cudaHostAlloc((void **)&x.h_status, sizeof(unsigned), cudaHostAllocMapped));
     *x.h_status = 0;
     int khz = 0;
@@ -1957,6 +2046,11 @@ int a2cu_xchg_connect_local(a2cu_engine *e, a2cu_engine *const *peers) {
 
 int a2cu_xchg_enable(a2cu_engine *e, int enabled) {
     if (!e) return A2CU_EINVAL;
+    if (!enabled && e->xchg.pending.valid) {
+        cudaSetDevice(e->device);
+        int r = xchg_drain_pending(e);
+        if (r) return r;
+    }
     if (enabled && !e->xchg.base) return fail(A2CU_EINVAL, "a2cu_xchg_enable: no exchange buffer%s");
     if (enabled)
         for (int r = 0; r < e->xchg.world; ++r)
@@ -1968,6 +2062,7 @@ int a2cu_xchg_enable(a2cu_engine *e, int enabled) {
 int a2cu_xchg_close(a2cu_engine *e) {
     if (!e) return A2CU_EINVAL;
     cudaSetDevice(e->device);
+    if (e->xchg.pending.valid) xchg_drain_pending(e);
     cudaStreamSynchronize(e->stream);
     xchg_release(e);
     return A2CU_OK;

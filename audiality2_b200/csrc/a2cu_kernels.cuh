@@ -61,6 +61,17 @@ struct XchgParams {
     unsigned *flags[kMaxPeers];         // every rank's buffer: flag area
     unsigned *status;                   // mapped host word: set to the epoch that timed out
     unsigned long long timeout_cycles;
+    // Lagged mode (pipelined a2cu_submit / a2cu_collect): this launch only PUBLISHES its root bus;
+    // the sum over the ranks and the root stage of the PREVIOUS window run here instead, when its
+    // rows have long arrived - the NVLink round trips (stores, system fence, flag, poll) leave the
+    // critical path, at the price of one window of output latency.
+    int lag;
+    int prev_valid;                     // a previous window is waiting for its root stage
+    unsigned prev_epoch;
+    int prev_W, prev_buffer, prev_nsplits;
+    int prev_splits[kMaxSplits];
+    int *prev_master;                   // where the previous window's master block goes
+    int *sum;                           // [max_frames][2] scratch: summed root bus of the previous window
 };
 
 A2CU_DEV void st_release_sys(unsigned *p, unsigned v) {
@@ -72,24 +83,43 @@ A2CU_DEV unsigned ld_acquire_sys(const unsigned *p) {
     return v;
 }
 
-// All threads of ONE CTA (nthreads of them) call this with the finished local root bus.
-A2CU_DEV void xchg_root_bus(const XchgParams &X, int *root, int W, int tid, int nthreads) {
+// All threads of ONE CTA (nthreads of them) call these with the finished local root bus.
+// Both are latency-bound single-CTA passes over a few KB, so every thread first issues ALL its
+// loads (four per round, independent), then stores; and the release is done ONCE, by the
+// flag-writing threads: st.release.sys after the CTA barrier is cumulative over the data stores the
+// barrier ordered before it (a membar.sys in each of 512 threads cost ~5 us, profiles/xchg_tail.py).
+// Publish: raw bus -> row [epoch & 1][rank] of every rank's buffer, then the flag.
+A2CU_DEV void xchg_publish(const XchgParams &X, int *root, int W, int tid, int nthreads, bool zero) {
     const int par = (int)(X.epoch & 1u);
     const size_t pitch = (size_t)X.max_frames * 2;
     const size_t myrow = ((size_t)par * X.world + X.rank) * pitch;
-    for (int i = tid; i < W * 2; i += nthreads) {
-        const int v = __ldcg(root + i);
-        for (int r = 0; r < X.world; ++r) X.data[r][myrow + i] = v;
+    const int n = W * 2;
+    for (int i0 = tid; i0 < n; i0 += 4 * nthreads) {
+        int v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = i0 + j * nthreads < n ? __ldcg(root + i0 + j * nthreads) : 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = i0 + j * nthreads;
+            if (i < n) {
+                for (int r = 0; r < X.world; ++r) X.data[r][myrow + i] = v[j];
+                if (zero) root[i] = 0;      // lagged mode: nobody else clears the local bus rows
+            }
+        }
     }
-    __threadfence_system();
     __syncthreads();
     if (tid < X.world) st_release_sys(X.flags[tid] + par * X.world + X.rank, X.epoch);
+}
+// Collect: wait until every rank's flag shows `epoch`, sum the rows into dst[W][2].
+A2CU_DEV void xchg_collect(const XchgParams &X, unsigned epoch, int *dst, int W, int tid, int nthreads) {
+    const int par = (int)(epoch & 1u);
+    const size_t pitch = (size_t)X.max_frames * 2;
     if (tid < X.world) {
         const unsigned *f = X.flags[X.rank] + par * X.world + tid;
         const long long t0 = clock64();
-        while ((int)(ld_acquire_sys(f) - X.epoch) < 0) {
+        while ((int)(ld_acquire_sys(f) - epoch) < 0) {
             if ((unsigned long long)(clock64() - t0) > X.timeout_cycles) {
-                *X.status = X.epoch;        // reported by a2cu_collect / a2cu_sync
+                *X.status = epoch;          // reported by a2cu_collect / a2cu_sync
                 break;
             }
             __nanosleep(64);
@@ -97,13 +127,26 @@ A2CU_DEV void xchg_root_bus(const XchgParams &X, int *root, int W, int tid, int 
     }
     __syncthreads();
     const int *mine = X.data[X.rank] + (size_t)par * X.world * pitch;
-    for (int i = tid; i < W * 2; i += nthreads) {
-        int s = 0;
-        for (int r = 0; r < X.world; ++r) s = wadd(s, __ldcg(mine + (size_t)r * pitch + i));
-        root[i] = s;
+    const int n = W * 2;
+    for (int i0 = tid; i0 < n; i0 += 4 * nthreads) {
+        int sacc[4] = {0, 0, 0, 0};
+        for (int r = 0; r < X.world; ++r) {
+            int v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                v[j] = i0 + j * nthreads < n ? __ldcg(mine + (size_t)r * pitch + i0 + j * nthreads) : 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sacc[j] = wadd(sacc[j], v[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (i0 + j * nthreads < n) dst[i0 + j * nthreads] = sacc[j];
     }
-    __threadfence_block();
     __syncthreads();
+}
+A2CU_DEV void xchg_root_bus(const XchgParams &X, int *root, int W, int tid, int nthreads) {
+    xchg_publish(X, root, W, tid, nthreads, false);
+    xchg_collect(X, X.epoch, root, W, tid, nthreads);
 }
 
 struct RenderParams {
@@ -487,6 +530,22 @@ A2CU_DEV void root_stage(const MixParams &P, int gtid, int gsize, bool cta0) {
         else { P.master[f * 2] = r0; P.master[f * 2 + 1] = r1; }
         if (clear) { root[f * 2] = 0; root[f * 2 + 1] = 0; }
     });
+}
+
+// Root stage of the window BEFORE this launch (lagged exchange): sum its rows - published one
+// launch ago by every rank - and run the root panmix into that window's output block.
+// `rstate`, `channels`, `root_stage_on` are those of the engine (they do not change per window).
+A2CU_DEV void xchg_finish_previous(const XchgParams &X, int *rstate, int channels, int root_stage_on, int tid,
+                                   int nthreads) {
+    xchg_collect(X, X.prev_epoch, X.sum, X.prev_W, tid, nthreads);
+    MixParams M;
+    M.acc = X.sum; M.W = X.prev_W; M.buffer = X.prev_buffer; M.ngroups = 0; M.channels = channels;
+    M.nsplits = X.prev_nsplits;
+    for (int i = 0; i < kMaxSplits; ++i) M.splits[i] = X.prev_splits[i];
+    M.gstate = nullptr; M.rstate = rstate; M.ev = nullptr; M.nev = 0;
+    M.master = X.prev_master; M.root_stage = root_stage_on; M.clear = 0; M.general = 0;
+    root_stage(M, tid, nthreads, true);
+    __syncthreads();
 }
 
 }  // namespace a2cu

@@ -61,6 +61,8 @@ constexpr int kOscWords = 8;        // published per oscillator and segment
 // other warps with id % 4 == 3 stay idle, helpers and control warps use the ids
 // with id % 4 != 3 in ascending order (logical index q = id - id / 4).
 // q < VS * NH: helper (set q / NH, index q % NH); then VS control warps.
+// (Measured: helpers on sub-partition 3 cost the recurrence warp 25-40 % of its speed even when it
+// has the highest warp id, i.e. issue priority - profiles/README.md - so that port stays its own.)
 template <bool FILT, int NH, int VS> struct SplitWarps {
     static constexpr int workers = VS * (NH + 1);
     static constexpr int rows = (workers + 2) / 3 > VS ? (workers + 2) / 3 : VS;     // FILT: groups of 4 warp ids
@@ -638,9 +640,27 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NH, VS>::threads) render_spli
             for (int i = 0; i < kMaxSplits; ++i) M.splits[i] = P.splits[i];
             M.gstate = nullptr; M.rstate = P.fuse_rstate; M.ev = nullptr; M.nev = 0;
             M.master = P.fuse_master; M.root_stage = P.fuse_root_stage; M.clear = 1; M.general = 0;
-            // sharded render: the root bus of all ranks is summed here, through NVLink peer memory
-            if (P.xchg.world > 1) xchg_root_bus(P.xchg, P.acc, P.W, tid, WR::threads);
-            root_stage(M, tid, WR::threads, true);
+            // tail timings for a2cu_split_trace: role 5, fragments 60..63 = start, after the previous
+            // window's root stage, after publish / root stage, (unused)
+            auto tmark = [&](int k) {
+                if (P.prof && tid == 0) P.prof[8 + ((5 * 64 + 60 + k) * 2)] = (unsigned long long)(clock64() - t_loop);
+            };
+            tmark(0);
+            if (P.xchg.world > 1 && P.xchg.lag) {
+                // sharded + pipelined: finish the PREVIOUS window (its rows arrived long ago), then
+                // publish this one without waiting for anybody (read-then-publish keeps two buffer
+                // halves enough: a peer publishes window k + 1 only after it saw our window k)
+                if (P.xchg.prev_valid)
+                    xchg_finish_previous(P.xchg, P.fuse_rstate, P.fuse_channels, P.fuse_root_stage, tid, WR::threads);
+                tmark(1);
+                xchg_publish(P.xchg, P.acc, P.W, tid, WR::threads, true);
+                tmark(2);
+            } else {
+                // sharded render: the root bus of all ranks is summed here, through NVLink peer memory
+                if (P.xchg.world > 1) xchg_root_bus(P.xchg, P.acc, P.W, tid, WR::threads);
+                root_stage(M, tid, WR::threads, true);
+                tmark(2);
+            }
             if (tid == 0) *P.fuse_counter = 0u;     // ready for the next launch
         }
     }

@@ -455,7 +455,7 @@ def _build_cuda_shard(scn, e, voice_ids):
             e.root_write(int(ev["reg"]), int(ev["value"]), t, int(ev["dur"]))
 
 
-def run_cuda_sharded(scn, nshards=2, window=None, split=True, mode="fused", stats=None):
+def run_cuda_sharded(scn, nshards=2, window=None, split=True, mode="fused", stats=None, pipelined=False):
     """Render `scn` on `nshards` engines of ONE process (all on cuda:0, one CUDA stream each),
     voices dealt round-robin, and return every shard's master output.
       mode "fused": in-kernel exchange over peer memory (a2cu_xchg_*): each window is submitted on
@@ -483,12 +483,21 @@ def run_cuda_sharded(scn, nshards=2, window=None, split=True, mode="fused", stat
                 e.xchg_connect_local(engines)
             outs = [[] for _ in engines]
             done = 0
+            inflight = [[] for _ in engines]
             while done < scn.frames:
                 n = min(window, scn.frames - done)
-                tickets = [e.submit(n, scn.buffer) for e in engines]
                 for s, e in enumerate(engines):
-                    outs[s].append(e.collect(tickets[s]))
+                    inflight[s].append(e.submit(n, scn.buffer))
                 done += n
+                # pipelined: up to three windows in flight per engine - a window's root stage then runs
+                # at the tail of the NEXT window's kernel (lagged exchange); otherwise every window is
+                # collected at once (a2cu_collect finishes it with the drain kernel)
+                while inflight[0] and (not pipelined or len(inflight[0]) > 2):
+                    for s, e in enumerate(engines):
+                        outs[s].append(e.collect(inflight[s].pop(0)))
+            while inflight[0]:
+                for s, e in enumerate(engines):
+                    outs[s].append(e.collect(inflight[s].pop(0)))
             if stats is not None:
                 stats["launches"] = [e.launches for e in engines]
                 stats["split_launches"] = [e.split_launches for e in engines]

@@ -44,8 +44,9 @@ def test_root_ramp_sharded_equals_single_engine_and_port():
     scn = _root_ramp_bank()
     whole = run_cuda(scn)
     assert np.array_equal(whole, run_oracle(scn)), _diff(whole, run_oracle(scn))
-    for o in run_cuda_sharded(scn, nshards=2, mode="fused", window=scn.buffer * 5):
-        assert np.array_equal(o, whole), _diff(o, whole)
+    for pipelined in (False, True):
+        for o in run_cuda_sharded(scn, nshards=2, mode="fused", window=scn.buffer * 5, pipelined=pipelined):
+            assert np.array_equal(o, whole), _diff(o, whole)
     cut = run_cuda_sharded(scn, nshards=2, mode="cut", window=scn.buffer * 5)[0]
     assert np.array_equal(cut, whole), _diff(cut, whole)
 
@@ -61,12 +62,16 @@ def test_cut_path_equals_single_engine(name):
     assert np.array_equal(whole, run_oracle(scn))
 
 
+@pytest.mark.parametrize("pipelined", [False, True])
 @pytest.mark.parametrize("nshards", [2, 3, 8])
-def test_fused_exchange_equals_single_engine(nshards):
+def test_fused_exchange_equals_single_engine(nshards, pipelined):
+    """pipelined: several windows in flight -> lagged exchange (window k's root stage runs at the
+    tail of kernel k + 1); otherwise a2cu_collect finishes each window with the drain kernel."""
     scn = CASES["bank256"]()
     whole = run_cuda(scn)
     st = {}
-    outs = run_cuda_sharded(scn, nshards=nshards, mode="fused", window=scn.buffer * 5, stats=st)
+    outs = run_cuda_sharded(scn, nshards=nshards, mode="fused", window=scn.buffer * 5, stats=st,
+                            pipelined=pipelined)
     assert all(x > 0 for x in st["split_launches"]), "fused tail of render_split expected"
     for o in outs:      # every rank ends up with the identical master block
         assert np.array_equal(o, whole), _diff(o, whole)
@@ -81,7 +86,7 @@ def test_fused_exchange_other_structures(name):
     if scn.ngroups:
         pytest.skip("root-level voices only")
     whole = run_cuda(scn)
-    for o in run_cuda_sharded(scn, nshards=2, mode="fused", window=scn.buffer * 7):
+    for o in run_cuda_sharded(scn, nshards=2, mode="fused", window=scn.buffer * 7, pipelined=True):
         assert np.array_equal(o, whole), _diff(o, whole)
 
 
