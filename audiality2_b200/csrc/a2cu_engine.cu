@@ -246,7 +246,8 @@ struct Bank {
     uint4 *d_ev = nullptr;
     size_t ev_cap = 0;
     bool has_noise = false;
-    bool exotic = false;    // selected a noise / non-mip / table-less wave: render_bank only
+    bool exotic = false;    // selected a noise / one-shot sampled wave: render_bank only
+    bool raw_taps = false;  // selected a wave without a coefficient table: render_split's raw-tap variant
     cudaEvent_t ev_consumed = nullptr;  // recorded after the last kernel that reads d_ev (bank mode)
     bool enabled = true;    // a2cu_bank_enable: a disabled bank is paused (not rendered, events kept)
     int stage_wave = -1;    // wave whose coefficient table render_split stages in shared memory
@@ -286,7 +287,8 @@ struct a2cu_engine {
     BlockStats bs;
     WindowStats ws;
     // environment toggles, read once in a2cu_open (A/B switches for profiles/)
-    bool env_stats = false, env_no_copy_stream = false, env_no_fuse = false, env_no_stage = false, env_one_set = false;
+    bool env_stats = false, env_no_copy_stream = false, env_no_fuse = false, env_no_stage = false, env_one_set = false,
+         env_no_side_streams = false;
     int sm_count = 148;
     int device = 0, samplerate = 48000, channels = 2;
     int basepitch = 0;
@@ -343,6 +345,12 @@ struct a2cu_engine {
     // kernels of window i (it only waits for the last kernel that read the same bank's event buffer)
     cudaStream_t copy_stream = nullptr;
     bool copy_used = false;         // this window's uploads went through copy_stream
+    // Banks of one window are independent until the bus stage (they only add into the buses with
+    // integer atomics): a window with several banks launches them on side streams, forked from and
+    // joined back into the engine's stream, so that small banks share the chip instead of queueing.
+    static const int kSideStreams = 3;
+    cudaStream_t side[kSideStreams] = {nullptr, nullptr, nullptr};
+    cudaEvent_t side_fork = nullptr, side_join[kSideStreams] = {nullptr, nullptr, nullptr};
     // pipelined API (a2cu_submit / a2cu_collect): result slots
     static const int kSlots = 4;
     struct Slot {
@@ -778,6 +786,7 @@ a2cu_engine *a2cu_open(int device, int samplerate, int channels) {
     e->env_no_fuse = getenv("A2CU_NO_FUSE") != nullptr;
     e->env_no_stage = getenv("A2CU_NO_STAGE") != nullptr;
     e->env_one_set = getenv("A2CU_ONE_SET") != nullptr;
+    e->env_no_side_streams = getenv("A2CU_NO_SIDE_STREAMS") != nullptr;
     cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e->sm_count <= 0) e->sm_count = 148;
     e->noise_ptr = &e->noiseseed;
@@ -836,6 +845,11 @@ void a2cu_close(a2cu_engine *e) {
     for (int *p : e->fbd_free) cudaFree(p);
     if (e->h_xfer) cudaFreeHost(e->h_xfer);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    for (int k = 0; k < a2cu_engine::kSideStreams; ++k) {
+        if (e->side[k]) cudaStreamDestroy(e->side[k]);
+        if (e->side_join[k]) cudaEventDestroy(e->side_join[k]);
+    }
+    if (e->side_fork) cudaEventDestroy(e->side_fork);
     for (int k = 0; k < a2cu_engine::kStageRing; ++k) {
         if (e->stage_buf[k]) cudaFreeHost(e->stage_buf[k]);
         if (e->stage_done[k]) cudaEventDestroy(e->stage_done[k]);
@@ -1167,6 +1181,9 @@ static int cook_write(a2cu_engine *e, Bank *b, int voice, int unit, int reg, int
         // (wtosc.c:301-358) need the frame-serial kernel
         if (hw.type == A2CU_WNOISE || (hw.type == A2CU_WWAVE && !(hw.flags & A2CU_LOOPED))) b->exotic = true;
         if (hw.type == A2CU_WNOISE) e->noise_seen = true;
+        // no Hermite-coefficient table (upload_waves), or a looped plain wave whose per-sample wrapped
+        // loop above A2_MAXPHINC reads raw taps (wtosc.c:301-358)
+        if (total > ((size_t)1 << 20) || hw.type == A2CU_WWAVE) b->raw_taps = true;
         if (hw.type == A2CU_WMIPWAVE && total <= ((size_t)1 << 20)) b->stage_wave = c[0].value;
     }
     for (int i = 0; i < n; ++i) push_event(b, when, voice, EV_WRITE, unit, c[i].reg, c[i].value, c[i].dur);
@@ -1645,9 +1662,34 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     const double ws_t2 = now_us();
     // inputs are resident from here on: ev0 .. ev1 brackets the render kernels
     if (e->timing) CK(cudaEventRecord(e->ev0, e->stream));
+    int nlive = 0, launched = 0;
+    for (Bank *b : e->banks)
+        if (!b->dynamic && b->nvoices && b->enabled) ++nlive;
+    const bool fan_out = nlive > 1 && !e->env_no_side_streams;
+    bool side_used[a2cu_engine::kSideStreams] = {false, false, false};
+    if (fan_out) {
+        if (!e->side_fork) {
+            CK(cudaEventCreateWithFlags(&e->side_fork, cudaEventDisableTiming));
+            for (int k = 0; k < a2cu_engine::kSideStreams; ++k) {
+                CK(cudaStreamCreateWithFlags(&e->side[k], cudaStreamNonBlocking));
+                CK(cudaEventCreateWithFlags(&e->side_join[k], cudaEventDisableTiming));
+            }
+        }
+        CK(cudaEventRecord(e->side_fork, e->stream));
+    }
     for (size_t bi = 0; bi < e->banks.size(); ++bi) {
         Bank *b = e->banks[bi];
         if (b->dynamic || !b->nvoices || !b->enabled) continue;
+        // bank k of the window runs on stream k mod 4: the engine's own stream or a side stream
+        cudaStream_t ls = e->stream;
+        const int lane = launched++ % (a2cu_engine::kSideStreams + 1);
+        if (fan_out && lane > 0) {
+            ls = e->side[lane - 1];
+            if (!side_used[lane - 1]) {
+                CK(cudaStreamWaitEvent(ls, e->side_fork, 0));
+                side_used[lane - 1] = true;
+            }
+        }
         bool split = e->use_split && b->k.split[0].fn && !b->exotic && nsplits <= 1;
         std::vector<HostEvent> bulk_probe;      // fast path: all voices share voice 0's event times
         if (fast[bi])
@@ -1683,6 +1725,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             params[bi].prof = e->d_prof;
             // two voice sets per CTA once the bank has more 32-voice sets than the chip has SMs
             int var = (b->k.split[1].fn && b->nvoices > e->sm_count * 32 && !e->env_one_set) ? 1 : 0;
+            if (b->raw_taps) var = 2;
             size_t smem = b->k.split[var].smem;
             if (b->stage_wave >= 0 && e->waves[b->stage_wave].cbegin >= 0 && !e->env_no_stage) {
                 // whole wave (all mip levels) + read-ahead slack, if it fits beside the pipeline buffers
@@ -1721,7 +1764,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
                 }
                 e->fused_root = true;
             }
-            sv.fn<<<grid, sv.threads, smem, e->stream>>>(params[bi]);
+            sv.fn<<<grid, sv.threads, smem, ls>>>(params[bi]);
             ++e->split_launches;
             if ((int)bi == fuse_bank && lag_consumed) {
                 r = xchg_pending_done(e);       // the previous window's output is complete after this launch
@@ -1729,13 +1772,18 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             }
         } else {
             int grid = (b->nvoices + kThreads - 1) / kThreads;
-            b->k.fn<<<grid, kThreads, 0, e->stream>>>(params[bi]);
+            b->k.fn<<<grid, kThreads, 0, ls>>>(params[bi]);
         }
         ++e->launches;
         if (!b->ev_consumed) CK(cudaEventCreateWithFlags(&b->ev_consumed, cudaEventDisableTiming));
-        CK(cudaEventRecord(b->ev_consumed, e->stream));
+        CK(cudaEventRecord(b->ev_consumed, ls));
         if (fast[bi]) b->bulk.clear();      // consumed (staged above)
     }
+    for (int k = 0; k < a2cu_engine::kSideStreams; ++k)
+        if (side_used[k]) {                 // join: the bus stage needs every bank's sums
+            CK(cudaEventRecord(e->side_join[k], e->side[k]));
+            CK(cudaStreamWaitEvent(e->stream, e->side_join[k], 0));
+        }
     if (e->timing) CK(cudaEventRecord(e->ev1, e->stream));
     const double ws_t3 = now_us();
 

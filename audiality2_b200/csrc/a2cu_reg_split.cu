@@ -6,13 +6,13 @@ using namespace a2cu;
 // room the staged Hermite-coefficient table of a builtin 2048-point wave needs (all mip levels)
 static constexpr size_t kTableRoom = 90 * 1024;
 
-template <int NOSC, bool FILT, int NH, int VS, int R>
+template <int NOSC, bool FILT, int NH, int VS, int R, bool RAW>
 static void reg_variant(KernelEntry &e, int slot) {
-    e.split[slot].fn = render_split<NOSC, FILT, NH, VS, R>;
+    e.split[slot].fn = render_split<NOSC, FILT, NH, VS, R, RAW>;
     e.split[slot].smem = split_smem_bytes<NOSC, FILT, R, VS>();
     e.split[slot].threads = SplitWarps<FILT, NH, VS>::threads;
     e.split[slot].voices = 32 * VS;
-    cudaFuncSetAttribute(render_split<NOSC, FILT, NH, VS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(render_split<NOSC, FILT, NH, VS, R, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)kMaxSplitSmem);
 }
 
@@ -20,14 +20,15 @@ static void reg_variant(KernelEntry &e, int slot) {
 template <int NOSC, bool FILT, int NH1, int NH2>
 static void reg_split(std::vector<a2cu_unitspec> specs) {
     KernelEntry &e = a2cu_registry()[sig_of(specs.data(), (int)specs.size())];
-    reg_variant<NOSC, FILT, NH1, 1, 4>(e, 0);
+    reg_variant<NOSC, FILT, NH1, 1, 4, false>(e, 0);
+    reg_variant<NOSC, FILT, NH1, 1, 4, true>(e, 2);     // banks that play table-less (large sampled) waves
     // two voice sets: pays where the recurrence warp is the critical path (helpers have slack) and
     // both sets and the table fit the 227 KB of one CTA
     if constexpr (!FILT) return;
     else if constexpr (split_smem_bytes<NOSC, FILT, 4, 2>() + kTableRoom <= kMaxSplitSmem)
-        reg_variant<NOSC, FILT, NH2, 2, 4>(e, 1);
+        reg_variant<NOSC, FILT, NH2, 2, 4, false>(e, 1);
     else if constexpr (split_smem_bytes<NOSC, FILT, 3, 2>() + kTableRoom <= kMaxSplitSmem)
-        reg_variant<NOSC, FILT, NH2, 2, 3>(e, 1);
+        reg_variant<NOSC, FILT, NH2, 2, 3, false>(e, 1);
 }
 
 void a2cu_register_split() {

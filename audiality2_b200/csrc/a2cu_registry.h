@@ -26,8 +26,9 @@ struct KernelEntry {
     int words;      // incl. the flags word
     const char *name;
     // [0]: one voice set per CTA (small banks: most CTAs, shortest critical path);
-    // [1]: two voice sets per CTA sharing one staged wavetable (large banks: more voices per SM)
-    SplitVariant split[2];
+    // [1]: two voice sets per CTA sharing one staged wavetable (large banks: more voices per SM);
+    // [2]: like [0] plus the raw-tap gather for waves without a coefficient table
+    SplitVariant split[3];
 };
 std::map<std::string, KernelEntry> &a2cu_registry();
 void a2cu_register_bank_wt();      // render_bank<...>: wavetable chains
@@ -52,6 +53,7 @@ static void reg_chain(std::vector<a2cu_unitspec> specs, const char *name) {
     e.name = name;
     e.split[0] = SplitVariant{nullptr, 0, 0, 0};
     e.split[1] = SplitVariant{nullptr, 0, 0, 0};
+    e.split[2] = SplitVariant{nullptr, 0, 0, 0};
     a2cu_registry()[sig_of(specs.data(), (int)specs.size())] = e;
 }
 // dynamic part; the kernel also has ~4.7 KB static (fused root stage); 227 KB per CTA

@@ -150,7 +150,10 @@ A2CU_DEV void filter_run(int *t, int a, int b, int &d1, int &d2, int f0v, int df
     for (; f < b; ++f) t[f * kTileStride] = step(t[f * kTileStride]);
 }
 
-template <int NOSC, bool FILT, int NH, int VS, int R>
+// RAW: the bank may play waves without a Hermite-coefficient table (large sampled waves): stage A
+// then carries the raw-tap gather as well. Kept out of the table-only instantiation, whose hot loop
+// should stay small (instruction-cache misses show up as `no_instruction` stalls in ncu).
+template <int NOSC, bool FILT, int NH, int VS, int R, bool RAW>
 __global__ void __launch_bounds__(SplitWarps<FILT, NH, VS>::threads) render_split(const RenderParams P) {
     typedef SplitLayout<NOSC, FILT, R> L;
     typedef SplitWarps<FILT, NH, VS> WR;
@@ -233,6 +236,7 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NH, VS>::threads) render_spli
         unsigned evp = 0, eve = 0;
         int next_ev = 0x7fffffff;
         bool in_seg = false;
+        unsigned open_mask = 0;
         if (valid) {
             alive = sp.ld(0) & 1;
 #pragma unroll
@@ -253,10 +257,9 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NH, VS>::threads) render_spli
             if (valid) {
                 int f = f0, seg = 0;
                 while (f < fe) {
-                    // ---- segment boundary: identical to render_bank ----
+                    // ---- segment boundary: as render_bank, except that an oscillator's
+                    // finish() / prepare() pair is skipped while nothing can change (see below) ----
                     if (in_seg) {
-#pragma unroll
-                        for (int i = 0; i < NOSC; ++i) osc[i].finish();
                         if (FILT) filt.finish();
                         pm.finish();
                     }
@@ -269,6 +272,7 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NH, VS>::threads) render_spli
 #pragma unroll
                             for (int i = 0; i < NOSC; ++i)
                                 if (unit == i) {
+                                    if ((open_mask >> i) & 1) { osc[i].finish(); open_mask &= ~(1u << i); }
                                     if (init) osc[i].init(c, (int)e.z, (unsigned)st);
                                     else osc[i].write(c, reg, (int)e.z, st, (int)e.w);
                                 }
@@ -290,9 +294,35 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NH, VS>::threads) render_spli
                         if (P.splits[k] > f) nxt = min(nxt, P.splits[k]);
                     in_seg = alive != 0;
                     const int n = nxt - f;
-                    if (in_seg) {
+                    // Oscillators. `open_mask` bit i: oscillator i has a segment open (its finish() is
+                    // still due). A mip-mapped oscillator whose rampers are at rest and that no event
+                    // touched runs the same segment again: wtosc.c:239-286 would recompute the same
+                    // mip level, increment and table, so only the loop wrap / end test of the
+                    // prologue is redone (phase >> mm << mm is the identity here: the low mm bits
+                    // are already zero). This prologue is ~400 dependent instructions per oscillator;
+                    // with eight oscillators it was the slowest role of the CTA by far.
 #pragma unroll
-                        for (int i = 0; i < NOSC; ++i) osc[i].prepare(c, n);
+                    for (int i = 0; i < NOSC; ++i) {
+                        const bool open = (open_mask >> i) & 1;
+                        bool fast = false;
+                        if (in_seg && open && osc[i].mode == OSC_MIP && osc[i].run == RUN_TABLE && !osc[i].p.timer &&
+                            !osc[i].p_ramping && osc[i].dphase && !osc[i].a.timer && !osc[i].astep &&
+                            osc[i].a.value == osc[i].a.target) {
+                            const WaveDesc &w = c.waves[osc[i].wave];
+                            const unsigned sz = w.size[osc[i].mm];
+                            if (w.flags & kLooped) {
+                                osc[i].ph = wrap_mod(osc[i].ph, (unsigned long long)sz << 24);
+                                fast = true;
+                            } else
+                                fast = (osc[i].ph >> 24) <= (unsigned long long)(sz + kWavePre);
+                        }
+                        if (!fast) {
+                            if (open) osc[i].finish();
+                            if (in_seg) osc[i].prepare(c, n);
+                            open_mask = in_seg ? (open_mask | (1u << i)) : (open_mask & ~(1u << i));
+                        }
+                    }
+                    if (in_seg) {
                         if (FILT) filt.prepare(c, n);
                         pm.prepare(c, n);
                     }
@@ -370,9 +400,10 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NH, VS>::threads) render_spli
             if (P.prof) busy += clock64() - tb;
         }
         if (valid) {
-            if (in_seg) {
 #pragma unroll
-                for (int i = 0; i < NOSC; ++i) osc[i].finish();
+            for (int i = 0; i < NOSC; ++i)
+                if ((open_mask >> i) & 1) osc[i].finish();
+            if (in_seg) {
                 if (FILT) filt.finish();
                 pm.finish();
             }
@@ -482,7 +513,7 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NH, VS>::threads) render_spli
                                     const int hv = hermite_cf_smem(cf, p16) + hermite_cf_smem(cf, p16 + half);
                                     acc[k] = wadd(acc[k], mulshr(hv, wadd(av0, wmul(astep, k)), 17));
                                 }
-                            } else {
+                            } else if (RAW) {
                                 // Raw int16 taps from the pool (sampled waves too large for a table): the
                                 // gather that goes to HBM. The phase is closed-form, so the taps of all
                                 // frames of the slice are requested before the first is used.
