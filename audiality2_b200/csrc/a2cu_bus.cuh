@@ -157,6 +157,18 @@ __device__ __noinline__ void bus_unit_dispatch(const Ctx &ctx, const BusCmd &c, 
         if (c.nin == 1) bus_unit_op<WaveShaper<1, false, false>>(ctx, c, st, acc, seed, seeded);
         else bus_unit_op<WaveShaper<2, false, false>>(ctx, c, st, acc, seed, seeded);
         break;
+    case 6:
+        if (c.nin == 1) bus_unit_op<Limiter<1, false, false>>(ctx, c, st, acc, seed, seeded);
+        else bus_unit_op<Limiter<2, false, false>>(ctx, c, st, acc, seed, seeded);
+        break;
+    case 7:
+        if (c.nin == 1) bus_unit_op<DcBlock<1, false, false>>(ctx, c, st, acc, seed, seeded);
+        else bus_unit_op<DcBlock<2, false, false>>(ctx, c, st, acc, seed, seeded);
+        break;
+    case 8:
+        if (c.nout == 1) bus_unit_op<Dc<1, false, false>>(ctx, c, st, acc, seed, seeded);
+        else bus_unit_op<Dc<2, false, false>>(ctx, c, st, acc, seed, seeded);
+        break;
     case 16: bus_unit_op<Fm<1, 0, 0, false, false>>(ctx, c, st, acc, seed, seeded); break;
     case 17: bus_unit_op<Fm<2, 1, 0, false, false>>(ctx, c, st, acc, seed, seeded); break;
     case 18: bus_unit_op<Fm<3, 2, 0, false, false>>(ctx, c, st, acc, seed, seeded); break;

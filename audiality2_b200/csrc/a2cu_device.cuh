@@ -666,6 +666,174 @@ struct WaveShaper {
 };
 
 // =============================================================================
+// dcblock (src/units/dcblock.c:65-94): the filter12 topology with a fixed high-pass output.
+// The coefficient (dcb_pitch2coeff, :57-63, host libm) arrives cooked from the host.
+// =============================================================================
+template <int CH, bool ADD, bool WIREOUT>
+struct DcBlock {
+    static constexpr int kWords = 1 + 2 * CH;
+    static constexpr bool kUsesFm = false;
+    int f1;
+    int d1[CH], d2[CH];
+    A2CU_DEV void load(const StatePtr &s, int w) {
+        f1 = s.ld(w);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) { d1[c] = s.ld(w + 1 + c); d2[c] = s.ld(w + 1 + CH + c); }
+    }
+    A2CU_DEV void store(const StatePtr &s, int w) const {
+        s.st(w, f1);
+#pragma unroll
+        for (int c = 0; c < CH; ++c) { s.st(w + 1 + c, d1[c]); s.st(w + 1 + CH + c, d2[c]); }
+    }
+    // dcblock.c:117-146; the default cutoff's coefficient follows as a cooked write
+    A2CU_DEV void init(const Ctx &, int, unsigned) {
+        f1 = 0;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) d1[c] = d2[c] = 0;
+    }
+    A2CU_DEV void write(const Ctx &, int reg, int v, int, int) { if (reg == 0) f1 = v; }
+    A2CU_DEV void prepare(const Ctx &, int) {}
+    A2CU_DEV void sample(const Ctx &, int &s0, int &s1, int &o0, int &o1) {
+        const int f = f1 >> 12;
+        int in[2] = { s0, s1 };
+        int out[2] = { 0, 0 };
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int d1s = d1[c] >> 4;
+            const int l = wadd(d2[c], wmul(f, d1s) >> 8);
+            const int h = wsub(wsub(in[c] >> 5, l), (int)((unsigned)d1s << 4));
+            const int b = wadd(wmul(f, h >> 4) >> 8, d1[c]);
+            out[c] = (int)((unsigned)h << 5);
+            d1[c] = b; d2[c] = l;
+        }
+        if (WIREOUT) { o0 = wadd(o0, out[0]); if (CH == 2) o1 = wadd(o1, out[1]); }
+        else if (ADD) { s0 = wadd(s0, out[0]); if (CH == 2) s1 = wadd(s1, out[1]); }
+        else { s0 = out[0]; if (CH == 2) s1 = out[1]; }
+    }
+    A2CU_DEV bool plain() const { return true; }
+    A2CU_DEV void sample_fast(const Ctx &c, int &s0, int &s1, int &o0, int &o1) { sample(c, s0, s1, o0, o1); }
+    A2CU_DEV void seed(unsigned) {}
+    A2CU_DEV void finish() {}
+};
+
+// =============================================================================
+// limiter (src/units/limiter.c:51-153). release and threshold arrive cooked
+// ((v << 8) / samplerate and max(v << 8, 256), :187-199); the peak follower's unsigned
+// arithmetic (peak -= release may wrap) is kept as written.
+// =============================================================================
+template <int CH, bool ADD, bool WIREOUT>
+struct Limiter {
+    static constexpr int kWords = 3;
+    static constexpr bool kUsesFm = false;
+    unsigned threshold, peak;
+    int release;
+    A2CU_DEV void load(const StatePtr &s, int w) {
+        threshold = (unsigned)s.ld(w); release = s.ld(w + 1); peak = (unsigned)s.ld(w + 2);
+    }
+    A2CU_DEV void store(const StatePtr &s, int w) const {
+        s.st(w, (int)threshold); s.st(w + 1, release); s.st(w + 2, (int)peak);
+    }
+    // limiter.c:156-184: arg = samplerate-cooked default release
+    A2CU_DEV void init(const Ctx &, int arg, unsigned) {
+        release = arg;
+        threshold = (unsigned)((1 << 16) << 8);
+        peak = 32768u << 8;
+    }
+    A2CU_DEV void write(const Ctx &, int reg, int v, int, int) {
+        if (reg == 0) release = v; else if (reg == 1) threshold = (unsigned)v;
+    }
+    A2CU_DEV void prepare(const Ctx &, int) {}
+    A2CU_DEV static unsigned uabs(int x) { return x < 0 ? 0u - (unsigned)x : (unsigned)x; }
+    A2CU_DEV void sample(const Ctx &, int &s0, int &s1, int &o0, int &o1) {
+        unsigned p;
+        if (CH == 1) p = uabs(s0);
+        else {
+            // limiter.c:109-113: int abs values, unsigned combination
+            const int lp = (int)uabs(s0), rp = (int)uabs(s1);
+            p = (unsigned)(lp > rp ? lp : rp);
+            p = p + ((p - uabs(wsub(lp, rp))) >> 1);
+        }
+        if (p > peak) peak = p;
+        else {
+            peak -= (unsigned)release;
+            if (peak < threshold) peak = threshold;
+            p = peak;
+        }
+        const int gain = (int)((32767LL << 16) / (long long)((p + 511u) >> 9));
+        const int r0 = mulshr(s0, gain, 16);
+        const int r1 = CH == 2 ? mulshr(s1, gain, 16) : 0;
+        if (WIREOUT) { o0 = wadd(o0, r0); if (CH == 2) o1 = wadd(o1, r1); }
+        else if (ADD) { s0 = wadd(s0, r0); if (CH == 2) s1 = wadd(s1, r1); }
+        else { s0 = r0; if (CH == 2) s1 = r1; }
+    }
+    A2CU_DEV bool plain() const { return true; }
+    A2CU_DEV void sample_fast(const Ctx &c, int &s0, int &s1, int &o0, int &o1) { sample(c, s0, s1, o0, o1); }
+    A2CU_DEV void seed(unsigned) {}
+    A2CU_DEV void finish() {}
+};
+
+// =============================================================================
+// dc (src/units/dc.c:57-140): a ramped (LINEAR) or stepped (STEP, one interpolated
+// "transient" sample at the switch point) constant on 1 or 2 outputs.
+// =============================================================================
+template <int NOUT, bool ADD, bool WIREOUT>
+struct Dc {
+    static constexpr int kWords = 5;
+    static constexpr bool kUsesFm = false;
+    Ramp value;
+    int mode;               // 0 STEP, 1 LINEAR (dc.c:34-43)
+    // segment-local (STEP): frames [0, fill_end) hold the old value, frame trans_at the transient
+    int k, fill_end, trans_at, tv, old_value;
+    A2CU_DEV void load(const StatePtr &s, int w) { s.ld_ramp(w, value); mode = s.ld(w + 4); k = 0; fill_end = 0; trans_at = -1; tv = 0; old_value = 0; }
+    A2CU_DEV void store(const StatePtr &s, int w) const { s.st_ramp(w, value); s.st(w + 4, mode); }
+    A2CU_DEV void init(const Ctx &, int, unsigned) { ramp_init(value, 0); mode = 1; }   // dc.c:153-180
+    // dc.c:183-247
+    A2CU_DEV void write(const Ctx &, int reg, int v, int start, int dur) {
+        if (reg == 1) {
+            mode = v >> 16;
+            if (mode != 0 && mode != 1) mode = 0;
+            return;
+        }
+        if (mode == 0) {
+            value.target = (int)((unsigned)v << 8);
+            value.timer = (int)(((unsigned)dur >> 1) - (unsigned)start);
+            if (value.timer <= 0) { value.value = value.target; value.timer = 0; }
+        } else
+            ramp_set(value, v, start, dur);
+    }
+    A2CU_DEV void prepare(const Ctx &, int frames) {
+        k = 0; fill_end = 0; trans_at = -1;
+        if (mode == 1) { ramp_prepare(value, frames); return; }
+        old_value = value.value;
+        int s = 0;
+        if (value.timer >= 256) {                           // dc.c:72-92
+            if ((value.timer >> 8) >= frames) { s = frames; value.timer -= frames << 8; }
+            else { s = value.timer >> 8; value.timer &= 0xff; }
+            fill_end = s;
+        }
+        if (value.timer < 256 && s < frames) {              // dc.c:94-108
+            tv = wadd(wmul(value.value >> 4, value.timer), wmul(value.target >> 4, 256 - value.timer)) >> 4;
+            trans_at = s;
+            value.timer = 0;
+            value.value = value.target;
+        }
+    }
+    A2CU_DEV void sample(const Ctx &, int &s0, int &s1, int &o0, int &o1) {
+        int v;
+        if (mode == 1) { v = value.value; value.value = wadd(value.value, value.delta); }
+        else v = k < fill_end ? old_value : (k == trans_at ? tv : value.target);
+        ++k;
+        if (WIREOUT) { o0 = wadd(o0, v); if (NOUT == 2) o1 = wadd(o1, v); }
+        else if (ADD) { s0 = wadd(s0, v); if (NOUT == 2) s1 = wadd(s1, v); }
+        else { s0 = v; if (NOUT == 2) s1 = v; }
+    }
+    A2CU_DEV bool plain() const { return true; }
+    A2CU_DEV void sample_fast(const Ctx &c, int &s0, int &s1, int &o0, int &o1) { sample(c, s0, s1, o0, o1); }
+    A2CU_DEV void seed(unsigned) {}
+    A2CU_DEV void finish() {}
+};
+
+// =============================================================================
 // fm1..fm4r (src/units/fm.c). NOPS operators, OSBITS oversampling bits,
 // PAR 0 = chain, 1 = parallel modulators, 2 = ring modulator pair.
 // As built, fm.c does not see A2_HIFI: fm1 1x, fm2/fm2r 2x, the rest 4x.

@@ -593,6 +593,9 @@ static int unit_words(const a2cu_unitspec &u) {
     case A2CU_FILTER12: return 12 + 2 * u.ninputs;
     case A2CU_WAVESHAPER: return 4;
     case A2CU_FBDELAY: return 10;
+    case A2CU_LIMITER: return 3;
+    case A2CU_DCBLOCK: return 1 + 2 * u.ninputs;
+    case A2CU_DC: return 5;
     default: {
         static const int nops[8] = {1, 2, 3, 4, 3, 4, 2, 4};
         return 16 * nops[u.kind - A2CU_FM1];
@@ -1136,6 +1139,23 @@ static int cook(a2cu_engine *e, int kind, int reg, int value, int start, uint32_
     case A2CU_FBDELAY:              // fbdelay.c:229-270: ms -> frames on the host, gains as they are
         if (reg > 6) return fail(A2CU_EINVAL, "fbdelay has 7 registers%s");
         if (reg < 3) value = (int)((int64_t)value * e->samplerate / 65536000);
+        break;
+    case A2CU_LIMITER:              // limiter.c:187-199
+        if (reg > 1) return fail(A2CU_EINVAL, "limiter has 2 registers%s");
+        if (reg == 0) value = (int)((unsigned)value << 8) / e->samplerate;
+        else {
+            unsigned t = (unsigned)value << 8;
+            value = (int)(t < 256 ? 256u : t);
+        }
+        break;
+    case A2CU_DCBLOCK: {            // dcblock.c:109-114: a2_P2I of the 16:16 pitch itself
+        if (reg > 0) return fail(A2CU_EINVAL, "dcblock has 1 register%s");
+        const int pitch = value + transpose;
+        value = tables().f12_coeff((int)((unsigned)pitch << 8), e->samplerate);
+        break;
+    }
+    case A2CU_DC:                   // dc.c:183-247: both registers go to the device as they are
+        if (reg > 1) return fail(A2CU_EINVAL, "dc has 2 registers%s");
         break;
     case A2CU_FILTER12:
         if (reg > 4) return fail(A2CU_EINVAL, "filter12 has 5 registers%s");
@@ -2396,10 +2416,12 @@ int a2cu_unit_alloc(a2cu_engine *e, int kind, int nin, int nout) {
     if (!e) return A2CU_EINVAL;
     a2cu_unitspec sp = {kind, nin, nout, 0, 0};
     bool known = kind == A2CU_WTOSC || kind == A2CU_PANMIX || kind == A2CU_FILTER12 || kind == A2CU_WAVESHAPER ||
-                 kind == A2CU_FBDELAY || (kind >= A2CU_FM1 && kind <= A2CU_FM4R);
+                 kind == A2CU_FBDELAY || kind == A2CU_LIMITER || kind == A2CU_DCBLOCK || kind == A2CU_DC ||
+                 (kind >= A2CU_FM1 && kind <= A2CU_FM4R);
     if (!known || nin < 0 || nin > 2 || nout < 1 || nout > 2 || unit_words(sp) > kUnitWords)
         return fail(A2CU_ENOTIMPL, "a2cu_unit_alloc: unsupported unit / channel count%s");
-    if ((kind == A2CU_FILTER12 || kind == A2CU_WAVESHAPER) && (nin != nout || nin < 1))
+    if ((kind == A2CU_FILTER12 || kind == A2CU_WAVESHAPER || kind == A2CU_LIMITER || kind == A2CU_DCBLOCK) &&
+        (nin != nout || nin < 1))
         return fail(A2CU_EINVAL, "a2cu_unit_alloc: unit needs matching i/o%s");
     if (kind == A2CU_FBDELAY && nin < 1) return fail(A2CU_EINVAL, "a2cu_unit_alloc: fbdelay needs an input%s");
     cudaSetDevice(e->device);
@@ -2473,7 +2495,11 @@ int a2cu_block_unit_init(a2cu_engine *e, int unit, int transpose, unsigned subst
         }
         return A2CU_OK;
     }
+    if (g->kind == A2CU_LIMITER)        // limiter.c:165-168: default release 64, cooked
+        arg = ((64 << 16) << 8) / e->samplerate;
     gunit_cmd(e, BUS_U_INIT, unit, *g, 0, arg, (int)(substart & 0xff), 0);
+    if (g->kind == A2CU_DCBLOCK)        // dcblock.c:127-128: default cutoff -5 (8.18 Hz), incl. transpose
+        return a2cu_block_unit_write(e, unit, 0, (int)((unsigned)-5 << 16), transpose, 0, 0);
     if (g->kind == A2CU_FILTER12)
         gunit_cmd(e, BUS_U_WRITE, unit, *g, 5, tables().f12_coeff((int)((unsigned)arg << 8), e->samplerate), 0, 0);
     if (g->kind == A2CU_WTOSC) {

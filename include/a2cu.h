@@ -61,6 +61,9 @@ typedef enum a2cu_error {
 enum {
 	A2CU_WTOSC = 1, A2CU_PANMIX = 2, A2CU_FILTER12 = 3, A2CU_WAVESHAPER = 4,
 	A2CU_FBDELAY = 5,	/* units/fbdelay.c; generic unit only */
+	A2CU_LIMITER = 6,	/* units/limiter.c; generic unit only */
+	A2CU_DCBLOCK = 7,	/* units/dcblock.c; generic unit only */
+	A2CU_DC = 8,		/* units/dc.c; generic unit only */
 	A2CU_FM1 = 16, A2CU_FM2, A2CU_FM3, A2CU_FM4,
 	A2CU_FM3P, A2CU_FM4P, A2CU_FM2R, A2CU_FM4R
 };

@@ -21,6 +21,9 @@
  *                              effect every song chains right after its
  *                              mix-down; on the host it would force a device
  *                              round trip per song and fragment)
+ *   src/units/limiter.h:28     a2_limiter_unitdesc   } the other bus effects of
+ *   src/units/dcblock.h:28     a2_dcblock_unitdesc   } SURVEY.md 8(f)1, same
+ *   src/units/dc.h:28          a2_dc_unitdesc        } reason
  *
  * Each descriptor carries the reference's name, flags, register names in VM
  * register order, constants and I/O limits (include/a2_units.h:225-252), so
@@ -29,7 +32,7 @@
  * :176 (Process).
  *
  * Build the host as the reference minus src/units/{wtosc,panmix,filter12,fm,
- * waveshaper,inline,fbdelay}.c and link this library in their place.
+ * waveshaper,inline,fbdelay,limiter,dcblock,dc}.c and link this library in their place.
  *
  * a2cu_RegisterDriver() additionally registers a "cuda" audio driver
  * (a2_RegisterDriver, include/a2_drivers.h:193) that behaves like the
@@ -61,6 +64,9 @@ extern const struct A2_unitdesc a2_fm2r_unitdesc;
 extern const struct A2_unitdesc a2_fm4r_unitdesc;
 extern const struct A2_unitdesc a2_inline_unitdesc;
 extern const struct A2_unitdesc a2_fbdelay_unitdesc;
+extern const struct A2_unitdesc a2_limiter_unitdesc;
+extern const struct A2_unitdesc a2_dcblock_unitdesc;
+extern const struct A2_unitdesc a2_dc_unitdesc;
 
 /* Returns an A2_errors code (0 = A2_OK). */
 int a2cu_RegisterDriver(void);

@@ -7,8 +7,9 @@
  *     a2_wtosc_unitdesc  a2_panmix_unitdesc  a2_filter12_unitdesc
  *     a2_waveshaper_unitdesc  a2_fm1 .. a2_fm4, a2_fm3p, a2_fm4p, a2_fm2r,
  *     a2_fm4r _unitdesc,  a2_inline_unitdesc (bus bracketing) and
- *     a2_fbdelay_unitdesc (the song-level effect that follows the mix-down,
- *     on the host it costs a device round trip per song)
+ *     a2_fbdelay_unitdesc, a2_limiter_unitdesc, a2_dcblock_unitdesc,
+ *     a2_dc_unitdesc (the bus / song-level effects that follow the mix-down,
+ *     on the host each costs a device round trip per call)
  *
  * The host (A2S compiler, VM, event scheduler, voice tree, drivers) is the
  * reference's own code, unmodified; it calls Initialize / write / Process /
@@ -565,6 +566,15 @@ static A2_errors unit_init(A2_unit *u, A2_vmstate *vms, void *statedata,
 		u->registers[0] = 65536;	/* panmix.c:264 */
 	else if(kind == A2CU_FILTER12)
 		u->registers[2] = 65536;	/* filter12.c:194 */
+	else if(kind == A2CU_LIMITER)
+	{
+		u->registers[0] = 64 << 16;	/* limiter.c:165-166 */
+		u->registers[1] = 1 << 16;
+	}
+	else if(kind == A2CU_DCBLOCK)
+		u->registers[0] = -5 << 16;	/* dcblock.c:127 */
+	else if(kind == A2CU_DC)
+		u->registers[1] = 1 << 16;	/* dc.c:164: LINEAR */
 	return A2_OK;
 }
 
@@ -1093,6 +1103,10 @@ INIT_CB(fm4p, A2CU_FM4P)
 INIT_CB(fm2r, A2CU_FM2R)
 INIT_CB(fm4r, A2CU_FM4R)
 
+INIT_CB(limiter, A2CU_LIMITER)
+INIT_CB(dcblock, A2CU_DCBLOCK)
+INIT_CB(dc, A2CU_DC)
+
 /* units/fbdelay.c:176-225: default register values */
 static A2_errors fbdelay_Initialize(A2_unit *u, A2_vmstate *vms,
 		void *statedata, unsigned flags)
@@ -1132,6 +1146,18 @@ static const A2_crdesc fbdelay_regs[] = {	/* fbdelay.c:286-296 */
 	{ "rdelay", unit_write2 }, { "drygain", unit_write3 },
 	{ "fbgain", unit_write4 }, { "lgain", unit_write5 },
 	{ "rgain", unit_write6 }, { NULL, NULL }
+};
+static const A2_crdesc limiter_regs[] = {	/* limiter.c:209-214 */
+	{ "release", unit_write0 }, { "threshold", unit_write1 }, { NULL, NULL }
+};
+static const A2_crdesc dcblock_regs[] = {	/* dcblock.c:157-161 */
+	{ "cutoff", unit_write0 }, { NULL, NULL }
+};
+static const A2_crdesc dc_regs[] = {		/* dc.c:249-254 */
+	{ "value", unit_write0 }, { "mode", unit_write1 }, { NULL, NULL }
+};
+static const A2_constdesc dc_constants[] = {	/* dc.c:256-265 */
+	{ "STEP", 0 << 16 }, { "LINEAR", 1 << 16 }, { NULL, 0 }
 };
 static const A2_crdesc waveshaper_regs[] = {	/* waveshaper.c:166-170 */
 	{ "amount", unit_write0 }, { NULL, NULL }
@@ -1196,6 +1222,12 @@ UNITDESC(a2_fm4r_unitdesc, "fm4r", 0, fm_regs, NULL, 0, 0, 1, 1,
 /* fbdelay.c:298-319 */
 UNITDESC(a2_fbdelay_unitdesc, "fbdelay", 0, fbdelay_regs, NULL, 1, 2, 1, 2,
 		fbdelay_Initialize)
+/* limiter.c:216-238, dcblock.c:163-185, dc.c:267-289 */
+UNITDESC(a2_limiter_unitdesc, "limiter", A2_MATCHIO, limiter_regs, NULL, 1, 2, 1, 2,
+		limiter_Initialize)
+UNITDESC(a2_dcblock_unitdesc, "dcblock", A2_MATCHIO, dcblock_regs, NULL, 1, 2, 1, 2,
+		dcblock_Initialize)
+UNITDESC(a2_dc_unitdesc, "dc", 0, dc_regs, dc_constants, 0, 0, 1, 2, dc_Initialize)
 /* units/inline.c:49-69 */
 UNITDESC(a2_inline_unitdesc, "inline", 0, NULL, NULL, 0, 0, 1, A2_MAXCHANNELS,
 		inline_Initialize)

@@ -385,4 +385,7 @@ SCRIPTS = {
     # replaced units outside fused leaf voices (generic per-unit device ops)
     "generic_chains": ("data/generic_chains.a2s", "Song", 40000, 48000, 64),
     "generic_chains_44k_b200": ("data/generic_chains.a2s", "Song", 30000, 44100, 200),
+    # limiter / dcblock / dc as device units
+    "bus_effects": ("data/bus_effects.a2s", "Song", 20000, 48000, 64),
+    "bus_effects_44k_b96": ("data/bus_effects.a2s", "Song", 16000, 44100, 96),
 }

@@ -88,7 +88,7 @@ def test_units_library_exports_every_descriptor():
     text = open(os.path.join(ROOT, "include", "a2cu_units.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     names = re.findall(r"extern const struct A2_unitdesc (a2_[a-z0-9]+_unitdesc);", text)
-    assert len(names) == 14
+    assert len(names) == 17
     import subprocess
     syms = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True).stdout
     for n in names + ["a2cu_RegisterDriver"]:
