@@ -99,32 +99,36 @@ struct BusVmParams {
     Ctx ctx;                // fmsine points at the global table here
 };
 
+// One call of one unit - Initialize / write / Process - on a voice's scratch channels.
+//   sp, w0   the unit's state: word w0 of the voice (AoS unit block: stride 1, w0 = 0; bank SoA: the bank's stride)
+//   scr      the voice's two scratch channels of this fragment, [frame][2]
+//   out      the voice's output bus of this fragment, [frame][2] (wire-out units add with atomics)
 template <class U>
-__device__ __noinline__ void bus_unit_op(const Ctx &ctx, const BusCmd &c, int *st, int *acc, unsigned seed, bool seeded) {
+__device__ __noinline__ void bus_unit_op(const Ctx &ctx, const BusCmd &c, const StatePtr sp, int w0, int *scr, int *out,
+                                         unsigned seed, bool seeded) {
     U u;
-    const StatePtr sp{st, 1};
     if (c.op == BUS_U_INIT) {
-        u.load(sp, 0);
+        u.load(sp, w0);
         u.init(ctx, c.value, (unsigned)c.start);
-        u.store(sp, 0);
+        u.store(sp, w0);
         return;
     }
-    u.load(sp, 0);
+    u.load(sp, w0);
     if (c.op == BUS_U_WRITE) {
         u.write(ctx, c.reg, c.value, c.start, c.dur);
-        u.store(sp, 0);
+        u.store(sp, w0);
         return;
     }
     const bool add = c.add & 1, wire = (c.add & 2) != 0;
     u.prepare(ctx, c.frames);
     if (seeded) u.seed(seed);
     for (int i = 0; i < c.frames; ++i) {
-        int *s = acc + ((size_t)c.in_bus * kMaxFrag + c.frame + i) * 2;
+        int *s = scr + (size_t)(c.frame + i) * 2;
         const int in0 = s[0], in1 = s[1];
         int s0 = in0, s1 = in1, o0 = 0, o1 = 0;
         u.sample(ctx, s0, s1, o0, o1);
         if (wire) {
-            int *o = acc + ((size_t)c.out_bus * kMaxFrag + c.frame + i) * 2;
+            int *o = out + (size_t)(c.frame + i) * 2;
             atomicAdd(o, s0);
             if (c.nout == 2) atomicAdd(o + 1, s1);
         } else if (add) {
@@ -136,49 +140,150 @@ __device__ __noinline__ void bus_unit_op(const Ctx &ctx, const BusCmd &c, int *s
         }
     }
     u.finish();
-    u.store(sp, 0);
+    u.store(sp, w0);
 }
 
-__device__ __noinline__ void bus_unit_dispatch(const Ctx &ctx, const BusCmd &c, int *st, int *acc, unsigned seed,
-                                               bool seeded) {
+__device__ __noinline__ void bus_unit_dispatch(const Ctx &ctx, const BusCmd &c, const StatePtr sp, int w0, int *scr,
+                                               int *out, unsigned seed, bool seeded) {
     switch (c.kind) {
-    case 1: bus_unit_op<WtOsc<false, false>>(ctx, c, st, acc, seed, seeded); break;
+    case 1: bus_unit_op<WtOsc<false, false>>(ctx, c, sp, w0, scr, out, seed, seeded); break;
     case 2:     // panmix normally takes the BUS_PM path; kept for completeness
-        if (c.nin == 1 && c.nout == 1) bus_unit_op<PanMix<1, 1, false, false>>(ctx, c, st, acc, seed, seeded);
-        else if (c.nin == 1) bus_unit_op<PanMix<1, 2, false, false>>(ctx, c, st, acc, seed, seeded);
-        else if (c.nout == 1) bus_unit_op<PanMix<2, 1, false, false>>(ctx, c, st, acc, seed, seeded);
-        else bus_unit_op<PanMix<2, 2, false, false>>(ctx, c, st, acc, seed, seeded);
+        if (c.nin == 1 && c.nout == 1) bus_unit_op<PanMix<1, 1, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded);
+        else if (c.nin == 1) bus_unit_op<PanMix<1, 2, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded);
+        else if (c.nout == 1) bus_unit_op<PanMix<2, 1, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded);
+        else bus_unit_op<PanMix<2, 2, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded);
         break;
     case 3:
-        if (c.nin == 1) bus_unit_op<Filter12<1, false, false>>(ctx, c, st, acc, seed, seeded);
-        else bus_unit_op<Filter12<2, false, false>>(ctx, c, st, acc, seed, seeded);
+        if (c.nin == 1) bus_unit_op<Filter12<1, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded);
+        else bus_unit_op<Filter12<2, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded);
         break;
     case 4:
-        if (c.nin == 1) bus_unit_op<WaveShaper<1, false, false>>(ctx, c, st, acc, seed, seeded);
-        else bus_unit_op<WaveShaper<2, false, false>>(ctx, c, st, acc, seed, seeded);
+        if (c.nin == 1) bus_unit_op<WaveShaper<1, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded);
+        else bus_unit_op<WaveShaper<2, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded);
         break;
     case 6:
-        if (c.nin == 1) bus_unit_op<Limiter<1, false, false>>(ctx, c, st, acc, seed, seeded);
-        else bus_unit_op<Limiter<2, false, false>>(ctx, c, st, acc, seed, seeded);
+        if (c.nin == 1) bus_unit_op<Limiter<1, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded);
+        else bus_unit_op<Limiter<2, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded);
         break;
     case 7:
-        if (c.nin == 1) bus_unit_op<DcBlock<1, false, false>>(ctx, c, st, acc, seed, seeded);
-        else bus_unit_op<DcBlock<2, false, false>>(ctx, c, st, acc, seed, seeded);
+        if (c.nin == 1) bus_unit_op<DcBlock<1, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded);
+        else bus_unit_op<DcBlock<2, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded);
         break;
     case 8:
-        if (c.nout == 1) bus_unit_op<Dc<1, false, false>>(ctx, c, st, acc, seed, seeded);
-        else bus_unit_op<Dc<2, false, false>>(ctx, c, st, acc, seed, seeded);
+        if (c.nout == 1) bus_unit_op<Dc<1, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded);
+        else bus_unit_op<Dc<2, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded);
         break;
-    case 16: bus_unit_op<Fm<1, 0, 0, false, false>>(ctx, c, st, acc, seed, seeded); break;
-    case 17: bus_unit_op<Fm<2, 1, 0, false, false>>(ctx, c, st, acc, seed, seeded); break;
-    case 18: bus_unit_op<Fm<3, 2, 0, false, false>>(ctx, c, st, acc, seed, seeded); break;
-    case 19: bus_unit_op<Fm<4, 2, 0, false, false>>(ctx, c, st, acc, seed, seeded); break;
-    case 20: bus_unit_op<Fm<3, 2, 1, false, false>>(ctx, c, st, acc, seed, seeded); break;
-    case 21: bus_unit_op<Fm<4, 2, 1, false, false>>(ctx, c, st, acc, seed, seeded); break;
-    case 22: bus_unit_op<Fm<2, 1, 2, false, false>>(ctx, c, st, acc, seed, seeded); break;
-    case 23: bus_unit_op<Fm<4, 2, 2, false, false>>(ctx, c, st, acc, seed, seeded); break;
+    case 16: bus_unit_op<Fm<1, 0, 0, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded); break;
+    case 17: bus_unit_op<Fm<2, 1, 0, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded); break;
+    case 18: bus_unit_op<Fm<3, 2, 0, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded); break;
+    case 19: bus_unit_op<Fm<4, 2, 0, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded); break;
+    case 20: bus_unit_op<Fm<3, 2, 1, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded); break;
+    case 21: bus_unit_op<Fm<4, 2, 1, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded); break;
+    case 22: bus_unit_op<Fm<2, 1, 2, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded); break;
+    case 23: bus_unit_op<Fm<4, 2, 2, false, false>>(ctx, c, sp, w0, scr, out, seed, seeded); break;
     default: break;
     }
+}
+
+// ---------------------------------------------------------------------------
+// render_generic: any voice structure, one thread per voice.
+//
+// The fused kernels (render_bank<Chain>, render_split) exist for the structures that carry the
+// load; every OTHER struct the compiler accepts (src/compiler.c:2991-3188: any list of units with
+// 0-2 scratch channels between them) runs here, the way the reference itself runs a voice: unit by
+// unit over each Process() segment (src/core.c:1875-1876), the scratch channels of the voice
+// (st->scratch[nest], core.c:364-395) in a private [64][2] row, wire-out units adding into the
+// voice's bus with integer atomics. The unit code is the same templates as everywhere else,
+// dispatched at run time (bus_unit_dispatch). Same state layout, event records and segment rules
+// as render_bank, in bank mode and in drop-in (explicit EV_PROC) mode.
+// ---------------------------------------------------------------------------
+constexpr int kMaxChain = 12;
+struct GenericChain {
+    int n;
+    int kind[kMaxChain], nin[kMaxChain], nout[kMaxChain];
+    int add[kMaxChain];         // bit 0 A2_PROCADD, bit 1 wire-out
+    int word[kMaxChain];        // first state word of the unit (after the voice's flags word)
+};
+
+__global__ void __launch_bounds__(kThreads) render_generic(const RenderParams P, const GenericChain G, int *scratch) {
+    const int idx = blockIdx.x * kThreads + threadIdx.x;
+    if (idx >= P.nvoices) return;
+    const bool expl = P.explicit_ != 0;
+    const int v = P.runs ? P.runs[idx].slot : idx;
+    Ctx c;
+    c.waves = P.waves; c.pool = P.pool; c.cpool = P.cpool; c.ptab = P.ptab; c.fmsine = P.fmsine; c.f12tab = P.f12tab;
+    c.samplerate = P.samplerate;
+    const StatePtr sp{P.state + v, P.stride};
+    int *scr = scratch + (size_t)v * kMaxFrag * 2;
+    int alive = sp.ld(0) & 1;
+    int mybus = expl ? -1 : P.bus_of[v];
+    unsigned evp = 0, eve = 0;
+    if (P.runs) { evp = P.runs[idx].ev_begin; eve = evp + P.runs[idx].ev_count; }
+    else if (P.ev_off) { evp = P.ev_off[v]; eve = P.ev_off[v + 1]; }
+    int next_ev = evp < eve ? (int)(P.ev[evp].x >> 8) : 0x7fffffff;
+    unsigned seeds[kMaxChain];
+    unsigned seeded = 0;
+    const int W = P.W;
+    BusCmd cmd;
+    auto unit_cmd = [&](int op, int u) {
+        cmd.op = op; cmd.kind = G.kind[u]; cmd.nin = G.nin[u]; cmd.nout = G.nout[u]; cmd.add = G.add[u];
+    };
+    auto apply = [&](const uint4 e) -> int {        // returns the frame count of an EV_PROC, else 0
+        const int kind = e.y & 0xff, unit = (e.y >> 8) & 0xff;
+        switch (kind) {
+        case EV_WRITE:
+        case EV_INIT:
+            if (unit < G.n) {
+                unit_cmd(kind == EV_INIT ? BUS_U_INIT : BUS_U_WRITE, unit);
+                cmd.reg = (e.y >> 16) & 0xff; cmd.value = (int)e.z; cmd.start = (int)(e.x & 0xff); cmd.dur = (int)e.w;
+                bus_unit_dispatch(c, cmd, sp, 1 + G.word[unit], nullptr, nullptr, 0, false);
+            }
+            break;
+        case EV_START: alive = 1; break;
+        case EV_STOP: alive = 0; break;
+        case EV_SEED: if (unit < G.n) { seeds[unit] = e.z; seeded |= 1u << unit; } break;
+        case EV_PROC: mybus = (int)e.z; return (e.y >> 8) & 0xff;
+        default: break;
+        }
+        return 0;
+    };
+    for (int f0 = 0; f0 < W;) {
+        const int fe = frag_end(f0, P.buffer, W);
+        int f = f0;
+        while (f < fe) {
+            int proc_n = 0;
+            while (next_ev <= f && !proc_n) {
+                proc_n = apply(P.ev[evp]);
+                ++evp;
+                next_ev = evp < eve ? (int)(P.ev[evp].x >> 8) : 0x7fffffff;
+            }
+            int nxt;
+            bool in_seg;
+            if (expl) {
+                nxt = proc_n ? min(fe, f + proc_n) : min(fe, next_ev);
+                in_seg = proc_n != 0;
+            } else {
+                nxt = min(fe, next_ev);
+                for (int k = 0; k < P.nsplits; ++k)
+                    if (P.splits[k] > f) nxt = min(nxt, P.splits[k]);
+                in_seg = alive != 0;
+            }
+            if (in_seg && mybus >= 0) {
+                int *out = P.acc + ((size_t)mybus * W + f0) * 2;
+                for (int u = 0; u < G.n; ++u) {         // core.c:1875-1876
+                    unit_cmd(BUS_U_RUN, u);
+                    cmd.frame = f - f0; cmd.frames = nxt - f;
+                    bus_unit_dispatch(c, cmd, sp, 1 + G.word[u], scr, out, seeds[u], (seeded >> u) & 1);
+                }
+            }
+            seeded = 0;
+            f = nxt;
+        }
+        f0 = fe;
+    }
+    if (expl)       // writes after the voice's last segment of the fragment (see render_bank)
+        while (evp < eve) apply(P.ev[evp++]);
+    sp.st(0, alive);
 }
 
 // fbdelay (units/fbdelay.c). State words: 0 fbdelay, 1 ldelay, 2 rdelay (frames,
@@ -258,7 +363,9 @@ __global__ void __launch_bounds__(kMaxFrag) bus_level(const BusVmParams P) {
             if (c.op == BUS_U_SEED) { seed = (unsigned)c.value; seeded = true; continue; }
             int *ust = P.ustate + (size_t)c.pm * kUnitWords;
             if (c.kind == kFbdKind) fbd_op(c, ust, acc, tid);
-            else if (tid == 0) bus_unit_dispatch(P.ctx, c, ust, acc, seed, seeded);
+            else if (tid == 0)
+                bus_unit_dispatch(P.ctx, c, StatePtr{ust, 1}, 0, acc + (size_t)c.in_bus * kMaxFrag * 2,
+                                  acc + (size_t)c.out_bus * kMaxFrag * 2, seed, seeded);
             if (c.op == BUS_U_RUN) seeded = false;
             __syncthreads();
             continue;

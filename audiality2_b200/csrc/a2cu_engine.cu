@@ -248,6 +248,10 @@ struct Bank {
     bool has_noise = false;
     bool exotic = false;    // selected a noise / one-shot sampled wave: render_bank only
     bool raw_taps = false;  // selected a wave without a coefficient table: render_split's raw-tap variant
+    // a structure without a fused kernel: render_generic (a2cu_bus.cuh) with a scratch row per voice
+    bool generic = false;
+    GenericChain gchain;
+    int *d_scratch = nullptr;
     cudaEvent_t ev_consumed = nullptr;  // recorded after the last kernel that reads d_ev (bank mode)
     bool enabled = true;    // a2cu_bank_enable: a disabled bank is paused (not rendered, events kept)
     int stage_wave = -1;    // wave whose coefficient table render_split stages in shared memory
@@ -603,6 +607,41 @@ static int unit_words(const a2cu_unitspec &u) {
     }
 }
 
+// Any struct of replaced units (0-2 scratch channels between them) that has no fused kernel runs
+// on render_generic. fbdelay is the exception: it is a CTA-cooperative bus unit (a2cu_bus.cuh).
+static bool generic_ok(const a2cu_unitspec *c, int n) {
+    if (n < 1 || n > kMaxChain) return false;
+    for (int i = 0; i < n; ++i) {
+        const int k = c[i].kind, ni = c[i].ninputs, no = c[i].noutputs;
+        const bool gen = k == A2CU_WTOSC || k == A2CU_DC || (k >= A2CU_FM1 && k <= A2CU_FM4R);
+        const bool matchio = k == A2CU_FILTER12 || k == A2CU_WAVESHAPER || k == A2CU_LIMITER || k == A2CU_DCBLOCK;
+        if (!gen && !matchio && k != A2CU_PANMIX) return false;
+        if (no < 1 || no > 2 || ni < 0 || ni > 2) return false;
+        if (gen && (ni != 0 || (k != A2CU_DC && no != 1))) return false;
+        if (matchio && (ni != no || ni < 1)) return false;
+        if (k == A2CU_PANMIX && ni < 1) return false;
+    }
+    return true;
+}
+static bool find_kernel(const a2cu_unitspec *chain, int n, KernelEntry *k, GenericChain *g, bool *generic) {
+    auto it = registry().find(sig_of(chain, n));
+    if (it != registry().end()) { *k = it->second; *generic = false; return true; }
+    if (!generic_ok(chain, n)) return false;
+    memset(k, 0, sizeof(*k));
+    memset(g, 0, sizeof(*g));
+    int w = 0;
+    g->n = n;
+    for (int i = 0; i < n; ++i) {
+        g->kind[i] = chain[i].kind; g->nin[i] = chain[i].ninputs; g->nout[i] = chain[i].noutputs;
+        g->add[i] = (chain[i].add ? 1 : 0) | (chain[i].wireout ? 2 : 0);
+        g->word[i] = w;
+        w += unit_words(chain[i]);
+    }
+    k->fn = nullptr; k->words = w + 1; k->name = "generic";
+    *generic = true;
+    return true;
+}
+
 // Read the control state of a voice's oscillators back from the device.
 static int mirror_create(a2cu_engine *e, int bank, int slot, VoiceMirror **out) {
     Bank *b = e->banks[bank];
@@ -835,7 +874,7 @@ void a2cu_close(a2cu_engine *e) {
     cudaStreamSynchronize(e->stream);
     xchg_release(e);
     for (Bank *b : e->banks) {
-        cudaFree(b->d_state); cudaFree(b->d_bus); cudaFree(b->d_noise);
+        cudaFree(b->d_state); cudaFree(b->d_bus); cudaFree(b->d_noise); cudaFree(b->d_scratch);
         cudaFree(b->d_ev); cudaFree(b->d_runs);
         if (b->ev_consumed) cudaEventDestroy(b->ev_consumed);
         delete b;
@@ -1028,7 +1067,15 @@ int a2cu_group_new(a2cu_engine *e) {
 
 int a2cu_chain_supported(const a2cu_unitspec *chain, int nunits) {
     register_all();
-    return registry().count(sig_of(chain, nunits)) ? 1 : 0;
+    return (registry().count(sig_of(chain, nunits)) || generic_ok(chain, nunits)) ? 1 : 0;
+}
+
+// Argument of a unit's EV_INIT / BUS_U_INIT record: what its Initialize() reads besides the registers.
+static int init_arg(const a2cu_engine *e, int kind, int transpose) {
+    if (kind == A2CU_WTOSC || kind >= A2CU_FM1) return transpose + e->basepitch;
+    if (kind == A2CU_FILTER12) return transpose;
+    if (kind == A2CU_LIMITER) return ((64 << 16) << 8) / e->samplerate;     // limiter.c:165-168, cooked
+    return 0;
 }
 
 static void push_event(Bank *b, uint64_t time, int voice, int kind, int unit, int reg, int value, uint32_t dur) {
@@ -1042,13 +1089,17 @@ static void push_event(Bank *b, uint64_t time, int voice, int kind, int unit, in
 int a2cu_bank_new(a2cu_engine *e, const a2cu_unitspec *chain, int nunits, int nvoices,
                   const int32_t *transpose, const int32_t *group, unsigned substart) {
     if (!e || !chain || nunits < 1 || nvoices < 1) return fail(A2CU_EINVAL, "a2cu_bank_new: bad args%s");
-    auto it = registry().find(sig_of(chain, nunits));
-    if (it == registry().end())
+    KernelEntry ke;
+    GenericChain gc;
+    bool generic = false;
+    if (!find_kernel(chain, nunits, &ke, &gc, &generic))
         return fail(A2CU_ENOTIMPL, "no kernel for voice structure %s", sig_of(chain, nunits).c_str());
     cudaSetDevice(e->device);
     Bank *b = new Bank();
     b->chain.assign(chain, chain + nunits);
-    b->k = it->second;
+    b->k = ke;
+    b->generic = generic;
+    b->gchain = gc;
     b->nvoices = nvoices;
     b->stamp = e->stamp++;
     b->stride = ((size_t)nvoices + kThreads - 1) / kThreads * kThreads;
@@ -1072,6 +1123,10 @@ int a2cu_bank_new(a2cu_engine *e, const a2cu_unitspec *chain, int nunits, int nv
     CK(cudaMemset(b->d_state, 0, sbytes));
     CK(cudaMemset(b->d_noise, 0, b->stride * sizeof(unsigned)));
     CK(cudaMemcpy(b->d_bus, bus.data(), b->stride * sizeof(int), cudaMemcpyHostToDevice));
+    if (b->generic) {
+        CK(cudaMalloc(&b->d_scratch, b->stride * kMaxFrag * 2 * sizeof(int)));
+        CK(cudaMemset(b->d_scratch, 0, b->stride * kMaxFrag * 2 * sizeof(int)));
+    }
     // Initialize() of every unit, in chain order, at the current time
     uint64_t t = (e->now & ~(uint64_t)0xff) | (substart & 0xff);
     const HostTables &tb = tables();
@@ -1079,13 +1134,14 @@ int a2cu_bank_new(a2cu_engine *e, const a2cu_unitspec *chain, int nunits, int nv
         push_event(b, t, i, EV_START, 0, 0, 0, 0);
         for (int u = 0; u < nunits; ++u) {
             int kind = chain[u].kind;
-            int arg = 0;
-            if (kind == A2CU_WTOSC || kind >= A2CU_FM1) arg = b->transpose[i] + e->basepitch;
-            else if (kind == A2CU_FILTER12) arg = b->transpose[i];
+            int arg = init_arg(e, kind, b->transpose[i]);
             push_event(b, t, i, EV_INIT, u, 0, arg, 0);
             if (kind == A2CU_FILTER12)      // exact coefficient from the host libm
                 push_event(b, t, i, EV_WRITE, u, 5,
                            tb.f12_coeff((int)((unsigned)arg << 8), e->samplerate), 0);
+            if (kind == A2CU_DCBLOCK)       // dcblock.c:127-128: default cutoff -5, cooked
+                push_event(b, t, i, EV_WRITE, u, 0,
+                           tb.f12_coeff((int)((unsigned)(b->transpose[i] - (5 << 16)) << 8), e->samplerate), 0);
         }
     }
     e->banks.push_back(b);
@@ -1792,7 +1848,8 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             }
         } else {
             int grid = (b->nvoices + kThreads - 1) / kThreads;
-            b->k.fn<<<grid, kThreads, 0, ls>>>(params[bi]);
+            if (b->generic) render_generic<<<grid, kThreads, 0, ls>>>(params[bi], b->gchain, b->d_scratch);
+            else b->k.fn<<<grid, kThreads, 0, ls>>>(params[bi]);
         }
         ++e->launches;
         if (!b->ev_consumed) CK(cudaEventCreateWithFlags(&b->ev_consumed, cudaEventDisableTiming));
@@ -2146,12 +2203,17 @@ int a2cu_pool_open(a2cu_engine *e, const a2cu_unitspec *chain, int nunits) {
     for (size_t i = 0; i < e->banks.size(); ++i)
         if (e->banks[i]->dynamic && sig_of(e->banks[i]->chain.data(), (int)e->banks[i]->chain.size()) == sig)
             return (int)i;
-    auto it = registry().find(sig);
-    if (it == registry().end()) return fail(A2CU_ENOTIMPL, "no kernel for voice structure %s", sig.c_str());
+    KernelEntry ke;
+    GenericChain gc;
+    bool generic = false;
+    if (!find_kernel(chain, nunits, &ke, &gc, &generic))
+        return fail(A2CU_ENOTIMPL, "no kernel for voice structure %s", sig.c_str());
     cudaSetDevice(e->device);
     Bank *b = new Bank();
     b->chain.assign(chain, chain + nunits);
-    b->k = it->second;
+    b->k = ke;
+    b->generic = generic;
+    b->gchain = gc;
     b->dynamic = true;
     b->nvoices = 0;
     b->stride = 1024;
@@ -2162,6 +2224,10 @@ int a2cu_pool_open(a2cu_engine *e, const a2cu_unitspec *chain, int nunits) {
     }
     CK(cudaMemset(b->d_state, 0, sbytes));
     CK(cudaMemset(b->d_noise, 0, b->stride * sizeof(unsigned)));
+    if (b->generic) {
+        CK(cudaMalloc(&b->d_scratch, b->stride * kMaxFrag * 2 * sizeof(int)));
+        CK(cudaMemset(b->d_scratch, 0, b->stride * kMaxFrag * 2 * sizeof(int)));
+    }
     e->banks.push_back(b);
     return (int)e->banks.size() - 1;
 }
@@ -2179,6 +2245,11 @@ static int pool_grow(a2cu_engine *e, Bank *b) {
                     b->k.words, cudaMemcpyDeviceToDevice));
     cudaFree(b->d_state); cudaFree(b->d_noise);
     b->d_state = nstate; b->d_noise = nnoise; b->stride = ns;
+    if (b->generic) {       // scratch rows hold nothing across fragments
+        cudaFree(b->d_scratch);
+        CK(cudaMalloc(&b->d_scratch, ns * kMaxFrag * 2 * sizeof(int)));
+        CK(cudaMemset(b->d_scratch, 0, ns * kMaxFrag * 2 * sizeof(int)));
+    }
     return A2CU_OK;
 }
 
@@ -2269,9 +2340,7 @@ int a2cu_block_init(a2cu_engine *e, int pool, int slot, int unit, int transpose,
     Bank *b = get_bank(e, pool);
     if (!b || !b->dynamic || unit < 0 || unit >= (int)b->chain.size()) return fail(A2CU_EINVAL, "bad pool/unit%s");
     int kind = b->chain[unit].kind;
-    int arg = 0;
-    if (kind == A2CU_WTOSC || kind >= A2CU_FM1) arg = transpose + e->basepitch;
-    else if (kind == A2CU_FILTER12) arg = transpose;
+    int arg = init_arg(e, kind, transpose);
     unsigned x = (frame << 8) | (substart & 0xff);
     if (unit == 0 && b->mirrored(slot)) {       // slot reused by a new voice
         e->mirrors.erase(((uint64_t)pool << 32) | (uint32_t)slot);
@@ -2281,6 +2350,9 @@ int a2cu_block_init(a2cu_engine *e, int pool, int slot, int unit, int transpose,
     if (kind == A2CU_FILTER12)
         block_rec(b, slot, x, EV_WRITE | ((unsigned)unit << 8) | (5u << 16),
                   tables().f12_coeff((int)((unsigned)arg << 8), e->samplerate), 0);
+    if (kind == A2CU_DCBLOCK)
+        block_rec(b, slot, x, EV_WRITE | ((unsigned)unit << 8),
+                  tables().f12_coeff((int)((unsigned)(transpose - (5 << 16)) << 8), e->samplerate), 0);
     return A2CU_OK;
 }
 
@@ -2481,9 +2553,7 @@ static void gunit_cmd(a2cu_engine *e, int op, int unit, const a2cu_engine::GUnit
 int a2cu_block_unit_init(a2cu_engine *e, int unit, int transpose, unsigned substart) {
     a2cu_engine::GUnit *g = get_gunit(e, unit);
     if (!g) return fail(A2CU_EINVAL, "a2cu_block_unit_init: bad unit%s");
-    int arg = 0;
-    if (g->kind == A2CU_WTOSC || g->kind >= A2CU_FM1) arg = transpose + e->basepitch;
-    else if (g->kind == A2CU_FILTER12) arg = transpose;
+    int arg = init_arg(e, g->kind, transpose);
     if (g->kind == A2CU_FBDELAY) {
         // fbdelay.c:176-208: cleared delay lines, default registers
         const uint64_t ptr = (uint64_t)(uintptr_t)g->fbd;
@@ -2495,8 +2565,6 @@ int a2cu_block_unit_init(a2cu_engine *e, int unit, int transpose, unsigned subst
         }
         return A2CU_OK;
     }
-    if (g->kind == A2CU_LIMITER)        // limiter.c:165-168: default release 64, cooked
-        arg = ((64 << 16) << 8) / e->samplerate;
     gunit_cmd(e, BUS_U_INIT, unit, *g, 0, arg, (int)(substart & 0xff), 0);
     if (g->kind == A2CU_DCBLOCK)        // dcblock.c:127-128: default cutoff -5 (8.18 Hz), incl. transpose
         return a2cu_block_unit_write(e, unit, 0, (int)((unsigned)-5 << 16), transpose, 0, 0);
@@ -2622,7 +2690,8 @@ static int block_flush_impl(a2cu_engine *e) {
         P.samplerate = e->samplerate;
         P.ev = b->d_ev; P.runs = b->d_runs; P.explicit_ = 1;
         int grid = ((int)nr + kThreads - 1) / kThreads;
-        b->k.fn<<<grid, kThreads, 0, e->stream>>>(P);
+        if (b->generic) render_generic<<<grid, kThreads, 0, e->stream>>>(P, b->gchain, b->d_scratch);
+        else b->k.fn<<<grid, kThreads, 0, e->stream>>>(P);
         ++e->launches;
         b->bev.clear(); b->bruns.clear(); b->cur_slot = -1;
     }
