@@ -39,8 +39,9 @@ __global__ void __launch_bounds__(512) mix_root_xchg(const MixParams P, const Xc
 }
 
 // The last window of a lagged sequence (nothing follows that could finish it).
-__global__ void __launch_bounds__(512) xchg_drain(const XchgParams X, int *rstate, int channels, int root_stage_on) {
-    xchg_finish_previous(X, rstate, channels, root_stage_on, threadIdx.x, blockDim.x);
+__global__ void __launch_bounds__(512) xchg_drain(const XchgParams X, int *rstate, int channels, int root_stage_on,
+                                                  int out_fmt) {
+    xchg_finish_previous(X, rstate, channels, root_stage_on, threadIdx.x, blockDim.x, out_fmt);
 }
 
 // ---------------------------------------------------------------------------

@@ -23,6 +23,7 @@
 #include "../../include/a2cu.h"
 #include "a2cu_kernels.cuh"
 #include "a2cu_bus.cuh"
+#include "a2cu_waves.cuh"
 #include "a2cu_registry.h"
 
 using namespace a2cu;
@@ -205,13 +206,18 @@ struct VoiceMirror {
 // ---------------------------------------------------------------------------
 // Engine objects
 // ---------------------------------------------------------------------------
+// A wave as the host knows it: geometry only. The samples live in the device pool; pads, mip
+// levels and Hermite coefficients are produced there (a2cu_waves.cuh).
 struct HostWave {
     int type;
     unsigned flags, period;
-    std::vector<int16_t> data[kMipLevels];  // incl. pads
-    unsigned size[kMipLevels];
+    unsigned size[kMipLevels];      // excluding pads
+    size_t first[kMipLevels];       // pool index of the level's FIRST PAD sample
+    size_t span[kMipLevels];        // samples incl. pads (0: level absent)
+    int coff[kMipLevels];           // coefficient-pool index of sample 0, -1: none
     std::string name;
-    int cbegin = -1, ccount = 0;            // range in the Hermite coefficient pool
+    int cbegin = -1, ccount = 0;    // range in the Hermite coefficient pool
+    size_t total() const { size_t t = 0; for (int l = 0; l < kMipLevels; ++l) t += span[l]; return t; }
 };
 
 struct HostEvent {
@@ -302,12 +308,14 @@ struct a2cu_engine {
     uint32_t noiseseed = 324357;
     cudaStream_t stream = 0;
     bool post_root = true;
+    int out_fmt = 0;            // a2cu_set_output_format
     std::vector<HostWave> waves;
     bool waves_dirty = true;
     WaveDesc *d_waves = nullptr;
     int16_t *d_pool = nullptr;
     int4 *d_cpool = nullptr;
     size_t pool_cap = 0, waves_cap = 0, cpool_cap = 0;
+    size_t pool_used = 0, cpool_used = 0;   // device arenas: waves are appended, never moved
     unsigned *d_ptab = nullptr;
     int16_t *d_fmsine = nullptr;
     int *d_f12tab = nullptr;        // f12_table(samplerate)
@@ -700,102 +708,106 @@ static int stage_release(a2cu_engine *e) {
 // Waves (host preparation; semantics of waves.c:59-151 and :629-708)
 // ---------------------------------------------------------------------------
 static const int kPost = 132;   // A2_WAVEPOST, a2_waves.h:63-64
+// Hermite coefficients (16 bytes per sample) only for waves up to this many samples incl. pads;
+// longer (sampled) waves are interpolated from the raw int16 data (render_split's raw-tap path)
+static const size_t kCoefMaxSamples = 1u << 20;
+static const size_t kCoefSlack = 64;    // zero entries after the last table: render_split reads ahead
 
-static void wave_pad(HostWave &w, int lvl) {
-    std::vector<int16_t> &d = w.data[lvl];
-    unsigned n = w.size[lvl];
-    if ((w.flags & A2CU_LOOPED) && n) {
-        d[0] = d[n];                                   // pre pad = last sample
-        for (int i = 0; i < kPost; ++i) d[kWavePre + n + i] = d[kWavePre + i % n];
-    } else {
-        d[0] = 0;
-        for (int i = 0; i < kPost; ++i) d[kWavePre + n + i] = 0;
+// Make room for `need` more elements in a device arena (contents are kept, new space is zeroed).
+template <class T>
+static int arena_reserve(a2cu_engine *e, T **buf, size_t *cap, size_t used, size_t need) {
+    if (used + need <= *cap) return A2CU_OK;
+    CK(cudaStreamSynchronize(e->stream));
+    size_t ncap = std::max((used + need) * 2, (size_t)1 << 16);
+    T *n = nullptr;
+    if (cudaMalloc(&n, ncap * sizeof(T)) != cudaSuccess)
+        return fail(A2CU_ENOMEM, "cudaMalloc wave pool: %s", cudaGetErrorString(cudaGetLastError()));
+    CK(cudaMemset(n, 0, ncap * sizeof(T)));
+    if (*buf) {
+        CK(cudaMemcpy(n, *buf, used * sizeof(T), cudaMemcpyDeviceToDevice));
+        cudaFree(*buf);
     }
+    *buf = n;
+    *cap = ncap;
+    return A2CU_OK;
 }
 
-static void wave_build(HostWave &w, const int16_t *src, unsigned length) {
-    int levels = w.type == A2CU_WMIPWAVE ? kMipLevels : (w.type == A2CU_WWAVE ? 1 : 0);
-    for (int l = 0; l < kMipLevels; ++l) w.size[l] = 0;
+// Geometry of a new wave (waves.c:59-88): level l holds ceil(length / 2^l) samples plus the pads.
+static void wave_layout(a2cu_engine *e, HostWave &w, const unsigned *sizes, int levels) {
+    size_t pos = e->pool_used;
+    for (int l = 0; l < kMipLevels; ++l) {
+        w.size[l] = 0; w.first[l] = 0; w.span[l] = 0; w.coff[l] = -1;
+        if (l < levels) {
+            w.size[l] = sizes[l];
+            w.first[l] = pos;
+            w.span[l] = (size_t)kWavePre + sizes[l] + kPost;
+            pos += w.span[l];
+        }
+    }
+    w.cbegin = -1; w.ccount = 0;
+}
+
+// Pads (unless the host already made them), and the coefficient tables, on the device.
+static int wave_finish_on_device(a2cu_engine *e, HostWave &w, int levels, bool build_levels) {
+    const int looped = (w.flags & A2CU_LOOPED) ? 1 : 0;
     for (int l = 0; l < levels; ++l) {
-        w.size[l] = (length + (1u << l) - 1) >> l;
-        w.data[l].assign(kWavePre + w.size[l] + kPost, 0);
+        int16_t *lvl = e->d_pool + w.first[l];
+        if (build_levels) {
+            if (l > 0 && w.size[l]) {       // waves.c:108-151: level l from level l - 1 (already padded)
+                const int16_t *src = e->d_pool + w.first[l - 1] + kWavePre;
+                wave_mip<<<(w.size[l] + 255) / 256, 256, 0, e->stream>>>(src, lvl + kWavePre, w.size[l]);
+                ++e->launches;
+            }
+            wave_pad<<<1, 256, 0, e->stream>>>(lvl, w.size[l], looped);     // waves.c:90-106
+            ++e->launches;
+        }
     }
-    if (!levels) return;
-    std::copy(src, src + length, w.data[0].begin() + kWavePre);
-    wave_pad(w, 0);
-    for (int l = 1; l < levels; ++l) {
-        const int16_t *sd = w.data[l - 1].data() + kWavePre;
-        int16_t *d = w.data[l].data() + kWavePre;
-        for (int s = 0; s < (int)w.size[l]; ++s)
-            d[s] = (int16_t)((((int)sd[s * 2] << 1) + sd[s * 2 - 1] + sd[s * 2 + 1]) >> 2);
-        wave_pad(w, l);
+    if (levels && w.total() <= kCoefMaxSamples) {
+        size_t need = 0;
+        for (int l = 0; l < levels; ++l) need += (size_t)w.size[l] + kPost - 2;
+        int r = arena_reserve(e, &e->d_cpool, &e->cpool_cap, e->cpool_used, need + kCoefSlack);
+        if (r) return r;
+        w.cbegin = (int)e->cpool_used;
+        for (int l = 0; l < levels; ++l) {
+            const int n = (int)w.size[l] + kPost - 2;
+            w.coff[l] = (int)e->cpool_used;
+            wave_coef<<<(n + 255) / 256, 256, 0, e->stream>>>(e->d_pool + w.first[l] + kWavePre, e->d_cpool + e->cpool_used, n);
+            ++e->launches;
+            e->cpool_used += (size_t)n;
+        }
+        w.ccount = (int)e->cpool_used - w.cbegin;
     }
+    CK(cudaGetLastError());
+    return A2CU_OK;
 }
 
+// The wave descriptor table is the only thing left to (re)upload when waves change.
 static int upload_waves(a2cu_engine *e) {
     if (!e->waves_dirty) return 0;
-    size_t total = 0;
-    for (auto &w : e->waves)
-        for (int l = 0; l < kMipLevels; ++l) total += w.data[l].size();
     std::vector<WaveDesc> desc(e->waves.size());
-    std::vector<int16_t> pool(total ? total : 1);
-    // Two-stage Hermite coefficients (a2_Hermite2c, a2_dsp.h:83-89) for every
-    // sample position the oscillator can address: i in [0, size + kPost - 3].
-    // 16 bytes per sample, so only waves up to kCoefMaxSamples get a table;
-    // longer (sampled) waves are interpolated from the raw int16 data.
-    const size_t kCoefMaxSamples = 1u << 20;
-    std::vector<int4> cpool;
-    size_t pos = 0;
     for (size_t i = 0; i < e->waves.size(); ++i) {
-        HostWave &w = e->waves[i];
+        const HostWave &w = e->waves[i];
         desc[i].type = w.type; desc[i].flags = w.flags; desc[i].period = w.period;
-        size_t wave_total = 0;
-        for (int l = 0; l < kMipLevels; ++l) wave_total += w.data[l].size();
-        w.cbegin = -1; w.ccount = 0;
         for (int l = 0; l < kMipLevels; ++l) {
             desc[i].size[l] = w.size[l];
-            desc[i].offset[l] = (unsigned)(pos + kWavePre);
-            desc[i].coff[l] = -1;
-            if (!w.data[l].empty()) {
-                std::copy(w.data[l].begin(), w.data[l].end(), pool.begin() + pos);
-                pos += w.data[l].size();
-                if (wave_total <= kCoefMaxSamples) {
-                    const int16_t *d = w.data[l].data() + kWavePre;
-                    int n = (int)w.size[l] + kPost - 2;
-                    desc[i].coff[l] = (int)cpool.size();
-                    if (w.cbegin < 0) w.cbegin = (int)cpool.size();
-                    w.ccount = (int)cpool.size() + n - w.cbegin;
-                    for (int k = 0; k < n; ++k) {
-                        int dm = d[k - 1], d0 = d[k], d1 = d[k + 1], d2 = d[k + 2];
-                        int c = (d1 - dm) >> 1;
-                        int a = (3 * (d0 - d1) + d2 - dm) >> 1;
-                        int b = dm - d0 + c - a;
-                        cpool.push_back(make_int4(d0, a, b, c));
-                    }
-                }
-            }
+            desc[i].offset[l] = (unsigned)(w.first[l] + kWavePre);
+            desc[i].coff[l] = w.coff[l];
         }
     }
     CK(cudaStreamSynchronize(e->stream));
-    if (pool.size() > e->pool_cap) {
-        if (e->d_pool) cudaFree(e->d_pool);
-        e->pool_cap = pool.size() * 2;
-        CK(cudaMalloc(&e->d_pool, e->pool_cap * sizeof(int16_t)));
-    }
     if (desc.size() > e->waves_cap) {
         if (e->d_waves) cudaFree(e->d_waves);
         e->waves_cap = desc.size() * 2 + 8;
         CK(cudaMalloc(&e->d_waves, e->waves_cap * sizeof(WaveDesc)));
     }
-    for (int k = 0; k < 64; ++k) cpool.push_back(make_int4(0, 0, 0, 0));   // slack: render_split reads ahead
-    if (cpool.size() > e->cpool_cap) {
-        if (e->d_cpool) cudaFree(e->d_cpool);
-        e->cpool_cap = cpool.size() * 2;
-        CK(cudaMalloc(&e->d_cpool, e->cpool_cap * sizeof(int4)));
+    if (!e->d_pool) {       // kernels take the pointers even when no wave has samples
+        int r = arena_reserve(e, &e->d_pool, &e->pool_cap, 0, 16);
+        if (r) return r;
     }
-    if (!cpool.empty())
-        CK(cudaMemcpy(e->d_cpool, cpool.data(), cpool.size() * sizeof(int4), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(e->d_pool, pool.data(), pool.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+    if (!e->d_cpool) {
+        int r = arena_reserve(e, &e->d_cpool, &e->cpool_cap, 0, kCoefSlack);
+        if (r) return r;
+    }
     if (!desc.empty())
         CK(cudaMemcpy(e->d_waves, desc.data(), desc.size() * sizeof(WaveDesc), cudaMemcpyHostToDevice));
     e->waves_dirty = false;
@@ -959,15 +971,40 @@ int a2cu_set_timing(a2cu_engine *e, int on) { e->timing = on != 0; return A2CU_O
 float a2cu_last_render_ms(a2cu_engine *e) { return e->last_ms; }
 float a2cu_last_mix_ms(a2cu_engine *e) { return e->last_mix_ms; }
 int a2cu_set_post_root_stage(a2cu_engine *e, int on) { e->post_root = on != 0; return A2CU_OK; }
+int a2cu_set_output_format(a2cu_engine *e, int fmt) {
+    if (!e || fmt < 0 || fmt > 2) return fail(A2CU_EINVAL, "a2cu_set_output_format: 0 int32, 1 float32, 2 int16%s");
+    e->out_fmt = fmt;
+    return A2CU_OK;
+}
+// bytes of one output sample (the raw root bus of the multi-GPU cut is always int32)
+static size_t out_sample_bytes(const a2cu_engine *e) { return (e->post_root && e->out_fmt == 2) ? 2 : 4; }
 
 // ---- waves -----------------------------------------------------------------
 int a2cu_wave_upload(a2cu_engine *e, int type, unsigned period, unsigned flags, const int16_t *data,
                      unsigned length) {
     if (!e || type < A2CU_WOFF || type > A2CU_WMIPWAVE) return fail(A2CU_EINVAL, "bad wave type%s");
     if ((type == A2CU_WWAVE || type == A2CU_WMIPWAVE) && !data && length) return fail(A2CU_EINVAL, "no data%s");
+    cudaSetDevice(e->device);
     HostWave w;
     w.type = type; w.flags = flags; w.period = period;
-    wave_build(w, data, length);
+    const int levels = type == A2CU_WMIPWAVE ? kMipLevels : (type == A2CU_WWAVE ? 1 : 0);
+    unsigned sizes[kMipLevels];
+    for (int l = 0; l < kMipLevels; ++l) sizes[l] = (length + (1u << l) - 1) >> l;
+    size_t need = 0;
+    for (int l = 0; l < levels; ++l) need += (size_t)kWavePre + sizes[l] + kPost;
+    int r = arena_reserve(e, &e->d_pool, &e->pool_cap, e->pool_used, need + 16);
+    if (r) return r;
+    wave_layout(e, w, sizes, levels);
+    if (levels) {
+        // only the raw samples cross the bus; pads, mip levels and coefficients are made on the device
+        if (length)
+            CK(cudaMemcpyAsync(e->d_pool + w.first[0] + kWavePre, data, (size_t)length * sizeof(int16_t),
+                               cudaMemcpyHostToDevice, e->stream));
+        e->h2d_bytes += (size_t)length * sizeof(int16_t);
+        e->pool_used += need;
+        r = wave_finish_on_device(e, w, levels, true);
+        if (r) return r;
+    }
     e->waves.push_back(std::move(w));
     e->waves_dirty = true;
     return (int)e->waves.size() - 1;
@@ -976,13 +1013,26 @@ int a2cu_wave_upload(a2cu_engine *e, int type, unsigned period, unsigned flags, 
 int a2cu_wave_upload_prepared(a2cu_engine *e, int type, unsigned period, unsigned flags,
                               const int16_t *const *data, const unsigned *size) {
     if (!e) return A2CU_EINVAL;
+    cudaSetDevice(e->device);
     HostWave w;
     w.type = type; w.flags = flags; w.period = period;
-    int levels = type == A2CU_WMIPWAVE ? kMipLevels : (type == A2CU_WWAVE ? 1 : 0);
-    for (int l = 0; l < kMipLevels; ++l) w.size[l] = 0;
-    for (int l = 0; l < levels; ++l) {
-        w.size[l] = size[l];
-        w.data[l].assign(data[l], data[l] + kWavePre + size[l] + kPost);
+    const int levels = type == A2CU_WMIPWAVE ? kMipLevels : (type == A2CU_WWAVE ? 1 : 0);
+    size_t need = 0;
+    for (int l = 0; l < levels; ++l) need += (size_t)kWavePre + size[l] + kPost;
+    int r = arena_reserve(e, &e->d_pool, &e->pool_cap, e->pool_used, need + 16);
+    if (r) return r;
+    wave_layout(e, w, size, levels);
+    if (levels) {
+        // the host's own prepared buffers, pads included, exactly as they are (a2_waves.h:88-103)
+        for (int l = 0; l < levels; ++l) {
+            CK(cudaMemcpyAsync(e->d_pool + w.first[l], data[l], w.span[l] * sizeof(int16_t), cudaMemcpyHostToDevice,
+                               e->stream));
+            e->h2d_bytes += w.span[l] * sizeof(int16_t);
+        }
+        CK(cudaStreamSynchronize(e->stream));       // the host may free or rewrite its buffers
+        e->pool_used += need;
+        r = wave_finish_on_device(e, w, levels, false);
+        if (r) return r;
     }
     e->waves.push_back(std::move(w));
     e->waves_dirty = true;
@@ -1036,11 +1086,15 @@ int a2cu_wave_unload(a2cu_engine *e, int wave) {
 
 int a2cu_wave_read(a2cu_engine *e, int wave, int level, int16_t *out, unsigned cap, unsigned *size) {
     if (!e || wave < 0 || wave >= (int)e->waves.size() || level < 0 || level >= kMipLevels) return A2CU_EINVAL;
-    const std::vector<int16_t> &d = e->waves[wave].data[level];
-    if (size) *size = e->waves[wave].size[level];
-    unsigned n = (unsigned)std::min((size_t)cap, d.size());
-    if (out) memcpy(out, d.data(), n * sizeof(int16_t));
-    return (int)n;
+    const HostWave &w = e->waves[wave];
+    if (size) *size = w.size[level];
+    unsigned n = (unsigned)std::min((size_t)cap, w.span[level]);
+    if (out && n) {
+        cudaSetDevice(e->device);
+        CK(cudaStreamSynchronize(e->stream));
+        CK(cudaMemcpy(out, e->d_pool + w.first[level], (size_t)n * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    }
+    return (int)(out ? n : w.span[level]);
 }
 
 // ---- groups and banks ------------------------------------------------------
@@ -1249,8 +1303,7 @@ static int cook_write(a2cu_engine *e, Bank *b, int voice, int unit, int reg, int
     if (n < 0) return n;
     if (b->chain[unit].kind == A2CU_WTOSC && c[0].reg == 0 && c[0].value >= 0) {
         const HostWave &hw = e->waves[c[0].value];
-        size_t total = 0;
-        for (int l = 0; l < kMipLevels; ++l) total += hw.data[l].size();
+        const size_t total = hw.total();
         // render_split evaluates oscillators in closed form: fine for every looped or mip-mapped
         // wave (coefficient table, or raw taps from the pool for large sampled waves); the shared
         // noise LCG and the per-sample end check of a one-shot wave above A2_MAXPHINC
@@ -1535,7 +1588,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             return fail(A2CU_EINVAL, "too many root events in one fragment%s");
         int r = run_window(e, h, b0, base, allow_lag);
         if (r) return r;
-        return run_window(e, frames - h, b1, base + (size_t)h * och, allow_lag);
+        return run_window(e, frames - h, b1, (int32_t *)((char *)base + (size_t)h * och * out_sample_bytes(e)), allow_lag);
     }
     int r = upload_waves(e);
     if (r) return r;
@@ -1823,6 +1876,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
                 params[bi].fuse_master = dev_out ? dev_out : e->d_master;
                 params[bi].fuse_channels = e->channels;
                 params[bi].fuse_root_stage = e->post_root ? 1 : 0;
+                params[bi].fuse_out_fmt = e->post_root ? e->out_fmt : 0;
                 params[bi].xchg = X;
                 if (X.world > 1 && allow_lag) {
                     // pipelined + sharded: this launch publishes its bus and finishes the pending window
@@ -1894,6 +1948,7 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
     }
     M.master = dev_out ? dev_out : e->d_master;
     M.root_stage = e->post_root ? 1 : 0;
+    M.out_fmt = e->post_root ? e->out_fmt : 0;
     M.clear = 1;
     if (e->root_written && t0 < e->root_until) { M.general = 1; e->root_extra = true; }
     else if (e->root_extra) { M.general = 1; e->root_extra = false; }
@@ -1940,7 +1995,7 @@ static int xchg_drain_pending(a2cu_engine *e) {
     }
     X.status = x.h_status; X.timeout_cycles = x.timeout_cycles;
     xchg_fill_prev(e, X);
-    xchg_drain<<<1, 512, 0, e->stream>>>(X, e->d_rstate, e->channels, e->post_root ? 1 : 0);
+    xchg_drain<<<1, 512, 0, e->stream>>>(X, e->d_rstate, e->channels, e->post_root ? 1 : 0, e->post_root ? e->out_fmt : 0);
     ++e->launches;
     CK(cudaGetLastError());
     x.pending.valid = false;
@@ -1984,12 +2039,12 @@ int a2cu_run(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *out) {
             e->hout_cap = n * 2;
             CK(cudaMallocHost(&e->h_out, e->hout_cap * sizeof(int32_t)));
         }
-        CK(cudaMemcpyAsync(e->h_out, e->d_master, n * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
-        e->d2h_bytes += n * sizeof(int32_t);
+        CK(cudaMemcpyAsync(e->h_out, e->d_master, n * out_sample_bytes(e), cudaMemcpyDeviceToHost, e->stream));
+        e->d2h_bytes += n * out_sample_bytes(e);
     }
     r = a2cu_sync(e);
     if (r) return r;
-    if (out) memcpy(out, e->h_out, n * sizeof(int32_t));
+    if (out) memcpy(out, e->h_out, n * out_sample_bytes(e));
     return A2CU_OK;
 }
 
@@ -2035,7 +2090,7 @@ static int submit_impl(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t
     // sharded + lagged: this window's output is finished by the next launch (or by a2cu_collect)
     if (e->xchg.pending.valid) e->xchg.deferred_slot = k;
     else CK(cudaEventRecord(sl.done, e->stream));
-    if (!dev_out) e->d2h_bytes += n * sizeof(int32_t);
+    if (!dev_out) e->d2h_bytes += n * out_sample_bytes(e);
     sl.n = dev_out ? 0 : n;
     sl.busy = true;
     e->slot_pos = (k + 1) % a2cu_engine::kSlots;
@@ -2052,7 +2107,7 @@ int a2cu_collect(a2cu_engine *e, int ticket, int32_t *out) {
         if (r) return r;
     }
     CK(cudaEventSynchronize(sl.done));
-    if (out && sl.n) memcpy(out, sl.h_out, sl.n * sizeof(int32_t));
+    if (out && sl.n) memcpy(out, sl.h_out, sl.n * out_sample_bytes(e));
     if (e->timing) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, sl.ev0, sl.ev1) == cudaSuccess) e->last_ms = ms;

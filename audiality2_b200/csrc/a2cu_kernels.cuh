@@ -185,6 +185,7 @@ struct RenderParams {
     int *fuse_master;
     int fuse_channels;
     int fuse_root_stage;    // 0: copy the raw root bus out (multi-GPU cut) instead of the root panmix
+    int fuse_out_fmt;       // MixParams::out_fmt of the fused root stage
     XchgParams xchg;        // world > 1: sum the root bus over all ranks before the root stage
 };
 
@@ -382,7 +383,18 @@ struct MixParams {
     int root_stage;
     int clear;              // consumers zero the bus rows they read, so the next window needs no memset
     int general;            // host: a root ramp may be in flight - one CTA replays segments, no steady path
+    int out_fmt;            // a2cu_set_output_format: 0 int32 8:24, 1 float32, 2 int16 (master block only)
 };
+
+// The driver edge, fused into the root stage: what the reference's audio drivers and wave writer do
+// with the int32 8:24 master buffers - float = v * (1 / 8388608) (drivers/sdldrv.c:55-65, jackdrv
+// alike), int16 = v >> 8 (a2_RenderWave -> a2_WaveWrite(A2_I24), waves.c:174-176). `i` indexes
+// samples of the interleaved block [frame][channel].
+A2CU_DEV void master_put(const MixParams &P, int i, int v) {
+    if (P.out_fmt == 1) reinterpret_cast<float *>(P.master)[i] = __int2float_rn(v) * (1.0f / 8388608.0f);
+    else if (P.out_fmt == 2) reinterpret_cast<short *>(P.master)[i] = (short)(v >> 8);
+    else P.master[i] = v;
+}
 
 A2CU_DEV void pm_load(const int *s, Ramp &vol, Ramp &pan) {
     vol.value = s[0]; vol.target = s[1]; vol.delta = s[2]; vol.timer = s[3];
@@ -518,16 +530,16 @@ A2CU_DEV void root_stage(const MixParams &P, int gtid, int gsize, bool cta0) {
         for (int f = gtid; f < P.W; f += gsize) {
             const int i0 = __ldcg(root + f * 2), i1 = __ldcg(root + f * 2 + 1);
             if (clear) { root[f * 2] = 0; root[f * 2 + 1] = 0; }
-            if (mono) P.master[f] = (int)(((long long)i0 * v0 + (long long)i1 * v1) >> 25);
-            else { P.master[f * 2] = mulshr(i0, v0, 24); P.master[f * 2 + 1] = mulshr(i1, v1, 24); }
+            if (mono) master_put(P, f, (int)(((long long)i0 * v0 + (long long)i1 * v1) >> 25));
+            else { master_put(P, f * 2, mulshr(i0, v0, 24)); master_put(P, f * 2 + 1, mulshr(i1, v1, 24)); }
         }
         if (gtid == 0 && P.W > 0) { P.rstate[2] = 0; P.rstate[6] = 0; }     // deltas as PrepareRamper leaves them
         return;
     }
     if (!cta0) return;
     pm_bus(P, -1, P.rstate, root, mono, [&](int f, int r0, int r1) {
-        if (mono) P.master[f] = r0;
-        else { P.master[f * 2] = r0; P.master[f * 2 + 1] = r1; }
+        if (mono) master_put(P, f, r0);
+        else { master_put(P, f * 2, r0); master_put(P, f * 2 + 1, r1); }
         if (clear) { root[f * 2] = 0; root[f * 2 + 1] = 0; }
     });
 }
@@ -536,14 +548,14 @@ A2CU_DEV void root_stage(const MixParams &P, int gtid, int gsize, bool cta0) {
 // launch ago by every rank - and run the root panmix into that window's output block.
 // `rstate`, `channels`, `root_stage_on` are those of the engine (they do not change per window).
 A2CU_DEV void xchg_finish_previous(const XchgParams &X, int *rstate, int channels, int root_stage_on, int tid,
-                                   int nthreads) {
+                                   int nthreads, int out_fmt = 0) {
     xchg_collect(X, X.prev_epoch, X.sum, X.prev_W, tid, nthreads);
     MixParams M;
     M.acc = X.sum; M.W = X.prev_W; M.buffer = X.prev_buffer; M.ngroups = 0; M.channels = channels;
     M.nsplits = X.prev_nsplits;
     for (int i = 0; i < kMaxSplits; ++i) M.splits[i] = X.prev_splits[i];
     M.gstate = nullptr; M.rstate = rstate; M.ev = nullptr; M.nev = 0;
-    M.master = X.prev_master; M.root_stage = root_stage_on; M.clear = 0; M.general = 0;
+    M.master = X.prev_master; M.root_stage = root_stage_on; M.clear = 0; M.general = 0; M.out_fmt = out_fmt;
     root_stage(M, tid, nthreads, true);
     __syncthreads();
 }

@@ -671,6 +671,7 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NH, VS>::threads) render_spli
             for (int i = 0; i < kMaxSplits; ++i) M.splits[i] = P.splits[i];
             M.gstate = nullptr; M.rstate = P.fuse_rstate; M.ev = nullptr; M.nev = 0;
             M.master = P.fuse_master; M.root_stage = P.fuse_root_stage; M.clear = 1; M.general = 0;
+            M.out_fmt = P.fuse_out_fmt;
             // tail timings for a2cu_split_trace: role 5, fragments 60..63 = start, after the previous
             // window's root stage, after publish / root stage, (unused)
             auto tmark = [&](int k) {
@@ -682,7 +683,8 @@ __global__ void __launch_bounds__(SplitWarps<FILT, NH, VS>::threads) render_spli
                 // publish this one without waiting for anybody (read-then-publish keeps two buffer
                 // halves enough: a peer publishes window k + 1 only after it saw our window k)
                 if (P.xchg.prev_valid)
-                    xchg_finish_previous(P.xchg, P.fuse_rstate, P.fuse_channels, P.fuse_root_stage, tid, WR::threads);
+                    xchg_finish_previous(P.xchg, P.fuse_rstate, P.fuse_channels, P.fuse_root_stage, tid, WR::threads,
+                                         P.fuse_out_fmt);
                 tmark(1);
                 xchg_publish(P.xchg, P.acc, P.W, tid, WR::threads, true);
                 tmark(2);

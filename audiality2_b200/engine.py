@@ -68,6 +68,7 @@ SYMBOLS = {
     "a2cu_submit_dev": (_I, [_VP, _U, _U, _VP]),
     "a2cu_collect": (_I, [_VP, _I, _VP]),
     "a2cu_set_post_root_stage": (_I, [_VP, _I]),
+    "a2cu_set_output_format": (_I, [_VP, _I]),
     "a2cu_apply_root_stage": (_I, [_VP, _VP, _VP, _U, _U, _U64]),
     "a2cu_xchg_create": (_I, [_VP, _I, _I, _U, _U, _VP]),
     "a2cu_xchg_connect_ipc": (_I, [_VP, _VP]),
@@ -146,6 +147,7 @@ class Engine:
         self.samplerate = samplerate
         self.channels = 1 if channels < 2 else 2
         self.post_root = True
+        self.out_dtype = np.int32
 
     def close(self):
         if getattr(self, "h", None):
@@ -230,6 +232,13 @@ class Engine:
         self._ck(self.L.a2cu_debug_f12_coeff(self.h, a.ctypes.data, a.size, out.ctypes.data))
         return out
 
+    def set_output_format(self, fmt):
+        """'i32' (8:24, default), 'f32' (v / 2^23, the audio drivers' edge) or 'i16' (v >> 8, the
+        wave writer's): converted inside the root stage."""
+        code = {"i32": 0, "f32": 1, "i16": 2}[fmt]
+        self._ck(self.L.a2cu_set_output_format(self.h, code))
+        self.out_dtype = {0: np.int32, 1: np.float32, 2: np.int16}[code]
+
     def set_post_root_stage(self, on):
         self.post_root = bool(on)
         self._ck(self.L.a2cu_set_post_root_stage(self.h, int(on)))
@@ -310,7 +319,7 @@ class Engine:
     def run(self, frames, buffer=64):
         """a2_Run() analogue: returns int32 8:24 [frames, channels] (host)."""
         ch = self.channels if self.post_root else 2
-        out = np.empty((frames, ch), dtype=np.int32)
+        out = np.empty((frames, ch), dtype=self.out_dtype if self.post_root else np.int32)
         self._ck(self.L.a2cu_run(self.h, frames, buffer, out.ctypes.data))
         return out
 
@@ -333,7 +342,7 @@ class Engine:
         """Wait for a submitted window and return its int32 8:24 output."""
         if out is None:
             ch = self.channels if self.post_root else 2
-            out = np.empty((self._frames_of[ticket], ch), dtype=np.int32)
+            out = np.empty((self._frames_of[ticket], ch), dtype=self.out_dtype if self.post_root else np.int32)
         self._ck(self.L.a2cu_collect(self.h, ticket, out.ctypes.data))
         return out
 

@@ -205,6 +205,18 @@ int a2cu_run(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t *out);
 int a2cu_run_async(a2cu_engine *e, unsigned frames, unsigned buffer,
 		int32_t *dev_out);
 int32_t *a2cu_master_devptr(a2cu_engine *e);
+/*
+ * Sample format of the master block that a2cu_run / a2cu_collect / dev_out
+ * deliver, converted inside the root stage (no extra pass): what the
+ * reference's drivers and wave writer do with the int32 8:24 buffers at the
+ * edge of the engine.
+ *   0  int32 8:24 (include/a2_drivers.h:301) - default
+ *   1  float32 = v * (1 / 8388608)           (src/drivers/sdldrv.c:55-65)
+ *   2  int16   = v >> 8                      (a2_RenderWave -> a2_WaveWrite with
+ *                                             A2_I24, src/waves.c:174-176)
+ * The caller's buffer holds frames * channels samples of that size.
+ */
+int a2cu_set_output_format(a2cu_engine *e, int format);
 int a2cu_sync(a2cu_engine *e);
 
 /*

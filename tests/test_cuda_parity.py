@@ -163,3 +163,64 @@ def test_paused_bank_keeps_state_and_pending_writes():
     assert np.array_equal(b2, ref[1]), _diff(b2, ref[1])
     assert np.array_equal(c2, ref[2]), _diff(c2, ref[2])
     assert not np.array_equal(other, ref[0])
+
+
+@pytest.mark.parametrize("name", ["bank256", "groups", "renderwave"])
+def test_output_formats_are_the_driver_edge_conversions(name):
+    """a2cu_set_output_format: float32 = v * 2^-23 (drivers/sdldrv.c:55-65) and int16 = v >> 8
+    (waves.c:174-176), produced inside the root stage, equal the conversions applied to the int32
+    render - through a2cu_run, a windowed a2cu_run and the pipelined submit / collect path."""
+    from audiality2_b200 import engine as eng
+    from audiality2_b200.chains import autowire
+    scn = CASES[name]()
+    ref = run_cuda(scn)
+
+    def render(fmt, pipelined):
+        e = eng.Engine(scn.samplerate, scn.channels)
+        try:
+            e.set_output_format(fmt)
+            for w in scn.waves:
+                e.builtin_wave(w)
+            for _ in range(scn.ngroups):
+                e.new_group()
+            banks = {}
+            where = []
+            for v in scn.voices:
+                key = tuple(v.kinds)
+                banks.setdefault(key, []).append(v)
+                where.append((key, len(banks[key]) - 1))
+            ids = {k: e.new_bank(autowire(list(k)), len(vs), transpose=[v.transpose for v in vs],
+                                 group=[v.group for v in vs]) for k, vs in banks.items()}
+            from oracle import a2oracle as ao
+            for ev in scn.events():
+                t, kind, tgt = int(ev["time"]), int(ev["kind"]), int(ev["voice"])
+                if kind == ao.EV_WRITE:
+                    k, slot = where[tgt]
+                    e.write(ids[k], slot, int(ev["unit"]), int(ev["reg"]), int(ev["value"]), t, int(ev["dur"]))
+                elif kind == ao.EV_WAKE:
+                    k, slot = where[tgt]
+                    e.wake(ids[k], slot, t)
+                elif kind == ao.EV_GROUPWRITE:
+                    e.group_write(tgt, int(ev["reg"]), int(ev["value"]), t, int(ev["dur"]))
+            if not pipelined:
+                return e.run(scn.frames, scn.buffer)
+            parts, tickets, done = [], [], 0
+            while done < scn.frames:
+                n = min(scn.buffer * 3, scn.frames - done)
+                tickets.append(e.submit(n, scn.buffer))
+                done += n
+                if len(tickets) > 2:
+                    parts.append(e.collect(tickets.pop(0)))
+            while tickets:
+                parts.append(e.collect(tickets.pop(0)))
+            return np.concatenate(parts, axis=0)
+        finally:
+            e.close()
+
+    f32 = ref.astype(np.float32) * np.float32(1.0 / 8388608.0)
+    i16 = (ref >> 8).astype(np.int16)
+    for pipelined in (False, True):
+        a = render("f32", pipelined)
+        assert a.dtype == np.float32 and np.array_equal(a, f32)
+        b = render("i16", pipelined)
+        assert b.dtype == np.int16 and np.array_equal(b, i16)
