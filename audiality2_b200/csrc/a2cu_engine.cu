@@ -298,7 +298,7 @@ struct a2cu_engine {
     WindowStats ws;
     // environment toggles, read once in a2cu_open (A/B switches for profiles/)
     bool env_stats = false, env_no_copy_stream = false, env_no_fuse = false, env_no_stage = false, env_one_set = false,
-         env_no_side_streams = false;
+         env_no_side_streams = false, env_split_always = false;
     int sm_count = 148;
     int device = 0, samplerate = 48000, channels = 2;
     int basepitch = 0;
@@ -841,6 +841,7 @@ a2cu_engine *a2cu_open(int device, int samplerate, int channels) {
     e->env_no_stage = getenv("A2CU_NO_STAGE") != nullptr;
     e->env_one_set = getenv("A2CU_ONE_SET") != nullptr;
     e->env_no_side_streams = getenv("A2CU_NO_SIDE_STREAMS") != nullptr;
+    e->env_split_always = getenv("A2CU_SPLIT_ALWAYS") != nullptr;
     cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e->sm_count <= 0) e->sm_count = 148;
     e->noise_ptr = &e->noiseseed;
@@ -1820,6 +1821,13 @@ static int run_window(a2cu_engine *e, unsigned frames, unsigned buffer, int32_t 
             }
         }
         bool split = e->use_split && b->k.split[0].fn && !b->exotic && nsplits <= 1;
+        // Large filtered banks: once every SM holds several hundred voices, one thread per voice
+        // (render_bank) keeps more recurrences in flight per SM than the warp-specialised kernel
+        // (profiles/r02_saturation.json: the curves cross between 32 k and 64 k voices on 148 SMs)
+        if (split && b->nvoices > e->sm_count * 288 && !e->env_split_always) {
+            for (const a2cu_unitspec &u : b->chain)
+                if (u.kind == A2CU_FILTER12) split = false;
+        }
         std::vector<HostEvent> bulk_probe;      // fast path: all voices share voice 0's event times
         if (fast[bi])
             for (auto &be : b->bulk) {

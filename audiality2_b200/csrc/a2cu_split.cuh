@@ -154,7 +154,8 @@ A2CU_DEV void filter_run(int *t, int a, int b, int &d1, int &d2, int f0v, int df
 // then carries the raw-tap gather as well. Kept out of the table-only instantiation, whose hot loop
 // should stay small (instruction-cache misses show up as `no_instruction` stalls in ncu).
 template <int NOSC, bool FILT, int NH, int VS, int R, bool RAW>
-__global__ void __launch_bounds__(SplitWarps<FILT, NH, VS>::threads) render_split(const RenderParams P) {
+__global__ void __launch_bounds__(SplitWarps<FILT, NH, VS>::threads, (RAW && NOSC == 1 && !FILT) ? 2 : 1)
+render_split(const RenderParams P) {
     typedef SplitLayout<NOSC, FILT, R> L;
     typedef SplitWarps<FILT, NH, VS> WR;
     constexpr int kSlice = WR::slice;

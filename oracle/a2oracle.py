@@ -183,7 +183,7 @@ def ref_available():
 
 def ref_render(a2s_path, program="Song", args=(), samplerate=48000, channels=2,
                buffer=64, frames=4800, noiseseed=None, binary="a2render",
-               driver=None, env=None, upload=None):
+               driver=None, env=None, upload=None, copies=None, cwd=None):
     """Run the reference (oracle/_ref/a2render) on a script; returns
     (int32 array [frames, channels], info dict)."""
     import json
@@ -198,12 +198,14 @@ def ref_render(a2s_path, program="Song", args=(), samplerate=48000, channels=2,
             cmd += ["-s", str(noiseseed)]
         if driver:
             cmd += ["-d", driver]
+        if copies:
+            cmd += ["-x", str(int(copies))]     # start the program that many times (transposed)
         if upload:
             # (type, period, flags, length, seed): the harness uploads a pseudo-random wave through
             # a2_UploadWave and passes its handle as the program's last argument
             cmd += ["-U", ":".join(str(int(x)) for x in upload)]
         cmd.append(a2s_path)
-        res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        res = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=cwd)
         if res.returncode:
             raise RuntimeError("a2render failed: %s\n%s" % (res.stdout, res.stderr))
         info = json.loads(res.stdout.strip().splitlines()[-1])

@@ -224,3 +224,33 @@ def test_output_formats_are_the_driver_edge_conversions(name):
         assert a.dtype == np.float32 and np.array_equal(a, f32)
         b = render("i16", pipelined)
         assert b.dtype == np.int16 and np.array_equal(b, i16)
+
+
+@pytest.mark.parametrize("wtype,flags,length", [(3, 0x100, 2048), (3, 0x100, 5000), (3, 0, 3001), (2, 0x100, 3001),
+                                                (2, 0, 777), (3, 0x100, 1)])
+def test_device_wave_preparation_equals_port(wtype, flags, length):
+    """Pads and mip levels are built by kernels in the device pool (csrc/a2cu_waves.cuh,
+    waves.c:90-151); every level, pads included, must equal what the port prepares on the CPU."""
+    from audiality2_b200 import engine as eng
+    from oracle import a2oracle as ao
+    r = np.random.RandomState(length)
+    data = r.randint(-32768, 32768, size=length).astype(np.int16)
+    e = eng.Engine(48000, 2)
+    o = ao.Oracle(48000, 2)
+    try:
+        we = e.upload_wave(wtype, 64, flags, data)
+        wo = o.upload_wave(wtype, 64, flags, data)
+        for lvl in range(10 if wtype == 3 else 1):
+            a, na = e.wave_data(we, lvl)
+            b, nb = o.wave_data(wo, lvl)
+            assert na == nb
+            assert np.array_equal(a[:1 + na + 132], b[:1 + nb + 132]), "level %d differs" % lvl
+        for name in ("saw", "pulse25", "sine", "triangle"):
+            be, bo = e.builtin_wave(name), o.builtin_wave(name)
+            for lvl in range(10):
+                a, na = e.wave_data(be, lvl)
+                b, nb = o.wave_data(bo, lvl)
+                assert na == nb and np.array_equal(a[:1 + na + 132], b[:1 + nb + 132]), (name, lvl)
+    finally:
+        e.close()
+        o.close()
