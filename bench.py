@@ -361,6 +361,30 @@ def secondary_configs(local, dev, world, rank, peak, args):
                          "note": "2 Hermite taps per output sample, each in its own 32-byte sector: 64 B per "
                                  "voice-sample (SURVEY.md 8(d))"}}
         e.close()
+    if world == 1:
+        # cfg2 at saturation: one bank of 262 144 voices in one launch (profiles/r02_saturation.json)
+        e = fresh()
+        V = 262144
+        bank, b = wl.setup_cfg2(e, V, ramp_frames=WINDOW)
+        ms_l = []
+        for k in range(9):
+            flush.zero_()
+            e.write_all(bank, 0, 2, [b["amp"] // (1 + k % 2)], dur=WINDOW << 8)
+            e.run(WINDOW, BLOCK)
+            if k >= 3:
+                ms_l.append(e.last_render_ms() + e.last_mix_ms())
+        ms = statistics.median(ms_l)
+        sb = e.bank_state_bytes(bank)
+        alg = V * (2 * sb + 20)
+        out["cfg2_262144"] = {
+            "workload": "cfg2 with 262 144 voices in one bank (one launch per 960-frame window)",
+            "value": V * WINDOW / (ms / 1e3), "unit": "voice-samples/s", "ms_per_window": ms,
+            "kernel": "%s<%s>" % ("render_split" if e.split_launches else "render_bank", e.bank_kernel_name(bank)),
+            "l2": "flushed between windows (192 MB write)",
+            "roofline": {"bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": alg / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg,
+                         "note": "one thread per voice above ~43 k voices: bound by INT32 issue"}}
+        e.close()
     # cfg4: 32 768 FM voices per GPU (BASELINE's named multi-GPU config: 262 144 voices over 8 GPUs)
     e = fresh()
     V = 32768
