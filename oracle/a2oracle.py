@@ -183,7 +183,7 @@ def ref_available():
 
 def ref_render(a2s_path, program="Song", args=(), samplerate=48000, channels=2,
                buffer=64, frames=4800, noiseseed=None, binary="a2render",
-               driver=None, env=None, upload=None, copies=None, cwd=None):
+               driver=None, env=None, upload=None, copies=None, cwd=None, shard=None):
     """Run the reference (oracle/_ref/a2render) on a script; returns
     (int32 array [frames, channels], info dict)."""
     import json
@@ -200,6 +200,8 @@ def ref_render(a2s_path, program="Song", args=(), samplerate=48000, channels=2,
             cmd += ["-d", driver]
         if copies:
             cmd += ["-x", str(int(copies))]     # start the program that many times (transposed)
+        if shard:
+            cmd += ["-X", "%d/%d" % tuple(shard)]   # (rank, world): only copies k with k % world == rank
         if upload:
             # (type, period, flags, length, seed): the harness uploads a pseudo-random wave through
             # a2_UploadWave and passes its handle as the program's last argument

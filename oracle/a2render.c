@@ -44,6 +44,7 @@ static void die(const char *what, int err)
 int main(int argc, char **argv)
 {
 	int rate = 48000, buffer = 64, channels = 2, nargs = 0, i, copies = 1;
+	int shard_rank = 0, shard_world = 1;
 	long frames = 48000, warmup = 0, done = 0;
 	int args[16];
 	int noiseseed = -1;
@@ -74,6 +75,16 @@ int main(int argc, char **argv)
 		else if(!strcmp(argv[i], "-s")) noiseseed = atoi(argv[++i]);
 		else if(!strcmp(argv[i], "-W")) dumpwave = argv[++i];
 		else if(!strcmp(argv[i], "-x")) copies = atoi(argv[++i]);
+		else if(!strcmp(argv[i], "-X"))		/* -X rank/world: start only copies k with k % world == rank */
+		{
+			if(sscanf(argv[++i], "%d/%d", &shard_rank, &shard_world) != 2 ||
+					shard_world < 1 || shard_rank < 0 ||
+					shard_rank >= shard_world)
+			{
+				fprintf(stderr, "a2render: -X rank/world\n");
+				return 2;
+			}
+		}
 		else if(!strcmp(argv[i], "-U")) upload = argv[++i];
 		else if(!strcmp(argv[i], "-a"))
 		{
@@ -183,6 +194,13 @@ int main(int argc, char **argv)
 	{
 		int a[16];
 		int na = nargs;
+		/*
+		 * Sharding over engine states / GPUs: whole sub-trees
+		 * under the root, dealt round-robin; the int32 outputs of the shards are
+		 * summed by the caller.
+		 */
+		if(i % shard_world != shard_rank)
+			continue;
 		memcpy(a, args, sizeof(a));
 		if(copies > 1)
 		{

@@ -186,3 +186,24 @@ def test_cfg5_k2trance_x100_dropin_equals_reference():
     assert oi["active_voices"] == ri["active_voices"] and ri["active_voices"] > 400
     assert np.abs(ref).max() > 1000000
     assert np.array_equal(out, ref), _diff(out, ref)
+
+
+def test_cfg5_sharded_dropin_equals_sharded_reference():
+    """Config 5 sharded: the Song instances dealt over two engine states. One state's
+    VM `rand` and noise oscillators share one LCG in tree-walk order, so the oracle of a sharded run
+    is the reference run on the same shards (its own way to use several cores); the int32 outputs of
+    the shards add up. Both drop-in shards run on cuda:0 here; profiles/cfg5_multi.py puts one process
+    on each GPU of the box."""
+    import os
+    song = os.path.join(ao.REF_DIR, "songs", "benchmark", "k2trance.a2s")
+    harness = os.path.join(ao.REF_DIR, "a2render_cuda")
+    if not (os.path.exists(song) and os.path.exists(harness)):
+        pytest.skip("reference build / drop-in harness not present")
+    kw = dict(samplerate=44100, channels=2, buffer=500, frames=20000, copies=40, cwd=os.path.dirname(song))
+    ref = sum(ao.ref_render(os.path.basename(song), "Song", shard=(r, 2), **kw)[0].astype(np.int64) for r in range(2))
+    out = sum(ao.ref_render(os.path.basename(song), "Song", shard=(r, 2), binary="a2render_cuda", **kw)[0]
+              .astype(np.int64) for r in range(2))
+    whole = ao.ref_render(os.path.basename(song), "Song", **kw)[0]
+    assert np.abs(ref).max() > 1000000
+    assert np.array_equal(out, ref), _diff(out, ref)
+    assert not np.array_equal(ref, whole.astype(np.int64))      # the shared LCG: sharding is a different song

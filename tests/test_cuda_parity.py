@@ -254,3 +254,17 @@ def test_device_wave_preparation_equals_port(wtype, flags, length):
     finally:
         e.close()
         o.close()
+
+
+def test_one_second_window_in_one_call():
+    """a2cu_run with a 48 000-frame window: more root wake-ups than one launch takes and far more
+    frames than render_split's per-launch limit, so the engine renders sub-windows, each into its own
+    part of the output block (int32 and the half-size int16 format) - must equal the port."""
+    from audiality2_b200 import engine as eng
+    scn = bank(96, frames=48000)
+    ref = run_oracle(scn)
+    one = run_cuda(scn)                      # one a2cu_run(48000)
+    assert np.array_equal(one, ref), _diff(one, ref)
+    piped = run_cuda(scn, window=16000, pipelined=True)
+    assert np.array_equal(piped, ref), _diff(piped, ref)
+    assert np.abs(ref[40000:]).max() > 1000
