@@ -130,17 +130,27 @@ A2CU_DEV int hermite4(int dm, int d0, int d1, int d2, unsigned ph) {
     a = wmul(a + b, x) >> 15;
     return d0 + (wmul(a + c, x) >> 15);
 }
-// The four taps d[i-1..i+2] are 8 consecutive bytes at a 2-byte aligned address: fetch the two
-// aligned 8-byte words that contain them and funnel-shift, instead of four 2-byte loads. For large
-// sampled waves (no coefficient table) every lane gathers somewhere else in HBM, so the kernel is
-// bound by sector requests through L1: this halves them (profiles/hbm_gather.py). The wave pool pads
-// each level with A2_WAVEPRE / A2_WAVEPOST samples, so the aligned words are always inside the pool.
+// The four taps d[i-1..i+2] are 8 consecutive bytes at a 2-byte aligned address. For large sampled
+// waves (no coefficient table) every lane gathers somewhere else in HBM and the kernel is bound by
+// sector requests through L1, so the taps are fetched with as few requests as alignment allows: the
+// aligned 16-byte chunk that holds the first tap, plus - only for the 3 of 8 alignments where the
+// taps run past it - the next 8 bytes (1.4 requests per tap on average; round 1: four 2-byte loads,
+// then two 8-byte loads). The pool pads each level with A2_WAVEPRE / A2_WAVEPOST samples and the
+// arena has slack behind the last wave, so these reads stay inside the allocation.
 A2CU_DEV int hermite(const int16_t *d, unsigned ph) {
     const unsigned long long a = (unsigned long long)(d + (int)(ph >> 8) - 1);
-    const unsigned long long *q = (const unsigned long long *)(a & ~7ull);
-    const unsigned long long lo = __ldg(q), hi = __ldg(q + 1);
-    const unsigned sh = (unsigned)(a & 7ull) * 8u;      // 0, 16, 32 or 48
-    const unsigned long long x = sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+    const uint4 c = __ldg(reinterpret_cast<const uint4 *>(a & ~15ull));
+    const unsigned o = (unsigned)(a & 15ull);           // 0, 2, ... 14
+    const unsigned long long lo = ((unsigned long long)c.y << 32) | c.x, hi = ((unsigned long long)c.w << 32) | c.z;
+    unsigned long long x;
+    if (o <= 8) {
+        const unsigned sh = o * 8u;                     // 0 .. 64
+        x = sh == 0 ? lo : sh == 64 ? hi : (lo >> sh) | (hi << (64u - sh));
+    } else {
+        const unsigned long long nx = __ldg(reinterpret_cast<const unsigned long long *>((a & ~15ull) + 16));
+        const unsigned sh = (o - 8u) * 8u;              // 16, 32, 48
+        x = (hi >> sh) | (nx << (64u - sh));
+    }
     return hermite4((short)x, (short)(x >> 16), (short)(x >> 32), (short)(x >> 48), ph);
 }
 // a2_Hermite2 (a2_dsp.h:91-98) on precomputed a2_Hermite2c coefficients

@@ -359,7 +359,12 @@ def secondary_configs(local, dev, world, rank, peak, args):
             "roofline": {"bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg,
                          "note": "2 Hermite taps per output sample, each in its own 32-byte sector: 64 B per "
-                                 "voice-sample (SURVEY.md 8(d))"}}
+                                 "voice-sample (SURVEY.md 8(d)). A pure random 8-byte gather over the same 403 MB "
+                                 "(profiles/ubench_gather.cu, no arithmetic, up to 32 loads in flight per thread) "
+                                 "tops out at 1 675-1 854 GB/s of sectors on this chip: sector-granular random "
+                                 "reads cannot reach the streaming peak this fraction is quoted against",
+                         "random_sector_ceiling": {"GBps": 1854.0, "source": "profiles/r02_ubench_gather.txt (static)",
+                                                   "frac": alg / (ms / 1e3) / 1e9 / 1854.0}}}
         e.close()
     if world == 1:
         # cfg2 at saturation: one bank of 262 144 voices in one launch (profiles/r02_saturation.json)
