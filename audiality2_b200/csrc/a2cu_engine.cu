@@ -956,6 +956,14 @@ int a2cu_split_profile(a2cu_engine *e, int enable, uint64_t out[8]) {
     if (!enable && e->d_prof) { cudaFree(e->d_prof); e->d_prof = nullptr; }
     return A2CU_OK;
 }
+// Reset the grid-wide wall-clock marks of the timeline (min / max slots) before a launch.
+int a2cu_split_trace_reset(a2cu_engine *e) {
+    if (!e || !e->d_prof) return A2CU_EINVAL;
+    cudaSetDevice(e->device);
+    uint64_t init[8] = {~0ull, 0, 0, 0, 0, 0, 0, 0};
+    CK(cudaMemcpyAsync(e->d_prof + 8 + (4 * 64 + 56) * 2, init, sizeof(init), cudaMemcpyHostToDevice, e->stream));
+    return A2CU_OK;
+}
 // Timeline of CTA 0 / voice set 0 of the LAST render_split launch while profiling is armed:
 // out[((role * 64 + fragment) * 2 + end)] cycles since the pipeline start; roles 0 control,
 // 1 filter recurrence, 2 / 3 stage A / C of helper 0, 4 / 5 of the last helper. 768 words.

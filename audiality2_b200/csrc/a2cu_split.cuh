@@ -164,6 +164,18 @@ render_split(const RenderParams P) {
     __shared__ __align__(8) unsigned long long s_bar[VS][4][R];     // P, A, B, C per slot
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long t_entry = P.prof ? clock64() : 0;
+    // wall-clock marks of the whole grid (globaltimer, ns) for a2cu_split_trace: role 4, fragments
+    // 56..59 = first CTA entry (min), last pipeline end (max), last CTA exit before the tail (max),
+    // end of the fused tail
+    auto gmark = [&](int k, bool is_min) {
+        if (P.prof && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            unsigned long long *p = P.prof + 8 + ((4 * 64 + 56 + k) * 2);
+            if (is_min) atomicMin(p, t); else atomicMax(p, t);
+        }
+    };
+    gmark(0, true);
     // ---- role of this warp ----
     const int q = FILT ? ((warp & 3) == 3 ? -1 : warp - (warp >> 2)) : warp;
     const bool is_helper = q >= 0 && q < VS * NH;
@@ -641,6 +653,7 @@ render_split(const RenderParams P) {
         }
     }
     __syncthreads();                        // all stage C work of this CTA is done
+    gmark(1, false);
     for (int s2 = 0; s2 < VS; ++s2) {
         const int first = (blockIdx.x * VS + s2) * 32;
         if (first >= P.nvoices) break;
@@ -652,6 +665,7 @@ render_split(const RenderParams P) {
         }
     }
     __syncthreads();                        // every bus reduction of this CTA has been issued
+    gmark(2, false);
     if (P.prof && tid == 0) {               // [6] prologue, [7] pipeline + state store, per CTA (a2cu_split_profile)
         atomicAdd(P.prof + 6, (unsigned long long)(t_loop - t_entry));
         atomicAdd(P.prof + 7, (unsigned long long)(clock64() - t_loop));
@@ -665,7 +679,8 @@ render_split(const RenderParams P) {
         }
         __syncthreads();
         if (s_last) {
-            __threadfence();
+            // (the root stage reads the bus with ld.cg, i.e. from L2 where the other CTAs' reductions
+            // were performed; thread 0's fence + ticket + the barrier above order them before us)
             MixParams M;
             M.acc = P.acc; M.W = P.W; M.buffer = P.buffer; M.ngroups = 0; M.channels = P.fuse_channels;
             M.nsplits = P.nsplits;          // root wake-ups cut the root panmix's segments too
@@ -695,6 +710,7 @@ render_split(const RenderParams P) {
                 root_stage(M, tid, WR::threads, true);
                 tmark(2);
             }
+            gmark(3, false);
             if (tid == 0) *P.fuse_counter = 0u;     // ready for the next launch
         }
     }

@@ -80,6 +80,7 @@ SYMBOLS = {
     "a2cu_set_split": (_I, [_VP, _I]),
     "a2cu_split_profile": (_I, [_VP, _I, C.POINTER(C.c_uint64)]),
     "a2cu_split_trace": (_I, [_VP, C.POINTER(C.c_uint64)]),
+    "a2cu_split_trace_reset": (_I, [_VP]),
     "a2cu_bank_kernel_name": (C.c_char_p, [_VP, _I]),
     "a2cu_bank_state_bytes": (_I, [_VP, _I]),
     "a2cu_last_render_ms": (C.c_float, [_VP]),
@@ -199,6 +200,9 @@ class Engine:
         out = (C.c_uint64 * 768)()
         self._ck(self.L.a2cu_split_trace(self.h, out))
         return np.array(list(out), dtype=np.int64).reshape(6, 64, 2)
+
+    def split_trace_reset(self):
+        self._ck(self.L.a2cu_split_trace_reset(self.h))
 
     def set_stream(self, cuda_stream):
         self._ck(self.L.a2cu_set_stream(self.h, cuda_stream))

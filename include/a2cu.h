@@ -299,6 +299,9 @@ int a2cu_split_profile(a2cu_engine *e, int enable, uint64_t out[8]);
  * panmix stage of helper 0, 4 / 5 of the last helper. out holds 768 words.
  */
 int a2cu_split_trace(a2cu_engine *e, uint64_t *out);
+/* Re-arm the grid-wide wall-clock marks (role 4, fragments 56..59: first CTA entry, last pipeline
+ * end, last CTA done, end of the fused tail; globaltimer ns) before the launch to be looked at. */
+int a2cu_split_trace_reset(a2cu_engine *e);
 /* Name of the render kernel a bank uses (for profiles/). */
 const char *a2cu_bank_kernel_name(a2cu_engine *e, int bank);
 /* Bytes of per-voice state a bank keeps in HBM (roofline arithmetic). */

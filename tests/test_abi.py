@@ -53,12 +53,28 @@ def test_open_fails_loudly_without_gpu():
 
 def test_chain_registry():
     from audiality2_b200 import engine
-    from scenarios import autowire
+    from audiality2_b200.chains import autowire
     for kinds in (["wtosc"], ["wtosc", "panmix"], ["wtosc", "filter12", "panmix"],
                   ["wtosc"] * 8 + ["panmix"], ["fm3", "panmix"], ["fm4r", "panmix"],
                   ["wtosc", "waveshaper", "panmix"]):
         assert engine.Engine.chain_supported(autowire(kinds)), kinds
     assert not engine.Engine.chain_supported([(99, 0, 1, 0, 1)])
+
+
+def test_any_structure_of_replaced_units_has_a_kernel():
+    """a2cu_chain_supported (host-side decision, no device needed): structures without a fused kernel
+    run on render_generic - two-channel filter12 / waveshaper, adding processors, the bus effects
+    inside a leaf chain; only malformed chains and fbdelay (a cooperative bus unit) are refused."""
+    from audiality2_b200 import engine
+    ok = engine.Engine.chain_supported
+    assert ok([(1, 0, 1, 0, 0), (2, 1, 2, 0, 0), (3, 2, 2, 0, 0), (4, 2, 2, 1, 0), (2, 2, 2, 1, 1)])
+    assert ok([(18, 0, 1, 0, 0), (1, 0, 1, 1, 0), (3, 1, 1, 0, 0), (2, 1, 1, 1, 1)])
+    assert ok([(1, 0, 1, 0, 0), (8, 0, 1, 1, 0), (7, 1, 1, 0, 0), (6, 1, 1, 0, 0), (2, 1, 2, 1, 1)])   # dc, dcblock, limiter
+    assert ok([(8, 0, 2, 1, 1)])                                        # struct { dc } on a stereo bus
+    assert not ok([(1, 0, 1, 0, 0), (5, 1, 1, 0, 0), (2, 1, 2, 1, 1)])  # fbdelay
+    assert not ok([(3, 1, 2, 0, 0), (2, 2, 2, 1, 1)])                   # filter12 must match its I/O
+    assert not ok([(1, 1, 1, 0, 0)])                                    # a generator has no inputs
+    assert not ok([(1, 0, 1, 0, 0)] * 13)                               # longer than any voice chain
 
 
 def test_dropin_fails_loudly_without_gpu(tmp_path):
