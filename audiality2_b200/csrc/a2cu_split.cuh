@@ -62,7 +62,13 @@ constexpr int kOscWords = 8;        // published per oscillator and segment
 // with id % 4 != 3 in ascending order (logical index q = id - id / 4).
 // q < VS * NH: helper (set q / NH, index q % NH); then VS control warps.
 // (Measured: helpers on sub-partition 3 cost the recurrence warp 25-40 % of its speed even when it
-// has the highest warp id, i.e. issue priority - profiles/README.md - so that port stays its own.)
+// has the highest warp id, i.e. issue priority - profiles/README.md - so that port stays its own.
+// What still slows it in the kernel - 60 cycles per frame against 45 alone - is shared-memory
+// contention with the helpers' gathers: profiles/ubench_serial.cu reproduces 73 / 127 cycles per
+// frame with 6 / 11 warps gathering. An 8-byte tap table instead of the 16-byte coefficient entries
+// halves the gather wavefronts and brought the chain to 52 cycles, but the extra arithmetic in
+// stage A and in render_bank cost more than that gained: 65.7 vs 68.7 G on cfg2, 25.8 vs 29.5 G on
+// cfg3, 161 vs 173 G at 262 144 voices - measured and reverted.)
 template <bool FILT, int NH, int VS> struct SplitWarps {
     static constexpr int workers = VS * (NH + 1);
     static constexpr int rows = (workers + 2) / 3 > VS ? (workers + 2) / 3 : VS;     // FILT: groups of 4 warp ids

@@ -202,6 +202,67 @@ static void run(const char *name, int warps, int warp_mask, Coef c) {
     cudaFree(d_cyc); cudaFree(d_sink);
 }
 
+// Contention: the recurrence warp (warp 3, alone on sub-partition 3) runs V0 while `nload` warps on
+// the other sub-partitions do what render_split's helpers do in stage A - data-dependent 16-byte
+// gathers from an 80 KB table in shared memory - back to back.
+__global__ void __launch_bounds__(512) bench_contended(int nload, Coef c, long long *cycles, int *sink, int nfr) {
+    extern __shared__ int sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int *ta = sm, *tb = sm + kFrames * kStride;
+    int4 *table = reinterpret_cast<int4 *>(sm + 3 * kFrames * kStride);
+    const int tabn = 5000;
+    for (int i = tid; i < tabn; i += blockDim.x) table[i] = make_int4(i, i * 3, i * 5, i * 7);
+    for (int i = tid; i < kFrames * kStride; i += blockDim.x) ta[i] = (i * 2654435761u) >> 8;
+    __shared__ volatile int stop;
+    if (tid == 0) stop = 0;
+    __syncthreads();
+    if (warp == 3) {
+        int d1[1] = {lane * 977}, d2[1] = {lane * 131};
+        c.f0 += lane; c.q += lane * 3;
+        long long t0 = clock64();
+        for (int r = 0; r < kReps; ++r) loop_base<1>(ta + lane, tb + lane, nfr, c, d1, d2);
+        long long t1 = clock64();
+        if (lane == 0) { cycles[blockIdx.x * 16 + warp] = t1 - t0; stop = 1; }
+        sink[blockIdx.x * blockDim.x + tid] = d1[0] + d2[0];
+        return;
+    }
+    const int q = (warp & 3) == 3 ? -1 : warp - (warp >> 2);
+    if (q < 0 || q >= nload) return;
+    unsigned x = tid * 2654435761u + 1;
+    int acc = 0;
+    while (!stop) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {          // 6 frames x 2 taps, like one helper's slice
+            x = x * 1664525u + 1013904223u;
+            const int4 e = table[(x >> 8) % tabn];
+            acc += e.x + ((e.y * (int)(x & 0x7fff)) >> 15) + e.z + e.w;
+        }
+    }
+    sink[blockIdx.x * blockDim.x + tid] = acc;
+}
+
+static void run_contended(int nload, Coef c) {
+    long long *d_cyc;
+    int *d_sink;
+    const int grid = 148;
+    cudaMalloc(&d_cyc, grid * 16 * sizeof(long long));
+    cudaMalloc(&d_sink, grid * 512 * sizeof(int));
+    cudaMemset(d_cyc, 0, grid * 16 * sizeof(long long));
+    size_t smem = (size_t)3 * kFrames * kStride * sizeof(int) + 5000 * 16;
+    cudaFuncSetAttribute(bench_contended, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    for (int it = 0; it < 3; ++it) bench_contended<<<grid, 512, smem>>>(nload, c, d_cyc, d_sink, kFrames);
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) { printf("contended: CUDA error %s\n", cudaGetErrorString(err)); return; }
+    long long h[148 * 16];
+    cudaMemcpy(h, d_cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double worst = 0, sum = 0; int cnt = 0;
+    for (int b = 0; b < grid; ++b)
+        if (h[b * 16 + 3]) { double v = (double)h[b * 16 + 3] / (kReps * kFrames); worst = v > worst ? v : worst; sum += v; ++cnt; }
+    printf("V0 on warp 3 with %2d warps gathering from shared memory on sub-partitions 0-2: %6.1f cyc/frame (avg %6.1f)\n",
+           nload, worst, sum / cnt);
+    cudaFree(d_cyc); cudaFree(d_sink);
+}
+
 int main() {
     Coef ramp = {3000 << 12, 37, 9000 << 12, 11, 256, 3, 5};
     Coef flat = {3000 << 12, 0, 9000 << 12, 0, 256, 0, 0};
@@ -229,5 +290,6 @@ int main() {
     run<3, 1>("V3 eight warps, two per sub-partition", 8, 0xff, flat);
     run<3, 1>("V3 sixteen warps, four per sub-partition", 16, 0xffff, flat);
     run<0, 1>("V0 sixteen warps, four per sub-partition", 16, 0xffff, ramp);
+    for (int n : {0, 3, 6, 11}) run_contended(n, ramp);
     return 0;
 }
