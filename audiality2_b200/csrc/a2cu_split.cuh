@@ -51,6 +51,19 @@
 
 namespace a2cu {
 
+#ifndef A2CU_SER_PF
+#define A2CU_SER_PF 16
+#endif
+// Stage A work split. 0: lane = voice, the fragment's frames sliced over the helpers. 1: lane = FRAME,
+// one voice (and 32-frame half) at a time: the 64 taps of a warp instruction then lie on a short
+// contiguous run of the wave - DRAM pages and cache lines are read whole instead of a sector here and
+// there (the HBM-bound gather), and a shared-memory table gather meets fewer bank conflicts.
+#ifndef A2CU_LF_RAW
+#define A2CU_LF_RAW 1
+#endif
+#ifndef A2CU_LF_TABLE
+#define A2CU_LF_TABLE 0
+#endif
 constexpr int kTileStride = 33;     // tile rows are frames, columns voices; 33 keeps both access patterns conflict-free
 constexpr int kOscWords = 8;        // published per oscillator and segment
 
@@ -113,8 +126,19 @@ A2CU_DEV void mbar_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// x % m for x < 2^52 (a phase accumulator a few increments past its wave): double estimate, corrected
+A2CU_DEV unsigned long long mod_near(unsigned long long x, unsigned long long m) {
+    const unsigned long long q = (unsigned long long)((double)x / (double)m);
+    long long r = (long long)(x - q * m);
+    if (r < 0) r += (long long)m;
+    else if ((unsigned long long)r >= m) r -= (long long)m;
+    return (unsigned long long)r;
+}
+
 // filter12.c:97-118 over frames [a, b) of one voice, in place on its tile column. Inputs are
-// fetched eight frames ahead of the dependent chain. (Tried and measured slower on the B200:
+// fetched A2CU_SER_PF frames ahead of the dependent chain: the helpers of a set all start their
+// gathers on the same barrier, a burst of ~1.2 k shared-memory wavefronts that a load issued by
+// this warp queues behind - the look-ahead has to cover it. (Tried and measured slower on the B200:
 // volatile loads/stores to pin the prefetch before the chain, 4.6 k instead of 3.7 k cycles per
 // fragment; taking (in>>5) - (q*d1s>>8) off the chain - ptxas already schedules the two shift-adds
 // behind l well, the explicit form only adds an instruction.)
@@ -136,21 +160,22 @@ A2CU_DEV void filter_run(int *t, int a, int b, int &d1, int &d2, int f0v, int df
         return out;
     };
     int f = a;
-    if (f + 8 <= b) {
-        int cur[8];
+    constexpr int PF = A2CU_SER_PF;
+    if (f + PF <= b) {
+        int cur[PF];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) cur[k] = t[(f + k) * kTileStride];
+        for (int k = 0; k < PF; ++k) cur[k] = t[(f + k) * kTileStride];
         while (true) {
-            const bool more = f + 16 <= b;
-            int nxt[8];
+            const bool more = f + 2 * PF <= b;
+            int nxt[PF];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) nxt[k] = more ? t[(f + 8 + k) * kTileStride] : 0;
+            for (int k = 0; k < PF; ++k) nxt[k] = more ? t[(f + PF + k) * kTileStride] : 0;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) t[(f + k) * kTileStride] = step(cur[k]);
-            f += 8;
+            for (int k = 0; k < PF; ++k) t[(f + k) * kTileStride] = step(cur[k]);
+            f += PF;
             if (!more) break;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
+            for (int k = 0; k < PF; ++k) cur[k] = nxt[k];
         }
     }
     for (; f < b; ++f) t[f * kTileStride] = step(t[f * kTileStride]);
@@ -165,6 +190,7 @@ render_split(const RenderParams P) {
     typedef SplitLayout<NOSC, FILT, R> L;
     typedef SplitWarps<FILT, NH, VS> WR;
     constexpr int kSlice = WR::slice;
+    constexpr bool LF = RAW ? (A2CU_LF_RAW != 0) : (A2CU_LF_TABLE != 0);
     extern __shared__ __align__(128) int sm_all[];
     __shared__ __align__(8) unsigned long long s_mbar;               // table staging (TMA)
     __shared__ __align__(8) unsigned long long s_bar[VS][4][R];     // P, A, B, C per slot
@@ -194,6 +220,30 @@ render_split(const RenderParams P) {
     const int v = (blockIdx.x * VS + set) * 32 + lane;
     const bool valid = v < P.nvoices;
     const int W = P.W;
+    // The voice state comes from HBM (a different bank every window in a large project): the control
+    // and recurrence warps request it first thing, so that the round trip overlaps the CTA prologue
+    // (accumulator clear, barrier setup, table staging) instead of following it.
+    StatePtr sp{P.state + (valid ? v : 0), P.stride};
+    SOsc osc[NOSC];
+    SFilt filt;
+    SPan pm;
+    int alive = 0;
+    unsigned evp = 0, eve = 0;
+    int next_ev = 0x7fffffff;
+    int d1 = 0, d2 = 0;
+    if (is_ctl && valid) {
+        alive = sp.ld(0) & 1;
+#pragma unroll
+        for (int i = 0; i < NOSC; ++i) osc[i].load(sp, 1 + 14 * i);
+        if (FILT) filt.load(sp, SplitLayout<NOSC, FILT, R>::filt_w);
+        pm.load(sp, SplitLayout<NOSC, FILT, R>::pm_w);
+        if (P.ev_off) { evp = P.ev_off[v]; eve = P.ev_off[v + 1]; }
+        next_ev = evp < eve ? (int)(P.ev[evp].x >> 8) : 0x7fffffff;
+    }
+    if (FILT && is_ser && valid) {
+        d1 = sp.ld(SplitLayout<NOSC, FILT, R>::filt_w + 12);
+        d2 = sp.ld(SplitLayout<NOSC, FILT, R>::filt_w + 13);
+    }
 
     int nfrag = 0;
     for (int f = 0; f < W; f = frag_end(f, P.buffer, W)) ++nfrag;
@@ -234,7 +284,6 @@ render_split(const RenderParams P) {
     Ctx c;
     c.waves = P.waves; c.pool = P.pool; c.cpool = P.cpool; c.ptab = P.ptab; c.fmsine = nullptr; c.f12tab = P.f12tab;
     c.samplerate = P.samplerate;
-    StatePtr sp{P.state + (valid ? v : 0), P.stride};
     const long long t_loop = P.prof ? clock64() : 0;
     long long busy = 0, busy2 = 0;
     // timeline of CTA 0 / set 0 (a2cu_split_trace): prof[8 + ((role * 64 + fragment) * 2 + end)]
@@ -248,23 +297,8 @@ render_split(const RenderParams P) {
     // control: events, prologues, publish
     // =====================================================================================
     if (is_ctl) {
-        SOsc osc[NOSC];
-        SFilt filt;
-        SPan pm;
-        int alive = 0;
-        unsigned evp = 0, eve = 0;
-        int next_ev = 0x7fffffff;
         bool in_seg = false;
         unsigned open_mask = 0;
-        if (valid) {
-            alive = sp.ld(0) & 1;
-#pragma unroll
-            for (int i = 0; i < NOSC; ++i) osc[i].load(sp, 1 + 14 * i);
-            if (FILT) filt.load(sp, L::filt_w);
-            pm.load(sp, L::pm_w);
-            if (P.ev_off) { evp = P.ev_off[v]; eve = P.ev_off[v + 1]; }
-            next_ev = evp < eve ? (int)(P.ev[evp].x >> 8) : 0x7fffffff;
-        }
         int f0 = 0;
         for (int it = 0; it < nfrag; ++it) {
             const int slot = it % R;
@@ -314,19 +348,19 @@ render_split(const RenderParams P) {
                     in_seg = alive != 0;
                     const int n = nxt - f;
                     // Oscillators. `open_mask` bit i: oscillator i has a segment open (its finish() is
-                    // still due). A mip-mapped oscillator whose rampers are at rest and that no event
+                    // still due). A mip-mapped oscillator whose PITCH ramper is at rest and that no event
                     // touched runs the same segment again: wtosc.c:239-286 would recompute the same
-                    // mip level, increment and table, so only the loop wrap / end test of the
-                    // prologue is redone (phase >> mm << mm is the identity here: the low mm bits
-                    // are already zero). This prologue is ~400 dependent instructions per oscillator;
-                    // with eight oscillators it was the slowest role of the CTA by far.
+                    // mip level, increment and table, so only the amplitude ramper and the loop wrap /
+                    // end test of the prologue are redone (phase >> mm << mm is the identity here: the
+                    // low mm bits are already zero). This prologue is ~400 dependent instructions per
+                    // oscillator; with eight oscillators it was the slowest role of the CTA by far, and
+                    // with one oscillator whose amplitude ramps it still out-lasted the recurrence warp.
 #pragma unroll
                     for (int i = 0; i < NOSC; ++i) {
                         const bool open = (open_mask >> i) & 1;
                         bool fast = false;
                         if (in_seg && open && osc[i].mode == OSC_MIP && osc[i].run == RUN_TABLE && !osc[i].p.timer &&
-                            !osc[i].p_ramping && osc[i].dphase && !osc[i].a.timer && !osc[i].astep &&
-                            osc[i].a.value == osc[i].a.target) {
+                            !osc[i].p_ramping && osc[i].dphase) {
                             const WaveDesc &w = c.waves[osc[i].wave];
                             const unsigned sz = w.size[osc[i].mm];
                             if (w.flags & kLooped) {
@@ -334,6 +368,12 @@ render_split(const RenderParams P) {
                                 fast = true;
                             } else
                                 fast = (osc[i].ph >> 24) <= (unsigned long long)(sz + kWavePre);
+                            // the amplitude may ramp (a script that fades a voice does so across many
+                            // fragments): its ramper is the only per-segment state left, wtosc.c:258
+                            if (fast) {
+                                ramp_prepare(osc[i].a, n);
+                                osc[i].astep = osc[i].a.delta;
+                            }
                         }
                         if (!fast) {
                             if (open) osc[i].finish();
@@ -445,8 +485,6 @@ render_split(const RenderParams P) {
     // serial: filter12 recurrence, in place on the tile
     // =====================================================================================
     if (is_ser) {
-        int d1 = 0, d2 = 0;
-        if (valid) { d1 = sp.ld(L::filt_w + 12); d2 = sp.ld(L::filt_w + 13); }
         for (int it = 0; it < nfrag; ++it) {
             const int slot = it % R, par = (it / R) & 1;
             const long long tw = P.prof ? clock64() : 0;
@@ -494,77 +532,123 @@ render_split(const RenderParams P) {
                 if (hq == 0) trace(2, it, 0);
                 if (hq == NH - 1) trace(4, it, 0);
                 const int n = sm[L::meta + slot * 2 + 1];
-                const int split = sm[L::split + slot * 32 + lane];
-                const int flags = sm[L::flags + slot * 32 + lane] & 0xff;
-                int *ta = sm + L::tile + slot * kMaxFrag * kTileStride + lane;
-                const int s0 = hq * kSlice, s1 = min(n, s0 + kSlice);
-                for (int seg = 0; seg < kSplitSegs; ++seg) {
-                    const int sa = seg ? split : 0;
-                    const int a = max(s0, sa), b = min(s1, seg ? n : split);
-                    if (a >= b) continue;
-                    int acc[kSlice];
-#pragma unroll
-                    for (int k = 0; k < kSlice; ++k) acc[k] = 0;
-                    if ((flags >> seg) & 1) {
+                if constexpr (LF) {
+                    // lane = frame: unit u = (voice u % 32, frames [32 (u / 32), +32)) of this fragment
+                    if (!tab_ready) { mbar_wait(&s_mbar, 0); tab_ready = true; }
+                    int *tslot = sm + L::tile + slot * kMaxFrag * kTileStride;
+                    const int nunits = ((n + 31) >> 5) << 5;
 #pragma unroll 1
-                        for (int i = 0; i < NOSC; ++i) {    // not unrolled: keeps the hot loop in the I-cache
-                            const int *o = sm + L::oscp + (((slot * kSplitSegs + seg) * NOSC + i) * kOscWords) * 32 + lane;
-                            const int mode = o[192];
-                            if (!mode) continue;            // silent segment of this oscillator
-                            const unsigned dph = (unsigned)o[96];
-                            unsigned long long ph = ((unsigned long long)(unsigned)o[64] << 32) | (unsigned)o[32];
-                            const int astep = o[160];
-                            const int av0 = wadd(o[128], wmul(astep, a - sa));
-                            const unsigned half = dph >> 17;
-                            if (mode == 1) {
-                                if (!tab_ready) { mbar_wait(&s_mbar, 0); tab_ready = true; }
-                                const int cfo = o[0];
-                                const int srel = cfo - P.stage_begin;
-                                // generic pointer: the staged copy in shared memory or the pool in global memory
-                                const int4 *cf = (srel >= 0 && srel < stage_n - 64) ? s_tab + srel : c.cpool + cfo;
-                                ph += (unsigned long long)dph * (unsigned)(a - sa);
-                                // all kSlice frames are evaluated (independent chains the scheduler can
-                                // overlap); frames past the segment end read table slack and are dropped
-                                // at the store (wtosc.c:226-233)
-#pragma unroll
-                                for (int k = 0; k < kSlice; ++k) {
-                                    const unsigned p16 = (unsigned)((ph + (unsigned long long)dph * (unsigned)k) >> 16);
-                                    const int hv = hermite_cf_smem(cf, p16) + hermite_cf_smem(cf, p16 + half);
-                                    acc[k] = wadd(acc[k], mulshr(hv, wadd(av0, wmul(astep, k)), 17));
+                    for (int u = hq; u < nunits; u += NH) {
+                        const int vo = u & 31;
+                        const int f = (u & ~31) + lane;
+                        const int split = sm[L::split + slot * 32 + vo];
+                        const int flags = sm[L::flags + slot * 32 + vo];
+                        const int seg = f >= split ? 1 : 0;
+                        const int k = f - (seg ? split : 0);
+                        int acc = 0;
+                        if (f < n && ((flags >> seg) & 1)) {
+#pragma unroll 1
+                            for (int i = 0; i < NOSC; ++i) {
+                                const int *o = sm + L::oscp + (((slot * kSplitSegs + seg) * NOSC + i) * kOscWords) * 32 + vo;
+                                const int mode = o[192];
+                                if (!mode) continue;            // silent segment of this oscillator
+                                const unsigned dph = (unsigned)o[96];
+                                unsigned long long ph = ((unsigned long long)(unsigned)o[64] << 32) | (unsigned)o[32];
+                                ph += (unsigned long long)dph * (unsigned)k;        // wtosc.c:231, k frames on
+                                const int av = wadd(o[128], wmul(o[160], k));
+                                const unsigned half = dph >> 17;
+                                int hv = 0;
+                                if (mode == 1) {
+                                    const int cfo = o[0];
+                                    const int srel = cfo - P.stage_begin;
+                                    const int4 *cf = (srel >= 0 && srel < stage_n - 64) ? s_tab + srel : c.cpool + cfo;
+                                    const unsigned p16 = (unsigned)(ph >> 16);
+                                    hv = hermite_cf_smem(cf, p16) + hermite_cf_smem(cf, p16 + half);
+                                } else if (RAW) {
+                                    // wtosc.c:301-358: the wrapped loop reads sample k at (ph + k dph) mod M
+                                    if (mode == 3) ph = mod_near(ph, (unsigned long long)(unsigned)o[224] << 24);
+                                    const int16_t *d = c.pool + o[0];
+                                    const unsigned p16 = (unsigned)(ph >> 16);
+                                    hv = hermite(d, p16) + hermite(d, p16 + half);
                                 }
-                            } else if (RAW) {
-                                // Raw int16 taps from the pool (sampled waves too large for a table): the
-                                // gather that goes to HBM. The phase is closed-form, so the taps of all
-                                // frames of the slice are requested before the first is used.
-                                const int16_t *d = c.pool + o[0];
-                                unsigned p16s[kSlice];
-                                if (mode == 3) {
-                                    const unsigned long long M = (unsigned long long)(unsigned)o[224] << 24;
-                                    unsigned long long x = (ph + (unsigned long long)dph * (unsigned)(a - sa)) % M;
-#pragma unroll
-                                    for (int k = 0; k < kSlice; ++k) {
-                                        p16s[k] = (unsigned)(x >> 16);
-                                        x = wrap_mod(x + dph, M);
-                                    }
-                                } else {
+                                acc = wadd(acc, mulshr(hv, av, 17));
+                            }
+                        }
+                        if (f < n) tslot[f * kTileStride + vo] = acc;
+                    }
+                } else {
+                    const int split = sm[L::split + slot * 32 + lane];
+                    const int flags = sm[L::flags + slot * 32 + lane] & 0xff;
+                    int *ta = sm + L::tile + slot * kMaxFrag * kTileStride + lane;
+                    const int s0 = hq * kSlice, s1 = min(n, s0 + kSlice);
+                    for (int seg = 0; seg < kSplitSegs; ++seg) {
+                        const int sa = seg ? split : 0;
+                        const int a = max(s0, sa), b = min(s1, seg ? n : split);
+                        if (a >= b) continue;
+                        int acc[kSlice];
+    #pragma unroll
+                        for (int k = 0; k < kSlice; ++k) acc[k] = 0;
+                        if ((flags >> seg) & 1) {
+    #pragma unroll 1
+                            for (int i = 0; i < NOSC; ++i) {    // not unrolled: keeps the hot loop in the I-cache
+                                const int *o = sm + L::oscp + (((slot * kSplitSegs + seg) * NOSC + i) * kOscWords) * 32 + lane;
+                                const int mode = o[192];
+                                if (!mode) continue;            // silent segment of this oscillator
+                                const unsigned dph = (unsigned)o[96];
+                                unsigned long long ph = ((unsigned long long)(unsigned)o[64] << 32) | (unsigned)o[32];
+                                const int astep = o[160];
+                                const int av0 = wadd(o[128], wmul(astep, a - sa));
+                                const unsigned half = dph >> 17;
+                                if (mode == 1) {
+                                    if (!tab_ready) { mbar_wait(&s_mbar, 0); tab_ready = true; }
+                                    const int cfo = o[0];
+                                    const int srel = cfo - P.stage_begin;
+                                    // generic pointer: the staged copy in shared memory or the pool in global memory
+                                    const int4 *cf = (srel >= 0 && srel < stage_n - 64) ? s_tab + srel : c.cpool + cfo;
                                     ph += (unsigned long long)dph * (unsigned)(a - sa);
-#pragma unroll
-                                    for (int k = 0; k < kSlice; ++k)
-                                        p16s[k] = (unsigned)((ph + (unsigned long long)dph * (unsigned)k) >> 16);
-                                }
-#pragma unroll
-                                for (int k = 0; k < kSlice; ++k) {
-                                    // frames past the segment end are not fetched (no table slack in the pool)
-                                    const bool in_range = a + k < b;
-                                    const int hv = in_range ? hermite(d, p16s[k]) + hermite(d, p16s[k] + half) : 0;
-                                    acc[k] = wadd(acc[k], mulshr(hv, wadd(av0, wmul(astep, k)), 17));
+                                    // all kSlice frames are evaluated (independent chains the scheduler can
+                                    // overlap); frames past the segment end read table slack and are dropped
+                                    // at the store (wtosc.c:226-233)
+    #pragma unroll
+                                    for (int k = 0; k < kSlice; ++k) {
+                                        const unsigned p16 = (unsigned)((ph + (unsigned long long)dph * (unsigned)k) >> 16);
+                                        const int hv = hermite_cf_smem(cf, p16) + hermite_cf_smem(cf, p16 + half);
+                                        acc[k] = wadd(acc[k], mulshr(hv, wadd(av0, wmul(astep, k)), 17));
+                                    }
+                                } else if (RAW) {
+                                    // Raw int16 taps from the pool (sampled waves too large for a table): the
+                                    // gather that goes to HBM. The phase is closed-form, so the taps of all
+                                    // frames of the slice are requested before the first is used.
+                                    const int16_t *d = c.pool + o[0];
+                                    unsigned p16s[kSlice];
+                                    if (mode == 3) {
+                                        const unsigned long long M = (unsigned long long)(unsigned)o[224] << 24;
+                                        unsigned long long x = (ph + (unsigned long long)dph * (unsigned)(a - sa)) % M;
+    #pragma unroll
+                                        for (int k = 0; k < kSlice; ++k) {
+                                            p16s[k] = (unsigned)(x >> 16);
+                                            x = wrap_mod(x + dph, M);
+                                        }
+                                    } else {
+                                        ph += (unsigned long long)dph * (unsigned)(a - sa);
+    #pragma unroll
+                                        for (int k = 0; k < kSlice; ++k)
+                                            p16s[k] = (unsigned)((ph + (unsigned long long)dph * (unsigned)k) >> 16);
+                                    }
+    #pragma unroll
+                                    for (int k = 0; k < kSlice; ++k) {
+                                        // frames past the segment end are not fetched (no table slack in the pool)
+                                        const bool in_range = a + k < b;
+                                        const int hv = in_range ? hermite(d, p16s[k]) + hermite(d, p16s[k] + half) : 0;
+                                        acc[k] = wadd(acc[k], mulshr(hv, wadd(av0, wmul(astep, k)), 17));
+                                    }
                                 }
                             }
                         }
+    #pragma unroll
+                        for (int k = 0; k < kSlice; ++k)
+                            if (a + k < b) ta[(a + k) * kTileStride] = acc[k];
                     }
-#pragma unroll
-                    for (int k = 0; k < kSlice; ++k)
-                        if (a + k < b) ta[(a + k) * kTileStride] = acc[k];
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&barA[slot]);

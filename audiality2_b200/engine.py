@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liba2cu.so")
+# A2CU_LIB: an alternative build of the same library (kernel A/B experiments, profiles/scripts/build_variant.sh)
+LIB_PATH = os.environ.get("A2CU_LIB") or os.path.join(HERE, "liba2cu.so")
 
 # unit kinds / wave types (include/a2cu.h)
 WTOSC, PANMIX, FILTER12, WAVESHAPER = 1, 2, 3, 4
