@@ -137,22 +137,30 @@ A2CU_DEV int hermite4(int dm, int d0, int d1, int d2, unsigned ph) {
 // taps run past it - the next 8 bytes (1.4 requests per tap on average; round 1: four 2-byte loads,
 // then two 8-byte loads). The pool pads each level with A2_WAVEPRE / A2_WAVEPOST samples and the
 // arena has slack behind the last wave, so these reads stay inside the allocation.
-A2CU_DEV int hermite(const int16_t *d, unsigned ph) {
+// Split in two so that a caller can request the taps of several samples before it uses the first
+// (the closed-form phase makes every address known up front).
+struct RawTaps { uint4 c; unsigned long long nx; };
+A2CU_DEV RawTaps hermite_fetch(const int16_t *d, unsigned ph) {
     const unsigned long long a = (unsigned long long)(d + (int)(ph >> 8) - 1);
-    const uint4 c = __ldg(reinterpret_cast<const uint4 *>(a & ~15ull));
-    const unsigned o = (unsigned)(a & 15ull);           // 0, 2, ... 14
-    const unsigned long long lo = ((unsigned long long)c.y << 32) | c.x, hi = ((unsigned long long)c.w << 32) | c.z;
-    unsigned long long x;
-    if (o <= 8) {
-        const unsigned sh = o * 8u;                     // 0 .. 64
-        x = sh == 0 ? lo : sh == 64 ? hi : (lo >> sh) | (hi << (64u - sh));
-    } else {
-        const unsigned long long nx = __ldg(reinterpret_cast<const unsigned long long *>((a & ~15ull) + 16));
-        const unsigned sh = (o - 8u) * 8u;              // 16, 32, 48
-        x = (hi >> sh) | (nx << (64u - sh));
-    }
-    return hermite4((short)x, (short)(x >> 16), (short)(x >> 32), (short)(x >> 48), ph);
+    RawTaps t;
+    t.c = __ldg(reinterpret_cast<const uint4 *>(a & ~15ull));
+    t.nx = (a & 15ull) > 8 ? __ldg(reinterpret_cast<const unsigned long long *>((a & ~15ull) + 16)) : 0ull;
+    return t;
 }
+// The taps are halfwords e .. e + 3 of the 24-byte window {c, nx}, e = byte offset / 2: two rounds of
+// word selects and two funnel shifts, branch-free (the first version branched on the alignment and
+// used 64-bit shifts: ~27 instructions per tap and a divergent warp; this is 12).
+A2CU_DEV int hermite_eval(const RawTaps &t, const int16_t *d, unsigned ph) {
+    const unsigned o = (unsigned)((unsigned long long)(d + (int)(ph >> 8) - 1) & 15ull);     // 0, 2, ... 14
+    const unsigned n0 = (unsigned)t.nx, n1 = (unsigned)(t.nx >> 32);
+    const bool up2 = (o & 8u) != 0, up1 = (o & 4u) != 0;
+    const unsigned a0 = up2 ? t.c.z : t.c.x, a1 = up2 ? t.c.w : t.c.y, a2 = up2 ? n0 : t.c.z, a3 = up2 ? n1 : t.c.w;
+    const unsigned b0 = up1 ? a1 : a0, b1 = up1 ? a2 : a1, b2 = up1 ? a3 : a2;
+    const unsigned sh = (o & 2u) << 3;                  // 0 or 16
+    const unsigned lo = __funnelshift_r(b0, b1, sh), hi = __funnelshift_r(b1, b2, sh);
+    return hermite4((short)lo, (int)lo >> 16, (short)hi, (int)hi >> 16, ph);
+}
+A2CU_DEV int hermite(const int16_t *d, unsigned ph) { return hermite_eval(hermite_fetch(d, ph), d, ph); }
 // a2_Hermite2 (a2_dsp.h:91-98) on precomputed a2_Hermite2c coefficients
 // (a2_dsp.h:83-89): term for term the same integers as a2_Hermite, but one
 // 16-byte load instead of four unaligned int16 loads.

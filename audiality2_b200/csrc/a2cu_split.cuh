@@ -61,6 +61,9 @@ namespace a2cu {
 #ifndef A2CU_LF_RAW
 #define A2CU_LF_RAW 1
 #endif
+#ifndef A2CU_LF_BATCH
+#define A2CU_LF_BATCH 1
+#endif
 #ifndef A2CU_LF_TABLE
 #define A2CU_LF_TABLE 0
 #endif
@@ -126,13 +129,12 @@ A2CU_DEV void mbar_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// x % m for x < 2^52 (a phase accumulator a few increments past its wave): double estimate, corrected
-A2CU_DEV unsigned long long mod_near(unsigned long long x, unsigned long long m) {
-    const unsigned long long q = (unsigned long long)((double)x / (double)m);
-    long long r = (long long)(x - q * m);
-    if (r < 0) r += (long long)m;
-    else if ((unsigned long long)r >= m) r -= (long long)m;
-    return (unsigned long long)r;
+// x % (wsize << 24) for a phase accumulator (24 fraction bits) less than 2^56: the fraction passes
+// through, the integer part is a 32-bit modulo (a 64-bit one is ~130 instructions, which made this
+// line a third of the gather kernel's instruction stream)
+A2CU_DEV unsigned long long mod_wave(unsigned long long x, unsigned wsize) {
+    const unsigned xi = (unsigned)(x >> 24);
+    return ((unsigned long long)(xi % wsize) << 24) | (x & 0xffffffull);
 }
 
 // filter12.c:97-118 over frames [a, b) of one voice, in place on its tile column. Inputs are
@@ -537,44 +539,71 @@ render_split(const RenderParams P) {
                     if (!tab_ready) { mbar_wait(&s_mbar, 0); tab_ready = true; }
                     int *tslot = sm + L::tile + slot * kMaxFrag * kTileStride;
                     const int nunits = ((n + 31) >> 5) << 5;
+                    // B units at a time: all their taps are requested before the first is used
+                    constexpr int B = RAW ? A2CU_LF_BATCH : 1;
 #pragma unroll 1
-                    for (int u = hq; u < nunits; u += NH) {
-                        const int vo = u & 31;
-                        const int f = (u & ~31) + lane;
-                        const int split = sm[L::split + slot * 32 + vo];
-                        const int flags = sm[L::flags + slot * 32 + vo];
-                        const int seg = f >= split ? 1 : 0;
-                        const int k = f - (seg ? split : 0);
-                        int acc = 0;
-                        if (f < n && ((flags >> seg) & 1)) {
+                    for (int u0 = hq; u0 < nunits; u0 += B * NH) {
+                        int vo[B], fr[B], kk[B], sg[B], acc[B];
+                        bool on[B];
+#pragma unroll
+                        for (int j = 0; j < B; ++j) {
+                            const int u = u0 + j * NH;
+                            vo[j] = u & 31;
+                            fr[j] = u < nunits ? (u & ~31) + lane : n;
+                            const int split = sm[L::split + slot * 32 + vo[j]];
+                            const int flags = sm[L::flags + slot * 32 + vo[j]];
+                            sg[j] = fr[j] >= split ? 1 : 0;
+                            kk[j] = fr[j] - (sg[j] ? split : 0);
+                            on[j] = fr[j] < n && ((flags >> sg[j]) & 1);
+                            acc[j] = 0;
+                        }
 #pragma unroll 1
-                            for (int i = 0; i < NOSC; ++i) {
-                                const int *o = sm + L::oscp + (((slot * kSplitSegs + seg) * NOSC + i) * kOscWords) * 32 + vo;
-                                const int mode = o[192];
-                                if (!mode) continue;            // silent segment of this oscillator
-                                const unsigned dph = (unsigned)o[96];
-                                unsigned long long ph = ((unsigned long long)(unsigned)o[64] << 32) | (unsigned)o[32];
-                                ph += (unsigned long long)dph * (unsigned)k;        // wtosc.c:231, k frames on
-                                const int av = wadd(o[128], wmul(o[160], k));
-                                const unsigned half = dph >> 17;
+                        for (int i = 0; i < NOSC; ++i) {
+                            int mode[B], av[B];
+                            unsigned p16[B], half[B];
+                            const int *o[B];
+                            RawTaps t0[B], t1[B];
+#pragma unroll
+                            for (int j = 0; j < B; ++j) {
+                                mode[j] = 0;
+                                if (!on[j]) continue;
+                                o[j] = sm + L::oscp + (((slot * kSplitSegs + sg[j]) * NOSC + i) * kOscWords) * 32 + vo[j];
+                                mode[j] = o[j][192];
+                                if (!mode[j]) continue;         // silent segment of this oscillator
+                                const unsigned dph = (unsigned)o[j][96];
+                                unsigned long long ph = ((unsigned long long)(unsigned)o[j][64] << 32) | (unsigned)o[j][32];
+                                ph += (unsigned long long)dph * (unsigned)kk[j];     // wtosc.c:231, k frames on
+                                av[j] = wadd(o[j][128], wmul(o[j][160], kk[j]));
+                                half[j] = dph >> 17;
+                                if (RAW && mode[j] >= 2) {
+                                    // wtosc.c:301-358: the wrapped loop reads sample k at (ph + k dph) mod M
+                                    if (mode[j] == 3) ph = mod_wave(ph, (unsigned)o[j][224]);
+                                    const int16_t *d = c.pool + o[j][0];
+                                    p16[j] = (unsigned)(ph >> 16);
+                                    t0[j] = hermite_fetch(d, p16[j]);
+                                    t1[j] = hermite_fetch(d, p16[j] + half[j]);
+                                } else
+                                    p16[j] = (unsigned)(ph >> 16);
+                            }
+#pragma unroll
+                            for (int j = 0; j < B; ++j) {
+                                if (!mode[j]) continue;
                                 int hv = 0;
-                                if (mode == 1) {
-                                    const int cfo = o[0];
+                                if (mode[j] == 1) {
+                                    const int cfo = o[j][0];
                                     const int srel = cfo - P.stage_begin;
                                     const int4 *cf = (srel >= 0 && srel < stage_n - 64) ? s_tab + srel : c.cpool + cfo;
-                                    const unsigned p16 = (unsigned)(ph >> 16);
-                                    hv = hermite_cf_smem(cf, p16) + hermite_cf_smem(cf, p16 + half);
+                                    hv = hermite_cf_smem(cf, p16[j]) + hermite_cf_smem(cf, p16[j] + half[j]);
                                 } else if (RAW) {
-                                    // wtosc.c:301-358: the wrapped loop reads sample k at (ph + k dph) mod M
-                                    if (mode == 3) ph = mod_near(ph, (unsigned long long)(unsigned)o[224] << 24);
-                                    const int16_t *d = c.pool + o[0];
-                                    const unsigned p16 = (unsigned)(ph >> 16);
-                                    hv = hermite(d, p16) + hermite(d, p16 + half);
+                                    const int16_t *d = c.pool + o[j][0];
+                                    hv = hermite_eval(t0[j], d, p16[j]) + hermite_eval(t1[j], d, p16[j] + half[j]);
                                 }
-                                acc = wadd(acc, mulshr(hv, av, 17));
+                                acc[j] = wadd(acc[j], mulshr(hv, av[j], 17));
                             }
                         }
-                        if (f < n) tslot[f * kTileStride + vo] = acc;
+#pragma unroll
+                        for (int j = 0; j < B; ++j)
+                            if (fr[j] < n) tslot[fr[j] * kTileStride + vo[j]] = acc[j];
                     }
                 } else {
                     const int split = sm[L::split + slot * 32 + lane];
