@@ -59,8 +59,8 @@ WINDOW = STEP_MS * RATE // 1000         # 960 frames = 15 blocks of 64
 BLOCK = 64
 WINDOWS_PER_STEP = 50                   # one step = 1 s of audio
 L2_BYTES = 126 * 1024 * 1024            # B200 L2
-NCU_SUMMARY = os.path.join("profiles", "r02_render_split_ncu.txt")
-NCU_FALLBACK = os.path.join("profiles", "r01_v5_render_split_ncu.txt")
+NCU_SUMMARY = os.path.join("profiles", "r02b_render_split_ncu.txt")
+NCU_FALLBACK = os.path.join("profiles", "r02_render_split_ncu.txt")
 
 
 def workload_name(voices):
@@ -341,31 +341,36 @@ def secondary_configs(local, dev, world, rank, peak, args):
                          "frac": alg / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg,
                          "note": "state read + written once per launch; bound by INT32 issue / smem gather"}}
         e.close()
-        # the HBM-bound gather: large sampled waves
-        e = fresh()
-        V = args.gather_voices
-        banks, info = wl.setup_gather(e, V)
-        frames = 256
-        e.run(frames, 64)               # uploads the 403 MB wave pool
-        ms = span_windows(e, frames, 64, 6, 1, None)
-        alg = float(V) * frames * info["bytes_per_voice_sample"]
-        out["gather"] = {
-            "workload": "%d voices wtosc->panmix on 12 sampled waves x 16.8 M samples (%.0f MB, 3x L2), "
-                        "64 wave samples per frame, %d-frame windows" % (V, info["wave_bytes"] / 1e6, frames),
-            "value": V * frames / (ms / 1e3), "unit": "voice-samples/s", "ms_per_window": ms,
-            "kernel": "%s<%s>" % ("render_split" if e.split_launches else "render_bank",
-                                  e.bank_kernel_name(banks[0])),
-            "l2": "no flush: inputs (wave pool) are 3x the L2",
-            "roofline": {"bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                         "frac": alg / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg,
-                         "note": "2 Hermite taps per output sample, each in its own 32-byte sector: 64 B per "
-                                 "voice-sample (SURVEY.md 8(d)). A pure random 8-byte gather over the same 403 MB "
-                                 "(profiles/ubench_gather.cu, no arithmetic, up to 32 loads in flight per thread) "
-                                 "tops out at 1 675-1 854 GB/s of sectors on this chip: sector-granular random "
-                                 "reads cannot reach the streaming peak this fraction is quoted against",
-                         "random_sector_ceiling": {"GBps": 1854.0, "source": "profiles/r02_ubench_gather.txt (static)",
-                                                   "frac": alg / (ms / 1e3) / 1e9 / 1854.0}}}
-        e.close()
+        # the HBM-bound gather: large sampled waves, at 64 and at 32 wave samples per output frame
+        for key, spf in (("gather", 64), ("gather32", 32)):
+            e = fresh()
+            V = args.gather_voices
+            banks, info = wl.setup_gather(e, V, samples_per_frame=spf)
+            frames = 256
+            e.run(frames, 64)               # uploads the 403 MB wave pool
+            ms = span_windows(e, frames, 64, 6, 1, None)
+            alg = float(V) * frames * info["bytes_per_voice_sample"]
+            note = ("2 Hermite taps per output sample, each in its own 32-byte sector: 64 B per voice-sample "
+                    "(SURVEY.md 8(d)). Stage A runs lane = frame, so one warp instruction reads a contiguous run "
+                    "of the wave; ")
+            if spf == 64:
+                note += ("at 64 samples per frame the taps are 64 B apart and only every other sector of the run "
+                         "is used, while DRAM delivers 64-byte atoms: ncu counts 3.2 GB read for 2.1 GB "
+                         "algorithmic (profiles/r02b_gather64_ncu.txt), i.e. DRAM itself runs at 1.5x this fraction")
+            else:
+                note += ("at 32 samples per frame every sector of the run is used: DRAM traffic = algorithmic "
+                         "bytes less L2 hits (profiles/r02b_gather32_ncu.txt)")
+            out[key] = {
+                "workload": "%d voices wtosc->panmix on 12 sampled waves x 16.8 M samples (%.0f MB, 3x L2), "
+                            "%d wave samples per frame, %d-frame windows" % (V, info["wave_bytes"] / 1e6, spf, frames),
+                "value": V * frames / (ms / 1e3), "unit": "voice-samples/s", "ms_per_window": ms,
+                "kernel": "%s<%s>" % ("render_split" if e.split_launches else "render_bank",
+                                      e.bank_kernel_name(banks[0])),
+                "l2": "no flush: inputs (wave pool) are 3x the L2",
+                "roofline": {"bound": "hbm", "achieved": alg / (ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": alg / (ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": alg,
+                             "note": note}}
+            e.close()
     if world == 1:
         # cfg2 at saturation: one bank of 262 144 voices in one launch (profiles/r02_saturation.json)
         e = fresh()

@@ -3,6 +3,7 @@
 # default build and every variant under audiality2_b200/build/variants/.
 tag=${1:-gather}
 mkdir -p gpurun_out
+shopt -s nullglob
 for lib in default audiality2_b200/build/variants/liba2cu_*.so; do
   n=$(basename $lib .so); n=${n#liba2cu_}
   if [ $lib = default ]; then unset A2CU_LIB; else export A2CU_LIB=$PWD/$lib; fi

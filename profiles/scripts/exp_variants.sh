@@ -6,6 +6,7 @@ tag=${1:-exp}
 mkdir -p gpurun_out
 show() { python -c "
 import json,sys; d=json.loads(sys.stdin.read()); print('$1', round(d['value']/1e9,2), 'G value', round(d['details']['ms_per_window']*1e3,2), 'us/window |', round(d['e2e']['value']/1e9,2), 'G e2e', {k: round(v['value']/1e9,1) for k,v in d.get('configs',{}).items()})"; }
+shopt -s nullglob
 for lib in default audiality2_b200/build/variants/liba2cu_*.so; do
   n=$(basename $lib .so); n=${n#liba2cu_}
   if [ $lib = default ]; then unset A2CU_LIB; else export A2CU_LIB=$PWD/$lib; fi
