@@ -157,6 +157,22 @@ static int a2cu_trace = -1;
 static int is_ours(const A2_unitdesc *d);
 
 /*
+ * A2CU_NULL=1: measurement aid, never a render mode. Every Process() / write
+ * callback returns at once (inline still recurses into the host's walk), so a
+ * run costs what the unmodified host spends on its own VM, event handling and
+ * voice tree walk plus the bare indirect calls - the floor no unit library can
+ * get under from behind the A2_unitdesc boundary (profiles/cfg5_k2trance.py
+ * reports it next to the real run). The output is silence.
+ */
+static int a2cu_null = -1;
+static inline int null_on(void)
+{
+	if(a2cu_null < 0)
+		a2cu_null = getenv("A2CU_NULL") ? 1 : 0;
+	return a2cu_null;
+}
+
+/*
  * A2CU_STATS=1: time spent inside the plug-in's callbacks (TSC ticks), printed
  * when the last engine state closes. Shows how much of a drop-in render is the
  * host's own VM + tree walk and how much is our recording.
@@ -597,6 +613,8 @@ static void unit_write_body(A2_unit *u, int reg, int value, unsigned start,
 static void unit_write(A2_unit *u, int reg, int value, unsigned start,
 		unsigned dur)
 {
+	if(null_on())
+		return;
 	if(stats_on())
 	{
 		unsigned long long t = tsc();
@@ -721,6 +739,8 @@ static void unit_process_body(A2_unit *u, unsigned offset, unsigned frames);
 /* Process() of every replaced DSP unit (never inline) */
 static void unit_process(A2_unit *u, unsigned offset, unsigned frames)
 {
+	if(null_on())
+		return;
 	if(stats_on())
 	{
 		unsigned long long t = tsc();
@@ -1039,6 +1059,11 @@ static void inline_process(A2_unit *u, unsigned offset, unsigned frames,
 
 static void inline_timed(A2_unit *u, unsigned offset, unsigned frames, int add)
 {
+	if(null_on())
+	{
+		a2_inline_ProcessAdd(u, offset, frames);	/* the host's recursion only */
+		return;
+	}
 	if(stats_on())
 	{
 		unsigned long long t = tsc();
