@@ -207,3 +207,43 @@ def test_cfg5_sharded_dropin_equals_sharded_reference():
     assert np.abs(ref).max() > 1000000
     assert np.array_equal(out, ref), _diff(out, ref)
     assert not np.array_equal(ref, whole.astype(np.int64))      # the shared LCG: sharding is a different song
+
+
+@pytest.mark.parametrize("kinds,buffer", [
+    (["wtosc", "panmix"], 64),
+    (["wtosc", "panmix"], 50),
+    (["wtosc", "wtosc", "panmix"], 64),
+    (["wtosc", "filter12", "panmix"], 64),
+])
+def test_raw_tap_gather_with_segments_and_chains(kinds, buffer):
+    """The raw-tap gather of render_split (stage A with lane = frame, csrc/a2cu_split.cuh) on a
+    sampled wave too long for a coefficient table, with everything that cuts a fragment into
+    segments: pitch / amplitude ramps and phase writes at times that are no multiple of the
+    fragment length, voices below and above A2_MAXPHINC samples per frame (plain and per-sample
+    wrapped loop, wtosc.c:200-236 and 301-358), two oscillators per voice, a filter behind the
+    oscillator, and a driver buffer that is not a multiple of 64. CUDA vs the oracle port."""
+    from scenarios import Scenario, run_cuda, run_oracle
+    from cases import W, P, A, PH, PAN
+    s = Scenario(48000, 2, buffer, 1500)
+    w = s.upload(2, 700, 0x100, (1 << 20) + 5003, 11)
+    nosc = kinds.count("wtosc")
+    pm = len(kinds) - 1
+    for i in range(40):
+        p0 = -2.5 + 0.27 * i            # up to +8 octaves: period 700 -> far above A2_MAXPHINC
+        steps = []
+        for k in range(nosc):
+            steps += [("ramp", k, W, w << 16), ("set", k, P, fx(p0 + 0.31 * k)), ("set", k, A, fx(0.08)),
+                      ("set", k, PH, fx(0.13 * i + k))]
+        if "filter12" in kinds:
+            steps += [("set", 1, 0, fx(p0 + 1.0)), ("set", 1, 1, fx(1.5))]
+        steps += [("set", pm, PAN, fx(-0.9 + 0.045 * i)), ("d", fx(3.1 + 0.07 * i)),
+                  ("ramp", 0, P, fx(p0 + 0.8)), ("ramp", 0, A, fx(0.03)), ("d", fx(9.25)),
+                  ("set", 0, PH, fx(0.5)), ("ramp", nosc - 1, A, fx(0.1)), ("d", fx(7.3)),
+                  ("ramp", 0, P, fx(p0 - 0.5)), ("d", fx(6))]
+        s.add_voice(kinds, steps)
+    stats = {}
+    out = run_cuda(s, stats=stats)
+    ref = run_oracle(s)
+    assert stats["split_launches"] > 0
+    assert np.abs(ref).max() > 10000
+    assert np.array_equal(out, ref), _diff(out, ref)
