@@ -247,8 +247,9 @@ render_split(const RenderParams P) {
         d2 = sp.ld(SplitLayout<NOSC, FILT, R>::filt_w + 13);
     }
 
-    int nfrag = 0;
-    for (int f = 0; f < W; f = frag_end(f, P.buffer, W)) ++nfrag;
+    // fragments restart at every driver buffer (frag_end): closed form instead of walking the window
+    const int nfrag = (W / P.buffer) * ((P.buffer + kMaxFrag - 1) / kMaxFrag) +
+                      ((W % P.buffer) + kMaxFrag - 1) / kMaxFrag;
     const int mybus = valid ? P.bus_of[v] : -1;
     // home bus of a voice set: the bus of its first voice
     const int home = (blockIdx.x * VS + set) * 32 < P.nvoices ? P.bus_of[(blockIdx.x * VS + set) * 32] : -1;
@@ -327,7 +328,12 @@ render_split(const RenderParams P) {
 #pragma unroll
                             for (int i = 0; i < NOSC; ++i)
                                 if (unit == i) {
-                                    if ((open_mask >> i) & 1) { osc[i].finish(); open_mask &= ~(1u << i); }
+                                    // an amplitude write (wtosc.c:498-501 only sets the ramper) leaves the
+                                    // segment open: the fast path below redoes a2_PrepareRamper for it
+                                    if (((open_mask >> i) & 1) && (init || reg != 2)) {
+                                        osc[i].finish();
+                                        open_mask &= ~(1u << i);
+                                    }
                                     if (init) osc[i].init(c, (int)e.z, (unsigned)st);
                                     else osc[i].write(c, reg, (int)e.z, st, (int)e.w);
                                 }
