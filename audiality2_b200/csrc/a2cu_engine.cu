@@ -74,6 +74,7 @@ static void register_split() { a2cu_register_split(); }
 struct HostTables {
     unsigned ptab[128];     // {base, coeff} x 64, pitch.c:70-96
     int16_t fmsine[2049];   // fm.c:486-501
+    int fmsine_packed[2048];    // {sine[i] | (sine[i + 1] - sine[i]) << 16}: what the kernels read (lerp16_packed)
     HostTables() {
         unsigned b = 0x80000000u;
         for (unsigned i = 0; i < 64; ++i) {
@@ -83,6 +84,8 @@ struct HostTables {
             b = b2;
         }
         for (int s = 0; s < 2049; ++s) fmsine[s] = (int16_t)(sin(s * 2.0f * M_PI / 2048) * 32767.0f);
+        for (int s = 0; s < 2048; ++s)
+            fmsine_packed[s] = (int)((unsigned)(uint16_t)fmsine[s] | ((unsigned)(fmsine[s + 1] - fmsine[s]) << 16));
     }
     unsigned p2i(int pitch) const {     // pitch.c:57-67 (shift count & 31 as on x86-64)
         int n = pitch & 0xffff;
@@ -298,6 +301,7 @@ struct a2cu_engine {
     WindowStats ws;
     // environment toggles, read once in a2cu_open (A/B switches for profiles/)
     bool env_stats = false, env_no_copy_stream = false, env_no_fuse = false, env_no_stage = false, env_one_set = false,
+         env_dry = false,     // A2CU_DRY: block mode records but launches nothing (measures the recording cost; silence)
          env_no_side_streams = false, env_split_always = false;
     int sm_count = 148;
     int device = 0, samplerate = 48000, channels = 2;
@@ -317,7 +321,7 @@ struct a2cu_engine {
     size_t pool_cap = 0, waves_cap = 0, cpool_cap = 0;
     size_t pool_used = 0, cpool_used = 0;   // device arenas: waves are appended, never moved
     unsigned *d_ptab = nullptr;
-    int16_t *d_fmsine = nullptr;
+    int *d_fmsine = nullptr;
     int *d_f12tab = nullptr;        // f12_table(samplerate)
     std::vector<Bank *> banks;
     std::vector<RenderParams> params;
@@ -840,6 +844,7 @@ a2cu_engine *a2cu_open(int device, int samplerate, int channels) {
     e->env_no_fuse = getenv("A2CU_NO_FUSE") != nullptr;
     e->env_no_stage = getenv("A2CU_NO_STAGE") != nullptr;
     e->env_one_set = getenv("A2CU_ONE_SET") != nullptr;
+    e->env_dry = getenv("A2CU_DRY") != nullptr;
     e->env_no_side_streams = getenv("A2CU_NO_SIDE_STREAMS") != nullptr;
     e->env_split_always = getenv("A2CU_SPLIT_ALWAYS") != nullptr;
     cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -856,10 +861,10 @@ a2cu_engine *a2cu_open(int device, int samplerate, int channels) {
     bool ok = cudaMalloc(&e->d_ptab, sizeof(t.ptab)) == cudaSuccess &&
               cudaMalloc(&e->d_f12tab, f12.size() * sizeof(int)) == cudaSuccess &&
               cudaMemcpy(e->d_f12tab, f12.data(), f12.size() * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
-              cudaMalloc(&e->d_fmsine, sizeof(t.fmsine)) == cudaSuccess &&
+              cudaMalloc(&e->d_fmsine, sizeof(t.fmsine_packed)) == cudaSuccess &&
               cudaMalloc(&e->d_rstate, 8 * sizeof(int)) == cudaSuccess &&
               cudaMemcpy(e->d_ptab, t.ptab, sizeof(t.ptab), cudaMemcpyHostToDevice) == cudaSuccess &&
-              cudaMemcpy(e->d_fmsine, t.fmsine, sizeof(t.fmsine), cudaMemcpyHostToDevice) == cudaSuccess;
+              cudaMemcpy(e->d_fmsine, t.fmsine_packed, sizeof(t.fmsine_packed), cudaMemcpyHostToDevice) == cudaSuccess;
     // root panmix: vol 1.0, pan 0 (panmix.c:252-262)
     int rs[8] = {65536 << 8, 65536 << 8, 0, 0, 0, 0, 0, 0};
     ok = ok && cudaMemcpy(e->d_rstate, rs, sizeof(rs), cudaMemcpyHostToDevice) == cudaSuccess;
@@ -2707,6 +2712,11 @@ int a2cu_block_flush(a2cu_engine *e) {
 static int block_flush_impl(a2cu_engine *e) {
     if (!e) return A2CU_EINVAL;
     cudaSetDevice(e->device);
+    if (e->env_dry) {       // measurement aid (profiles/cfg5_k2trance.py --breakdown): drop what was recorded
+        for (Bank *b : e->banks) { b->bev.clear(); b->bruns.clear(); b->cur_slot = -1; b->dup_runs = false; ++b->flush_id; }
+        e->buscmds.clear(); e->runs.clear(); e->cur_run = -1; ++e->flush_serial;
+        return A2CU_OK;
+    }
     {
         int wr = upload_waves(e);           // waves first seen in this block
         if (wr) return wr;
@@ -2859,6 +2869,10 @@ int a2cu_block_download(a2cu_engine *e, int bus, int nch, unsigned frame, unsign
     if (r) return r;
     r = ensure_xfer(e);
     if (r) return r;
+    if (e->env_dry) {
+        if (!add) for (int c = 0; c < nch; ++c) memset(dst[c] + frame, 0, frames * sizeof(int32_t));
+        return A2CU_OK;
+    }
     double t0 = now_us();
     CK(cudaMemcpyAsync(e->h_xfer, e->d_bacc + ((size_t)bus * kMaxFrag + frame) * 2, frames * 2 * sizeof(int32_t),
                        cudaMemcpyDeviceToHost, e->stream));

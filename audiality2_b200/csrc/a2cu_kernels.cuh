@@ -165,7 +165,7 @@ struct RenderParams {
     const int16_t *pool;
     const int4 *cpool;
     const unsigned *ptab;
-    const int16_t *fmsine;
+    const int *fmsine;        // packed FM sine, Ctx::fmsine
     const int *f12tab;
     int samplerate;
     // drop-in ("block") mode: thread i renders runs[i]; segments are the
@@ -200,7 +200,7 @@ A2CU_DEV int frag_end(int f, int buffer, int W) {
 template <class CH>
 __global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
     __shared__ int sacc[kMaxFrag][2];
-    __shared__ int16_t s_sine[CH::kUsesFm ? 2049 : 1];
+    __shared__ int s_sine[CH::kUsesFm ? 2048 : 1];
     __shared__ int s_home;
 
     const int tid = threadIdx.x;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kThreads) render_bank(const RenderParams P) {
     const int v = (valid && P.runs) ? P.runs[idx].slot : idx;
 
     if (CH::kUsesFm)
-        for (int i = tid; i < 2049; i += kThreads) s_sine[i] = P.fmsine[i];
+        for (int i = tid; i < 2048; i += kThreads) s_sine[i] = P.fmsine[i];
     if (tid < kMaxFrag) { sacc[tid][0] = 0; sacc[tid][1] = 0; }
     int mybus = (valid && !expl) ? P.bus_of[v] : -1;
     if (tid == 0) s_home = expl ? -2 : mybus;
