@@ -61,6 +61,9 @@ namespace a2cu {
 #ifndef A2CU_LF_RAW
 #define A2CU_LF_RAW 1
 #endif
+#ifndef A2CU_XCHG_OVERLAP
+#define A2CU_XCHG_OVERLAP 1
+#endif
 #ifndef A2CU_LF_BATCH
 #define A2CU_LF_BATCH 1
 #endif
@@ -823,11 +826,30 @@ render_split(const RenderParams P) {
                 // sharded + pipelined: finish the PREVIOUS window (its rows arrived long ago), then
                 // publish this one without waiting for anybody (read-then-publish keeps two buffer
                 // halves enough: a peer publishes window k + 1 only after it saw our window k)
-                if (P.xchg.prev_valid)
-                    xchg_finish_previous(P.xchg, P.fuse_rstate, P.fuse_channels, P.fuse_root_stage, tid, WR::threads,
-                                         P.fuse_out_fmt);
-                tmark(1);
-                xchg_publish(P.xchg, P.acc, P.W, tid, WR::threads, true);
+                // Both halves are chains of L2 / NVLink round trips (flags, rows, root state, peer stores,
+                // release) of ~6 k cycles each: they run side by side on the two halves of the CTA. The one
+                // ordering the protocol needs is kept with a named barrier: the flag writers wait until the
+                // reading half has loaded the previous window's rows. The root stage's segment replay
+                // (root panmix ramping, a2cu_kernels.cuh pm_bus) synchronises the whole CTA, so a window
+                // with the root rampers in motion takes the sequential order.
+                constexpr int T = WR::threads, H = (T / 64) * 32;
+                const int4 ra = __ldcg(reinterpret_cast<const int4 *>(P.fuse_rstate));
+                const int4 rb = __ldcg(reinterpret_cast<const int4 *>(P.fuse_rstate) + 1);
+                const bool at_rest = !P.fuse_root_stage || (ra.w == 0 && rb.w == 0 && ra.x == ra.y && rb.x == rb.y);
+                if (P.xchg.prev_valid && at_rest && H >= 32 && A2CU_XCHG_OVERLAP) {
+                    if (tid < H)
+                        xchg_finish_previous(P.xchg, P.fuse_rstate, P.fuse_channels, P.fuse_root_stage, tid, H,
+                                             P.fuse_out_fmt, GroupBar{1, H}, GroupBar{2, T});
+                    else
+                        xchg_publish(P.xchg, P.acc, P.W, tid - H, T - H, true, GroupBar{2, T});
+                    tmark(1);
+                } else {
+                    if (P.xchg.prev_valid)
+                        xchg_finish_previous(P.xchg, P.fuse_rstate, P.fuse_channels, P.fuse_root_stage, tid, WR::threads,
+                                             P.fuse_out_fmt);
+                    tmark(1);
+                    xchg_publish(P.xchg, P.acc, P.W, tid, WR::threads, true);
+                }
                 tmark(2);
             } else {
                 // sharded render: the root bus of all ranks is summed here, through NVLink peer memory

@@ -2,7 +2,7 @@
 fragments 60..62): two engines of one process on cuda:0 / cuda:1 (or both on cuda:0), cfg2 banks,
 pipelined submit/collect so the lagged exchange is active.
 
-    python profiles/xchg_tail.py [ndev]
+    python profiles/xchg_tail.py [ndev] [engines]
 """
 import sys
 sys.path.insert(0, '.')
@@ -12,9 +12,10 @@ from audiality2_b200 import engine as eng
 from audiality2_b200.workloads import setup_cfg2
 
 ndev = int(sys.argv[1]) if len(sys.argv) > 1 else min(2, torch.cuda.device_count())
+NE = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 W = 960
 engines, banks, amps, streams = [], [], [], []
-for r in range(2):
+for r in range(NE):
     d = r % ndev
     torch.cuda.set_device(d)
     e = eng.Engine(48000, 2, device=d)
@@ -24,7 +25,7 @@ for r in range(2):
     bank, b = setup_cfg2(e, 4096, seed=324357 + r)
     engines.append(e); banks.append(bank); amps.append(b['amp']); streams.append(st)
 for r, e in enumerate(engines):
-    e.xchg_create(r, 2, W, timeout_ms=5000)
+    e.xchg_create(r, NE, W, timeout_ms=5000)
 for e in engines:
     e.xchg_connect_local(engines)
 
@@ -50,7 +51,7 @@ run(20)
 for e in engines:
     e.split_profile(True, False)
 ms = run(40)
-print('2 engines on %d device(s): kernel span %.1f us (median), %.1f (min)' % (ndev, 1e3 * np.median(ms), 1e3 * min(ms)))
+print('%d engines on %d device(s): kernel span %.1f us (median), %.1f (min)' % (NE, ndev, 1e3 * np.median(ms), 1e3 * min(ms)))
 for r, e in enumerate(engines):
     tr = e.split_trace()
     t = tr[5, 60:63, 0]
