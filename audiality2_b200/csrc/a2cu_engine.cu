@@ -50,6 +50,21 @@ static int fail(int code, const char *fmt, const char *detail = "") {
             return fail(A2CU_ECUDA, #call ": %s", cudaGetErrorString(err__)); \
     } while (0)
 
+// cudaMemset runs on the legacy default stream and may return before the device is done. The engine's
+// kernels run on e->stream, which a caller may have set to a NON-BLOCKING stream (torch.cuda.Stream is
+// one): nothing then orders a creation-time clear before the first render kernel. Every such clear is
+// therefore completed before the call returns (creation paths only, never per window).
+static cudaError_t memcpy_done(void *dst, const void *src, size_t n, cudaMemcpyKind kind) {
+    cudaError_t r = cudaMemcpy(dst, src, n, kind);      // (H2D from pageable memory returns once staged, D2D at once)
+    if (r == cudaSuccess) r = cudaStreamSynchronize(0);
+    return r;
+}
+static cudaError_t memset_done(void *p, int v, size_t n) {
+    cudaError_t r = cudaMemset(p, v, n);
+    if (r == cudaSuccess) r = cudaStreamSynchronize(0);
+    return r;
+}
+
 // ---------------------------------------------------------------------------
 // Chain registry: signature string -> kernel. The kernels are instantiated in
 // their own translation units (a2cu_reg_*.cu, compiled in parallel by build.py).
@@ -663,7 +678,7 @@ static int mirror_create(a2cu_engine *e, int bank, int slot, VoiceMirror **out) 
     VoiceMirror vm;
     CK(cudaStreamSynchronize(e->stream));
     int flags = 0;
-    CK(cudaMemcpy(&flags, b->d_state + slot, sizeof(int), cudaMemcpyDeviceToHost));
+    CK(memcpy_done(&flags, b->d_state + slot, sizeof(int), cudaMemcpyDeviceToHost));
     vm.alive = flags & 1;
     int base = 1;
     for (size_t u = 0; u < b->chain.size(); ++u) {
@@ -726,9 +741,9 @@ static int arena_reserve(a2cu_engine *e, T **buf, size_t *cap, size_t used, size
     T *n = nullptr;
     if (cudaMalloc(&n, ncap * sizeof(T)) != cudaSuccess)
         return fail(A2CU_ENOMEM, "cudaMalloc wave pool: %s", cudaGetErrorString(cudaGetLastError()));
-    CK(cudaMemset(n, 0, ncap * sizeof(T)));
+    CK(memset_done(n, 0, ncap * sizeof(T)));
     if (*buf) {
-        CK(cudaMemcpy(n, *buf, used * sizeof(T), cudaMemcpyDeviceToDevice));
+        CK(memcpy_done(n, *buf, used * sizeof(T), cudaMemcpyDeviceToDevice));
         cudaFree(*buf);
     }
     *buf = n;
@@ -813,7 +828,7 @@ static int upload_waves(a2cu_engine *e) {
         if (r) return r;
     }
     if (!desc.empty())
-        CK(cudaMemcpy(e->d_waves, desc.data(), desc.size() * sizeof(WaveDesc), cudaMemcpyHostToDevice));
+        CK(memcpy_done(e->d_waves, desc.data(), desc.size() * sizeof(WaveDesc), cudaMemcpyHostToDevice));
     e->waves_dirty = false;
     return 0;
 }
@@ -860,14 +875,14 @@ a2cu_engine *a2cu_open(int device, int samplerate, int channels) {
     const std::vector<int> &f12 = f12_table(samplerate);
     bool ok = cudaMalloc(&e->d_ptab, sizeof(t.ptab)) == cudaSuccess &&
               cudaMalloc(&e->d_f12tab, f12.size() * sizeof(int)) == cudaSuccess &&
-              cudaMemcpy(e->d_f12tab, f12.data(), f12.size() * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
+              memcpy_done(e->d_f12tab, f12.data(), f12.size() * sizeof(int), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMalloc(&e->d_fmsine, sizeof(t.fmsine_packed)) == cudaSuccess &&
               cudaMalloc(&e->d_rstate, 8 * sizeof(int)) == cudaSuccess &&
-              cudaMemcpy(e->d_ptab, t.ptab, sizeof(t.ptab), cudaMemcpyHostToDevice) == cudaSuccess &&
-              cudaMemcpy(e->d_fmsine, t.fmsine_packed, sizeof(t.fmsine_packed), cudaMemcpyHostToDevice) == cudaSuccess;
+              memcpy_done(e->d_ptab, t.ptab, sizeof(t.ptab), cudaMemcpyHostToDevice) == cudaSuccess &&
+              memcpy_done(e->d_fmsine, t.fmsine_packed, sizeof(t.fmsine_packed), cudaMemcpyHostToDevice) == cudaSuccess;
     // root panmix: vol 1.0, pan 0 (panmix.c:252-262)
     int rs[8] = {65536 << 8, 65536 << 8, 0, 0, 0, 0, 0, 0};
-    ok = ok && cudaMemcpy(e->d_rstate, rs, sizeof(rs), cudaMemcpyHostToDevice) == cudaSuccess;
+    ok = ok && memcpy_done(e->d_rstate, rs, sizeof(rs), cudaMemcpyHostToDevice) == cudaSuccess;
     ok = ok && cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess &&
          cudaEventCreate(&e->ev2) == cudaSuccess;
     if (!ok) {
@@ -952,12 +967,12 @@ int a2cu_split_profile(a2cu_engine *e, int enable, uint64_t out[8]) {
     cudaSetDevice(e->device);
     if (out && e->d_prof) {
         CK(cudaStreamSynchronize(e->stream));
-        CK(cudaMemcpy(out, e->d_prof, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        CK(memcpy_done(out, e->d_prof, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     }
     if (enable && !e->d_prof) {
         CK(cudaMalloc(&e->d_prof, kProfWords * sizeof(uint64_t)));
     }
-    if (e->d_prof) CK(cudaMemset(e->d_prof, 0, 8 * sizeof(uint64_t)));
+    if (e->d_prof) CK(memset_done(e->d_prof, 0, 8 * sizeof(uint64_t)));
     if (!enable && e->d_prof) { cudaFree(e->d_prof); e->d_prof = nullptr; }
     return A2CU_OK;
 }
@@ -976,7 +991,7 @@ int a2cu_split_trace(a2cu_engine *e, uint64_t *out) {
     if (!e || !out || !e->d_prof) return A2CU_EINVAL;
     cudaSetDevice(e->device);
     CK(cudaStreamSynchronize(e->stream));
-    CK(cudaMemcpy(out, e->d_prof + 8, (kProfWords - 8) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CK(memcpy_done(out, e->d_prof + 8, (kProfWords - 8) * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return A2CU_OK;
 }
 uint64_t a2cu_h2d_bytes(const a2cu_engine *e) { return e->h2d_bytes; }
@@ -1106,7 +1121,7 @@ int a2cu_wave_read(a2cu_engine *e, int wave, int level, int16_t *out, unsigned c
     if (out && n) {
         cudaSetDevice(e->device);
         CK(cudaStreamSynchronize(e->stream));
-        CK(cudaMemcpy(out, e->d_pool + w.first[level], (size_t)n * sizeof(int16_t), cudaMemcpyDeviceToHost));
+        CK(memcpy_done(out, e->d_pool + w.first[level], (size_t)n * sizeof(int16_t), cudaMemcpyDeviceToHost));
     }
     return (int)(out ? n : w.span[level]);
 }
@@ -1121,14 +1136,14 @@ int a2cu_group_new(a2cu_engine *e) {
         CK(cudaMalloc(&n, (size_t)ncap * 8 * sizeof(int)));
         CK(cudaStreamSynchronize(e->stream));
         if (e->d_gstate) {
-            CK(cudaMemcpy(n, e->d_gstate, (size_t)e->ngroups * 8 * sizeof(int), cudaMemcpyDeviceToDevice));
+            CK(memcpy_done(n, e->d_gstate, (size_t)e->ngroups * 8 * sizeof(int), cudaMemcpyDeviceToDevice));
             cudaFree(e->d_gstate);
         }
         e->d_gstate = n;
         e->gstate_cap = ncap;
     }
     int gs[8] = {65536 << 8, 65536 << 8, 0, 0, 0, 0, 0, 0};
-    CK(cudaMemcpy(e->d_gstate + (size_t)e->ngroups * 8, gs, sizeof(gs), cudaMemcpyHostToDevice));
+    CK(memcpy_done(e->d_gstate + (size_t)e->ngroups * 8, gs, sizeof(gs), cudaMemcpyHostToDevice));
     e->gstamp.push_back(e->stamp++);
     return e->ngroups++;
 }
@@ -1188,12 +1203,12 @@ int a2cu_bank_new(a2cu_engine *e, const a2cu_unitspec *chain, int nunits, int nv
         delete b;
         return fail(A2CU_ENOMEM, "cudaMalloc bank state: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    CK(cudaMemset(b->d_state, 0, sbytes));
-    CK(cudaMemset(b->d_noise, 0, b->stride * sizeof(unsigned)));
-    CK(cudaMemcpy(b->d_bus, bus.data(), b->stride * sizeof(int), cudaMemcpyHostToDevice));
+    CK(memset_done(b->d_state, 0, sbytes));
+    CK(memset_done(b->d_noise, 0, b->stride * sizeof(unsigned)));
+    CK(memcpy_done(b->d_bus, bus.data(), b->stride * sizeof(int), cudaMemcpyHostToDevice));
     if (b->generic) {
         CK(cudaMalloc(&b->d_scratch, b->stride * kMaxFrag * 2 * sizeof(int)));
-        CK(cudaMemset(b->d_scratch, 0, b->stride * kMaxFrag * 2 * sizeof(int)));
+        CK(memset_done(b->d_scratch, 0, b->stride * kMaxFrag * 2 * sizeof(int)));
     }
     // Initialize() of every unit, in chain order, at the current time
     uint64_t t = (e->now & ~(uint64_t)0xff) | (substart & 0xff);
@@ -2159,7 +2174,7 @@ int a2cu_debug_f12_coeff(a2cu_engine *e, const int32_t *cutoff_values, int n, in
     cudaSetDevice(e->device);
     int *d = nullptr;
     CK(cudaMalloc(&d, (size_t)n * 2 * sizeof(int)));
-    cudaError_t err = cudaMemcpy(d, cutoff_values, (size_t)n * sizeof(int), cudaMemcpyHostToDevice);
+    cudaError_t err = memcpy_done(d, cutoff_values, (size_t)n * sizeof(int), cudaMemcpyHostToDevice);
     Ctx c;
     memset(&c, 0, sizeof(c));
     c.ptab = e->d_ptab; c.f12tab = e->d_f12tab; c.samplerate = e->samplerate;
@@ -2167,7 +2182,7 @@ int a2cu_debug_f12_coeff(a2cu_engine *e, const int32_t *cutoff_values, int n, in
         f12_coeff_probe<<<(n + 255) / 256, 256, 0, e->stream>>>(c, d, n, d + n);
         err = cudaStreamSynchronize(e->stream);
     }
-    if (err == cudaSuccess) err = cudaMemcpy(out, d + n, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost);
+    if (err == cudaSuccess) err = memcpy_done(out, d + n, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (err != cudaSuccess) return fail(A2CU_ECUDA, "a2cu_debug_f12_coeff: %s", cudaGetErrorString(err));
     return A2CU_OK;
@@ -2188,7 +2203,7 @@ int a2cu_xchg_create(a2cu_engine *e, int rank, int world, unsigned max_frames, u
     const size_t bytes = kXchgFlagBytes + (size_t)2 * world * max_frames * 2 * sizeof(int);
     if (cudaMalloc(&x.base, bytes) != cudaSuccess)
         return fail(A2CU_ENOMEM, "cudaMalloc exchange buffer: %s", cudaGetErrorString(cudaGetLastError()));
-    CK(cudaMemset(x.base, 0, bytes));
+    CK(memset_done(x.base, 0, bytes));
     CK(cudaMalloc(&x.d_sum, (size_t)max_frames * 2 * sizeof(int)));
     CK(cudaHostAlloc((void **)&x.h_status, sizeof(unsigned), cudaHostAllocMapped));
     *x.h_status = 0;
@@ -2298,11 +2313,11 @@ int a2cu_pool_open(a2cu_engine *e, const a2cu_unitspec *chain, int nunits) {
         delete b;
         return fail(A2CU_ENOMEM, "cudaMalloc pool: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    CK(cudaMemset(b->d_state, 0, sbytes));
-    CK(cudaMemset(b->d_noise, 0, b->stride * sizeof(unsigned)));
+    CK(memset_done(b->d_state, 0, sbytes));
+    CK(memset_done(b->d_noise, 0, b->stride * sizeof(unsigned)));
     if (b->generic) {
         CK(cudaMalloc(&b->d_scratch, b->stride * kMaxFrag * 2 * sizeof(int)));
-        CK(cudaMemset(b->d_scratch, 0, b->stride * kMaxFrag * 2 * sizeof(int)));
+        CK(memset_done(b->d_scratch, 0, b->stride * kMaxFrag * 2 * sizeof(int)));
     }
     e->banks.push_back(b);
     return (int)e->banks.size() - 1;
@@ -2315,8 +2330,8 @@ static int pool_grow(a2cu_engine *e, Bank *b) {
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaMalloc(&nstate, (size_t)b->k.words * ns * sizeof(int)));
     CK(cudaMalloc(&nnoise, ns * sizeof(unsigned)));
-    CK(cudaMemset(nstate, 0, (size_t)b->k.words * ns * sizeof(int)));
-    CK(cudaMemset(nnoise, 0, ns * sizeof(unsigned)));
+    CK(memset_done(nstate, 0, (size_t)b->k.words * ns * sizeof(int)));
+    CK(memset_done(nnoise, 0, ns * sizeof(unsigned)));
     CK(cudaMemcpy2D(nstate, ns * sizeof(int), b->d_state, b->stride * sizeof(int), b->stride * sizeof(int),
                     b->k.words, cudaMemcpyDeviceToDevice));
     cudaFree(b->d_state); cudaFree(b->d_noise);
@@ -2324,7 +2339,7 @@ static int pool_grow(a2cu_engine *e, Bank *b) {
     if (b->generic) {       // scratch rows hold nothing across fragments
         cudaFree(b->d_scratch);
         CK(cudaMalloc(&b->d_scratch, ns * kMaxFrag * 2 * sizeof(int)));
-        CK(cudaMemset(b->d_scratch, 0, ns * kMaxFrag * 2 * sizeof(int)));
+        CK(memset_done(b->d_scratch, 0, ns * kMaxFrag * 2 * sizeof(int)));
     }
     return A2CU_OK;
 }
@@ -2386,9 +2401,9 @@ int a2cu_block_bus(a2cu_engine *e) {
         int *n = nullptr;
         CK(cudaStreamSynchronize(e->stream));
         CK(cudaMalloc(&n, (size_t)ncap * kMaxFrag * 2 * sizeof(int)));
-        CK(cudaMemset(n, 0, (size_t)ncap * kMaxFrag * 2 * sizeof(int)));
+        CK(memset_done(n, 0, (size_t)ncap * kMaxFrag * 2 * sizeof(int)));
         if (e->d_bacc) {
-            CK(cudaMemcpy(n, e->d_bacc, (size_t)e->bacc_cap * kMaxFrag * 2 * sizeof(int), cudaMemcpyDeviceToDevice));
+            CK(memcpy_done(n, e->d_bacc, (size_t)e->bacc_cap * kMaxFrag * 2 * sizeof(int), cudaMemcpyDeviceToDevice));
             cudaFree(e->d_bacc);
         }
         e->d_bacc = n;
@@ -2519,7 +2534,7 @@ int a2cu_pm_alloc(a2cu_engine *e) {
             CK(cudaStreamSynchronize(e->stream));
             CK(cudaMalloc(&n, (size_t)ncap * 8 * sizeof(int)));
             if (e->d_pmstate) {
-                CK(cudaMemcpy(n, e->d_pmstate, (size_t)e->pm_cap * 8 * sizeof(int), cudaMemcpyDeviceToDevice));
+                CK(memcpy_done(n, e->d_pmstate, (size_t)e->pm_cap * 8 * sizeof(int), cudaMemcpyDeviceToDevice));
                 cudaFree(e->d_pmstate);
             }
             e->d_pmstate = n; e->pm_cap = ncap;
@@ -2589,9 +2604,9 @@ int a2cu_unit_alloc(a2cu_engine *e, int kind, int nin, int nout) {
             int *n = nullptr;
             CK(cudaStreamSynchronize(e->stream));
             CK(cudaMalloc(&n, (size_t)ncap * kUnitWords * sizeof(int)));
-            CK(cudaMemset(n, 0, (size_t)ncap * kUnitWords * sizeof(int)));
+            CK(memset_done(n, 0, (size_t)ncap * kUnitWords * sizeof(int)));
             if (e->d_ustate) {
-                CK(cudaMemcpy(n, e->d_ustate, (size_t)e->ustate_cap * kUnitWords * sizeof(int),
+                CK(memcpy_done(n, e->d_ustate, (size_t)e->ustate_cap * kUnitWords * sizeof(int),
                               cudaMemcpyDeviceToDevice));
                 cudaFree(e->d_ustate);
             }

@@ -89,25 +89,7 @@ A2CU_DEV unsigned ld_acquire_sys(const unsigned *p) {
 // flag-writing threads: st.release.sys after the CTA barrier is cumulative over the data stores the
 // barrier ordered before it (a membar.sys in each of 512 threads cost ~5 us, profiles/xchg_tail.py).
 // Publish: raw bus -> row [epoch & 1][rank] of every rank's buffer, then the flag.
-// Sub-CTA barriers (PTX named barriers 1..15; 0 is __syncthreads): the fused tail of a sharded,
-// pipelined launch runs "finish the previous window" and "publish this one" on two halves of the CTA
-// at the same time - both are chains of L2 / NVLink round trips, not throughput.
-struct GroupBar {
-    int id, n;          // id 0: the whole CTA (__syncthreads)
-    A2CU_DEV void sync() const {
-        if (id) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
-        else __syncthreads();
-    }
-    A2CU_DEV void arrive() const {      // non-blocking; id 0: nothing to tell anybody
-        if (id) asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
-    }
-};
-// `before_flags`: the barrier the flag writers pass before they release (default: the publishing
-// threads themselves). In the overlapped tail it also counts the reading half, which arrives once its
-// loads of the previous window's rows are done - a peer that sees our flag may go on to overwrite
-// those rows two windows later, so the release must not overtake the reads.
-A2CU_DEV void xchg_publish(const XchgParams &X, int *root, int W, int tid, int nthreads, bool zero,
-                           GroupBar before_flags = GroupBar{0, 0}) {
+A2CU_DEV void xchg_publish(const XchgParams &X, int *root, int W, int tid, int nthreads, bool zero) {
     const int par = (int)(X.epoch & 1u);
     const size_t pitch = (size_t)X.max_frames * 2;
     const size_t myrow = ((size_t)par * X.world + X.rank) * pitch;
@@ -125,13 +107,11 @@ A2CU_DEV void xchg_publish(const XchgParams &X, int *root, int W, int tid, int n
             }
         }
     }
-    before_flags.sync();
+    __syncthreads();
     if (tid < X.world) st_release_sys(X.flags[tid] + par * X.world + X.rank, X.epoch);
 }
 // Collect: wait until every rank's flag shows `epoch`, sum the rows into dst[W][2].
-// `grp`: the threads that take part; `loaded`: told (arrive) when this thread has read its rows.
-A2CU_DEV void xchg_collect(const XchgParams &X, unsigned epoch, int *dst, int W, int tid, int nthreads,
-                           GroupBar grp = GroupBar{0, 0}, GroupBar loaded = GroupBar{0, 0}) {
+A2CU_DEV void xchg_collect(const XchgParams &X, unsigned epoch, int *dst, int W, int tid, int nthreads) {
     const int par = (int)(epoch & 1u);
     const size_t pitch = (size_t)X.max_frames * 2;
     if (tid < X.world) {
@@ -145,32 +125,24 @@ A2CU_DEV void xchg_collect(const XchgParams &X, unsigned epoch, int *dst, int W,
             __nanosleep(64);
         }
     }
-    grp.sync();
+    __syncthreads();
     const int *mine = X.data[X.rank] + (size_t)par * X.world * pitch;
     const int n = W * 2;
     for (int i0 = tid; i0 < n; i0 += 4 * nthreads) {
         int sacc[4] = {0, 0, 0, 0};
-        // eight ranks' rows per round, every load issued before the first sum: one L2 round trip for
-        // a box of up to 8 GPUs instead of one per rank (the tail is a chain of such round trips)
-        for (int r0 = 0; r0 < X.world; r0 += 8) {
-            int v[8][4];
+        for (int r = 0; r < X.world; ++r) {
+            int v[4];
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
+            for (int j = 0; j < 4; ++j)
+                v[j] = i0 + j * nthreads < n ? __ldcg(mine + (size_t)r * pitch + i0 + j * nthreads) : 0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    v[r][j] = (r0 + r < X.world && i0 + j * nthreads < n)
-                                  ? __ldcg(mine + (size_t)(r0 + r) * pitch + i0 + j * nthreads) : 0;
-#pragma unroll
-            for (int r = 0; r < 8; ++r)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) sacc[j] = wadd(sacc[j], v[r][j]);
+            for (int j = 0; j < 4; ++j) sacc[j] = wadd(sacc[j], v[j]);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j)
             if (i0 + j * nthreads < n) dst[i0 + j * nthreads] = sacc[j];
     }
-    loaded.arrive();
-    grp.sync();
+    __syncthreads();
 }
 A2CU_DEV void xchg_root_bus(const XchgParams &X, int *root, int W, int tid, int nthreads) {
     xchg_publish(X, root, W, tid, nthreads, false);
@@ -586,9 +558,8 @@ A2CU_DEV void root_stage(const MixParams &P, int gtid, int gsize, bool cta0) {
 // launch ago by every rank - and run the root panmix into that window's output block.
 // `rstate`, `channels`, `root_stage_on` are those of the engine (they do not change per window).
 A2CU_DEV void xchg_finish_previous(const XchgParams &X, int *rstate, int channels, int root_stage_on, int tid,
-                                   int nthreads, int out_fmt = 0, GroupBar grp = GroupBar{0, 0},
-                                   GroupBar loaded = GroupBar{0, 0}) {
-    xchg_collect(X, X.prev_epoch, X.sum, X.prev_W, tid, nthreads, grp, loaded);
+                                   int nthreads, int out_fmt = 0) {
+    xchg_collect(X, X.prev_epoch, X.sum, X.prev_W, tid, nthreads);
     MixParams M;
     M.acc = X.sum; M.W = X.prev_W; M.buffer = X.prev_buffer; M.ngroups = 0; M.channels = channels;
     M.nsplits = X.prev_nsplits;
@@ -596,7 +567,7 @@ A2CU_DEV void xchg_finish_previous(const XchgParams &X, int *rstate, int channel
     M.gstate = nullptr; M.rstate = rstate; M.ev = nullptr; M.nev = 0;
     M.master = X.prev_master; M.root_stage = root_stage_on; M.clear = 0; M.general = 0; M.out_fmt = out_fmt;
     root_stage(M, tid, nthreads, true);
-    grp.sync();
+    __syncthreads();
 }
 
 }  // namespace a2cu

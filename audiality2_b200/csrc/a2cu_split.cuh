@@ -61,12 +61,6 @@ namespace a2cu {
 #ifndef A2CU_LF_RAW
 #define A2CU_LF_RAW 1
 #endif
-#ifndef A2CU_LDS_PATH
-#define A2CU_LDS_PATH 1
-#endif
-#ifndef A2CU_XCHG_OVERLAP
-#define A2CU_XCHG_OVERLAP 1
-#endif
 #ifndef A2CU_LF_BATCH
 #define A2CU_LF_BATCH 1
 #endif
@@ -131,17 +125,6 @@ constexpr size_t split_smem_bytes() {     // + 16 B per staged table entry
     return (size_t)VS * (SplitLayout<NOSC, FILT, R>::set_ints + kSplitMaxWin * 2) * sizeof(int);
 }
 
-// hermite_cf_smem through an explicit shared-memory address (ld.shared.v4 instead of a generic load)
-A2CU_DEV int hermite_cf_lds(unsigned base, unsigned ph) {
-    int4 e;
-    asm("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];"
-        : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w)
-        : "r"(base + (ph >> 8) * 16u));
-    int x = (int)((ph & 0xff) << 7);
-    int a = wmul(e.y, x) >> 15;
-    a = wmul(a + e.z, x) >> 15;
-    return e.x + (wmul(a + e.w, x) >> 15);
-}
 A2CU_DEV void mbar_arrive(unsigned long long *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -655,30 +638,17 @@ render_split(const RenderParams P) {
                                     if (!tab_ready) { mbar_wait(&s_mbar, 0); tab_ready = true; }
                                     const int cfo = o[0];
                                     const int srel = cfo - P.stage_begin;
-                                    const bool staged = srel >= 0 && srel < stage_n - 64;
+                                    // generic pointer: the staged copy in shared memory or the pool in global memory
+                                    const int4 *cf = (srel >= 0 && srel < stage_n - 64) ? s_tab + srel : c.cpool + cfo;
                                     ph += (unsigned long long)dph * (unsigned)(a - sa);
                                     // all kSlice frames are evaluated (independent chains the scheduler can
                                     // overlap); frames past the segment end read table slack and are dropped
                                     // at the store (wtosc.c:226-233)
-                                    if (A2CU_LDS_PATH && __ballot_sync(__activemask(), !staged) == 0) {
-                                        // every lane here plays the staged wave (the usual bank): plain
-                                        // shared-memory loads instead of generic ones
-                                        const unsigned base = smem_u32(s_tab + srel);
     #pragma unroll
-                                        for (int k = 0; k < kSlice; ++k) {
-                                            const unsigned p16 = (unsigned)((ph + (unsigned long long)dph * (unsigned)k) >> 16);
-                                            const int hv = hermite_cf_lds(base, p16) + hermite_cf_lds(base, p16 + half);
-                                            acc[k] = wadd(acc[k], mulshr(hv, wadd(av0, wmul(astep, k)), 17));
-                                        }
-                                    } else {
-                                        // generic pointer: the staged copy in shared memory or the pool in global memory
-                                        const int4 *cf = staged ? s_tab + srel : c.cpool + cfo;
-    #pragma unroll
-                                        for (int k = 0; k < kSlice; ++k) {
-                                            const unsigned p16 = (unsigned)((ph + (unsigned long long)dph * (unsigned)k) >> 16);
-                                            const int hv = hermite_cf_smem(cf, p16) + hermite_cf_smem(cf, p16 + half);
-                                            acc[k] = wadd(acc[k], mulshr(hv, wadd(av0, wmul(astep, k)), 17));
-                                        }
+                                    for (int k = 0; k < kSlice; ++k) {
+                                        const unsigned p16 = (unsigned)((ph + (unsigned long long)dph * (unsigned)k) >> 16);
+                                        const int hv = hermite_cf_smem(cf, p16) + hermite_cf_smem(cf, p16 + half);
+                                        acc[k] = wadd(acc[k], mulshr(hv, wadd(av0, wmul(astep, k)), 17));
                                     }
                                 } else if (RAW) {
                                     // Raw int16 taps from the pool (sampled waves too large for a table): the
@@ -853,30 +823,11 @@ render_split(const RenderParams P) {
                 // sharded + pipelined: finish the PREVIOUS window (its rows arrived long ago), then
                 // publish this one without waiting for anybody (read-then-publish keeps two buffer
                 // halves enough: a peer publishes window k + 1 only after it saw our window k)
-                // Both halves are chains of L2 / NVLink round trips (flags, rows, root state, peer stores,
-                // release) of ~6 k cycles each: they run side by side on the two halves of the CTA. The one
-                // ordering the protocol needs is kept with a named barrier: the flag writers wait until the
-                // reading half has loaded the previous window's rows. The root stage's segment replay
-                // (root panmix ramping, a2cu_kernels.cuh pm_bus) synchronises the whole CTA, so a window
-                // with the root rampers in motion takes the sequential order.
-                constexpr int T = WR::threads, H = (T / 64) * 32;
-                const int4 ra = __ldcg(reinterpret_cast<const int4 *>(P.fuse_rstate));
-                const int4 rb = __ldcg(reinterpret_cast<const int4 *>(P.fuse_rstate) + 1);
-                const bool at_rest = !P.fuse_root_stage || (ra.w == 0 && rb.w == 0 && ra.x == ra.y && rb.x == rb.y);
-                if (P.xchg.prev_valid && at_rest && H >= 32 && A2CU_XCHG_OVERLAP) {
-                    if (tid < H)
-                        xchg_finish_previous(P.xchg, P.fuse_rstate, P.fuse_channels, P.fuse_root_stage, tid, H,
-                                             P.fuse_out_fmt, GroupBar{1, H}, GroupBar{2, T});
-                    else
-                        xchg_publish(P.xchg, P.acc, P.W, tid - H, T - H, true, GroupBar{2, T});
-                    tmark(1);
-                } else {
-                    if (P.xchg.prev_valid)
-                        xchg_finish_previous(P.xchg, P.fuse_rstate, P.fuse_channels, P.fuse_root_stage, tid, WR::threads,
-                                             P.fuse_out_fmt);
-                    tmark(1);
-                    xchg_publish(P.xchg, P.acc, P.W, tid, WR::threads, true);
-                }
+                if (P.xchg.prev_valid)
+                    xchg_finish_previous(P.xchg, P.fuse_rstate, P.fuse_channels, P.fuse_root_stage, tid, WR::threads,
+                                         P.fuse_out_fmt);
+                tmark(1);
+                xchg_publish(P.xchg, P.acc, P.W, tid, WR::threads, true);
                 tmark(2);
             } else {
                 // sharded render: the root bus of all ranks is summed here, through NVLink peer memory
