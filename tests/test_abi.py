@@ -109,3 +109,19 @@ def test_units_library_exports_every_descriptor():
     syms = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True).stdout
     for n in names + ["a2cu_RegisterDriver"]:
         assert (" " + n + "\n") in syms, n
+
+
+def test_setup_time_clears_and_copies_are_completed():
+    """The engine's kernels run on a stream the caller may replace with a NON-BLOCKING one
+    (a2cu_set_stream; torch.cuda.Stream is non-blocking). cudaMemset / cudaMemcpy are issued on the
+    legacy default stream and may return before the device is done (memset always, memcpy for
+    device-to-device and staged pageable copies), and nothing orders them before work on such a
+    stream: every creation / growth path must go through memset_done / memcpy_done, which complete
+    the operation before returning. Source check (no GPU needed)."""
+    import re
+    src = open(os.path.join(ROOT, "audiality2_b200", "csrc", "a2cu_engine.cu")).read()
+    body = src.replace("cudaError_t r = cudaMemset(p, v, n);", "").replace(
+        "cudaError_t r = cudaMemcpy(dst, src, n, kind);", "")
+    assert not re.findall(r"(?<![A-Za-z_])cudaMemset\(", body)
+    assert not re.findall(r"(?<![A-Za-z_])cudaMemcpy\(", body)
+    assert "cudaStreamSynchronize(0)" in src
